@@ -1,0 +1,148 @@
+/* b200ode -- C ABI of the B200-native antisymmetric-ResNet Euler-block hot path.
+ *
+ * Drop-in boundary.  Every entry point replaces a piece of the
+ * reference's TensorFlow graph for ONE path; citations are relative to the reference
+ * repository (pierluigiferrari/differential_equations_resnet):
+ *
+ *   layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:85-155,210-293   kernel assembly (build)
+ *   layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:157-171          call(): conv2d SAME + bias
+ *   layers/tfkeras_layer_Conv2DAntisymmetric.py:90-175,216-270       general-k twin
+ *   models/tfkeras_resnets.py:69-92                                  Euler step (conv, BN?, relu, h*, +x)
+ *   training/training.py:300-301                                     backward (TF autodiff) + Adam
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all tensor arguments are raw DEVICE pointers, NHWC,
+ *     contiguous; shapes are explicit ints; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success or a negative b200ode_status; the message is
+ *     available through b200ode_last_error() (thread local).  Nothing aborts or throws.
+ *   - stream-ordered and asynchronous: no hidden device synchronisation.
+ *   - the caller owns every tensor; the library owns only the opaque handles (staged
+ *     weights, TMA descriptors, split-K workspace).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200ODE_H_
+#define B200ODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ODE_VERSION 100
+
+typedef enum {
+  B200ODE_OK = 0,
+  B200ODE_ERR_INVALID = -1,     /* bad argument / shape / alignment            */
+  B200ODE_ERR_UNSUPPORTED = -2, /* configuration has no GPU kernel (no fallback) */
+  B200ODE_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed          */
+  B200ODE_ERR_NOT_PACKED = -4   /* compute call before b200ode_pack_kernel      */
+} b200ode_status;
+
+/* precision_mode */
+#define B200ODE_PREC_STRICT 0     /* tcgen05 3xTF32 split, fp32 accumulate, fp32 I/O  (<=1e-5 rel) */
+#define B200ODE_PREC_FAST_TF32 1  /* tcgen05 1xTF32, fp32 accumulate, fp32 I/O                     */
+#define B200ODE_PREC_FAST_BF16 2  /* tcgen05 bf16 operands, fp32 accumulate, bf16 I/O              */
+#define B200ODE_PREC_SIMT_FP32 3  /* CUDA-core fp32 FMA kernels (any C, any k, any stride)         */
+
+/* param_layout: order of the free parameters in the flat packed vector = the
+ * reference's variable creation order, each variable flattened C-order. */
+#define B200ODE_LAYOUT_3BY3 0     /* [a,b,c,d (C each), W_0..W_{C-2} ([3,3,C-o-1]), bias]  (3By3.py:119-153,219-245) */
+#define B200ODE_LAYOUT_GENERAL 1  /* per o: diag scalars, W_o [k,k,C-o-1,1]; bias last (Conv2DAntisymmetric.py:117-157) */
+
+/* fuse_flags of the Euler forward/backward */
+#define B200ODE_F_BIAS 1       /* z = conv + bias                                 */
+#define B200ODE_F_RELU 2       /* r = relu(z)                                     */
+#define B200ODE_F_SCALE 4      /* r = h * r      (models/tfkeras_resnets.py:90-91) */
+#define B200ODE_F_RESIDUAL 8   /* y = r + x      (models/tfkeras_resnets.py:92)    */
+#define B200ODE_F_EULER (1 | 2 | 4 | 8)
+
+typedef struct b200ode_layer b200ode_layer_t;
+
+int b200ode_version(void);
+const char* b200ode_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is usable, else 0 (message set). */
+int b200ode_device_ok(void);
+
+/* ---- layer handle: replaces Conv2DAntisymmetric3By3.__init__/build (3By3.py:60-155) and
+ *      Conv2DAntisymmetric.__init__/build (Conv2DAntisymmetric.py:60-159) ---- */
+int b200ode_layer_create(int channels, int ksize, float gamma, int stride_h, int stride_w, int use_bias,
+                         int antisymmetric, int precision_mode, int param_layout, b200ode_layer_t** out);
+int b200ode_layer_destroy(b200ode_layer_t* layer);
+/* number of floats in the packed parameter vector (bias included when use_bias) */
+int64_t b200ode_layer_num_params(const b200ode_layer_t* layer);
+/* precision mode actually in effect (SIMT is selected for shapes the tensor path cannot take) */
+int b200ode_layer_effective_mode(const b200ode_layer_t* layer);
+
+/* ---- K1 antisym_pack: replaces the assembly graph 3By3.py:113-141,268-293 (re-executed every
+ *      sess.run by the reference).  params: device fp32 [num_params].  Writes the handle's
+ *      staged tensor-core operand copies and, when K_dense_hwio != NULL, the dense fp32
+ *      [k,k,C,C] kernel that get_kernel() (3By3.py:188-199) returns. ---- */
+int b200ode_pack_kernel(b200ode_layer_t* layer, const float* params, float* K_dense_hwio, void* stream);
+
+/* ---- K2 forward: tf.nn.conv2d(SAME)+bias (3By3.py:159-169) fused with relu, h*, +x
+ *      (models/tfkeras_resnets.py:89-92) according to fuse_flags.
+ *      x, y: [N,H,W,C] (fp32, or bf16 in FAST_BF16 mode); y: [N,ceil(H/sh),ceil(W/sw),C].
+ *      relu_mask: nullable; when given receives 1 bit per output element, row pitch
+ *      ceil(C/8) bytes per pixel, bit c%8 of byte c/8 = (z > 0).
+ *      z_out: nullable fp32 pre-activation output (needed by the BatchNorm path). ---- */
+int b200ode_euler_fwd(b200ode_layer_t* layer, const void* x, void* y, uint8_t* relu_mask, float* z_out, int N, int H,
+                      int W, float h, int fuse_flags, void* stream);
+
+/* ---- K3 data gradient (TF autodiff Conv2DBackpropInput, training/training.py:300):
+ *      dx = [dy_skip] + conv_transpose_K(dz).  For the antisymmetric kernel this is
+ *      dy_skip - conv_K(dz) + 2*gamma*dz, i.e. the forward kernel with the forward weights.
+ *      dz: [N,Ho,Wo,C]; dy_skip: nullable [N,H,W,C] added to the result; dx: [N,H,W,C]. ---- */
+int b200ode_euler_dgrad(b200ode_layer_t* layer, const void* dz, const void* dy_skip, void* dx, int N, int H, int W,
+                        void* stream);
+
+/* ---- K4 weight gradient (Conv2DBackpropFilter + backprop through the assembly graph):
+ *      dense G = sum_pixels x^T dz, folded onto the free parameters
+ *      (S = G - rot180(G)^T); grad_params: fp32 [num_params] (bias
+ *      gradient = sum_pixels dz in the bias slot).  G_dense: nullable fp32 [k,k,C,C].
+ *      accumulate != 0 adds into grad_params instead of overwriting. ---- */
+int b200ode_euler_wgrad(b200ode_layer_t* layer, const void* x, const void* dz, float* grad_params, float* G_dense,
+                        int N, int H, int W, int accumulate, void* stream);
+
+/* ---- elementwise / reduction tails (K5/K6) ---- */
+/* dz = h * dy * mask   (backward of relu + Lambda(h*x)); dtype = layer I/O dtype */
+int b200ode_relu_scale_bwd(const void* dy, const uint8_t* relu_mask, void* dz, int64_t pixels, int channels, float h,
+                           int is_bf16, void* stream);
+/* y = h * relu(z * scale[c] + shift[c]) + x ; optional mask (same format as euler_fwd) */
+int b200ode_euler_tail(const float* z, const float* scale, const float* shift, const float* x, float* y,
+                       uint8_t* relu_mask, int64_t pixels, int channels, float h, int fuse_flags, void* stream);
+/* per-channel sums over pixels: out_sum[c] = sum a[p,c], out_sumsq[c] = sum a[p,c]*b[p,c] (b nullable -> a*a).
+ * workspace: device fp32 [2 * B200ODE_COLSUM_PARTS * channels]. Deterministic. */
+#define B200ODE_COLSUM_PARTS 256
+int b200ode_colsum(const float* a, const float* b, float* out_sum, float* out_sumprod, float* workspace, int64_t pixels,
+                   int channels, void* stream);
+/* training-mode BatchNormalization(axis=3) (models/tfkeras_resnets.py:85-87; Keras eps 1e-3):
+ * from sums -> mean, inv_std, and the affine (scale, shift) that b200ode_euler_tail consumes;
+ * updates moving statistics (momentum) when moving_mean != NULL. */
+int b200ode_bn_finalize(const float* sum, const float* sumsq, const float* bn_gamma, const float* bn_beta, float* mean,
+                        float* inv_std, float* scale, float* shift, float* moving_mean, float* moving_var,
+                        int64_t pixels, int channels, float eps, float momentum, void* stream);
+/* BN backward, two passes: (1) du = h*dy*[u>0] with u = z*scale+shift; sums of du and du*zhat
+ * via b200ode_colsum-like reduction into dbeta/dgamma; (2) dz. */
+int b200ode_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, const float* mean,
+                          const float* inv_std, float* dgamma, float* dbeta, float* workspace, int64_t pixels,
+                          int channels, float h, void* stream);
+int b200ode_bn_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift, const float* mean,
+                         const float* inv_std, const float* bn_gamma, const float* dgamma, const float* dbeta,
+                         float* dz, int64_t pixels, int channels, float h, void* stream);
+
+/* ---- optimiser step: tf.train.AdamOptimizer (training/training.py:300-301; eps 1e-7 in the
+ *      notebooks).  step_counter: device int32, 1-based step of THIS update (read, not written).
+ *      grad_scale multiplies the gradient first (1/world_size after an all-reduce sum). ---- */
+int b200ode_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int32_t* step_counter,
+                      float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+int b200ode_increment(int32_t* counter, void* stream);
+
+/* test hook: number of kernel launches issued by this library in this process */
+int64_t b200ode_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ODE_H_ */
