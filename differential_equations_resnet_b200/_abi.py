@@ -1,0 +1,95 @@
+"""ctypes binding of libb200ode.so (C ABI declared in include/b200ode.h).
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device
+is present, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200ode.so")
+
+PREC_STRICT, PREC_FAST_TF32, PREC_FAST_BF16, PREC_SIMT_FP32 = 0, 1, 2, 3
+PRECISIONS = {"strict": PREC_STRICT, "fast_tf32": PREC_FAST_TF32, "fast": PREC_FAST_TF32,
+              "fast_bf16": PREC_FAST_BF16, "simt": PREC_SIMT_FP32}
+LAYOUT_3BY3, LAYOUT_GENERAL = 0, 1
+F_BIAS, F_RELU, F_SCALE, F_RESIDUAL = 1, 2, 4, 8
+F_EULER = 15
+COLSUM_PARTS = 256
+
+_lib = None
+
+c_void_p, c_int, c_float, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64
+
+_SIGNATURES = {
+    "b200ode_version": (c_int, []),
+    "b200ode_last_error": (ctypes.c_char_p, []),
+    "b200ode_device_ok": (c_int, []),
+    "b200ode_launch_count": (c_int64, []),
+    "b200ode_layer_create": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     ctypes.POINTER(c_void_p)]),
+    "b200ode_layer_destroy": (c_int, [c_void_p]),
+    "b200ode_layer_num_params": (c_int64, [c_void_p]),
+    "b200ode_layer_effective_mode": (c_int, [c_void_p]),
+    "b200ode_pack_kernel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200ode_euler_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                  c_int, c_void_p]),
+    "b200ode_euler_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200ode_euler_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    "b200ode_relu_scale_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "b200ode_euler_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                   c_float, c_int, c_void_p]),
+    "b200ode_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b200ode_bn_finalize": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_float, c_float, c_void_p]),
+    "b200ode_bn_bwd_reduce": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_void_p]),
+    "b200ode_bn_bwd_apply": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_float, c_void_p]),
+    "b200ode_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
+                                  c_float, c_float, c_float, c_void_p]),
+    "b200ode_increment": (c_int, [c_void_p, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class B200OdeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200OdeError(
+                "native library %s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(differential_equations_resnet_b200/csrc/build.sh).  There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().b200ode_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc in (-1, -2):
+        raise ValueError("b200ode: %s" % msg)
+    raise B200OdeError("b200ode (status %d): %s" % (rc, msg))
+
+
+def require_device():
+    if not lib().b200ode_device_ok():
+        raise B200OdeError("b200ode: %s" % last_error())
+
+
+def launch_count() -> int:
+    return int(lib().b200ode_launch_count())

@@ -1,0 +1,730 @@
+// C-ABI implementation (include/b200ode.h): handles, planning, tensor-map encoding, launches.
+#include "../../include/b200ode.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "kernels_basic.cuh"
+#include "kernels_conv_tc.cuh"
+#include "kernels_wgrad_tc.cuh"
+
+using namespace b200ode;
+
+// ------------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (x);                                                                              \
+    if (e__ != cudaSuccess) return fail(B200ODE_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
+  } while (0)
+#define LAUNCH_CHECK(name)                                                                                 \
+  do {                                                                                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                                  \
+    if (e__ != cudaSuccess) return fail(B200ODE_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int g_num_sms = 0;
+static int device_check() {
+  static int state = 0;  // 0 unknown, 1 ok, -1 bad
+  if (state == 1) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(B200ODE_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  int dev = 0, major = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10) return fail(B200ODE_ERR_UNSUPPORTED, "compute capability %d.x: kernels are built for sm_100a only", major);
+  state = 1;
+  return 0;
+}
+
+// process-wide scratch (split-K partials, SIMT pre-activations); stream-ordered single-stream use
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+static Scratch g_scratch[2];
+static std::mutex g_scratch_mu;
+static int get_scratch(int slot, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  Scratch& s = g_scratch[slot];
+  if (s.bytes < bytes) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B200ODE_ERR_CUDA, "scratch allocation of %zu bytes failed (%s); run one eager warm-up call before CUDA-graph capture",
+                  bytes, cudaGetErrorString(e));
+    }
+    (void)st;
+    // the old block may still be in use by queued work: leak-free deferred free is not needed for
+    // correctness of stream order because cudaFree synchronises the device.
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = np;
+    s.bytes = bytes;
+  }
+  *out = s.ptr;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer handle
+// ------------------------------------------------------------------------------------------------
+struct b200ode_layer {
+  LayerGeom g;
+  int sh, sw, mode_req, mode_eff;
+  bool packed;
+  float* Kdense;   // [k,k,C,C]
+  float* Gdense;   // [k,k,C,C]
+  float* w_hi;     // [taps][C][C] tf32 (hi)
+  float* w_lo;     // strict only
+  __nv_bfloat16* w_bf;
+  float* bias;     // [C]
+  float* colsum_ws;
+  CUtensorMap map_w_hi, map_w_lo, map_w_bf;
+};
+
+static void build_diag_tab(LayerGeom& g) {
+  const int k = g.k;
+  DiagTab& t = g.tab;
+  memset(&t, 0, sizeof(t));
+  for (int i = 0; i < MAX_K * MAX_K; ++i) { t.slot[i] = -1; t.sign[i] = 1; }
+  if (g.layout == B200ODE_LAYOUT_3BY3) {
+    // [[a,b,c],[d,gamma,-d],[-c,-b,-a]]  (tfkeras_layer_Conv2DAntisymmetric3By3.py:262-275)
+    const int pos[4][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 0}};
+    for (int s = 0; s < 4; ++s) {
+      const int a = pos[s][0], b = pos[s][1];
+      t.slot[a * 3 + b] = (int8_t)s; t.sign[a * 3 + b] = 1;
+      t.slot[(2 - a) * 3 + (2 - b)] = (int8_t)s; t.sign[(2 - a) * 3 + (2 - b)] = -1;
+    }
+    t.nd = 4;
+    return;
+  }
+  // general layer: free scalars in creation order (tfkeras_layer_Conv2DAntisymmetric.py:231-264)
+  int nd = 0;
+  for (int i = 0; i < k; ++i)
+    for (int j = i; j < k; ++j) {
+      if (j > i || (j == i && i <= k / 2 - 1)) {
+        t.slot[i * k + j] = (int8_t)nd; t.sign[i * k + j] = 1;
+        t.slot[(k - 1 - i) * k + (k - 1 - j)] = (int8_t)nd;
+        t.sign[(k - 1 - i) * k + (k - 1 - j)] = g.antisym ? -1 : 1;
+        ++nd;
+      } else if (j == i && i == k / 2 && (k % 2) == 1 && !g.antisym) {
+        t.slot[i * k + j] = (int8_t)nd; t.sign[i * k + j] = 1;
+        ++nd;
+      }
+    }
+  t.nd = nd;
+}
+
+static bool tc_channels_ok(int C) { return C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
+
+static int make_w_map(CUtensorMap* m, void* ptr, int C, int eb, int kb, int tw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)C * eb, (cuuint64_t)C * C * eb};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)C, (cuuint32_t)tw};
+  cuuint32_t es[3] = {1, 1, 1};
+  const int rowb = kb * eb;
+  CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  return 0;
+}
+
+static int taps_per_w_stage(int mode, int C) {
+  const int eb = mode == MODE_BF16 ? 2 : 4;
+  const int rowb = C * eb >= 128 ? 128 : C * eb;
+  const int per_tap = C * rowb * (mode == MODE_STRICT ? 2 : 1);
+  if (per_tap * 9 <= 40 * 1024) return 9;
+  if (per_tap * 3 <= 56 * 1024) return 3;
+  return 1;
+}
+
+extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
+extern "C" const char* b200ode_last_error(void) { return g_err.c_str(); }
+extern "C" int b200ode_device_ok(void) { return device_check() == 0 ? 1 : 0; }
+extern "C" int64_t b200ode_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h, int stride_w, int use_bias,
+                                    int antisymmetric, int precision_mode, int param_layout, b200ode_layer_t** out) {
+  if (!out) return fail(B200ODE_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (C < 1) return fail(B200ODE_ERR_INVALID, "channels must be >= 1 (got %d)", C);
+  if (ksize < 1 || ksize > MAX_K || (ksize % 2) == 0) return fail(B200ODE_ERR_UNSUPPORTED, "kernel_size %d: odd sizes 1..%d are supported", ksize, MAX_K);
+  if (stride_h < 1 || stride_w < 1) return fail(B200ODE_ERR_INVALID, "strides must be >= 1");
+  if (precision_mode < 0 || precision_mode > 3) return fail(B200ODE_ERR_INVALID, "unknown precision_mode %d", precision_mode);
+  if (param_layout != B200ODE_LAYOUT_3BY3 && param_layout != B200ODE_LAYOUT_GENERAL) return fail(B200ODE_ERR_INVALID, "unknown param_layout %d", param_layout);
+  if (param_layout == B200ODE_LAYOUT_3BY3 && (ksize != 3 || !antisymmetric)) return fail(B200ODE_ERR_INVALID, "LAYOUT_3BY3 implies kernel_size 3 and antisymmetric");
+  if (int rc = device_check()) return rc;
+  b200ode_layer* L = new b200ode_layer();
+  memset(L, 0, sizeof(*L));
+  LayerGeom& g = L->g;
+  g.C = C; g.k = ksize; g.layout = param_layout; g.antisym = antisymmetric ? 1 : 0; g.use_bias = use_bias ? 1 : 0; g.gamma = gamma;
+  build_diag_tab(g);
+  const long long kk = (long long)ksize * ksize;
+  g.bias_off = (long long)g.tab.nd * C + kk * C * (C - 1) / 2;
+  g.nparams = g.bias_off + (use_bias ? C : 0);
+  L->sh = stride_h; L->sw = stride_w; L->mode_req = precision_mode;
+  const bool tc_ok = tc_channels_ok(C) && ksize == 3 && stride_h == 1 && stride_w == 1 && antisymmetric;
+  L->mode_eff = (precision_mode != B200ODE_PREC_SIMT_FP32 && tc_ok) ? precision_mode : B200ODE_PREC_SIMT_FP32;
+  if (precision_mode == B200ODE_PREC_FAST_BF16 && !tc_ok) {
+    delete L;
+    return fail(B200ODE_ERR_UNSUPPORTED, "FAST_BF16 needs C in {16,32,64,128,256}, k=3, strides (1,1), antisymmetric");
+  }
+  const size_t kbytes = (size_t)kk * C * C * sizeof(float);
+  cudaError_t e = cudaMalloc(&L->Kdense, kbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&L->Gdense, kbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&L->bias, (size_t)C * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&L->colsum_ws, (size_t)2 * B200ODE_COLSUM_PARTS * C * sizeof(float));
+  if (e == cudaSuccess && L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    if (L->mode_eff == B200ODE_PREC_FAST_BF16) e = cudaMalloc(&L->w_bf, (size_t)9 * C * C * 2);
+    else {
+      e = cudaMalloc(&L->w_hi, kbytes);
+      if (e == cudaSuccess && L->mode_eff == B200ODE_PREC_STRICT) e = cudaMalloc(&L->w_lo, kbytes);
+    }
+  }
+  if (e != cudaSuccess) {
+    b200ode_layer_destroy(L);
+    return fail(B200ODE_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+  }
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    const int eb = L->mode_eff == B200ODE_PREC_FAST_BF16 ? 2 : 4;
+    const int kb = (C * eb >= 128 ? 128 : C * eb) / eb;
+    const int tw = taps_per_w_stage(L->mode_eff, C);
+    int rc = 0;
+    if (L->w_bf) rc = make_w_map(&L->map_w_bf, L->w_bf, C, 2, kb, tw);
+    if (!rc && L->w_hi) rc = make_w_map(&L->map_w_hi, L->w_hi, C, 4, kb, tw);
+    if (!rc && L->w_lo) rc = make_w_map(&L->map_w_lo, L->w_lo, C, 4, kb, tw);
+    if (rc) { b200ode_layer_destroy(L); return rc; }
+  }
+  *out = L;
+  return 0;
+}
+
+extern "C" int b200ode_layer_destroy(b200ode_layer_t* L) {
+  if (!L) return 0;
+  cudaFree(L->Kdense); cudaFree(L->Gdense); cudaFree(L->w_hi); cudaFree(L->w_lo); cudaFree(L->w_bf);
+  cudaFree(L->bias); cudaFree(L->colsum_ws);
+  delete L;
+  return 0;
+}
+extern "C" int64_t b200ode_layer_num_params(const b200ode_layer_t* L) { return L ? L->g.nparams : -1; }
+extern "C" int b200ode_layer_effective_mode(const b200ode_layer_t* L) { return L ? L->mode_eff : -1; }
+
+extern "C" int b200ode_pack_kernel(b200ode_layer_t* L, const float* params, float* K_dense_hwio, void* stream) {
+  if (!L || !params) return fail(B200ODE_ERR_INVALID, "layer/params is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)L->g.k * L->g.k * L->g.C * L->g.C;
+  const long long n = total > L->g.C ? total : L->g.C;
+  pack_kernel<<<blocks_for(n, 256), 256, 0, st>>>(L->g, params, L->Kdense, K_dense_hwio, L->w_hi, L->w_lo, L->w_bf, L->bias,
+                                                 L->mode_eff == B200ODE_PREC_STRICT);
+  LAUNCH_CHECK("pack_kernel");
+  L->packed = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core convolution planning
+// ------------------------------------------------------------------------------------------------
+struct TcPlan {
+  ConvTcParams p;
+  size_t smem;
+  int grid;
+  int box_rows, box_imgs;
+};
+
+static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
+  const int eb = mode == MODE_BF16 ? 2 : 4;
+  const int rowb = C * eb >= 128 ? 128 : C * eb;
+  const int nkb = C * eb / rowb;
+  const bool strict = mode == MODE_STRICT;
+  const int P = W + 1;
+  if (P > 256 || H + 2 > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= 254 and W <= 255 (got %dx%d)", H, W);
+  const long long Q = (long long)H * P;
+  const int tw = taps_per_w_stage(mode, C);
+  const uint32_t w_bytes = (uint32_t)tw * C * rowb;
+  const uint32_t w_stride = w_bytes * (strict ? 2 : 1);
+  const int max_smem = 227 * 1024 - 2048;
+  double best_cost = 1e30;
+  TcPlan best;
+  bool found = false;
+  for (int whole = 0; whole < 2; ++whole) {
+    for (int a = 1; a <= 32; ++a) {
+      int spi, nimg, tpi, RB;
+      if (whole) {
+        spi = (int)((Q + 127) / 128); nimg = a; tpi = 1; RB = H + 2;
+        if (nimg > N && nimg > 1) break;
+      } else {
+        spi = a; nimg = 1; tpi = (int)((Q + 128LL * spi - 1) / (128LL * spi)); RB = (128 * spi) / P + 4;
+        if (128LL * (spi - 1) >= Q) break;
+        if (tpi == 1) continue;  // covered by whole-image mode
+      }
+      const int mt = nimg * spi;
+      if (mt * C > 512 || RB > 256 || nimg > 256) continue;
+      const int acc_stages = 2 * mt * C <= 512 ? 2 : 1;
+      const uint32_t a_bytes = (uint32_t)nimg * RB * P * rowb;
+      const uint32_t a_lo_off = align_up(a_bytes, 1024);
+      const uint32_t a_stride = strict ? 2 * a_lo_off : a_lo_off;
+      // stages: at least 2 of each when possible
+      int sw = 9 / tw >= 3 ? 3 : 2;
+      if (tw == 9) sw = 2;
+      int sa = 2;
+      long long need = (long long)sa * a_stride + (long long)sw * w_stride + 1024;
+      if (need > max_smem) { sa = 1; need = (long long)sa * a_stride + (long long)sw * w_stride + 1024; }
+      if (need > max_smem) continue;
+      while (sw < 6 && tw == 1 && need + w_stride <= max_smem) { ++sw; need += w_stride; }
+      if (nkb > 1 || true) while (sa < 3 && need + a_stride <= max_smem) { ++sa; need += a_stride; }
+      const long long tiles = whole ? (N + nimg - 1) / nimg : (long long)N * tpi;
+      // rough per-tile cycle model: tensor issue vs L2->smem fill vs epilogue traffic
+      const double per_mma = (C / 2 > 32 ? C / 2 : 32) * (strict ? 3.0 : 1.0);
+      const double mma_clk = (double)mt * nkb * 9 * (rowb / 32) * per_mma;
+      const double load_clk = ((double)nimg * RB * P * C * eb + 9.0 * C * C * eb * (strict ? 2 : 1)) / 40.0;
+      const double epi_clk = (double)mt * 128 * C * 4 * 2 / 40.0;
+      double tile_clk = mma_clk > load_clk ? mma_clk : load_clk;
+      if (acc_stages == 1) tile_clk += epi_clk; else if (epi_clk > tile_clk) tile_clk = epi_clk;
+      if (sa == 1) tile_clk = mma_clk + load_clk + (acc_stages == 1 ? epi_clk : 0);
+      tile_clk += 600;
+      const int sms = g_num_sms > 0 ? g_num_sms : 148;
+      const double waves = std::ceil((double)tiles / sms);
+      const double cost = waves * tile_clk;
+      if (cost < best_cost) {
+        best_cost = cost; found = true;
+        memset(&best, 0, sizeof(best));
+        ConvTcParams& p = best.p;
+        p.N = N; p.H = H; p.W = W; p.P = P; p.RB = RB; p.nimg = nimg; p.spi = spi; p.tpi = tpi; p.total_tiles = (int)tiles;
+        p.sa = sa; p.sw = sw; p.tw = tw;
+        p.a_bytes = a_bytes; p.a_lo_off = a_lo_off; p.a_stride = a_stride; p.w_bytes = w_bytes; p.w_stride = w_stride;
+        p.a_off = 0; p.w_off = (uint32_t)sa * a_stride; p.bar_off = p.w_off + (uint32_t)sw * w_stride;
+        uint32_t cols = (uint32_t)acc_stages * mt * C, pc = 32;
+        while (pc < cols) pc <<= 1;
+        p.tmem_cols = pc;
+        best.smem = (size_t)p.bar_off + 512 + 1024;
+        best.grid = (int)(tiles < sms ? tiles : sms);
+        best.box_rows = RB; best.box_imgs = nimg;
+      }
+    }
+  }
+  if (!found) return fail(B200ODE_ERR_UNSUPPORTED, "no tensor-core tiling fits shared memory for C=%d H=%d W=%d", C, H, W);
+  *plan = best;
+  return 0;
+}
+
+static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int eb, int kb, int box_w, int box_rows,
+                        int box_imgs, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(B200ODE_ERR_INVALID, "activation pointer must be 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+  cuuint32_t box[4] = {(cuuint32_t)kb, (cuuint32_t)box_w, (cuuint32_t)box_rows, (cuuint32_t)box_imgs};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr),
+                   dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+  return 0;
+}
+
+template <int MODE, int C>
+static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
+  auto kern = conv_tc_kernel<MODE, C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const CUtensorMap& mw = MODE == MODE_BF16 ? L->map_w_bf : L->map_w_hi;
+  const CUtensorMap& mwl = MODE == MODE_STRICT ? L->map_w_lo : mw;
+  kern<<<plan.grid, ConvTcCfg<MODE, C>::NWARPS * 32, plan.smem, st>>>(map_a, mw, mwl, plan.p);
+  LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
+template <int MODE>
+static int launch_conv_tc_m(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
+  switch (L->g.C) {
+    case 16: return launch_conv_tc_t<MODE, 16>(L, plan, map_a, st);
+    case 32: return launch_conv_tc_t<MODE, 32>(L, plan, map_a, st);
+    case 64: return launch_conv_tc_t<MODE, 64>(L, plan, map_a, st);
+    case 128: return launch_conv_tc_t<MODE, 128>(L, plan, map_a, st);
+    case 256: return launch_conv_tc_t<MODE, 256>(L, plan, map_a, st);
+  }
+  return fail(B200ODE_ERR_UNSUPPORTED, "tensor path: unsupported channel count %d", L->g.C);
+}
+
+// conv_K(input) with a fused epilogue; shared by forward and data gradient
+static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, int W, ConvTcParams epi, cudaStream_t st) {
+  const int mode = L->mode_eff, C = L->g.C;
+  TcPlan plan;
+  if (int rc = plan_conv_tc(mode, C, N, H, W, &plan)) return rc;
+  ConvTcParams& p = plan.p;
+  p.in = epi.in; p.skip = epi.skip; p.out = epi.out; p.z_out = epi.z_out; p.mask = epi.mask; p.bias = epi.bias;
+  p.acc_scale = epi.acc_scale; p.c_in = epi.c_in; p.h = epi.h; p.relu = epi.relu; p.scale_h = epi.scale_h;
+  const int eb = mode == MODE_BF16 ? 2 : 4;
+  const int rowb = C * eb >= 128 ? 128 : C * eb;
+  CUtensorMap map_a;
+  CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (int rc = make_act_map(&map_a, input, N, H, W, C, eb, rowb / eb, p.P, plan.box_rows, plan.box_imgs, sw)) return rc;
+  switch (mode) {
+    case MODE_STRICT: return launch_conv_tc_m<MODE_STRICT>(L, plan, map_a, st);
+    case MODE_TF32: return launch_conv_tc_m<MODE_TF32>(L, plan, map_a, st);
+    case MODE_BF16: return launch_conv_tc_m<MODE_BF16>(L, plan, map_a, st);
+  }
+  return fail(B200ODE_ERR_INVALID, "bad mode");
+}
+
+static ConvGeom conv_geom(const b200ode_layer* L, int N, int H, int W) {
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.C = L->g.C; g.k = L->g.k; g.sh = L->sh; g.sw = L->sw;
+  g.Ho = (H + L->sh - 1) / L->sh; g.Wo = (W + L->sw - 1) / L->sw;
+  const int ph = (g.Ho - 1) * L->sh + g.k - H, pw = (g.Wo - 1) * L->sw + g.k - W;
+  g.pt = (ph > 0 ? ph : 0) / 2; g.pl = (pw > 0 ? pw : 0) / 2;  // TF SAME: pad_before = total // 2
+  return g;
+}
+
+extern "C" int b200ode_euler_tail(const float* z, const float* scale, const float* shift, const float* x, float* y,
+                                  uint8_t* relu_mask, int64_t pixels, int channels, float h, int fuse_flags, void* stream) {
+  if (!z) return fail(B200ODE_ERR_INVALID, "z is NULL");
+  if ((fuse_flags & B200ODE_F_RESIDUAL) && !x) return fail(B200ODE_ERR_INVALID, "RESIDUAL needs x");
+  const long long n = pixels * ((channels + 7) / 8);
+  if (n == 0) return 0;
+  euler_tail_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, x, y, relu_mask, pixels, channels, h,
+                                                                          fuse_flags);
+  LAUNCH_CHECK("euler_tail_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_euler_fwd(b200ode_layer_t* L, const void* x, void* y, uint8_t* relu_mask, float* z_out, int N, int H,
+                                 int W, float h, int fuse_flags, void* stream) {
+  if (!L || !x) return fail(B200ODE_ERR_INVALID, "layer/x is NULL");
+  if (!L->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_pack_kernel must run before compute calls");
+  if (N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
+  if (!y && !z_out) return fail(B200ODE_ERR_INVALID, "need y or z_out");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool residual = fuse_flags & B200ODE_F_RESIDUAL;
+  if (residual && (L->sh != 1 || L->sw != 1)) return fail(B200ODE_ERR_INVALID, "RESIDUAL needs strides (1,1)");
+  // Lambda(h*x) exists only when h != 1.0 (models/tfkeras_resnets.py:90)
+  const int scale_h = (fuse_flags & B200ODE_F_SCALE) && h != 1.0f;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    ConvTcParams e;
+    memset(&e, 0, sizeof(e));
+    e.in = residual ? x : nullptr; e.skip = nullptr; e.out = y; e.z_out = z_out; e.mask = relu_mask;
+    e.bias = (fuse_flags & B200ODE_F_BIAS) && L->g.use_bias ? L->bias : nullptr;
+    e.acc_scale = 1.0f; e.c_in = 1.0f; e.h = h; e.relu = (fuse_flags & B200ODE_F_RELU) ? 1 : 0; e.scale_h = scale_h;
+    return run_conv_tc(L, x, N, H, W, e, st);
+  }
+  const ConvGeom g = conv_geom(L, N, H, W);
+  const long long total = (long long)N * g.Ho * g.Wo * g.C;
+  const bool plain = !(fuse_flags & (B200ODE_F_RELU | B200ODE_F_RESIDUAL)) && !scale_h && !relu_mask;
+  float* zbuf = z_out;
+  if (!zbuf) {
+    if (plain) zbuf = (float*)y;
+    else if (int rc = get_scratch(0, (size_t)total * sizeof(float), (void**)&zbuf)) return rc;
+  }
+  simt_conv_fwd<<<blocks_for(total, 256), 256, 0, st>>>(g, (const float*)x, L->Kdense,
+                                                       (fuse_flags & B200ODE_F_BIAS) && L->g.use_bias ? L->bias : nullptr, zbuf);
+  LAUNCH_CHECK("simt_conv_fwd");
+  if (plain) {
+    if (y && zbuf != y) CUDA_TRY(cudaMemcpyAsync(y, zbuf, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (!y && !relu_mask) return 0;
+  return b200ode_euler_tail(zbuf, nullptr, nullptr, residual ? (const float*)x : nullptr, (float*)y, relu_mask,
+                            (long long)N * g.Ho * g.Wo, g.C, h, (fuse_flags & ~B200ODE_F_SCALE) | (scale_h ? B200ODE_F_SCALE : 0), st);
+}
+
+extern "C" int b200ode_euler_dgrad(b200ode_layer_t* L, const void* dz, const void* dy_skip, void* dx, int N, int H, int W,
+                                   void* stream) {
+  if (!L || !dz || !dx) return fail(B200ODE_ERR_INVALID, "layer/dz/dx is NULL");
+  if (!L->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_pack_kernel must run before compute calls");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    // rot180(K)^T = -K + 2*gamma*delta  =>  dx = dy_skip - conv_K(dz) + 2*gamma*dz
+    ConvTcParams e;
+    memset(&e, 0, sizeof(e));
+    e.in = L->g.gamma != 0.0f ? dz : nullptr; e.skip = dy_skip; e.out = dx;
+    e.acc_scale = -1.0f; e.c_in = 2.0f * L->g.gamma; e.h = 1.0f;
+    return run_conv_tc(L, dz, N, H, W, e, st);
+  }
+  const ConvGeom g = conv_geom(L, N, H, W);
+  const long long total = (long long)N * H * W * g.C;
+  simt_conv_dgrad<<<blocks_for(total, 256), 256, 0, st>>>(g, (const float*)dz, L->Kdense, (const float*)dy_skip, (float*)dx);
+  LAUNCH_CHECK("simt_conv_dgrad");
+  return 0;
+}
+
+static int colsum_impl(ColsumArgs A, float* out0, float* out1, float* ws, long long pixels, int C, cudaStream_t st) {
+  const int parts = (int)(pixels < B200ODE_COLSUM_PARTS ? (pixels > 0 ? pixels : 1) : B200ODE_COLSUM_PARTS);
+  colsum_stage1<<<parts, 256, 2 * 256 * sizeof(float), st>>>(A, ws, pixels, C, parts);
+  LAUNCH_CHECK("colsum_stage1");
+  colsum_stage2<<<blocks_for(C, 128), 128, 0, st>>>(ws, out0, out1, C, parts);
+  LAUNCH_CHECK("colsum_stage2");
+  return 0;
+}
+
+extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, float* out_sumprod, float* workspace,
+                              int64_t pixels, int channels, void* stream) {
+  if (!a || !workspace) return fail(B200ODE_ERR_INVALID, "a/workspace is NULL");
+  ColsumArgs A;
+  memset(&A, 0, sizeof(A));
+  A.a = a; A.b = b; A.mode = 0;
+  return colsum_impl(A, out_sum, out_sumprod, workspace, pixels, channels, (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core weight gradient planning + launch
+// ------------------------------------------------------------------------------------------------
+static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, int N, int H, int W, float* G, float* G_user,
+                        cudaStream_t st) {
+  const int mode = L->mode_eff, C = L->g.C;
+  const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
+  const int eb = bf16 ? 2 : 4;
+  const int UKP = bf16 ? 16 : 8;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1;
+  if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
+  p.CH = bf16 ? (C < 64 ? C : 64) : 32;
+  p.RWB = p.CH * eb;
+  const int Cpad = C > p.CH ? C : p.CH;
+  p.xchunks = Cpad / p.CH;
+  p.trick = (p.xchunks == 1 && 4 * p.CH <= 128) ? 1 : 0;
+  if (p.trick) {
+    p.TG = 9; p.NT = p.CH; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 4 * p.CH; p.dchunks = 1;
+  } else {
+    p.Mblk = Cpad < 128 ? Cpad : 128;
+    p.MB = Cpad / p.Mblk;
+    double best = 1e30;
+    for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
+      for (int TG : {9, 3, 1}) {
+        if (TG * p.MB * NT > 512) continue;
+        const double load = (double)(C + NT) * UKP * eb / 40.0;
+        const double per = (double)(NT / 2 > p.Mblk / 4 ? NT / 2 : p.Mblk / 4);
+        const double mma = (double)TG * p.MB * per * (strict ? 3 : 1);
+        const double t = (load > mma ? load : mma) * (9 / TG) * (C / NT);
+        if (t < best - 1e-9) { best = t; p.TG = TG; p.NT = NT; }
+      }
+    if (best > 1e29) return fail(B200ODE_ERR_UNSUPPORTED, "no wgrad tiling for C=%d", C);
+    p.ntapgroups = 9 / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
+  }
+  const int ngroups = p.ntapgroups * p.nngroups;
+  const int nent = p.trick ? 3 : p.TG * p.MB;
+  uint32_t cols = (uint32_t)nent * p.NT, pc = 32;
+  while (pc < cols) pc <<= 1;
+  p.tmem_cols = pc;
+  // positions per tile: as large as fits two stages (one as a fallback)
+  const long long Q = (long long)H * p.P;
+  const int max_smem = 227 * 1024 - 2048;
+  int KT = 0, stages = 0;
+  for (int st_try = 2; st_try >= 1 && !KT; --st_try) {
+    for (int kt = 512; kt >= UKP; kt -= UKP) {
+      const int RBx = (p.P - 1 + kt + 2 * p.P + 4 + p.P - 1) / p.P, RBd = (p.P - 1 + kt + p.P - 1) / p.P;
+      if (RBx > 256) continue;
+      const uint32_t xs = align_up((uint32_t)RBx * p.P * p.RWB, 1024), ds = align_up((uint32_t)RBd * p.P * p.RWB, 1024);
+      const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
+      if (stage * st_try + 1024 <= max_smem) { KT = kt; stages = st_try; break; }
+    }
+  }
+  if (!KT) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad strips do not fit shared memory (C=%d W=%d)", C, W);
+  if (KT > Q) KT = (int)((Q + UKP - 1) / UKP * UKP);
+  p.tpi = (int)((Q + KT - 1) / KT);
+  KT = (int)(((Q + p.tpi - 1) / p.tpi + UKP - 1) / UKP * UKP);
+  p.KT = KT; p.stages = stages;
+  p.RBx = (p.P - 1 + KT + 2 * p.P + 4 + p.P - 1) / p.P;
+  p.RBd = (p.P - 1 + KT + p.P - 1) / p.P;
+  p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.RWB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.RWB;
+  p.x_chunk_stride = align_up(p.x_chunk_bytes, 1024); p.d_chunk_stride = align_up(p.d_chunk_bytes, 1024);
+  p.x_off = 0; p.d_off = p.xchunks * p.x_chunk_stride;
+  const uint32_t hi_bytes = p.d_off + p.dchunks * p.d_chunk_stride;
+  p.x_lo_off = hi_bytes; p.d_lo_off = hi_bytes + p.d_off;
+  p.stage_stride = strict ? 2 * hi_bytes : hi_bytes;
+  p.bar_off = p.stage_stride * stages;
+  const size_t smem = (size_t)p.bar_off + 256 + 1024;
+  p.total_tiles = N * p.tpi;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int nparts = sms / ngroups;
+  if (nparts < 1) nparts = 1;
+  if (nparts > p.total_tiles) nparts = p.total_tiles;
+  p.nparts = nparts;
+  const long long total = 9LL * C * C;
+  float* ws = nullptr;
+  if (int rc = get_scratch(1, (size_t)nparts * total * sizeof(float), (void**)&ws)) return rc;
+  p.partials = ws;
+  CUtensorMap mx, md;
+  const CUtensorMapSwizzle sw = bf16 ? (p.RWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.RWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)
+                                     : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (int rc = make_act_map(&mx, x, N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc;
+  if (int rc = make_act_map(&md, dz, N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
+  dim3 grid(nparts, ngroups);
+#define WG_LAUNCH(M_)                                                                                          \
+  do {                                                                                                         \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    wgrad_tc_kernel<M_><<<grid, (M_ == MODE_STRICT ? 10 : 6) * 32, smem, st>>>(mx, md, p);                     \
+  } while (0)
+  if (mode == MODE_STRICT) WG_LAUNCH(MODE_STRICT);
+  else if (mode == MODE_TF32) WG_LAUNCH(MODE_TF32);
+  else WG_LAUNCH(MODE_BF16);
+#undef WG_LAUNCH
+  LAUNCH_CHECK("wgrad_tc_kernel");
+  reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
+  LAUNCH_CHECK("reduce_parts");
+  return 0;
+}
+
+extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void* dz, float* grad_params, float* G_dense,
+                                   int N, int H, int W, int accumulate, void* stream) {
+  if (!L || !x || !dz || !grad_params) return fail(B200ODE_ERR_INVALID, "layer/x/dz/grad_params is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvGeom g = conv_geom(L, N, H, W);
+  const long long total = (long long)g.k * g.k * g.C * g.C;
+  const long long npix = (long long)N * g.Ho * g.Wo;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    if (int rc = run_wgrad_tc(L, x, dz, N, H, W, L->Gdense, G_dense, st)) return rc;
+  } else {
+    int parts = (int)(npix / 64);
+    if (parts < 1) parts = 1;
+    if (parts > 128) parts = 128;
+    float* ws = nullptr;
+    if (int rc = get_scratch(1, (size_t)parts * total * sizeof(float), (void**)&ws)) return rc;
+    dim3 grid(blocks_for(total, 128), parts);
+    simt_conv_wgrad<<<grid, 128, 0, st>>>(g, (const float*)x, (const float*)dz, ws, parts);
+    LAUNCH_CHECK("simt_conv_wgrad");
+    reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, parts, total, L->Gdense, G_dense);
+    LAUNCH_CHECK("reduce_parts");
+  }
+  const long long nfree = L->g.use_bias ? L->g.bias_off : L->g.nparams;
+  fold_grad<<<blocks_for(nfree, 256), 256, 0, st>>>(L->g, L->Gdense, grad_params, accumulate);
+  LAUNCH_CHECK("fold_grad");
+  if (L->g.use_bias) {
+    if (accumulate) return fail(B200ODE_ERR_UNSUPPORTED, "accumulate with bias is not implemented");
+    if (L->mode_eff == B200ODE_PREC_FAST_BF16) {
+      return fail(B200ODE_ERR_UNSUPPORTED, "bias gradient in FAST_BF16 mode: use b200ode_colsum on an fp32 dz");
+    }
+    ColsumArgs A;
+    memset(&A, 0, sizeof(A));
+    A.a = (const float*)dz; A.mode = 0;
+    return colsum_impl(A, grad_params + L->g.bias_off, nullptr, L->colsum_ws, npix, g.C, st);
+  }
+  return 0;
+}
+
+extern "C" int b200ode_relu_scale_bwd(const void* dy, const uint8_t* relu_mask, void* dz, int64_t pixels, int channels, float h,
+                                      int is_bf16, void* stream) {
+  if (!dy || !relu_mask || !dz) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  const long long n = pixels * ((channels + 7) / 8);
+  if (n == 0) return 0;
+  if (is_bf16)
+    relu_scale_bwd_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, relu_mask, (__nv_bfloat16*)dz, pixels, channels, h);
+  else
+    relu_scale_bwd_kernel<float><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)dy, relu_mask, (float*)dz,
+                                                                                       pixels, channels, h);
+  LAUNCH_CHECK("relu_scale_bwd_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_bn_finalize(const float* sum, const float* sumsq, const float* bn_gamma, const float* bn_beta, float* mean,
+                                   float* inv_std, float* scale, float* shift, float* moving_mean, float* moving_var,
+                                   int64_t pixels, int channels, float eps, float momentum, void* stream) {
+  if (!sum || !sumsq || !bn_gamma || !bn_beta || !mean || !inv_std || !scale || !shift) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  bn_finalize_kernel<<<blocks_for(channels, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, bn_gamma, bn_beta, mean, inv_std, scale,
+                                                                                  shift, moving_mean, moving_var, pixels, channels,
+                                                                                  eps, momentum);
+  LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_bn_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, const float* mean,
+                                     const float* inv_std, float* dgamma, float* dbeta, float* workspace, int64_t pixels,
+                                     int channels, float h, void* stream) {
+  if (!dy || !z || !workspace) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  ColsumArgs A;
+  A.a = dy; A.b = z; A.scale = scale; A.shift = shift; A.mean = mean; A.inv = inv_std; A.h = h; A.mode = 1;
+  return colsum_impl(A, dbeta, dgamma, workspace, pixels, channels, (cudaStream_t)stream);
+}
+
+extern "C" int b200ode_bn_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift, const float* mean,
+                                    const float* inv_std, const float* bn_gamma, const float* dgamma, const float* dbeta,
+                                    float* dz, int64_t pixels, int channels, float h, void* stream) {
+  if (!dy || !z || !dz) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  const long long n = pixels * channels;
+  if (n == 0) return 0;
+  bn_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, mean, inv_std, bn_gamma, dgamma,
+                                                                            dbeta, dz, pixels, channels, h);
+  LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int32_t* step_counter,
+                                 float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!params || !grads || !m || !v || !step_counter) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (n == 0) return 0;
+  adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, step_counter, lr, beta1, beta2, eps,
+                                                                    grad_scale);
+  LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_increment(int32_t* counter, void* stream) {
+  if (!counter) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  increment_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter);
+  LAUNCH_CHECK("increment_kernel");
+  return 0;
+}

@@ -1,0 +1,410 @@
+// K1 antisym_pack, the CUDA-core (SIMT) convolution kernels, the gradient fold and the
+// memory-bound tails (relu/scale/residual, BatchNorm, column sums, Adam).
+//
+// Reference semantics (paths relative to the reference repository):
+//   assembly   layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:113-141, 210-293
+//              layers/tfkeras_layer_Conv2DAntisymmetric.py:107-145, 216-270
+//   conv+bias  layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:157-171
+//   Euler tail models/tfkeras_resnets.py:85-92
+//   backward   training/training.py:300 (TF autodiff), closed forms in SURVEY.md App. A.3/A.4
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ode {
+
+constexpr int MAX_K = 7;
+
+// Where each tap of a diagonal block K[:,:,o,o] comes from.
+struct DiagTab {
+  int8_t slot[MAX_K * MAX_K];  // free-scalar slot index, or -1 = the constant gamma centre
+  int8_t sign[MAX_K * MAX_K];  // +1 / -1
+  int nd;                      // free scalars per diagonal block
+};
+
+struct LayerGeom {
+  int C, k, layout, antisym, use_bias;
+  float gamma;
+  long long nparams, bias_off;
+  DiagTab tab;
+};
+
+// flat offset of the first free scalar that belongs to output channel o (W_o block start)
+__host__ __device__ inline long long w_block_off(const LayerGeom& g, int o) {
+  const long long kk = (long long)g.k * g.k;
+  const long long pairs = (long long)o * g.C - (long long)o * (o + 1) / 2;  // sum_{o'<o} (C-o'-1)
+  if (g.layout == 0) return 4LL * g.C + kk * pairs;                          // [a,b,c,d | W_0.. | bias]
+  return (long long)o * g.tab.nd + kk * pairs + g.tab.nd;                    // per-o: diag scalars, W_o
+}
+__host__ __device__ inline long long diag_param_off(const LayerGeom& g, int o, int slot) {
+  if (g.layout == 0) return (long long)slot * g.C + o;
+  return (long long)o * g.tab.nd + (long long)g.k * g.k * ((long long)o * g.C - (long long)o * (o + 1) / 2) + slot;
+}
+
+// value of K[a,b,ci,o] from the packed free parameters (closed form)
+__device__ __forceinline__ float kernel_entry(const LayerGeom& g, const float* __restrict__ p, int a, int b, int ci,
+                                              int o) {
+  const int k = g.k;
+  if (ci == o) {
+    const int t = a * k + b;
+    const int s = g.tab.slot[t];
+    if (s < 0) return g.gamma;
+    const float v = p[diag_param_off(g, o, s)];
+    return g.tab.sign[t] > 0 ? v : -v;
+  }
+  if (ci > o) return p[w_block_off(g, o) + (long long)(a * k + b) * (g.C - o - 1) + (ci - o - 1)];
+  // ci < o: negated, 180-degree rotated copy of W_ci[:, :, o-ci-1]   (3By3.py:133-135, 277-293)
+  return -p[w_block_off(g, ci) + (long long)((k - 1 - a) * k + (k - 1 - b)) * (g.C - ci - 1) + (o - ci - 1)];
+}
+
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// One thread per staged element (tap, o, ci), ci fastest: staged tensor-core operand copies
+// W[tap][o][ci] (K-major B operand) in up to three formats plus the dense HWIO kernel.
+__global__ void pack_kernel(LayerGeom g, const float* __restrict__ params, float* __restrict__ K_dense,
+                            float* __restrict__ K_user, float* __restrict__ w_hi, float* __restrict__ w_lo,
+                            __nv_bfloat16* __restrict__ w_bf, float* __restrict__ bias_out, int strict) {
+  const long long total = (long long)g.k * g.k * g.C * g.C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.C && bias_out) bias_out[i] = g.use_bias ? params[g.bias_off + i] : 0.0f;
+  if (i >= total) return;
+  const int ci = (int)(i % g.C);
+  const int o = (int)((i / g.C) % g.C);
+  const int tap = (int)(i / ((long long)g.C * g.C));
+  const float v = kernel_entry(g, params, tap / g.k, tap % g.k, ci, o);
+  const long long dense = ((long long)tap * g.C + ci) * g.C + o;  // [a,b,ci,o]
+  if (K_dense) K_dense[dense] = v;
+  if (K_user) K_user[dense] = v;
+  if (w_hi) {
+    if (strict) {  // hi + lo == v exactly; the tensor core truncates its tf32 inputs (probe)
+      const float hi = tf32_trunc(v);
+      w_hi[i] = hi;
+      w_lo[i] = tf32_rna(v - hi);
+    } else {
+      w_hi[i] = tf32_rna(v);
+    }
+  }
+  if (w_bf) w_bf[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT convolution family (any C, odd k, any stride; TF SAME padding).  fp32.
+// ---------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int N, H, W, C, Ho, Wo, k, sh, sw, pt, pl;
+};
+
+// z[n,oy,ox,o] = bias[o] + sum_{a,b,ci} x[n, oy*sh+a-pt, ox*sw+b-pl, ci] * K[a,b,ci,o]
+__global__ void simt_conv_fwd(ConvGeom g, const float* __restrict__ x, const float* __restrict__ Kd,
+                              const float* __restrict__ bias, float* __restrict__ z) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)g.N * g.Ho * g.Wo * g.C;
+  if (idx >= total) return;
+  const int o = (int)(idx % g.C);
+  long long p = idx / g.C;
+  const int ox = (int)(p % g.Wo); p /= g.Wo;
+  const int oy = (int)(p % g.Ho);
+  const int n = (int)(p / g.Ho);
+  float acc = bias ? bias[o] : 0.0f;
+  for (int a = 0; a < g.k; ++a) {
+    const int iy = oy * g.sh + a - g.pt;
+    if (iy < 0 || iy >= g.H) continue;
+    for (int b = 0; b < g.k; ++b) {
+      const int ix = ox * g.sw + b - g.pl;
+      if (ix < 0 || ix >= g.W) continue;
+      const float* xp = x + (((long long)n * g.H + iy) * g.W + ix) * g.C;
+      const float* kp = Kd + ((long long)(a * g.k + b) * g.C) * g.C + o;
+      for (int ci = 0; ci < g.C; ++ci) acc = fmaf(xp[ci], kp[(long long)ci * g.C], acc);
+    }
+  }
+  z[idx] = acc;
+}
+
+// dx[n,iy,ix,ci] = skip + sum_{a,b,o} dz[n,oy,ox,o] * K[a,b,ci,o],  oy*sh + a - pt == iy
+__global__ void simt_conv_dgrad(ConvGeom g, const float* __restrict__ dz, const float* __restrict__ Kd,
+                                const float* __restrict__ skip, float* __restrict__ dx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)g.N * g.H * g.W * g.C;
+  if (idx >= total) return;
+  const int ci = (int)(idx % g.C);
+  long long p = idx / g.C;
+  const int ix = (int)(p % g.W); p /= g.W;
+  const int iy = (int)(p % g.H);
+  const int n = (int)(p / g.H);
+  float acc = skip ? skip[idx] : 0.0f;
+  for (int a = 0; a < g.k; ++a) {
+    const int ty = iy + g.pt - a;
+    if (ty < 0 || ty % g.sh) continue;
+    const int oy = ty / g.sh;
+    if (oy >= g.Ho) continue;
+    for (int b = 0; b < g.k; ++b) {
+      const int tx = ix + g.pl - b;
+      if (tx < 0 || tx % g.sw) continue;
+      const int ox = tx / g.sw;
+      if (ox >= g.Wo) continue;
+      const float* dp = dz + (((long long)n * g.Ho + oy) * g.Wo + ox) * g.C;
+      const float* kp = Kd + ((long long)(a * g.k + b) * g.C + ci) * g.C;
+      for (int o = 0; o < g.C; ++o) acc = fmaf(dp[o], kp[o], acc);
+    }
+  }
+  dx[idx] = acc;
+}
+
+// partial dense weight gradient: Gpart[part][a,b,ci,o] = sum over this part's output pixels
+__global__ void simt_conv_wgrad(ConvGeom g, const float* __restrict__ x, const float* __restrict__ dz,
+                                float* __restrict__ Gpart, int nparts) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)g.k * g.k * g.C * g.C;
+  if (e >= total) return;
+  const int part = blockIdx.y;
+  const int o = (int)(e % g.C);
+  const int ci = (int)((e / g.C) % g.C);
+  const int tap = (int)(e / ((long long)g.C * g.C));
+  const int a = tap / g.k, b = tap % g.k;
+  const long long npix = (long long)g.N * g.Ho * g.Wo;
+  const long long per = (npix + nparts - 1) / nparts;
+  const long long p0 = part * per, p1 = min(npix, p0 + per);
+  float acc = 0.0f;
+  for (long long p = p0; p < p1; ++p) {
+    const int ox = (int)(p % g.Wo);
+    const int oy = (int)((p / g.Wo) % g.Ho);
+    const int n = (int)(p / ((long long)g.Wo * g.Ho));
+    const int iy = oy * g.sh + a - g.pt, ix = ox * g.sw + b - g.pl;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) continue;
+    acc = fmaf(x[(((long long)n * g.H + iy) * g.W + ix) * g.C + ci], dz[p * g.C + o], acc);
+  }
+  Gpart[(long long)part * total + e] = acc;
+}
+
+// deterministic reduction of split-K partials: G[e] = sum_part Gpart[part][e]
+__global__ void reduce_parts(const float* __restrict__ Gpart, int nparts, long long total, float* __restrict__ G,
+                             float* __restrict__ G_user) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float acc = 0.0f;
+  for (int p = 0; p < nparts; ++p) acc += Gpart[(long long)p * total + e];
+  G[e] = acc;
+  if (G_user) G_user[e] = acc;
+}
+
+// Fold the dense gradient onto the free parameters: every free scalar feeds
+// exactly two kernel entries (one for a trainable centre); its gradient is sum_i sign_i * G[entry_i].
+__global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __restrict__ grad, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nfree = g.use_bias ? g.bias_off : g.nparams;
+  if (i >= nfree) return;
+  const int k = g.k, C = g.C;
+  const long long kk = (long long)k * k;
+  float val;
+  int o;
+  long long rem;
+  bool is_diag;
+  int slot = 0;
+  if (g.layout == 0) {
+    if (i < 4LL * C) { is_diag = true; slot = (int)(i / C); o = (int)(i % C); rem = 0; }
+    else {
+      is_diag = false;
+      int lo = 0, hi = C - 1;  // largest o with w_block_off(o) <= i
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (w_block_off(g, mid) <= i) lo = mid; else hi = mid - 1; }
+      o = lo; rem = i - w_block_off(g, o);
+    }
+  } else {
+    int lo = 0, hi = C - 1;  // block of o starts at w_block_off(o) - nd
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (w_block_off(g, mid) - g.tab.nd <= i) lo = mid; else hi = mid - 1; }
+    o = lo;
+    rem = i - (w_block_off(g, o) - g.tab.nd);
+    if (rem < g.tab.nd) { is_diag = true; slot = (int)rem; }
+    else { is_diag = false; rem -= g.tab.nd; }
+  }
+  if (is_diag) {
+    val = 0.0f;
+    for (int t = 0; t < k * k; ++t)
+      if (g.tab.slot[t] == slot) val += (g.tab.sign[t] > 0 ? 1.0f : -1.0f) * G[((long long)t * C + o) * C + o];
+  } else {
+    const int n = C - o - 1;
+    const int tap = (int)(rem / n), j = (int)(rem % n), ci = o + 1 + j;
+    const int rt = (int)(kk - 1 - tap);  // (k-1-a)*k + (k-1-b)
+    val = G[((long long)tap * C + ci) * C + o] - G[((long long)rt * C + o) * C + ci];
+  }
+  grad[i] = accumulate ? grad[i] + val : val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory-bound tails
+// ---------------------------------------------------------------------------------------------
+// y = [h *] relu?(z*scale[c]+shift[c]) [+ x];  mask bit = (u > 0).  One thread per 8 channels.
+__global__ void euler_tail_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ x, float* __restrict__ y,
+                                  uint8_t* __restrict__ mask, long long pixels, int C, float h, int flags) {
+  const int groups = (C + 7) / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * groups) return;
+  const long long p = idx / groups;
+  const int c0 = (int)(idx % groups) * 8;
+  const int nc = min(8, C - c0);
+  const long long base = p * C + c0;
+  float u[8], xr[8];
+  if (nc == 8 && (C % 4) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(z + base), b = *reinterpret_cast<const float4*>(z + base + 4);
+    u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+    if (x && (flags & 8)) {
+      const float4 c = *reinterpret_cast<const float4*>(x + base), d = *reinterpret_cast<const float4*>(x + base + 4);
+      xr[0] = c.x; xr[1] = c.y; xr[2] = c.z; xr[3] = c.w; xr[4] = d.x; xr[5] = d.y; xr[6] = d.z; xr[7] = d.w;
+    }
+  } else {
+    for (int j = 0; j < nc; ++j) { u[j] = z[base + j]; if (x && (flags & 8)) xr[j] = x[base + j]; }
+  }
+  uint32_t bits = 0;
+  for (int j = 0; j < nc; ++j) {
+    float v = u[j];
+    if (scale) v = fmaf(v, scale[c0 + j], shift[c0 + j]);
+    if (v > 0.0f) bits |= 1u << j;
+    if (flags & 2) v = fmaxf(v, 0.0f);
+    if (flags & 4) v = h * v;              // Lambda(h*x): own rounding, then add (two roundings)
+    if (x && (flags & 8)) v = v + xr[j];
+    u[j] = v;
+  }
+  if (mask) mask[p * groups + c0 / 8] = (uint8_t)bits;
+  if (y) {
+    if (nc == 8 && (C % 4) == 0) {
+      *reinterpret_cast<float4*>(y + base) = make_float4(u[0], u[1], u[2], u[3]);
+      *reinterpret_cast<float4*>(y + base + 4) = make_float4(u[4], u[5], u[6], u[7]);
+    } else {
+      for (int j = 0; j < nc; ++j) y[base + j] = u[j];
+    }
+  }
+}
+
+// dz = h * dy * mask      (fp32 or bf16 I/O)
+template <typename T>
+__global__ void relu_scale_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ mask, T* __restrict__ dz,
+                                      long long pixels, int C, float h) {
+  const int groups = (C + 7) / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * groups) return;
+  const long long p = idx / groups;
+  const int c0 = (int)(idx % groups) * 8;
+  const int nc = min(8, C - c0);
+  const uint32_t bits = mask[p * groups + c0 / 8];
+  for (int j = 0; j < nc; ++j) {
+    const float g = (bits >> j) & 1u ? h * static_cast<float>(dy[p * C + c0 + j]) : 0.0f;
+    dz[p * C + c0 + j] = static_cast<T>(g);
+  }
+}
+
+// Column sums over pixels, two deterministic stages.  mode 0: (a, a*b or a*a);
+// mode 1 (BN backward): du = h*dy*[z*scale+shift > 0], zhat = (z-mean)*inv -> (du, du*zhat).
+struct ColsumArgs {
+  const float* a; const float* b;
+  const float* scale; const float* shift; const float* mean; const float* inv;
+  float h; int mode;
+};
+__device__ __forceinline__ void colsum_vals(const ColsumArgs& A, long long p, int C, int c, float& v0, float& v1) {
+  const float a = A.a[p * C + c];
+  if (A.mode == 0) {
+    v0 = a; v1 = A.b ? a * A.b[p * C + c] : a * a;
+  } else {
+    const float zz = A.b[p * C + c];
+    const float u = fmaf(zz, A.scale[c], A.shift[c]);
+    const float du = u > 0.0f ? A.h * a : 0.0f;
+    v0 = du; v1 = du * ((zz - A.mean[c]) * A.inv[c]);
+  }
+}
+__global__ void colsum_stage1(ColsumArgs A, float* __restrict__ ws, long long pixels, int C, int nparts) {
+  // block = one part; threads stride over (row, channel) with channel = tid % C when C <= blockDim
+  extern __shared__ float sm[];
+  const int part = blockIdx.x;
+  const long long per = (pixels + nparts - 1) / nparts;
+  const long long p0 = part * per, p1 = min(pixels, p0 + per);
+  const int T = blockDim.x;
+  for (int cbase = 0; cbase < C; cbase += T) {
+    const int lanes = min(C - cbase, T);          // channels handled this pass
+    const int rows = T / lanes;                   // pixel rows processed in parallel
+    const int c = cbase + threadIdx.x % lanes;
+    const int r = threadIdx.x / lanes;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (r < rows)
+      for (long long p = p0 + r; p < p1; p += rows) { float v0, v1; colsum_vals(A, p, C, c, v0, v1); s0 += v0; s1 += v1; }
+    sm[threadIdx.x] = s0; sm[T + threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < lanes) {
+      float t0 = 0.0f, t1 = 0.0f;
+      for (int rr = 0; rr < rows; ++rr) { t0 += sm[rr * lanes + threadIdx.x]; t1 += sm[T + rr * lanes + threadIdx.x]; }
+      ws[(long long)part * C + c] = t0;
+      ws[(long long)(nparts + part) * C + c] = t1;
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ ws, float* __restrict__ out0, float* __restrict__ out1, int C,
+                              int nparts) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t0 = 0.0f, t1 = 0.0f;
+  for (int p = 0; p < nparts; ++p) { t0 += ws[(long long)p * C + c]; t1 += ws[(long long)(nparts + p) * C + c]; }
+  if (out0) out0[c] = t0;
+  if (out1) out1[c] = t1;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                   const float* __restrict__ gam, const float* __restrict__ bet, float* __restrict__ mean,
+                                   float* __restrict__ inv, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mmean, float* __restrict__ mvar, long long pixels, int C, float eps,
+                                   float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sum[c] / (float)pixels;
+  const float var = fmaxf(sumsq[c] / (float)pixels - m * m, 0.0f);  // biased variance
+  const float is = rsqrtf(var + eps);
+  mean[c] = m; inv[c] = is;
+  const float sc = gam[c] * is;
+  scale[c] = sc; shift[c] = bet[c] - m * sc;
+  if (mmean) {
+    const float unb = var * ((float)pixels / fmaxf((float)pixels - 1.0f, 1.0f));
+    mmean[c] = mmean[c] * momentum + m * (1.0f - momentum);
+    mvar[c] = mvar[c] * momentum + unb * (1.0f - momentum);
+  }
+}
+
+// dz = gamma*inv * (du - mean(du) - zhat*mean(du*zhat)),  du = h*dy*[u>0]
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ inv,
+                                    const float* __restrict__ gam, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, float* __restrict__ dz, long long pixels, int C,
+                                    float h) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * C) return;
+  const int c = (int)(idx % C);
+  const float zz = z[idx];
+  const float u = fmaf(zz, scale[c], shift[c]);
+  const float du = u > 0.0f ? h * dy[idx] : 0.0f;
+  const float zhat = (zz - mean[c]) * inv[c];
+  const float invM = 1.0f / (float)pixels;
+  dz[idx] = gam[c] * inv[c] * (du - dbeta[c] * invM - zhat * dgamma[c] * invM);
+}
+
+// tf.train.AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const int* __restrict__ step, float lr, float b1, float b2,
+                            float eps, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)(*step);
+  const float lr_t = lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+__global__ void increment_kernel(int* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
+
+}  // namespace b200ode

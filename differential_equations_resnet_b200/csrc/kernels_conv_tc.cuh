@@ -1,0 +1,359 @@
+// K2/K3: 3x3 SAME stride-1 implicit-GEMM convolution on tcgen05 tensor cores with a fused
+// Euler-step epilogue.  Used for the forward pass (x -> y = x + h*relu(conv_K(x)+b)) and, through
+// the antisymmetry identity dX = dY - conv_K(dZ) + 2*gamma*dZ, for the data
+// gradient with the SAME staged weights.
+//
+// Reference ops replaced: tf.nn.conv2d + bias (layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:
+// 159-169), Activation('relu') / Lambda(h*x) / add (models/tfkeras_resnets.py:89-92).
+//
+// Data flow per CTA (persistent, static round-robin over tiles):
+//   * ONE TMA box load per K-block brings a halo strip of the NHWC input into shared memory:
+//     rows of pitch P = W+1 pixels (column 0 = the zero column left of the image; the zero column
+//     right of the image is column 0 of the next row), halo rows above/below zero-filled by TMA
+//     out-of-bounds handling.  In this "padded linear" space every 3x3 tap is a constant row
+//     offset (alpha*P + beta), so all nine A operands are the same strip addressed through UMMA
+//     descriptors whose start address is shifted by whole rows (verified by csrc/umma_probe.cu).
+//     The input is read from L2/HBM once per tile, not nine times.
+//   * weights W[tap][o][ci] (K-major B operand, staged by pack_kernel) stream through a ring.
+//   * tcgen05.mma accumulates 128-position segments into TMEM (double buffered across tiles).
+//   * strict mode: converter warps write lo = x - trunc_tf32(x) next to each strip and every
+//     (tap, k-step) issues hi*hi + hi*lo + lo*hi (3xTF32, fp32-level accuracy).
+//   * epilogue warps: tcgen05.ld -> bias/relu/h/residual (+ relu bit mask, optional z) -> NHWC.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "sm100_ptx.cuh"
+
+namespace b200ode {
+
+enum { MODE_STRICT = 0, MODE_TF32 = 1, MODE_BF16 = 2 };
+
+struct ConvTcParams {
+  int N, H, W;
+  int P;            // padded row pitch in pixels (W + 1)
+  int RB;           // halo rows per image in one strip (TMA box rows)
+  int nimg;         // images per tile
+  int spi;          // 128-position segments per image per tile
+  int tpi;          // tiles per image (1 when nimg >= 1 covers whole images)
+  int total_tiles;
+  // shared memory plan (bytes from the 1024-aligned base)
+  int sa, sw, tw;   // A stages, W stages, taps per W stage
+  uint32_t a_bytes, a_lo_off, a_stride, w_bytes, w_stride, a_off, w_off, bar_off;
+  uint32_t tmem_cols;
+  // epilogue
+  const void* in;      // conv input (centre term c_in * in[p]); nullable
+  const void* skip;    // nullable
+  void* out;           // nullable
+  float* z_out;        // nullable, fp32 pre-activation
+  uint8_t* mask;       // nullable
+  const float* bias;   // nullable
+  float acc_scale, c_in, h;
+  int relu, scale_h;
+};
+
+template <int MODE, int C>
+struct ConvTcCfg {
+  static constexpr int EB = MODE == MODE_BF16 ? 2 : 4;            // operand element bytes
+  static constexpr int ROWB = (C * EB >= 128) ? 128 : C * EB;      // bytes per pixel row in one K-block
+  static constexpr int KB = ROWB / EB;                             // channels per K-block
+  static constexpr int NKB = C / KB;
+  static constexpr int KS = ROWB / 32;                             // 32-byte k-steps per K-block
+  static constexpr bool STRICT = MODE == MODE_STRICT;
+  static constexpr int NWARPS = STRICT ? 10 : 6;                   // TMA, MMA, 4 epilogue (+4 converter)
+};
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+
+template <int MODE, int C>
+__global__ void __launch_bounds__(ConvTcCfg<MODE, C>::NWARPS * 32, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
+  using Cfg = ConvTcCfg<MODE, C>;
+  constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS;
+  constexpr bool STRICT = Cfg::STRICT;
+  constexpr uint32_t LT = ROWB == 128 ? SWZ_128B : ROWB == 64 ? SWZ_64B : SWZ_32B;
+  constexpr uint32_t SBO = 8 * ROWB;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a_full = bars;                 // [sa]
+  uint64_t* a_empty = a_full + p.sa;       // [sa]
+  uint64_t* a_conv = a_empty + p.sa;       // [sa] (strict)
+  uint64_t* w_full = a_conv + p.sa;        // [sw]
+  uint64_t* w_empty = w_full + p.sw;       // [sw]
+  uint64_t* acc_full = w_empty + p.sw;     // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = p.nimg * p.spi;           // segments (accumulators) per tile
+  const int T = p.spi * 128;               // positions per image per tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    if (STRICT) tma_prefetch_desc(&map_w_lo);
+    for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_conv[i], 4); }
+    for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_stages = (2 * mt * C <= 512) ? 2 : 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t ia = 0, iw = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile / p.tpi) * p.nimg;
+        const int q0 = (tile % p.tpi) * T;
+        const int row0 = q0 / p.P;  // first halo row of the strip (halo row r <-> image row r-1)
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
+          mbar_wait(&a_empty[s], ph ^ 1);
+          mbar_expect_tx(&a_full[s], p.a_bytes);
+          tma_load_4d(smem + p.a_off + s * p.a_stride, &map_a, &a_full[s], kb * KB, -1, row0 - 1, n0);
+          ++ia;
+          for (int tg = 0; tg < 9; tg += p.tw) {
+            const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
+            mbar_wait(&w_empty[sw_], phw ^ 1);
+            mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
+            uint8_t* wdst = smem + p.w_off + sw_ * p.w_stride;
+            tma_load_3d(wdst, &map_w, &w_full[sw_], kb * KB, 0, tg);
+            if (STRICT) tma_load_3d(wdst + p.w_bytes, &map_w_lo, &w_full[sw_], kb * KB, 0, tg);
+            ++iw;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(MODE == MODE_BF16 ? FMT_BF16 : FMT_TF32, 128, C, 0, 0);
+      const uint64_t desc_hi = (static_cast<uint64_t>(SBO >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                               (static_cast<uint64_t>(LT) << 61) | (static_cast<uint64_t>(1) << 16);
+      const uint32_t smem_base = smem_u32(smem);
+      uint32_t ia = 0, iw = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int q0 = (tile % p.tpi) * T;
+        const int off0 = q0 - (q0 / p.P) * p.P;
+        const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
+          mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
+          const uint32_t a_base = smem_base + p.a_off + s * p.a_stride;
+          for (int tg = 0; tg < 9; tg += p.tw) {
+            const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
+            mbar_wait(&w_full[sw_], phw);
+            tc_fence_after_sync();
+            const uint32_t w_base = smem_base + p.w_off + sw_ * p.w_stride;
+            for (int tt = 0; tt < p.tw; ++tt) {
+              const int tap = tg + tt;
+              const int shift = (tap / 3) * p.P + (tap % 3);
+              for (int sg = 0; sg < mt; ++sg) {
+                const int pix = (sg / p.spi) * p.RB * p.P + off0 + (sg % p.spi) * 128 + shift;
+                const uint32_t d_tmem = tmem_base + (as * mt + sg) * C;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                  const uint32_t a_addr = a_base + pix * ROWB + ks * 32;
+                  const uint32_t b_addr = w_base + tt * (C * ROWB) + ks * 32;
+                  const uint64_t da = desc_hi | ((a_addr >> 4) & 0x3FFF);
+                  const uint64_t db = desc_hi | ((b_addr >> 4) & 0x3FFF);
+                  const uint32_t acc = (kb | tap | ks) != 0;
+                  if (MODE == MODE_BF16) {
+                    umma_f16(d_tmem, da, db, idesc, acc);
+                  } else {
+                    umma_tf32(d_tmem, da, db, idesc, acc);
+                    if (STRICT) {
+                      const uint64_t da_lo = desc_hi | (((a_addr + p.a_lo_off) >> 4) & 0x3FFF);
+                      const uint64_t db_lo = desc_hi | (((b_addr + p.w_bytes) >> 4) & 0x3FFF);
+                      umma_tf32(d_tmem, da, db_lo, idesc, 1);
+                      umma_tf32(d_tmem, da_lo, db, idesc, 1);
+                    }
+                  }
+                }
+              }
+            }
+            umma_commit(&w_empty[sw_]);
+            ++iw;
+          }
+          umma_commit(&a_empty[s]);
+          ++ia;
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t it = 0;
+    using IoT = typename std::conditional<MODE == MODE_BF16, __nv_bfloat16, float>::type;
+    const IoT* in = reinterpret_cast<const IoT*>(p.in);
+    const IoT* skip = reinterpret_cast<const IoT*>(p.skip);
+    IoT* out = reinterpret_cast<IoT*>(p.out);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int n0 = (tile / p.tpi) * p.nimg;
+      const int q0 = (tile % p.tpi) * T;
+      const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after_sync();
+      for (int sg = 0; sg < mt; ++sg) {
+        const int n = n0 + sg / p.spi;
+        const int q = q0 + (sg % p.spi) * 128 + row;
+        const int y = q / p.P;
+        const int xq = q - y * p.P;
+        const bool valid = (n < p.N) && (y < p.H) && (xq < p.W);
+        const long long pix = ((long long)n * p.H + y) * p.W + xq;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = p.acc_scale * __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+            }
+            if (p.z_out) {
+              float4* zp = reinterpret_cast<float4*>(p.z_out + pix * C + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.mask) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
+              *reinterpret_cast<uint16_t*>(p.mask + pix * (C / 8) + c0 / 8) = static_cast<uint16_t>(bits);
+            }
+            if (out) {
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+              }
+              if (p.scale_h) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = p.h * v[j];
+              }
+              if (MODE == MODE_BF16) {
+                if (in) {
+                  const uint4* ip = reinterpret_cast<const uint4*>(in + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint4 u = ip[j];
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      v[8 * j + 2 * e] += p.c_in * __uint_as_float(w[e] << 16);
+                      v[8 * j + 2 * e + 1] += p.c_in * __uint_as_float(w[e] & 0xFFFF0000u);
+                    }
+                  }
+                }
+                if (skip) {
+                  const uint4* sp = reinterpret_cast<const uint4*>(skip + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint4 u = sp[j];
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      v[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
+                      v[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                    }
+                  }
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                  pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                uint4* op = reinterpret_cast<uint4*>(out + pix * C + c0);
+                op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              } else {
+                if (in) {
+                  const float4* ip = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 u = ip[j];
+                    // c_in == 1 in the forward pass: plain add of x (the reference's add layer)
+                    v[4 * j] = fmaf(p.c_in, u.x, v[4 * j]); v[4 * j + 1] = fmaf(p.c_in, u.y, v[4 * j + 1]);
+                    v[4 * j + 2] = fmaf(p.c_in, u.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(p.c_in, u.w, v[4 * j + 3]);
+                  }
+                }
+                if (skip) {
+                  const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(skip) + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 u = sp[j];
+                    v[4 * j] += u.x; v[4 * j + 1] += u.y; v[4 * j + 2] += u.z; v[4 * j + 3] += u.w;
+                  }
+                }
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * C + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  } else {
+    // ===================== strict-mode converter warps 6..9 =====================
+    if (STRICT) {
+      const int ctid = threadIdx.x - 6 * 32;  // 0..127
+      uint32_t ia = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
+          mbar_wait(&a_full[s], ph);
+          const uint4* src = reinterpret_cast<const uint4*>(smem + p.a_off + s * p.a_stride);
+          uint4* dst = reinterpret_cast<uint4*>(smem + p.a_off + s * p.a_stride + p.a_lo_off);
+          const int n16 = p.a_bytes / 16;
+          for (int i = ctid; i < n16; i += 128) {
+            const uint4 u = src[i];
+            uint4 o;
+            o.x = __float_as_uint(tf32_rna(__uint_as_float(u.x) - __uint_as_float(u.x & 0xFFFFE000u)));
+            o.y = __float_as_uint(tf32_rna(__uint_as_float(u.y) - __uint_as_float(u.y & 0xFFFFE000u)));
+            o.z = __float_as_uint(tf32_rna(__uint_as_float(u.z) - __uint_as_float(u.z & 0xFFFFE000u)));
+            o.w = __float_as_uint(tf32_rna(__uint_as_float(u.w) - __uint_as_float(u.w & 0xFFFFE000u)));
+            dst[i] = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_conv[s]);
+          ++ia;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace b200ode

@@ -1,0 +1,215 @@
+// K4: dense weight gradient G[tap][ci][o] = sum_q x_halo[q + shift(tap), ci] * dZ[q, o] on tcgen05
+// tensor cores (replaces TF's Conv2DBackpropFilter, training/training.py:300).
+//
+// GEMM view: M = input channel, N = output channel, K = pixel position in the same padded linear
+// space the forward kernel uses (pitch P = W+1).  Both operands arrive NHWC, i.e. with the M/N index
+// contiguous and K strided, so they are consumed as MN-major UMMA operands straight from the TMA
+// halo strips -- no transposition anywhere:
+//   * tf32 modes: 128B-swizzle / 32B-atom layout (the only MN-major layout tf32 accepts), chunks of
+//     32 channels, 4-position groups (SBO = 512B); C = 16 is zero-padded to 32 by TMA OOB fill.
+//   * bf16 mode : canonical 32/64/128B swizzles, chunks of min(C,64) channels, 8-position groups.
+// A 3x3 tap is a whole-row shift of the x strip's start address.  When all channels fit one chunk
+// ("beta trick") the M-chunk stride (LBO) is set to ONE position so a single M=4*chunk MMA covers
+// the three taps beta=0,1,2 of a kernel row (4th chunk is junk) -- 3 instead of 9 MMAs per k-step.
+// The junk padded column of dZ is zero (TMA OOB), so junk positions add nothing.
+// Each CTA owns (tap group, N range, slice of positions), keeps its accumulators in TMEM for its
+// whole slice and writes ONE fp32 partial; partials are reduced deterministically afterwards.
+// Strict mode = 3xTF32: x_hi*dz_hi + x_hi*dz_lo + x_lo*dz_hi with lo strips produced by converter warps.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "kernels_conv_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200ode {
+
+struct WgradParams {
+  int N, H, W, C, P;
+  int KT;            // positions per tile (multiple of the MMA K extent)
+  int tpi;           // tiles per image
+  int total_tiles, nparts;
+  int RBx, RBd;      // strip rows of x (halo) and dz
+  int CH;            // channels per chunk
+  int RWB;           // bytes per position row within a chunk
+  int xchunks;       // x chunks per stage (all input channels)
+  int dchunks;       // dz chunks per stage (this CTA's N range)
+  int trick;         // beta trick: one MMA per kernel row
+  int TG;            // taps per CTA group (normal mode)
+  int NT;            // output channels per CTA group
+  int ntapgroups, nngroups;
+  int MB, Mblk;      // M blocks per tap and rows per block (normal mode)
+  uint32_t x_chunk_bytes, d_chunk_bytes, x_chunk_stride, d_chunk_stride;
+  uint32_t x_off, d_off, x_lo_off, d_lo_off, stage_stride, bar_off;
+  int stages;
+  uint32_t tmem_cols;
+  float* partials;   // [nparts][9][C][C]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__((MODE == MODE_STRICT ? 10 : 6) * 32, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
+  constexpr bool STRICT = MODE == MODE_STRICT;
+  constexpr bool BF16 = MODE == MODE_BF16;
+  constexpr int UKP = BF16 ? 16 : 8;  // positions per MMA
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.bar_off);  // [stages]
+  uint64_t* empty = full + p.stages;
+  uint64_t* conv = empty + p.stages;
+  uint64_t* acc_full = conv + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.y;
+  const int tapgroup = group / p.nngroups, ngroup = group % p.nngroups;
+  const int part = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_d);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&conv[i], 4); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stage_bytes = p.xchunks * p.x_chunk_bytes + p.dchunks * p.d_chunk_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
+        const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.KT, row0 = q0 / p.P;
+        const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], stage_bytes);
+        uint8_t* sb = smem + s * p.stage_stride;
+        for (int c = 0; c < p.xchunks; ++c)
+          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, &map_x, &full[s], c * p.CH, -1, row0 - 1, n);
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
+      const uint32_t idesc = make_instr_desc(BF16 ? FMT_BF16 : FMT_TF32, Mrows, p.NT, 1, 1);
+      const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
+      const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
+      const uint64_t hi_common = (static_cast<uint64_t>(sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                                 (static_cast<uint64_t>(lt) << 61);
+      const uint64_t hi_a = hi_common | (static_cast<uint64_t>(((p.trick ? (uint32_t)p.RWB : p.x_chunk_stride) >> 4) & 0x3FFF) << 16);
+      const uint64_t hi_b = hi_common | (static_cast<uint64_t>((p.d_chunk_stride >> 4) & 0x3FFF) << 16);
+      const uint32_t smem_base = smem_u32(smem);
+      const int nent = p.trick ? 3 : p.TG * p.MB;
+      const int ksteps = p.KT / UKP;
+      uint32_t it = 0;
+      for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
+        const int q0 = (tile % p.tpi) * p.KT;
+        const int off0 = q0 - (q0 / p.P) * p.P;
+        const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+        mbar_wait(STRICT ? &conv[s] : &full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t xb = smem_base + s * p.stage_stride + p.x_off;
+        const uint32_t db = smem_base + s * p.stage_stride + p.d_off;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t b_addr = db + (off0 + ks * UKP) * p.RWB;
+          const uint64_t dsc_b = hi_b | ((b_addr >> 4) & 0x3FFF);
+          const uint32_t accum = (it | ks) != 0;
+          for (int e = 0; e < nent; ++e) {
+            int shift;
+            uint32_t a_off;
+            if (p.trick) { shift = e * p.P; a_off = 0; }
+            else {
+              const int tap = tapgroup * p.TG + e / p.MB;
+              shift = (tap / 3) * p.P + (tap % 3);
+              a_off = (e % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
+            }
+            const uint32_t a_addr = xb + a_off + (off0 + ks * UKP + shift) * p.RWB;
+            const uint64_t dsc_a = hi_a | ((a_addr >> 4) & 0x3FFF);
+            const uint32_t d_tmem = tmem_base + e * p.NT;
+            if (BF16) umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum);
+            else {
+              umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
+              if (STRICT) {
+                const uint64_t dsc_a_lo = hi_a | (((a_addr - p.x_off + p.x_lo_off) >> 4) & 0x3FFF);
+                const uint64_t dsc_b_lo = hi_b | (((b_addr - p.d_off + p.d_lo_off) >> 4) & 0x3FFF);
+                umma_tf32(d_tmem, dsc_a, dsc_b_lo, idesc, 1);
+                umma_tf32(d_tmem, dsc_a_lo, dsc_b, idesc, 1);
+              }
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp < 6) {
+    // epilogue: TMEM accumulators -> this part's fp32 partial
+    const int quarter = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
+    const int nent = p.trick ? 3 : p.TG * p.MB;
+    int m;  // accumulator row held by this thread's TMEM lane
+    bool row_ok;
+    if (Mrows == 128) { m = quarter * 32 + lane; row_ok = true; }
+    else { m = quarter * 16 + lane; row_ok = lane < 16; }   // M=64: 16 lanes per quarter
+    float* part_base = p.partials + (size_t)part * 9 * p.C * p.C;
+    for (int e = 0; e < nent; ++e) {
+      int tap, ci;
+      bool ok = row_ok;
+      if (p.trick) { const int beta = m / p.CH; tap = e * 3 + beta; ci = m % p.CH; ok = ok && beta < 3; }
+      else { tap = tapgroup * p.TG + e / p.MB; ci = (e % p.MB) * p.Mblk + m; }
+      ok = ok && ci < p.C && tap < 9;
+      float* dst = part_base + ((size_t)tap * p.C + ci) * p.C + ngroup * p.NT;
+      for (int c0 = 0; c0 < p.NT; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * p.NT + c0, r);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (ngroup * p.NT + c0 + j < p.C)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    }
+  } else if (STRICT) {
+    const int ctid = threadIdx.x - 6 * 32;
+    uint32_t it = 0;
+    for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
+      const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+      mbar_wait(&full[s], ph);
+      uint8_t* sb = smem + s * p.stage_stride;
+      for (int which = 0; which < 2; ++which) {
+        const uint4* src = reinterpret_cast<const uint4*>(sb + (which ? p.d_off : p.x_off));
+        uint4* dst = reinterpret_cast<uint4*>(sb + (which ? p.d_lo_off : p.x_lo_off));
+        const int n16 = (which ? p.dchunks * p.d_chunk_stride : p.xchunks * p.x_chunk_stride) / 16;
+        for (int i = ctid; i < n16; i += 128) {
+          const uint4 u = src[i];
+          uint4 o;
+          o.x = __float_as_uint(tf32_rna(__uint_as_float(u.x) - __uint_as_float(u.x & 0xFFFFE000u)));
+          o.y = __float_as_uint(tf32_rna(__uint_as_float(u.y) - __uint_as_float(u.y & 0xFFFFE000u)));
+          o.z = __float_as_uint(tf32_rna(__uint_as_float(u.z) - __uint_as_float(u.z & 0xFFFFE000u)));
+          o.w = __float_as_uint(tf32_rna(__uint_as_float(u.w) - __uint_as_float(u.w & 0xFFFFE000u)));
+          dst[i] = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[s]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace b200ode
