@@ -310,8 +310,9 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
         if (tpi == 1) continue;  // covered by whole-image mode
       }
       const int mt = nimg * spi;
-      if (mt * C > 512 || RB > 256 || nimg > 256) continue;
-      const int acc_stages = 2 * mt * C <= 512 ? 2 : 1;
+      const int accw = strict ? 2 * C : C;
+      if (mt * accw > 512 || RB > 256 || nimg > 256) continue;
+      const int acc_stages = 2 * mt * accw <= 512 ? 2 : 1;
       const uint32_t a_bytes = (uint32_t)nimg * RB * P * rowb;
       const uint32_t a_lo_off = align_up(a_bytes, 1024);
       const uint32_t a_stride = strict ? 2 * a_lo_off : a_lo_off;
@@ -345,7 +346,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
         p.sa = sa; p.sw = sw; p.tw = tw;
         p.a_bytes = a_bytes; p.a_lo_off = a_lo_off; p.a_stride = a_stride; p.w_bytes = w_bytes; p.w_stride = w_stride;
         p.a_off = 0; p.w_off = (uint32_t)sa * a_stride; p.bar_off = p.w_off + (uint32_t)sw * w_stride;
-        uint32_t cols = (uint32_t)acc_stages * mt * C, pc = 32;
+        uint32_t cols = (uint32_t)acc_stages * mt * accw, pc = 32;
         while (pc < cols) pc <<= 1;
         p.tmem_cols = pc;
         best.smem = (size_t)p.bar_off + 512 + 1024;

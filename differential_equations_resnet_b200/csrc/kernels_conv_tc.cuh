@@ -111,7 +111,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int acc_stages = (2 * mt * C <= 512) ? 2 : 1;
+  // strict mode keeps two accumulators per segment: the hi*hi sum and the small hi*lo + lo*hi
+  // correction sum.  The tensor core truncates when it accumulates, so the error grows with the
+  // number of accumulation steps into one register; splitting keeps the 2/3 of the MMAs that carry
+  // ~2^-11-sized terms away from the main sum (they are added once, in fp32, in the epilogue).
+  constexpr int ACCW = STRICT ? 2 * C : C;   // TMEM columns per segment
+  const int acc_stages = (2 * mt * ACCW <= 512) ? 2 : 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -167,7 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int shift = (tap / 3) * p.P + (tap % 3);
               for (int sg = 0; sg < mt; ++sg) {
                 const int pix = (sg / p.spi) * p.RB * p.P + off0 + (sg % p.spi) * 128 + shift;
-                const uint32_t d_tmem = tmem_base + (as * mt + sg) * C;
+                const uint32_t d_tmem = tmem_base + (as * mt + sg) * ACCW;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                   const uint32_t a_addr = a_base + pix * ROWB + ks * 32;
@@ -182,8 +187,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (STRICT) {
                       const uint64_t da_lo = desc_hi | (((a_addr + p.a_lo_off) >> 4) & 0x3FFF);
                       const uint64_t db_lo = desc_hi | (((b_addr + p.w_bytes) >> 4) & 0x3FFF);
-                      umma_tf32(d_tmem, da, db_lo, idesc, 1);
-                      umma_tf32(d_tmem, da_lo, db, idesc, 1);
+                      umma_tf32(d_tmem + C, da, db_lo, idesc, acc);
+                      umma_tf32(d_tmem + C, da_lo, db, idesc, 1);
                     }
                   }
                 }
@@ -220,12 +225,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int xq = q - y * p.P;
         const bool valid = (n < p.N) && (y < p.H) && (xq < p.W);
         const long long pix = ((long long)n * p.H + y) * p.W + xq;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * C;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * ACCW;
 #pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += 16) {
           uint32_t r[16];
           tmem_ld_x16(taddr + c0, r);
-          tmem_ld_wait();
+          if (STRICT) {
+            uint32_t r2[16];
+            tmem_ld_x16(taddr + C + c0, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            tmem_ld_wait();
+          }
           if (valid) {
             float v[16];
 #pragma unroll

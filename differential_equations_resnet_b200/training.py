@@ -1,0 +1,344 @@
+"""Train-step engine for the antisymmetric single-block ResNet.
+
+Mirrors the *step semantics* of the reference trainer (training/training.py:283-304 of the
+reference: softmax output -> mean Keras categorical cross-entropy -> gradients -> Adam with
+epsilon 1e-7) and the model assembly of models/tfkeras_resnets.py:511-604 for
+kernel_type='antisymmetric'.  It is not a port of the TF1 session plumbing.
+
+Hot path (hand-written CUDA, libb200ode.so): every Euler step
+x_{n+1} = x_n + h*relu(conv_K(x_n)+b) forward and backward, weight packing, gradient fold,
+Adam.  Stem / transition / head (<= 5 layers per net) run as torch ops.
+
+Data parallel: one process per GPU; parameters replicated, batch sharded, ONE flat fp32 gradient
+bucket (packed free parameters, not dense kernels) all-reduced with NCCL via torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _abi
+from .layers._base import LayerHandle, truncated_normal_, _ptr, _stream_ptr
+
+
+class NetSpec:
+    """Keyword mirror of get_single_block_resnet_build_function (models/tfkeras_resnets.py:511-527)."""
+
+    def __init__(self, num_stages=4, blocks_per_stage=(3, 3, 3), filters_per_block=(16, 32, 64),
+                 strides=((1, 1), (2, 2), (2, 2)), h=1.0, gamma=0.0, num_classes=10, use_batch_norm=False,
+                 subtract_mean=127.5, divide_by_stddev=127.5, kernel_size=3, in_channels=3):
+        if use_batch_norm:
+            raise NotImplementedError("the fused trainer covers the reference's no-BN configuration "
+                                      "(experiments v6/v7); BN Euler blocks are available in models.tfkeras_resnets")
+        if kernel_size != 3:
+            raise ValueError("antisymmetric Euler blocks are 3x3")
+        self.num_stages, self.blocks_per_stage = num_stages, list(blocks_per_stage)
+        self.filters_per_block, self.strides = list(filters_per_block), [tuple(s) for s in strides]
+        self.h, self.gamma, self.num_classes = float(h), float(gamma), num_classes
+        self.subtract_mean, self.divide_by_stddev = subtract_mean, divide_by_stddev
+        self.kernel_size, self.in_channels = kernel_size, in_channels
+
+    def plan(self):
+        """Graph order of (kind, C_in, C_out, stride, name); stage loop models/tfkeras_resnets.py:575-593."""
+        fp, st = self.filters_per_block, self.strides
+        ops = [("stem", self.in_channels, fp[0], st[0], "conv1")]
+        for s in range(self.num_stages - 1):
+            if s == 0 or (fp[s] == fp[s - 1] and st[s] == (1, 1)):
+                for b in range(self.blocks_per_stage[s]):
+                    ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
+            else:
+                ops.append(("transition", fp[s - 1], fp[s], st[s], "res%d_0_branch" % (s + 2)))
+                for b in range(1, self.blocks_per_stage[s]):
+                    ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
+        return ops
+
+
+def _same_pad(in_size, k, s):
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return total // 2, total - total // 2
+
+
+def conv2d_same_nhwc(x, w_hwio, bias, strides):
+    """Regular Keras Conv2D(padding='same') on NHWC tensors with TF's asymmetric SAME padding."""
+    kh, kw = w_hwio.shape[0], w_hwio.shape[1]
+    pt, pb = _same_pad(x.shape[1], kh, strides[0])
+    pl, pr = _same_pad(x.shape[2], kw, strides[1])
+    xn = x.permute(0, 3, 1, 2)
+    if pt != pb or pl != pr:
+        xn = F.pad(xn, (pl, pr, pt, pb))
+        pad = (0, 0)
+    else:
+        pad = (pt, pl)
+    y = F.conv2d(xn, w_hwio.permute(3, 2, 0, 1), bias, stride=strides, padding=pad)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+class _Chain:
+    """One run of consecutive Euler steps with equal shape: handles + saved activations."""
+
+    def __init__(self, C, n_layers, gamma, precision, offset):
+        self.C, self.n = C, n_layers
+        self.handles = [LayerHandle(C, 3, gamma, (1, 1), True, True, _abi.PRECISIONS[precision], _abi.LAYOUT_3BY3)
+                        for _ in range(n_layers)]
+        self.np_layer = self.handles[0].num_params
+        self.offset = offset                      # offset of layer 0 in the flat Euler bucket
+        self.acts = None
+        self.masks = None
+
+    def ensure_buffers(self, shape, device):
+        if self.acts is not None and self.acts[1].shape == shape:
+            return
+        N, H, W, C = shape
+        self.acts = [None] + [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(self.n)]
+        self.masks = [torch.empty((N, H, W, C // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
+        self.dz = torch.empty(shape, dtype=torch.float32, device=device)
+        self.dx = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+
+
+class _ChainFn(torch.autograd.Function):
+    """All Euler steps of a chain as ONE autograd node; parameter gradients are written by the
+    wgrad/fold kernels straight into the flat gradient bucket (side effect), not returned."""
+
+    @staticmethod
+    def forward(ctx, x, chain, net):
+        lib, st = _abi.lib(), _stream_ptr()
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        chain.ensure_buffers(tuple(x.shape), x.device)
+        chain.acts[0] = x                         # input of layer 0 is the caller's tensor (no copy)
+        for l, hd in enumerate(chain.handles):
+            off = chain.offset + l * chain.np_layer
+            _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(net.theta_euler[off:]), None, st))
+            _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(chain.acts[l]), _ptr(chain.acts[l + 1]), _ptr(chain.masks[l]),
+                                             None, N, H, W, net.spec.h, _abi.F_EULER, st))
+        ctx.chain, ctx.net, ctx.shape = chain, net, (N, H, W, C)
+        return chain.acts[chain.n].view(N, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        chain, net = ctx.chain, ctx.net
+        N, H, W, C = ctx.shape
+        lib, st = _abi.lib(), _stream_ptr()
+        dy = dy.contiguous()
+        cur = dy
+        for l in range(chain.n - 1, -1, -1):
+            hd = chain.handles[l]
+            off = chain.offset + l * chain.np_layer
+            _abi.check(lib.b200ode_relu_scale_bwd(_ptr(cur), _ptr(chain.masks[l]), _ptr(chain.dz), N * H * W, C,
+                                                  net.spec.h, 0, st))
+            nxt = chain.dx[l & 1]
+            _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(chain.dz), _ptr(cur), _ptr(nxt), N, H, W, st))
+            _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(chain.acts[l]), _ptr(chain.dz), _ptr(net.grad_euler[off:]),
+                                               None, N, H, W, 0, st))
+            cur = nxt
+        return cur.view(N, H, W, C), None, None
+
+
+class EulerNet:
+    """Antisymmetric single-block ResNet with a fused train step.
+
+    precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', or 'simt'."""
+
+    def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
+                 world_size=1):
+        _abi.require_device()
+        self.spec, self.precision, self.device = spec, precision, torch.device(device)
+        self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
+        gen = torch.Generator().manual_seed(seed)
+        plan = spec.plan()
+        # ---- flat Euler bucket -------------------------------------------------------------------
+        self.segments = []          # graph order: ('torch', name, ...) or ('chain', _Chain)
+        off = 0
+        i = 0
+        while i < len(plan):
+            kind, ci, co, st, name = plan[i]
+            if kind == "euler":
+                j = i
+                while j < len(plan) and plan[j][0] == "euler" and plan[j][2] == co:
+                    j += 1
+                ch = _Chain(co, j - i, spec.gamma, precision, off)
+                off += ch.np_layer * ch.n
+                self.segments.append(("chain", ch))
+                i = j
+            else:
+                self.segments.append((kind, ci, co, st, name))
+                i += 1
+        self.n_euler_params = off
+        # ---- regular (torch-op) parameters, appended to the same flat buffers --------------------
+        self.torch_shapes = []
+        k = spec.kernel_size
+        for seg in self.segments:
+            if seg[0] == "stem":
+                _, ci, co, st, name = seg
+                self.torch_shapes += [(name + "/kernel", (k, k, ci, co), k * k * ci), (name + "/bias", (co,), 0)]
+            elif seg[0] == "transition":
+                _, ci, co, st, name = seg
+                self.torch_shapes += [(name + "2/kernel", (k, k, ci, co), k * k * ci), (name + "2/bias", (co,), 0),
+                                      (name + "1/kernel", (1, 1, ci, co), ci), (name + "1/bias", (co,), 0)]
+        c_last = spec.filters_per_block[spec.num_stages - 2]
+        self.torch_shapes += [("fc/kernel", (c_last, spec.num_classes), c_last), ("fc/bias", (spec.num_classes,), 0)]
+        n_torch = sum(math.prod(s) for _, s, _ in self.torch_shapes)
+        self.n_params = off + n_torch
+        theta = torch.zeros(self.n_params, dtype=torch.float32)
+        # Euler layers: truncated normal sigma = sqrt(2/(9C)), zero bias (reference 3By3.py:95-98,148-153)
+        for seg in self.segments:
+            if seg[0] != "chain":
+                continue
+            ch = seg[1]
+            for l in range(ch.n):
+                a = ch.offset + l * ch.np_layer
+                truncated_normal_(theta[a:a + ch.np_layer - ch.C], math.sqrt(2.0 / (9 * ch.C)), gen)
+        cur = off
+        self.torch_params = {}
+        for name, shape, fan_in in self.torch_shapes:
+            n = math.prod(shape)
+            if fan_in:  # Keras he_normal (VarianceScaling(2, fan_in, truncated normal))
+                std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+                truncated_normal_(theta[cur:cur + n], std, gen)
+            self.torch_params[name] = (cur, shape)
+            cur += n
+        self.theta = theta.to(self.device)
+        self.grad = torch.zeros_like(self.theta)
+        self.adam_m = torch.zeros_like(self.theta)
+        self.adam_v = torch.zeros_like(self.theta)
+        self.theta_euler = self.theta[:off]
+        self.grad_euler = self.grad[:off]
+        self.step_counter = torch.ones(1, dtype=torch.int32, device=self.device)
+        # leaf views for torch ops; their .grad are views of the flat gradient bucket
+        self.leaves = {}
+        for name, (a, shape) in self.torch_params.items():
+            n = math.prod(shape)
+            p = self.theta[a:a + n].view(shape).detach().requires_grad_(True)
+            p.grad = self.grad[a:a + n].view(shape)
+            self.leaves[name] = p
+        self._graph = None
+        self._static_in = None
+
+    # ----------------------------------------------------------------------------------------------
+    def forward(self, images):
+        """images: uint8 or float [N,H,W,3] -> softmax probabilities."""
+        spec = self.spec
+        x = images.to(torch.float32)
+        if spec.subtract_mean is not None:
+            x = x - spec.subtract_mean
+        if spec.divide_by_stddev is not None:
+            x = x / spec.divide_by_stddev
+        L = self.leaves
+        for seg in self.segments:
+            if seg[0] == "stem":
+                _, ci, co, st, name = seg
+                x = torch.relu(conv2d_same_nhwc(x, L[name + "/kernel"], L[name + "/bias"], st))
+            elif seg[0] == "transition":
+                _, ci, co, st, name = seg
+                main = conv2d_same_nhwc(x, L[name + "2/kernel"], L[name + "2/bias"], st)
+                short = conv2d_same_nhwc(x, L[name + "1/kernel"], L[name + "1/bias"], st)
+                x = torch.relu(main) + short          # models/tfkeras_resnets.py:266-267
+            else:
+                x = _ChainFn.apply(x, seg[1], self)
+        x = x.mean(dim=(1, 2))
+        logits = x @ L["fc/kernel"] + L["fc/bias"]
+        return torch.softmax(logits, dim=-1)
+
+    @staticmethod
+    def loss_fn(probs, onehot, eps=1e-7):
+        """mean K.categorical_crossentropy(from_logits=False) (training/training.py:295)."""
+        p = probs / probs.sum(dim=-1, keepdim=True)
+        p = torch.clamp(p, eps, 1.0 - eps)
+        return -(onehot * torch.log(p)).sum(dim=-1).mean()
+
+    def _fwd_bwd(self, images, onehot):
+        self.grad.zero_()
+        loss = self.loss_fn(self.forward(images), onehot)
+        loss.backward()
+        return loss
+
+    def _optimizer(self):
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grad)
+        lib, st = _abi.lib(), _stream_ptr()
+        _abi.check(lib.b200ode_adam_step(_ptr(self.theta), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                                         self.n_params, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,
+                                         1.0 / self.world_size, st))
+        _abi.check(lib.b200ode_increment(_ptr(self.step_counter), st))
+
+    def train_step(self, images, onehot):
+        """Eager step; returns the loss tensor (device)."""
+        loss = self._fwd_bwd(images, onehot)
+        self._optimizer()
+        return loss.detach()
+
+    # ----------------------------------------------------------------------------------------------
+    def capture(self, images, onehot, warmup=3):
+        """Capture the whole train step in a CUDA graph (inputs are copied into static buffers)."""
+        self._static_in = (images.clone(), onehot.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.train_step(*self._static_in)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.train_step(*self._static_in)
+        return self
+
+    def train_step_graph(self, images=None, onehot=None):
+        if images is not None:
+            self._static_in[0].copy_(images, non_blocking=True)
+            self._static_in[1].copy_(onehot, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
+    # ----------------------------------------------------------------------------------------------
+    def export_params(self):
+        """dict name -> CPU tensor: '<layer>/packed' for Euler layers (reference variable order,
+        flattened), '<layer>/kernel' (HWIO) and '<layer>/bias' for regular layers."""
+        out = {}
+        th = self.theta.detach().cpu()
+        for name, off, n, C in self.layer_param_slices():
+            out[name + "/packed"] = th[off:off + n].clone()
+        for name, (a, shape) in self.torch_params.items():
+            out[name] = th[a:a + math.prod(shape)].view(shape).clone()
+        return out
+
+    def import_params(self, params):
+        with torch.no_grad():
+            for name, off, n, C in self.layer_param_slices():
+                self.theta[off:off + n].copy_(params[name + "/packed"].reshape(-1))
+            for name, (a, shape) in self.torch_params.items():
+                self.theta[a:a + math.prod(shape)].copy_(params[name].reshape(-1))
+
+    def export_grads(self):
+        out = {}
+        g = self.grad.detach().cpu()
+        for name, off, n, C in self.layer_param_slices():
+            out[name + "/packed"] = g[off:off + n].clone()
+        for name, (a, shape) in self.torch_params.items():
+            out[name] = g[a:a + math.prod(shape)].view(shape).clone()
+        return out
+
+    def layer_param_slices(self):
+        """(name, offset, size, C) of every Euler layer in the flat bucket, graph order."""
+        out, idx = [], 0
+        plan = [p for p in self.spec.plan() if p[0] == "euler"]
+        for seg in self.segments:
+            if seg[0] != "chain":
+                continue
+            ch = seg[1]
+            for l in range(ch.n):
+                out.append((plan[idx][4], ch.offset + l * ch.np_layer, ch.np_layer, ch.C))
+                idx += 1
+        return out
+
+    def gradient_mean_norms(self):
+        """Per-layer ||g||_2 / size over the kernel variables (training/training.py:385-407)."""
+        res = {}
+        for name, off, n, C in self.layer_param_slices():
+            g = self.grad[off:off + n - C]
+            res[name] = float(g.norm() / g.numel())
+        return res

@@ -285,4 +285,4 @@ def train_step(spec, P, M, V, t, images, onehot, lr=1e-3, assembly="closed"):
             V[n].mul_(0.999).addcmul_(g, g, value=0.001)
             P[n].sub_(lr_t * M[n] / (V[n].sqrt() + 1e-7))
             out_g[n] = g
-    return float(loss), out_g
+    return float(loss.detach()), out_g

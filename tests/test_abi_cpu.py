@@ -1,0 +1,77 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/b200ode.h declares, and fails
+loudly (no CPU fallback) when no CUDA device is present."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200ode.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200ode_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from differential_equations_resnet_b200 import _abi
+    lib = _abi.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_abi.EXPORTED_SYMBOLS) == syms
+    assert lib.b200ode_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine without a GPU")
+def test_no_cpu_fallback():
+    import differential_equations_resnet_b200 as pkg
+    from differential_equations_resnet_b200 import _abi
+    assert _abi.lib().b200ode_device_ok() == 0
+    layer = pkg.Conv2DAntisymmetric3By3(gamma=0.0)
+    with pytest.raises(_abi.B200OdeError, match="no CPU fallback"):
+        layer(torch.zeros(1, 4, 4, 16))
+
+
+def test_layer_constructor_signatures_match_reference():
+    """Same keyword names and defaults as the reference constructors
+    (layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:60-66, tfkeras_layer_Conv2DAntisymmetric.py:60-68)."""
+    import inspect
+    import differential_equations_resnet_b200 as pkg
+    s3 = inspect.signature(pkg.Conv2DAntisymmetric3By3.__init__)
+    assert list(s3.parameters)[:6] == ["self", "gamma", "strides", "use_bias", "kernel_initializer", "kernel_regularizer"]
+    assert s3.parameters["gamma"].default == 0.0 and s3.parameters["strides"].default == (1, 1)
+    assert s3.parameters["use_bias"].default is True and s3.parameters["kernel_initializer"].default == "he_normal"
+    sg = inspect.signature(pkg.Conv2DAntisymmetric.__init__)
+    assert list(sg.parameters)[:8] == ["self", "kernel_size", "gamma", "strides", "use_bias", "kernel_initializer",
+                                       "kernel_regularizer", "antisymmetric"]
+    assert sg.parameters["antisymmetric"].default is True
+    layer = pkg.Conv2DAntisymmetric3By3(gamma=-0.1, name="res2_0_branch2")
+    assert layer.name == "res2_0_branch2" and layer.compute_output_shape((1, 2, 3, 4)) == (1, 2, 3, 4)
+    cfg = layer.get_config()
+    assert cfg["strides"] == (1, 1) and cfg["use_bias"] is True and cfg["gamma"] == -0.1
+
+
+def test_variable_shapes_follow_reference_order():
+    import differential_equations_resnet_b200 as pkg
+    from oracle import antisym_numpy as O0
+    layer = pkg.Conv2DAntisymmetric3By3()
+    layer.num_channels, layer.use_bias = 16, True
+    shapes = layer._variable_shapes()
+    assert len(shapes) == 20 and shapes[:4] == [(1, 1, 1, 16)] * 4 and shapes[4] == (3, 3, 15) and shapes[-1] == (16,)
+    gl = pkg.Conv2DAntisymmetric(5, antisymmetric=True)
+    gl.num_channels, gl.use_bias = 3, True
+    import numpy as np
+    assert sum(int(np.prod(s)) for s in gl._variable_shapes()) == O0.num_params_general(3, 5, True)
+
+
+def test_netspec_plan_matches_oracle_plan():
+    from differential_equations_resnet_b200.training import NetSpec
+    from oracle import antisym_torch as O1
+    kw = dict(blocks_per_stage=(36, 37, 37), filters_per_block=(16, 32, 64), h=8 / 108)
+    assert NetSpec(**kw).plan() == O1.NetSpec(**kw).plan()
+    kinds = [p[0] for p in NetSpec(**kw).plan()]
+    assert kinds.count("euler") == 108 and kinds.count("transition") == 2

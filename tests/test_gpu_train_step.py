@@ -1,0 +1,61 @@
+"""GPU parity of the whole train step (forward, Keras CE loss, backward, TF1 Adam) against the O1
+oracle with identical parameters and inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import antisym_torch as O1
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(precision, tol_loss, tol_grad, graph=False):
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    kw = dict(blocks_per_stage=(3, 3, 2), filters_per_block=(16, 32, 64), h=0.25, gamma=-0.05)
+    ospec = O1.NetSpec(**kw)
+    P = O1.init_net_params(ospec, seed=5)
+    gen = torch.Generator().manual_seed(3)
+    for k in P:                      # non-zero biases everywhere
+        if k.endswith("/bias"):
+            P[k] = torch.randn(P[k].shape, generator=gen) * 0.05
+        if k.endswith("/packed"):
+            C = int(k and [c for c in (16, 32, 64) if P[k].numel() == 4 * c + 9 * c * (c - 1) // 2 + c][0])
+            P[k][-C:] = torch.randn(C, generator=gen) * 0.05
+    net = EulerNet(NetSpec(**kw), precision=precision, seed=0)
+    net.import_params(P)
+    img = torch.randint(0, 256, (8, 32, 32, 3), generator=gen, dtype=torch.uint8)
+    lab = torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=gen), 10).float()
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    losses_ref, losses = [], []
+    if graph:
+        net.capture(img.cuda(), lab.cuda(), warmup=1)
+        net.import_params(P)
+        net.adam_m.zero_(); net.adam_v.zero_(); net.step_counter.fill_(1)
+    for t in (1, 2, 3):
+        lr, gr = O1.train_step(ospec, P, M, V, t, img, lab)
+        losses_ref.append(lr)
+        l = net.train_step_graph() if graph else net.train_step(img.cuda(), lab.cuda())
+        losses.append(float(l))
+        if t == 1:
+            g = net.export_grads()
+            for k in gr:
+                err = float((g[k].double() - gr[k].double()).norm() / max(float(gr[k].double().norm()), 1e-30))
+                assert err <= tol_grad, (k, err)
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) <= tol_loss * max(1.0, abs(b)), (losses, losses_ref)
+    th = net.export_params()
+    for k in P:   # after 3 Adam steps the parameters moved by ~3e-3; compare the updates
+        assert float((th[k] - P[k]).abs().max()) <= (2e-4 if precision == "strict" else 2e-3), k
+
+
+def test_train_step_strict_matches_oracle():
+    _run("strict", 1e-5, 2e-4)
+
+
+def test_train_step_fast_tf32_matches_oracle():
+    _run("fast_tf32", 2e-3, 3e-2)
+
+
+def test_train_step_cuda_graph_matches_oracle():
+    _run("strict", 1e-5, 2e-4, graph=True)
