@@ -289,7 +289,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
   const int nkb = C * eb / rowb;
   const bool strict = mode == MODE_STRICT;
   const int P = W + 1;
-  if (P > 256 || H + 2 > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= 254 and W <= 255 (got %dx%d)", H, W);
+  if (P > 256 || H + 3 > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= 253 and W <= 255 (got %dx%d)", H, W);
   const long long Q = (long long)H * P;
   const int tw = taps_per_w_stage(mode, C);
   const uint32_t w_bytes = (uint32_t)tw * C * rowb;
@@ -302,7 +302,9 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
     for (int a = 1; a <= 32; ++a) {
       int spi, nimg, tpi, RB;
       if (whole) {
-        spi = (int)((Q + 127) / 128); nimg = a; tpi = 1; RB = H + 2;
+        // H+2 halo rows plus one: tap (2,2) of the last pixel reads the first pixel of halo row H+2
+        // (the shared zero column), which must come from TMA zero fill, not stale shared memory
+        spi = (int)((Q + 127) / 128); nimg = a; tpi = 1; RB = H + 3;
         if (nimg > N && nimg > 1) break;
       } else {
         spi = a; nimg = 1; tpi = (int)((Q + 128LL * spi - 1) / (128LL * spi)); RB = (128 * spi) / P + 4;

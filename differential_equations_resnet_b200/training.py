@@ -109,7 +109,7 @@ class _ChainFn(torch.autograd.Function):
         x = x.contiguous()
         N, H, W, C = x.shape
         chain.ensure_buffers(tuple(x.shape), x.device)
-        chain.acts[0] = x                         # input of layer 0 is the caller's tensor (no copy)
+        chain.acts[0] = x.detach()                # layer 0 reads the caller's tensor (no copy, no graph reference)
         for l, hd in enumerate(chain.handles):
             off = chain.offset + l * chain.np_layer
             _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(net.theta_euler[off:]), None, st))
@@ -208,13 +208,13 @@ class EulerNet:
         self.theta_euler = self.theta[:off]
         self.grad_euler = self.grad[:off]
         self.step_counter = torch.ones(1, dtype=torch.int32, device=self.device)
-        # leaf views for torch ops; their .grad are views of the flat gradient bucket
+        # leaf views of the flat parameter buffer for the torch ops
         self.leaves = {}
         for name, (a, shape) in self.torch_params.items():
             n = math.prod(shape)
-            p = self.theta[a:a + n].view(shape).detach().requires_grad_(True)
-            p.grad = self.grad[a:a + n].view(shape)
-            self.leaves[name] = p
+            self.leaves[name] = self.theta[a:a + n].view(shape).detach().requires_grad_(True)
+        self._leaf_list = list(self.leaves.values())
+        self._leaf_grad_views = [self.grad[a:a + math.prod(shape)].view(shape) for a, shape in self.torch_params.values()]
         self._graph = None
         self._static_in = None
 
@@ -251,9 +251,16 @@ class EulerNet:
         return -(onehot * torch.log(p)).sum(dim=-1).mean()
 
     def _fwd_bwd(self, images, onehot):
-        self.grad.zero_()
+        # strict mode: the few torch-op layers (stem / transitions / head) must not use TF32 either
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "strict"):
+            return self._fwd_bwd_inner(images, onehot)
+
+    def _fwd_bwd_inner(self, images, onehot):
         loss = self.loss_fn(self.forward(images), onehot)
-        loss.backward()
+        # torch.autograd.grad (no AccumulateGrad nodes -> CUDA-graph capturable); the Euler chains write
+        # their parameter gradients into the flat bucket as a side effect of their backward node.
+        grads = torch.autograd.grad(loss, self._leaf_list)
+        torch._foreach_copy_(self._leaf_grad_views, list(grads))
         return loss
 
     def _optimizer(self):

@@ -100,7 +100,7 @@ def test_general_layer_pack(k, anti, C):
     want = O0.assemble_kernel_general_literal(O0.split_params_general(flat, C, k, anti), C, k, np.float32(0.2), anti)
     assert np.array_equal(layer.get_kernel(), want)
     x, x64 = rand_x((2, 8, 8, C), 5, "strict")
-    y = layer(x).cpu().numpy()
+    y = layer(x).detach().cpu().numpy()
     assert rel(y, O0.layer_call(x64, want.astype(np.float64), flat[-C:].astype(np.float64))) <= 1e-5
 
 
@@ -118,12 +118,12 @@ def test_conv_known_answer_on_gpu(golden_dir):
     layer.set_weights([np.float32(ks[0, 0]).reshape(1, 1, 1, 1), np.float32(ks[0, 1]).reshape(1, 1, 1, 1),
                        np.float32(ks[0, 2]).reshape(1, 1, 1, 1), np.float32(ks[1, 1]).reshape(1, 1, 1, 1),
                        np.float32(ks[1, 2]).reshape(1, 1, 1, 1)])
-    y = layer(x)
+    y = layer(x).detach()
     la = pkg.Conv2DAntisymmetric(3, antisymmetric=True, use_bias=False, precision="simt")
     la.build((1, 7, 7, 1))
     la.set_weights([np.float32(ka[0, 0]).reshape(1, 1, 1, 1), np.float32(ka[0, 1]).reshape(1, 1, 1, 1),
                     np.float32(ka[0, 2]).reshape(1, 1, 1, 1), np.float32(ka[1, 2]).reshape(1, 1, 1, 1)])
-    y = (y + la(x)).cpu().numpy().reshape(-1)
+    y = (y + la(x).detach()).cpu().numpy().reshape(-1)
     assert np.abs(y - np.array(g["output_7x7"], np.float32)).max() < 2e-6
 
 
@@ -155,7 +155,7 @@ def test_euler_step_forward_backward(shape, precision):
     tol = TOL[precision]
 
     # plain layer call (reference call(): conv + bias)
-    z = layer(x).float().cpu().numpy()
+    z = layer(x).detach().float().cpu().numpy()
     z_ref = O0.layer_call(x64, K, flat[-C:])
     assert rel(z, z_ref) <= tol, "conv+bias"
 
@@ -177,8 +177,11 @@ def test_euler_step_forward_backward(shape, precision):
     dX, G, dbias, _, dZ = O0.euler_step_bwd(dy64, cache, K, h)
     gflat = O0.fold_grad_3by3(G, C, dbias)
     # relu mask flips on |z| ~ 0 are measure-zero for strict; loose modes may flip a few
-    assert rel(xr.grad.float().cpu().numpy(), dX) <= tol * (1 if precision in ("strict", "simt") else 3), "dgrad"
-    assert rel(layer.packed.grad.cpu().numpy(), gflat) <= tol * (1 if precision in ("strict", "simt") else 3), "wgrad+fold"
+    # fast modes: the tensor core TRUNCATES fp32 operands to tf32 (biased, probe-verified) and a few
+    # relu-mask bits flip where |z| ~ 1e-3; the folded gradient S = G - rot180(G)^T additionally cancels.
+    gtol = {"strict": (1e-5, 1e-5), "simt": (1e-5, 1e-5), "fast_tf32": (1e-2, 5e-2)}[precision]
+    assert rel(xr.grad.float().cpu().numpy(), dX) <= gtol[0], "dgrad"
+    assert rel(layer.packed.grad.cpu().numpy(), gflat) <= gtol[1], "wgrad+fold"
 
 
 @pytest.mark.parametrize("precision", ["strict", "fast_tf32", "fast_bf16"])
@@ -234,8 +237,9 @@ def test_linearity_and_antisymmetry_at_full_size():
     layer = make_layer(64, "strict", gamma=gamma, bias_std=0)
     x, _ = rand_x((256, 32, 32, 64), 1, "strict")
     y, _ = rand_x((256, 32, 32, 64), 2, "strict")
-    kx, ky = layer(x), layer(y)
-    kxy = layer(2.0 * x - 3.0 * y)
+    with torch.no_grad():
+        kx, ky = layer(x), layer(y)
+        kxy = layer(2.0 * x - 3.0 * y)
     lin = (kxy - (2.0 * kx - 3.0 * ky)).double().norm() / kxy.double().norm()
     assert float(lin) <= 2e-5
     quad = (x.double() * kx.double()).sum() / (x.double() * x.double()).sum()
