@@ -531,7 +531,7 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
 // tensor-core weight gradient planning + launch
 // ------------------------------------------------------------------------------------------------
 static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, int N, int H, int W, float* G, float* G_user,
-                        cudaStream_t st) {
+                        float* grad_params, int accumulate, cudaStream_t st) {
   const int mode = L->mode_eff, C = L->g.C;
   const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
   const int eb = bf16 ? 2 : 4;
@@ -553,7 +553,7 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
       for (int TG : {9, 3, 1}) {
-        if (TG * p.MB * NT > 512) continue;
+        if (TG * p.MB * NT * (strict ? 2 : 1) > 512) continue;
         const double load = (double)(C + NT) * UKP * eb / 40.0;
         const double per = (double)(NT / 2 > p.Mblk / 4 ? NT / 2 : p.Mblk / 4);
         const double mma = (double)TG * p.MB * per * (strict ? 3 : 1);
@@ -565,7 +565,8 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   }
   const int ngroups = p.ntapgroups * p.nngroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;
-  uint32_t cols = (uint32_t)nent * p.NT, pc = 32;
+  if (p.trick && strict && 3 * p.NT * 2 > 512) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad TMEM");
+  uint32_t cols = (uint32_t)nent * p.NT * (strict ? 2 : 1), pc = 32;
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
   // positions per tile: as large as fits two stages (one as a fallback)
@@ -578,7 +579,7 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
       if (RBx > 256) continue;
       const uint32_t xs = align_up((uint32_t)RBx * p.P * p.RWB, 1024), ds = align_up((uint32_t)RBd * p.P * p.RWB, 1024);
       const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
-      if (stage * st_try + 1024 <= max_smem) { KT = kt; stages = st_try; break; }
+      if (stage * st_try + 1024 + 4608 <= max_smem) { KT = kt; stages = st_try; break; }
     }
   }
   if (!KT) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad strips do not fit shared memory (C=%d W=%d)", C, W);
@@ -594,7 +595,9 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   const uint32_t hi_bytes = p.d_off + p.dchunks * p.d_chunk_stride;
   p.x_lo_off = hi_bytes; p.d_lo_off = hi_bytes + p.d_off;
   p.stage_stride = strict ? 2 * hi_bytes : hi_bytes;
-  p.bar_off = p.stage_stride * stages;
+  p.ent_off = p.stage_stride * stages;
+  p.bsum_off = p.ent_off + 128;
+  p.bar_off = p.bsum_off + 4096;
   const size_t smem = (size_t)p.bar_off + 256 + 1024;
   p.total_tiles = N * p.tpi;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
@@ -604,8 +607,9 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   p.nparts = nparts;
   const long long total = 9LL * C * C;
   float* ws = nullptr;
-  if (int rc = get_scratch(1, (size_t)nparts * total * sizeof(float), (void**)&ws)) return rc;
+  if (int rc = get_scratch(1, (size_t)nparts * (total + C) * sizeof(float), (void**)&ws)) return rc;
   p.partials = ws;
+  p.bias_partials = ws + (size_t)nparts * total;
   CUtensorMap mx, md;
   const CUtensorMapSwizzle sw = bf16 ? (p.RWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.RWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)
                                      : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -626,8 +630,13 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   else WG_LAUNCH(MODE_BF16);
 #undef WG_LAUNCH
   LAUNCH_CHECK("wgrad_tc_kernel");
-  reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
-  LAUNCH_CHECK("reduce_parts");
+  if (G_user) {   // dense gradient requested (tests / diagnostics)
+    reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
+    LAUNCH_CHECK("reduce_parts");
+  }
+  const long long nout = (L->g.use_bias ? L->g.nparams : L->g.bias_off);
+  fold_reduce_kernel<<<blocks_for(nout * 16, 256), 256, 0, st>>>(L->g, ws, nparts, total, p.bias_partials, grad_params, accumulate);
+  LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }
 
@@ -639,7 +648,7 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long npix = (long long)N * g.Ho * g.Wo;
   if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
-    if (int rc = run_wgrad_tc(L, x, dz, N, H, W, L->Gdense, G_dense, st)) return rc;
+    return run_wgrad_tc(L, x, dz, N, H, W, L->Gdense, G_dense, grad_params, accumulate, st);
   } else {
     int parts = (int)(npix / 64);
     if (parts < 1) parts = 1;

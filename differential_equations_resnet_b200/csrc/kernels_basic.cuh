@@ -194,21 +194,17 @@ __global__ void reduce_parts(const float* __restrict__ Gpart, int nparts, long l
   if (G_user) G_user[e] = acc;
 }
 
-// Fold the dense gradient onto the free parameters: every free scalar feeds
-// exactly two kernel entries (one for a trainable centre); its gradient is sum_i sign_i * G[entry_i].
-__global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __restrict__ grad, int accumulate) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nfree = g.use_bias ? g.bias_off : g.nparams;
-  if (i >= nfree) return;
+// Which kernel entries a free scalar feeds: every free scalar appears in exactly
+// two entries of K (one for a trainable centre); dL/dparam = s1*G[e1] + s2*G[e2].
+__device__ __forceinline__ void param_entries(const LayerGeom& g, long long i, long long& e1, float& s1, long long& e2,
+                                              float& s2) {
   const int k = g.k, C = g.C;
   const long long kk = (long long)k * k;
-  float val;
-  int o;
-  long long rem;
+  int o, slot = 0;
+  long long rem = 0;
   bool is_diag;
-  int slot = 0;
   if (g.layout == 0) {
-    if (i < 4LL * C) { is_diag = true; slot = (int)(i / C); o = (int)(i % C); rem = 0; }
+    if (i < 4LL * C) { is_diag = true; slot = (int)(i / C); o = (int)(i % C); }
     else {
       is_diag = false;
       int lo = 0, hi = C - 1;  // largest o with w_block_off(o) <= i
@@ -223,17 +219,64 @@ __global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __res
     if (rem < g.tab.nd) { is_diag = true; slot = (int)rem; }
     else { is_diag = false; rem -= g.tab.nd; }
   }
+  e1 = e2 = 0; s1 = s2 = 0.0f;
   if (is_diag) {
-    val = 0.0f;
+    int found = 0;
     for (int t = 0; t < k * k; ++t)
-      if (g.tab.slot[t] == slot) val += (g.tab.sign[t] > 0 ? 1.0f : -1.0f) * G[((long long)t * C + o) * C + o];
+      if (g.tab.slot[t] == slot) {
+        const long long e = ((long long)t * C + o) * C + o;
+        const float sg = g.tab.sign[t] > 0 ? 1.0f : -1.0f;
+        if (found == 0) { e1 = e; s1 = sg; } else { e2 = e; s2 = sg; }
+        ++found;
+      }
   } else {
     const int n = C - o - 1;
     const int tap = (int)(rem / n), j = (int)(rem % n), ci = o + 1 + j;
     const int rt = (int)(kk - 1 - tap);  // (k-1-a)*k + (k-1-b)
-    val = G[((long long)tap * C + ci) * C + o] - G[((long long)rt * C + o) * C + ci];
+    e1 = ((long long)tap * C + ci) * C + o; s1 = 1.0f;
+    e2 = ((long long)rt * C + o) * C + ci; s2 = -1.0f;
   }
+}
+
+// Fold a (reduced) dense gradient onto the free parameters.
+__global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __restrict__ grad, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nfree = g.use_bias ? g.bias_off : g.nparams;
+  if (i >= nfree) return;
+  long long e1, e2; float s1, s2;
+  param_entries(g, i, e1, s1, e2, s2);
+  const float val = s1 * G[e1] + s2 * G[e2];
   grad[i] = accumulate ? grad[i] + val : val;
+}
+
+// Split-K reduction + fold + bias gradient in one launch: 16 lanes per output sum the partials
+// (lane l takes parts l, l+16, ...) and combine through a fixed-order shuffle tree -> deterministic.
+__global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
+                                   const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = gid >> 4;
+  const int l = (int)(gid & 15);
+  const long long nfree = g.use_bias ? g.bias_off : g.nparams;
+  const long long total = nfree + ((g.use_bias && bias_part) ? g.C : 0);
+  if (i >= total) return;
+  const unsigned mask = __activemask();
+  float val = 0.0f;
+  if (i < nfree) {
+    long long e1, e2; float s1, s2;
+    param_entries(g, i, e1, s1, e2, s2);
+    for (int p = l; p < nparts; p += 16) {
+      const float* Gp = Gpart + (long long)p * part_stride;
+      val += s1 * Gp[e1] + s2 * Gp[e2];
+    }
+  } else {
+    const int c = (int)(i - nfree);
+    for (int p = l; p < nparts; p += 16) val += bias_part[(long long)p * g.C + c];
+  }
+  val += __shfl_xor_sync(mask, val, 8, 16);
+  val += __shfl_xor_sync(mask, val, 4, 16);
+  val += __shfl_xor_sync(mask, val, 2, 16);
+  val += __shfl_xor_sync(mask, val, 1, 16);
+  if (l == 0) grad[i] = accumulate ? grad[i] + val : val;
 }
 
 // ---------------------------------------------------------------------------------------------

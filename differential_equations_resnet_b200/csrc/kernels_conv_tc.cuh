@@ -146,62 +146,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(MODE == MODE_BF16 ? FMT_BF16 : FMT_TF32, 128, C, 0, 0);
-      const uint64_t desc_hi = (static_cast<uint64_t>(SBO >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-                               (static_cast<uint64_t>(LT) << 61) | (static_cast<uint64_t>(1) << 16);
-      const uint32_t smem_base = smem_u32(smem);
-      uint32_t ia = 0, iw = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int q0 = (tile % p.tpi) * T;
-        const int off0 = q0 - (q0 / p.P) * p.P;
-        const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
-        tc_fence_after_sync();
-        for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
-          mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
-          const uint32_t a_base = smem_base + p.a_off + s * p.a_stride;
-          for (int tg = 0; tg < 9; tg += p.tw) {
-            const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
-            mbar_wait(&w_full[sw_], phw);
-            tc_fence_after_sync();
-            const uint32_t w_base = smem_base + p.w_off + sw_ * p.w_stride;
-            for (int tt = 0; tt < p.tw; ++tt) {
-              const int tap = tg + tt;
-              const int shift = (tap / 3) * p.P + (tap % 3);
-              for (int sg = 0; sg < mt; ++sg) {
-                const int pix = (sg / p.spi) * p.RB * p.P + off0 + (sg % p.spi) * 128 + shift;
-                const uint32_t d_tmem = tmem_base + (as * mt + sg) * ACCW;
+    // The whole warp runs the (uniform) control flow so descriptors live in uniform registers; one
+    // elected lane issues the tcgen05 instructions.  Descriptor low words are advanced by adds of
+    // precomputed 16-byte-unit offsets: a handful of integer instructions per MMA.
+    const bool leader = elect_one();
+    const uint32_t idesc = make_instr_desc(MODE == MODE_BF16 ? FMT_BF16 : FMT_TF32, 128, C, 0, 0);
+    const uint32_t desc_hi32 = (SBO >> 4) | (1u << 14) | (LT << 29);   // bits 32..63 of the smem descriptor
+    constexpr uint32_t LBO_FIELD = 1u << 16;
+    constexpr uint32_t RU = ROWB >> 4;                                  // 16-byte units per pixel row
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t seg_img_step = (uint32_t)(p.RB * p.P) * RU;          // next image inside the strip
+    const uint32_t a_lo_units = p.a_lo_off >> 4, w_lo_units = p.w_bytes >> 4;
+    const uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;               // one tap's weight tile
+    auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
+    uint32_t ia = 0, iw = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int q0 = (tile % p.tpi) * T;
+      const uint32_t off0_units = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
+      const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tile = tmem_base + as * mt * ACCW;
+      for (int kb = 0; kb < NKB; ++kb) {
+        const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
+        mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
+        const uint32_t a_units = ((smem_base + p.a_off + s * p.a_stride) >> 4) + off0_units;
+        int alpha = 0, beta = 0;
+        for (int tg = 0; tg < 9; tg += p.tw) {
+          const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
+          mbar_wait(&w_full[sw_], phw);
+          tc_fence_after_sync();
+          uint32_t b_units = (smem_base + p.w_off + sw_ * p.w_stride) >> 4;
+          for (int tt = 0; tt < p.tw; ++tt, b_units += tap_units) {
+            const uint32_t a_tap = a_units + (uint32_t)(alpha * p.P + beta) * RU;
+            const uint32_t first = (kb | tg | tt) == 0 ? 0u : 1u;
+            uint32_t a_img = a_tap, d_seg = d_tile;
+            for (int im = 0; im < p.nimg; ++im, a_img += seg_img_step) {
+              uint32_t a_sg = a_img;
+              for (int j = 0; j < p.spi; ++j, a_sg += 128 * RU, d_seg += ACCW) {
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                  const uint32_t a_addr = a_base + pix * ROWB + ks * 32;
-                  const uint32_t b_addr = w_base + tt * (C * ROWB) + ks * 32;
-                  const uint64_t da = desc_hi | ((a_addr >> 4) & 0x3FFF);
-                  const uint64_t db = desc_hi | ((b_addr >> 4) & 0x3FFF);
-                  const uint32_t acc = (kb | tap | ks) != 0;
-                  if (MODE == MODE_BF16) {
-                    umma_f16(d_tmem, da, db, idesc, acc);
-                  } else {
-                    umma_tf32(d_tmem, da, db, idesc, acc);
-                    if (STRICT) {
-                      const uint64_t da_lo = desc_hi | (((a_addr + p.a_lo_off) >> 4) & 0x3FFF);
-                      const uint64_t db_lo = desc_hi | (((b_addr + p.w_bytes) >> 4) & 0x3FFF);
-                      umma_tf32(d_tmem + C, da, db_lo, idesc, acc);
-                      umma_tf32(d_tmem + C, da_lo, db, idesc, 1);
+                  const uint64_t da = mk(a_sg + 2 * ks), db = mk(b_units + 2 * ks);
+                  const uint32_t acc = ks ? 1u : first;
+                  if (leader) {
+                    if (MODE == MODE_BF16) {
+                      umma_f16(d_seg, da, db, idesc, acc);
+                    } else {
+                      umma_tf32(d_seg, da, db, idesc, acc);
+                      if (STRICT) {
+                        umma_tf32(d_seg + C, da, mk(b_units + w_lo_units + 2 * ks), idesc, acc);
+                        umma_tf32(d_seg + C, mk(a_sg + a_lo_units + 2 * ks), db, idesc, 1);
+                      }
                     }
                   }
                 }
               }
             }
-            umma_commit(&w_empty[sw_]);
-            ++iw;
+            if (++beta == 3) { beta = 0; ++alpha; }
           }
-          umma_commit(&a_empty[s]);
-          ++ia;
+          if (leader) umma_commit(&w_empty[sw_]);
+          ++iw;
         }
-        umma_commit(&acc_full[as]);
+        if (leader) umma_commit(&a_empty[s]);
+        ++ia;
       }
+      if (leader) umma_commit(&acc_full[as]);
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================

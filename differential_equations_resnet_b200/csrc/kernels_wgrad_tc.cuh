@@ -44,6 +44,8 @@ struct WgradParams {
   int stages;
   uint32_t tmem_cols;
   float* partials;   // [nparts][9][C][C]
+  float* bias_partials;  // [nparts][C] column sums of dz (bias gradient), written by tap group 0
+  uint32_t ent_off, bsum_off;  // smem offsets: per-entry A offsets (uint32[32]) and bias scratch (float[4][256])
 };
 
 template <int MODE>
@@ -69,7 +71,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_d);
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&conv[i], 4); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], group / p.nngroups == 0 ? 5 : 1); mbar_init(&conv[i], 4); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -96,62 +98,120 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
-      const uint32_t idesc = make_instr_desc(BF16 ? FMT_BF16 : FMT_TF32, Mrows, p.NT, 1, 1);
-      const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
-      const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
-      const uint64_t hi_common = (static_cast<uint64_t>(sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-                                 (static_cast<uint64_t>(lt) << 61);
-      const uint64_t hi_a = hi_common | (static_cast<uint64_t>(((p.trick ? (uint32_t)p.RWB : p.x_chunk_stride) >> 4) & 0x3FFF) << 16);
-      const uint64_t hi_b = hi_common | (static_cast<uint64_t>((p.d_chunk_stride >> 4) & 0x3FFF) << 16);
-      const uint32_t smem_base = smem_u32(smem);
-      const int nent = p.trick ? 3 : p.TG * p.MB;
-      const int ksteps = p.KT / UKP;
+    // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
+    const bool leader = elect_one();
+    const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
+    const uint32_t idesc = make_instr_desc(BF16 ? FMT_BF16 : FMT_TF32, Mrows, p.NT, 1, 1);
+    const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
+    const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
+    const uint32_t hi32 = (sbo >> 4) | (1u << 14) | (lt << 29);
+    const uint32_t lbo_a = (((p.trick ? (uint32_t)p.RWB : p.x_chunk_stride) >> 4) & 0x3FFF) << 16;
+    const uint32_t lbo_b = ((p.d_chunk_stride >> 4) & 0x3FFF) << 16;
+    auto mk = [&](uint32_t lo, uint32_t lbo) -> uint64_t { return (static_cast<uint64_t>(hi32) << 32) | (lo | lbo); };
+    const uint32_t RU = (uint32_t)p.RWB >> 4;
+    const uint32_t smem_base = smem_u32(smem);
+    const int nent = p.trick ? 3 : p.TG * p.MB;
+    const int ACCW = STRICT ? 2 * p.NT : p.NT;   // strict: main + correction accumulators (see conv kernel)
+    uint32_t* ent = reinterpret_cast<uint32_t*>(smem + p.ent_off);
+    if (lane < nent) {
+      int shift; uint32_t a_off;
+      if (p.trick) { shift = lane * p.P; a_off = 0; }
+      else {
+        const int tap = tapgroup * p.TG + lane / p.MB;
+        shift = (tap / 3) * p.P + (tap % 3);
+        a_off = (lane % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
+      }
+      ent[lane] = (uint32_t)shift * RU + (a_off >> 4);
+    }
+    __syncwarp();
+    const int ksteps = p.KT / UKP;
+    const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
+    uint32_t it = 0;
+    for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
+      const int q0 = (tile % p.tpi) * p.KT;
+      const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
+      const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+      mbar_wait(STRICT ? &conv[s] : &full[s], ph);
+      tc_fence_after_sync();
+      uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
+      uint32_t du = ((smem_base + s * p.stage_stride + p.d_off) >> 4) + off0;
+      for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+        const uint64_t dsc_b = mk(du, lbo_b);
+        const uint32_t accum = (it | ks) != 0;
+        uint32_t d_tmem = tmem_base;
+        for (int e = 0; e < nent; ++e, d_tmem += ACCW) {
+          const uint32_t au = xu + ent[e];
+          const uint64_t dsc_a = mk(au, lbo_a);
+          if (leader) {
+            if (BF16) umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum);
+            else {
+              umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
+              if (STRICT) {
+                umma_tf32(d_tmem + p.NT, dsc_a, mk(du + lo_d, lbo_b), idesc, accum);
+                umma_tf32(d_tmem + p.NT, mk(au + lo_x, lbo_a), dsc_b, idesc, 1);
+              }
+            }
+          }
+        }
+      }
+      if (leader) umma_commit(&empty[s]);
+      __syncwarp();
+    }
+    if (leader) umma_commit(acc_full);
+  } else if (warp < 6) {
+    // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
+    // to accumulate the bias gradient sum_q dz[q, o] from the dz strips already in shared memory
+    // (no extra HBM traffic; junk / out-of-image positions are TMA zero fill).
+    const int quarter = warp & 3;
+    const int w4 = warp - 2;
+    const int ACCW = STRICT ? 2 * p.NT : p.NT;
+    if (tapgroup == 0) {
+      float bsum[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
+      const int per_chunk = (p.CH + 31) / 32;
       uint32_t it = 0;
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
         const int q0 = (tile % p.tpi) * p.KT;
         const int off0 = q0 - (q0 / p.P) * p.P;
         const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-        mbar_wait(STRICT ? &conv[s] : &full[s], ph);
-        tc_fence_after_sync();
-        const uint32_t xb = smem_base + s * p.stage_stride + p.x_off;
-        const uint32_t db = smem_base + s * p.stage_stride + p.d_off;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t b_addr = db + (off0 + ks * UKP) * p.RWB;
-          const uint64_t dsc_b = hi_b | ((b_addr >> 4) & 0x3FFF);
-          const uint32_t accum = (it | ks) != 0;
-          for (int e = 0; e < nent; ++e) {
-            int shift;
-            uint32_t a_off;
-            if (p.trick) { shift = e * p.P; a_off = 0; }
-            else {
-              const int tap = tapgroup * p.TG + e / p.MB;
-              shift = (tap / 3) * p.P + (tap % 3);
-              a_off = (e % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
-            }
-            const uint32_t a_addr = xb + a_off + (off0 + ks * UKP + shift) * p.RWB;
-            const uint64_t dsc_a = hi_a | ((a_addr >> 4) & 0x3FFF);
-            const uint32_t d_tmem = tmem_base + e * p.NT;
-            if (BF16) umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum);
-            else {
-              umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
-              if (STRICT) {
-                const uint64_t dsc_a_lo = hi_a | (((a_addr - p.x_off + p.x_lo_off) >> 4) & 0x3FFF);
-                const uint64_t dsc_b_lo = hi_b | (((b_addr - p.d_off + p.d_lo_off) >> 4) & 0x3FFF);
-                umma_tf32(d_tmem, dsc_a, dsc_b_lo, idesc, 1);
-                umma_tf32(d_tmem, dsc_a_lo, dsc_b, idesc, 1);
+        mbar_wait(&full[s], ph);
+        const uint8_t* dbase = smem + s * p.stage_stride + p.d_off;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ck = i / per_chunk, c = (i % per_chunk) * 32 + lane;
+          if (ck < p.dchunks && c < p.CH) {
+            const uint8_t* cb = dbase + ck * p.d_chunk_stride;
+            float acc = 0.0f;
+            for (int pos = w4; pos < p.KT; pos += 4) {
+              uint32_t a = (uint32_t)(off0 + pos) * p.RWB + c * (BF16 ? 2 : 4);
+              if (BF16) {
+                a = swizzle_addr(a, p.RWB);
+                acc += __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(cb + a)) << 16);
+              } else {
+                a ^= ((a >> 7) & 3u) << 5;
+                acc += *reinterpret_cast<const float*>(cb + a);
               }
             }
+            bsum[i] += acc;
           }
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
       }
-      umma_commit(acc_full);
+      float* bs = reinterpret_cast<float*>(smem + p.bsum_off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bs[w4 * 256 + i * 32 + lane] = bsum[i];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int per_chunk_i = per_chunk;
+      for (int idx = threadIdx.x - 64; idx < 256; idx += 128) {
+        const int i = idx / 32, l = idx % 32;
+        const int ck = i / per_chunk_i, c = (i % per_chunk_i) * 32 + l;
+        const int ch = ngroup * p.NT + ck * p.CH + c;
+        if (ck < p.dchunks && c < p.CH && ch < p.C)
+          p.bias_partials[(size_t)part * p.C + ch] = bs[idx] + bs[256 + idx] + bs[512 + idx] + bs[768 + idx];
+      }
     }
-  } else if (warp < 6) {
-    // epilogue: TMEM accumulators -> this part's fp32 partial
-    const int quarter = warp & 3;
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
     const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
@@ -170,8 +230,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       float* dst = part_base + ((size_t)tap * p.C + ci) * p.C + ngroup * p.NT;
       for (int c0 = 0; c0 < p.NT; c0 += 16) {
         uint32_t r[16];
-        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * p.NT + c0, r);
-        tmem_ld_wait();
+        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * ACCW + c0, r);
+        if (STRICT) {
+          uint32_t r2[16];
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * ACCW + p.NT + c0, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)

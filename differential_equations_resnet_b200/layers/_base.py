@@ -142,10 +142,8 @@ class _ConvFn(torch.autograd.Function):
 
 
 def _wgrad_any(hd, x, dz):
-    """Weight + bias gradient; in bf16 mode the bias gradient is reduced from an fp32 copy of dz."""
-    if hd.effective_mode != _abi.PREC_FAST_BF16:
-        return hd.wgrad(x, dz)
-    raise NotImplementedError("FAST_BF16 weight gradients go through training.EulerNet (fp32 dz for the bias sum)")
+    """Weight + bias gradient (the bias column sums are accumulated inside the wgrad kernel)."""
+    return hd.wgrad(x, dz)
 
 
 class _EulerFn(torch.autograd.Function):
