@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's model builders for the single-block (Euler) ResNets
+(reference models/tfkeras_resnets.py:28-94 `single_layer_identity_block`, :204-269
+`single_layer_conv_block`, :427-509 `build_single_block_resnet`, :511-604
+`get_single_block_resnet_build_function`): same function names, argument names and defaults.
+
+The reference builds a static tf.keras graph; here the same calls build an eager `Model` whose
+layers are created on first use and reused afterwards.  The Euler step
+x_{n+1} = x_n + h*relu(BN?(conv_K(x_n)+b)) runs on the hand-written CUDA kernels
+(fused single kernel without BN; conv + column-sum + BN finalize + fused tail with BN).
+Stem / transition / head layers are regular Keras layers in the reference and run as torch ops here
+(SURVEY.md section 8f-1).  The bottleneck ResNet-50/101/152 builders are out of scope (SURVEY.md
+section 2, row 6).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import _abi
+from ..layers._base import _ptr, _stream_ptr, as_torch, relu_scale_bwd, truncated_normal_
+from ..layers.tfkeras_layer_Conv2DAntisymmetric3By3 import Conv2DAntisymmetric3By3
+from ..training import conv2d_same_nhwc
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99     # Keras BatchNormalization defaults
+
+
+# ---------------------------------------------------------------------------------------------------
+# build scope: layers are registered by name so that repeated calls reuse them
+# ---------------------------------------------------------------------------------------------------
+class _Scope:
+    current = None
+
+    def __init__(self, precision="strict", seed=None, training=True):
+        self.layers, self.order = {}, []
+        self.precision, self.seed, self.training = precision, seed, training
+
+    def get(self, name, factory):
+        if name not in self.layers:
+            self.layers[name] = factory()
+            self.order.append(name)
+        return self.layers[name]
+
+
+def _scope():
+    if _Scope.current is None:
+        _Scope.current = _Scope()
+    return _Scope.current
+
+
+class _RegularConv:
+    """Keras Conv2D(padding='same', kernel_initializer='he_normal') as torch ops."""
+
+    def __init__(self, filters, kernel_size, strides, name, seed=None):
+        self.filters, self.kernel_size, self.strides, self.name = filters, kernel_size, tuple(strides), name
+        self.kernel = self.bias = None
+        self.seed = seed
+
+    def __call__(self, x):
+        if self.kernel is None:
+            k, ci = self.kernel_size, x.shape[-1]
+            g = torch.Generator().manual_seed(self.seed) if self.seed is not None else None
+            w = truncated_normal_(torch.empty(k, k, ci, self.filters), math.sqrt(2.0 / (k * k * ci)) / 0.87962566103423978, g)
+            self.kernel = w.to(x.device).requires_grad_(True)
+            self.bias = torch.zeros(self.filters, device=x.device, requires_grad=True)
+        return conv2d_same_nhwc(x, self.kernel, self.bias, self.strides)
+
+    @property
+    def trainable_weights(self):
+        return [self.kernel, self.bias]
+
+
+class _BatchNorm:
+    """tf.keras.layers.BatchNormalization(axis=3) state (gamma, beta, moving statistics)."""
+
+    def __init__(self, name):
+        self.name, self.gamma = name, None
+
+    def ensure(self, C, device):
+        if self.gamma is None:
+            self.gamma = torch.ones(C, device=device, requires_grad=True)
+            self.beta = torch.zeros(C, device=device, requires_grad=True)
+            self.moving_mean = torch.zeros(C, device=device)
+            self.moving_var = torch.ones(C, device=device)
+
+    def torch_apply(self, x, training):
+        self.ensure(x.shape[-1], x.device)
+        if training:
+            mu, var = x.mean(dim=(0, 1, 2)), x.var(dim=(0, 1, 2), unbiased=False)
+            with torch.no_grad():
+                M = x.numel() // x.shape[-1]
+                self.moving_mean.mul_(BN_MOMENTUM).add_(mu.detach(), alpha=1 - BN_MOMENTUM)
+                self.moving_var.mul_(BN_MOMENTUM).add_(var.detach() * (M / max(M - 1, 1)), alpha=1 - BN_MOMENTUM)
+        else:
+            mu, var = self.moving_mean, self.moving_var
+        return self.gamma * (x - mu) / torch.sqrt(var + BN_EPS) + self.beta
+
+    @property
+    def trainable_weights(self):
+        return [self.gamma, self.beta]
+
+
+class _EulerBNFn(torch.autograd.Function):
+    """x + h*relu(BN(conv_K(x)+b)) in training mode on the CUDA kernels: conv (z) -> column sums ->
+    bn_finalize -> fused tail; backward: BN reductions, BN apply (dz), dgrad with skip, wgrad + fold."""
+
+    @staticmethod
+    def forward(ctx, x, params, bn_gamma, bn_beta, layer, bn, h):
+        lib, st = _abi.lib(), _stream_ptr()
+        hd = layer._handle
+        hd.pack(params)
+        N, H, W, C = x.shape
+        M = N * H * W
+        _, _, z = hd.forward(x, 1.0, _abi.F_BIAS, want_z=True, want_y=False)
+        dev = x.device
+        ws = torch.empty(2 * _abi.COLSUM_PARTS * C, device=dev)
+        s1, s2 = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        _abi.check(lib.b200ode_colsum(_ptr(z), None, _ptr(s1), _ptr(s2), _ptr(ws), M, C, st))
+        mean, inv, scale, shift = (torch.empty(C, device=dev) for _ in range(4))
+        _abi.check(lib.b200ode_bn_finalize(_ptr(s1), _ptr(s2), _ptr(bn_gamma), _ptr(bn_beta), _ptr(mean), _ptr(inv),
+                                           _ptr(scale), _ptr(shift), _ptr(bn.moving_mean), _ptr(bn.moving_var), M, C,
+                                           BN_EPS, BN_MOMENTUM, st))
+        y = torch.empty_like(x)
+        flags = _abi.F_RELU | _abi.F_RESIDUAL | (_abi.F_SCALE if h != 1.0 else 0)
+        _abi.check(lib.b200ode_euler_tail(_ptr(z), _ptr(scale), _ptr(shift), _ptr(x), _ptr(y), None, M, C, float(h), flags, st))
+        ctx.save_for_backward(x, params, bn_gamma, z, mean, inv, scale, shift)
+        ctx.hd, ctx.h, ctx.ws = hd, h, ws
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, params, bn_gamma, z, mean, inv, scale, shift = ctx.saved_tensors
+        lib, st, hd, h = _abi.lib(), _stream_ptr(), ctx.hd, ctx.h
+        dy = dy.contiguous()
+        N, H, W, C = x.shape
+        M = N * H * W
+        dgamma, dbeta = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
+        _abi.check(lib.b200ode_bn_bwd_reduce(_ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(inv),
+                                             _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), M, C, float(h), st))
+        dz = torch.empty_like(x)
+        _abi.check(lib.b200ode_bn_bwd_apply(_ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(inv),
+                                            _ptr(bn_gamma), _ptr(dgamma), _ptr(dbeta), _ptr(dz), M, C, float(h), st))
+        hd.pack(params)
+        dx = hd.dgrad(dz, dy, (H, W))
+        gp = hd.wgrad(x, dz)
+        return dx, gp, dgamma, dbeta, None, None, None
+
+
+def single_layer_identity_block(input_tensor,
+                                kernel_size,
+                                antisymmetric,
+                                use_batch_norm,
+                                stage,
+                                block,
+                                h=1.0,
+                                gamma=0.0,
+                                kernel_regularizer=None,
+                                bias_regularizer=None):
+    """Euler step: conv -> BN? -> relu -> h* (only if h != 1.0) -> + input
+    (reference models/tfkeras_resnets.py:28-94)."""
+    sc = _scope()
+    x = as_torch(input_tensor)
+    conv_name_base = 'res' + str(stage) + '_' + str(block) + '_branch'
+    bn_name_base = 'bn' + str(stage) + '_' + str(block) + '_branch'
+    if antisymmetric:
+        layer = sc.get(conv_name_base + '2', lambda: Conv2DAntisymmetric3By3(
+            gamma=gamma, strides=(1, 1), use_bias=True, kernel_initializer='he_normal',
+            kernel_regularizer=kernel_regularizer, name=conv_name_base + '2', precision=sc.precision, seed=sc.seed))
+        if not use_batch_norm:
+            return layer.euler_step(x, h)                       # one fused kernel
+        if not layer.built:
+            layer.build(tuple(x.shape))
+        bn = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2'))
+        bn.ensure(x.shape[-1], x.device)
+        if sc.training:
+            return _EulerBNFn.apply(layer._check_input(x), layer.packed, bn.gamma, bn.beta, layer, bn, float(h))
+        y = bn.torch_apply(layer(x), False)
+    else:
+        conv = sc.get(conv_name_base + '2', lambda: _RegularConv(int(x.shape[-1]), kernel_size, (1, 1), conv_name_base + '2', sc.seed))
+        y = conv(x)
+        if use_batch_norm:
+            y = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2')).torch_apply(y, sc.training)
+    y = torch.relu(y)
+    if h != 1.0:
+        y = h * y
+    return y + x
+
+
+def single_layer_conv_block(input_tensor,
+                            kernel_size,
+                            num_filters,
+                            strides,
+                            use_batch_norm,
+                            stage,
+                            block,
+                            kernel_regularizer=None,
+                            bias_regularizer=None):
+    """Transition block: strided regular conv + 1x1 strided shortcut, no h
+    (reference models/tfkeras_resnets.py:204-269)."""
+    sc = _scope()
+    x = as_torch(input_tensor)
+    conv_name_base = 'res' + str(stage) + '_' + str(block) + '_branch'
+    bn_name_base = 'bn' + str(stage) + '_' + str(block) + '_branch'
+    main = sc.get(conv_name_base + '2', lambda: _RegularConv(num_filters, kernel_size, strides, conv_name_base + '2', sc.seed))(x)
+    short = sc.get(conv_name_base + '1', lambda: _RegularConv(num_filters, 1, strides, conv_name_base + '1', sc.seed))(x)
+    if use_batch_norm:
+        main = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2')).torch_apply(main, sc.training)
+        short = sc.get(bn_name_base + '1', lambda: _BatchNorm(bn_name_base + '1')).torch_apply(short, sc.training)
+    return torch.relu(main) + short
+
+
+class Model:
+    """Eager stand-in for tf.keras.models.Model: callable, `predict`, `layers`, `trainable_weights`."""
+
+    def __init__(self, fn, name, precision, seed):
+        self._fn, self.name = fn, name
+        self.scope = _Scope(precision, seed)
+
+    def __call__(self, images, training=True):
+        prev, _Scope.current = _Scope.current, self.scope
+        self.scope.training = training
+        try:
+            return self._fn(as_torch(images))
+        finally:
+            _Scope.current = prev
+
+    def predict(self, images, batch_size=32):
+        x = torch.as_tensor(np.asarray(images)) if not isinstance(images, torch.Tensor) else images
+        outs = []
+        with torch.no_grad():
+            for i in range(0, x.shape[0], batch_size):
+                outs.append(self(x[i:i + batch_size].cuda(), training=False).cpu())
+        return torch.cat(outs).numpy()
+
+    @property
+    def layers(self):
+        return [self.scope.layers[n] for n in self.scope.order]
+
+    def get_layer(self, name):
+        return self.scope.layers[name]
+
+    @property
+    def trainable_weights(self):
+        out = []
+        for l in self.layers:
+            out += list(l.trainable_weights)
+        return out
+
+
+def get_single_block_resnet_build_function(kernel_type='antisymmetric',
+                                           kernel_size=3,
+                                           h=1.0,
+                                           gamma=0.0,
+                                           num_stages=5,
+                                           blocks_per_stage=[3, 4, 6, 3],
+                                           filters_per_block=[64, 128, 256, 512],
+                                           strides=[(2, 2), (2, 2), (2, 2), (2, 2)],
+                                           include_top=True,
+                                           fc_activation='softmax',
+                                           num_classes=None,
+                                           use_batch_norm=False,
+                                           use_max_pooling=[False, False, False, False],
+                                           l2_regularization=0.0,
+                                           subtract_mean=None,
+                                           divide_by_stddev=None,
+                                           verbose=False,
+                                           precision='strict',
+                                           seed=None):
+    """Reference models/tfkeras_resnets.py:511-604 (same keywords; `precision`/`seed` are additions)."""
+    if include_top and (num_classes is None):
+        raise ValueError("You must pass a positive integer for `num_classes` if `include_top` is `True`.")
+    antisymmetric = kernel_type == 'antisymmetric'
+    name = 'single_block_resnet' + ('_antisymmetric' if antisymmetric else '_regular')
+    strides = [tuple(s) for s in strides]
+
+    def _forward(x):
+        sc = _scope()
+        x = x.to(torch.float32)
+        if subtract_mean is not None:
+            x = x - torch.as_tensor(np.array(subtract_mean), dtype=torch.float32, device=x.device)
+        if divide_by_stddev is not None:
+            x = x / torch.as_tensor(np.array(divide_by_stddev), dtype=torch.float32, device=x.device)
+        x = sc.get('conv1', lambda: _RegularConv(filters_per_block[0], kernel_size, strides[0], 'conv1', sc.seed))(x)
+        if use_batch_norm:
+            x = sc.get('bn_conv1', lambda: _BatchNorm('bn_conv1')).torch_apply(x, sc.training)
+        x = torch.relu(x)
+        for s in range(num_stages - 1):
+            if use_max_pooling[s]:
+                x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
+            ident = (s == 0 and not use_max_pooling[s]) or (s > 0 and not use_max_pooling[s] and
+                                                             filters_per_block[s] == filters_per_block[s - 1] and strides[s] == (1, 1))
+            if ident:
+                for b in range(0, blocks_per_stage[s]):
+                    x = single_layer_identity_block(x, kernel_size, antisymmetric, use_batch_norm, stage=s + 2, block=b, h=h, gamma=gamma)
+            else:
+                x = single_layer_conv_block(x, kernel_size, filters_per_block[s], strides[s], use_batch_norm, stage=s + 2, block=0)
+                for b in range(1, blocks_per_stage[s]):
+                    x = single_layer_identity_block(x, kernel_size, antisymmetric, use_batch_norm, stage=s + 2, block=b, h=h, gamma=gamma)
+        if include_top:
+            x = x.mean(dim=(1, 2))
+            fc = sc.get('fc', lambda: _Dense(num_classes, fc_activation, sc.seed))
+            x = fc(x)
+        return x
+
+    def _build_function(input_tensor):
+        model = Model(_forward, name, precision, seed)
+        if input_tensor is not None and isinstance(input_tensor, torch.Tensor) and input_tensor.is_cuda:
+            with torch.no_grad():
+                model(input_tensor)                      # instantiate the layers, like Keras graph building
+        return model
+
+    return _build_function
+
+
+class _Dense:
+    def __init__(self, units, activation, seed=None):
+        self.units, self.activation, self.kernel, self.seed = units, activation, None, seed
+
+    def __call__(self, x):
+        if self.kernel is None:
+            g = torch.Generator().manual_seed(self.seed) if self.seed is not None else None
+            w = truncated_normal_(torch.empty(x.shape[-1], self.units), math.sqrt(2.0 / x.shape[-1]) / 0.87962566103423978, g)
+            self.kernel = w.to(x.device).requires_grad_(True)
+            self.bias = torch.zeros(self.units, device=x.device, requires_grad=True)
+        y = x @ self.kernel + self.bias
+        return torch.softmax(y, dim=-1) if self.activation == 'softmax' else y
+
+    @property
+    def trainable_weights(self):
+        return [self.kernel, self.bias]
+
+
+def build_single_block_resnet(image_shape, sample_input=None, **kwargs):
+    """Reference models/tfkeras_resnets.py:427-509: build function applied to an Input of `image_shape`.
+    Layers are created lazily on the first call unless a CUDA `sample_input` is given."""
+    return get_single_block_resnet_build_function(**kwargs)(sample_input)

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import _abi
 from .layers._base import LayerHandle, truncated_normal_, _ptr, _stream_ptr
+from .parallel import allreduce_bucket
 
 
 class NetSpec:
@@ -264,8 +265,7 @@ class EulerNet:
         return loss
 
     def _optimizer(self):
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.grad)
+        allreduce_bucket(self.grad, self.world_size)
         lib, st = _abi.lib(), _stream_ptr()
         _abi.check(lib.b200ode_adam_step(_ptr(self.theta), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
                                          self.n_params, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,

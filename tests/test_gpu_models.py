@@ -1,0 +1,75 @@
+"""GPU tests of the reference-shaped model builders: BatchNorm Euler step and whole-model forward
+against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import antisym_numpy as O0
+from oracle import antisym_torch as O1
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("C,shape", [(16, (4, 8, 8)), (64, (3, 6, 5)), (5, (2, 7, 7))])
+def test_batchnorm_euler_step_forward_backward(C, shape):
+    from differential_equations_resnet_b200.models import tfkeras_resnets as M
+    N, H, W = shape
+    gamma, h = -0.2, 0.25
+    M._Scope.current = M._Scope(precision="strict", seed=1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((N, H, W, C), generator=g)
+    dy = torch.randn((N, H, W, C), generator=g)
+    xr = x.cuda().requires_grad_(True)
+    y = M.single_layer_identity_block(xr, 3, True, True, stage=2, block=0, h=h, gamma=gamma)
+    sc = M._Scope.current
+    layer, bn = sc.layers["res2_0_branch2"], sc.layers["bn2_0_branch2"]
+    with torch.no_grad():
+        bn.gamma.copy_(torch.rand(C, generator=g) + 0.5); bn.beta.copy_(torch.randn(C, generator=g) * 0.1)
+        layer.packed[-C:] = torch.randn(C, generator=g).cuda() * 0.1
+    y = M.single_layer_identity_block(xr, 3, True, True, stage=2, block=0, h=h, gamma=gamma)
+    y.backward(dy.cuda())
+    flat = layer.packed.detach().cpu().numpy().astype(np.float64)
+    K = O0.assemble_kernel_3by3_closed(flat, C, gamma)
+    bg, bb = bn.gamma.detach().cpu().numpy().astype(np.float64), bn.beta.detach().cpu().numpy().astype(np.float64)
+    y_ref, cache = O0.euler_step_fwd(x.numpy().astype(np.float64), K, flat[-C:], h, (bg, bb))
+    dX, G, dbias, bn_grads, _ = O0.euler_step_bwd(dy.numpy().astype(np.float64), cache, K, h, bg)
+    assert rel(y.detach().cpu().numpy(), y_ref) <= 1e-5
+    assert rel(xr.grad.cpu().numpy(), dX) <= 2e-5
+    gref = O0.fold_grad_3by3(G, C, dbias)
+    assert rel(layer.packed.grad.cpu().numpy()[:-C], gref[:-C]) <= 2e-5
+    assert np.abs(layer.packed.grad.cpu().numpy()[-C:]).max() <= 1e-4      # bias grad vanishes under BN
+    assert rel(bn.gamma.grad.cpu().numpy(), bn_grads[0]) <= 2e-5 and rel(bn.beta.grad.cpu().numpy(), bn_grads[1]) <= 2e-5
+    M._Scope.current = None
+
+
+def test_model_forward_matches_oracle_and_predict_runs():
+    from differential_equations_resnet_b200.models import get_single_block_resnet_build_function
+    kw = dict(h=0.5, gamma=-0.1, num_stages=4, blocks_per_stage=[2, 2, 2], filters_per_block=[16, 32, 64],
+              strides=[(1, 1), (2, 2), (2, 2)], num_classes=10, subtract_mean=127.5, divide_by_stddev=127.5)
+    img = torch.randint(0, 256, (4, 32, 32, 3), generator=torch.Generator().manual_seed(0), dtype=torch.uint8)
+    model = get_single_block_resnet_build_function(kernel_type='antisymmetric', precision='strict', seed=7, **kw)(img.cuda())
+    assert model.name == 'single_block_resnet_antisymmetric'
+    names = [l.name for l in model.layers if hasattr(l, "name")]
+    assert names[:3] == ['conv1', 'res2_0_branch2', 'res2_1_branch2'] and 'res3_0_branch2' in names and 'res3_0_branch1' in names
+    # copy the parameters into the oracle's layout and compare probabilities
+    ospec = O1.NetSpec(blocks_per_stage=(2, 2, 2), h=0.5, gamma=-0.1)
+    P = {}
+    for l in model.layers:
+        n = getattr(l, "name", None)
+        if isinstance(l, type(model.get_layer('conv1'))):
+            P[n + "/kernel"], P[n + "/bias"] = l.kernel.detach().cpu(), l.bias.detach().cpu()
+        elif n is not None and n.startswith("res"):
+            P[n + "/packed"] = l.packed.detach().cpu()
+    fc = model.get_layer('fc')
+    P["fc/kernel"], P["fc/bias"] = fc.kernel.detach().cpu(), fc.bias.detach().cpu()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        probs = model(img.cuda()).detach().cpu()
+    ref = O1.net_forward(ospec, P, img)
+    assert float((probs - ref).abs().max()) <= 2e-5
+    out = model.predict(img.numpy(), batch_size=2)
+    assert out.shape == (4, 10) and np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
