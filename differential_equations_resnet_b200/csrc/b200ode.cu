@@ -46,6 +46,9 @@ static int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(B200ODE_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+static uint64_t* g_trace = nullptr;   // debug timeline buffer (device), see b200ode_debug_set_trace
+extern "C" int b200ode_debug_set_trace(void* device_buffer) { g_trace = (uint64_t*)device_buffer; return 0; }
+
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -413,6 +416,7 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   ConvTcParams& p = plan.p;
   p.in = epi.in; p.skip = epi.skip; p.out = epi.out; p.z_out = epi.z_out; p.mask = epi.mask; p.bias = epi.bias;
   p.acc_scale = epi.acc_scale; p.c_in = epi.c_in; p.h = epi.h; p.relu = epi.relu; p.scale_h = epi.scale_h;
+  p.trace = g_trace;
   const int eb = mode == MODE_BF16 ? 2 : 4;
   const int rowb = C * eb >= 128 ? 128 : C * eb;
   CUtensorMap map_a;
@@ -609,6 +613,7 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   float* ws = nullptr;
   if (int rc = get_scratch(1, (size_t)nparts * (total + C) * sizeof(float), (void**)&ws)) return rc;
   p.partials = ws;
+  p.trace = g_trace;
   p.bias_partials = ws + (size_t)nparts * total;
   CUtensorMap mx, md;
   const CUtensorMapSwizzle sw = bf16 ? (p.RWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.RWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)

@@ -52,6 +52,7 @@ struct ConvTcParams {
   const float* bias;   // nullable
   float acc_scale, c_in, h;
   int relu, scale_h;
+  uint64_t* trace;     // nullable timeline buffer (debug)
 };
 
 template <int MODE, int C>
@@ -91,6 +92,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  Trace tr;
+  tr.begin(p.trace);
+  if (threadIdx.x == 0) tr.wall(0);
   const int mt = p.nimg * p.spi;           // segments (accumulators) per tile
   const int T = p.spi * 128;               // positions per image per tile
 
@@ -111,6 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tr.mark(1);
   // strict mode keeps two accumulators per segment: the hi*hi sum and the small hi*lo + lo*hi
   // correction sum.  The tensor core truncates when it accumulates, so the error grows with the
   // number of accumulation steps into one register; splitting keeps the 2/3 of the MMAs that carry
@@ -170,11 +175,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int kb = 0; kb < NKB; ++kb) {
         const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
         mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
+        if (it == 0 && kb == 0 && lane == 0) tr.mark(2);
         const uint32_t a_units = ((smem_base + p.a_off + s * p.a_stride) >> 4) + off0_units;
         int alpha = 0, beta = 0;
         for (int tg = 0; tg < 9; tg += p.tw) {
           const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
           mbar_wait(&w_full[sw_], phw);
+          if (it == 0 && kb == 0 && tg == 0 && lane == 0) tr.mark(3);
           tc_fence_after_sync();
           uint32_t b_units = (smem_base + p.w_off + sw_ * p.w_stride) >> 4;
           for (int tt = 0; tt < p.tw; ++tt, b_units += tap_units) {
@@ -211,8 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ++ia;
       }
       if (leader) umma_commit(&acc_full[as]);
+      if (it == 0 && lane == 0) tr.mark(4);
       __syncwarp();
     }
+    if (lane == 0) tr.mark(5);
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     const int quarter = warp & 3;
@@ -227,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int q0 = (tile % p.tpi) * T;
       const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
       mbar_wait(&acc_full[as], aph);
+      if (it == 0 && threadIdx.x == 64) tr.mark(6);
       tc_fence_after_sync();
       for (int sg = 0; sg < mt; ++sg) {
         const int n = n0 + sg / p.spi;
@@ -343,7 +353,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (it == 0 && threadIdx.x == 64) tr.mark(7);
     }
+    if (threadIdx.x == 64) tr.mark(8);
   } else {
     // ===================== strict-mode converter warps 6..9 =====================
     if (STRICT) {
@@ -377,6 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) { tr.mark(9); tr.wall(15); }
 }
 
 }  // namespace b200ode

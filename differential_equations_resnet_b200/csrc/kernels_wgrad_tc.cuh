@@ -46,6 +46,7 @@ struct WgradParams {
   float* partials;   // [nparts][9][C][C]
   float* bias_partials;  // [nparts][C] column sums of dz (bias gradient), written by tap group 0
   uint32_t ent_off, bsum_off;  // smem offsets: per-entry A offsets (uint32[32]) and bias scratch (float[4][256])
+  uint64_t* trace;             // nullable timeline buffer (debug)
 };
 
 template <int MODE>
@@ -64,6 +65,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Trace tr;
+  tr.begin(p.trace);
+  if (threadIdx.x == 0) tr.wall(0);
   const int group = blockIdx.y;
   const int tapgroup = group / p.nngroups, ngroup = group % p.nngroups;
   const int part = blockIdx.x;
@@ -80,6 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tr.mark(1);
   const uint32_t stage_bytes = p.xchunks * p.x_chunk_bytes + p.dchunks * p.d_chunk_bytes;
 
   if (warp == 0) {
@@ -132,6 +137,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
       mbar_wait(STRICT ? &conv[s] : &full[s], ph);
+      if (it == 0 && lane == 0) tr.mark(2);
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
       uint32_t du = ((smem_base + s * p.stage_stride + p.d_off) >> 4) + off0;
@@ -155,9 +161,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
       if (leader) umma_commit(&empty[s]);
+      if (it == 0 && lane == 0) tr.mark(3);
       __syncwarp();
     }
     if (leader) umma_commit(acc_full);
+    if (lane == 0) tr.mark(4);
   } else if (warp < 6) {
     // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
     // to accumulate the bias gradient sum_q dz[q, o] from the dz strips already in shared memory
@@ -212,7 +220,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           p.bias_partials[(size_t)part * p.C + ch] = bs[idx] + bs[256 + idx] + bs[512 + idx] + bs[768 + idx];
       }
     }
+    if (threadIdx.x == 64) tr.mark(5);
     mbar_wait(acc_full, 0);
+    if (threadIdx.x == 64) tr.mark(6);
     tc_fence_after_sync();
     const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
     const int nent = p.trick ? 3 : p.TG * p.MB;
@@ -275,9 +285,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (lane == 0) mbar_arrive(&conv[s]);
     }
   }
+  if (threadIdx.x == 64) tr.mark(7);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) { tr.mark(9); tr.wall(15); }
 }
 
 }  // namespace b200ode

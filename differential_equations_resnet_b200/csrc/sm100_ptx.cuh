@@ -30,6 +30,30 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------
+// optional timeline trace (b200ode_debug_set_trace): 16 slots per CTA, slot 0/15 = globaltimer ns at
+// kernel start/end, the others SM-clock deltas since the start of the CTA
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Trace {
+  uint64_t* buf;
+  long long t0;
+  __device__ __forceinline__ void begin(uint64_t* base) {
+    buf = base ? base + (size_t)blockIdx.x * 16 + (size_t)blockIdx.y * gridDim.x * 16 : nullptr;
+    if (buf) { t0 = clock64(); }
+  }
+  __device__ __forceinline__ void mark(int slot) const {
+    if (buf) buf[slot] = (uint64_t)(clock64() - t0);
+  }
+  __device__ __forceinline__ void wall(int slot) const {
+    if (buf) buf[slot] = globaltimer_ns();
+  }
+};
+
+// ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -141,6 +141,9 @@ int b200ode_increment(int32_t* counter, void* stream);
 
 /* test hook: number of kernel launches issued by this library in this process */
 int64_t b200ode_launch_count(void);
+/* debug hook: device buffer of uint64 [ctas][16] that the tensor-core kernels fill with a per-CTA
+ * timeline (slot 0/15: %globaltimer ns at CTA start/end; others: SM clock deltas); NULL disables. */
+int b200ode_debug_set_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }
