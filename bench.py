@@ -170,56 +170,55 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 def kernel_microbench(torch, precision, batch):
-    """CUDA-event timing of the three tensor-core kernels at the three stage shapes, rotating through
-    buffers larger than L2 (so every launch reads from HBM); returns per-kernel records."""
+    """CUDA-event timing of the persistent chain kernels (forward sweep, backward sweep, layer-batched
+    weight gradient) at the three stage shapes of cfg3 with the real chain length (36 steps): every
+    launch streams 36 saved activations / dZ tensors (75-300 MB per launch, >> L2 together with the
+    other buffers touched in between), so no artificial rotation is needed."""
     from differential_equations_resnet_b200 import _abi
-    from differential_equations_resnet_b200.layers._base import LayerHandle, _ptr
-    lib = _abi.lib()
-    st = torch.cuda.current_stream().cuda_stream
+    from differential_equations_resnet_b200.layers._base import ChainHandle
     recs = []
-    for (C, HW, layers) in ((16, 32, 36), (32, 16, 36), (64, 8, 36)):
+    L = 36
+    for (C, HW) in ((16, 32), (32, 16), (64, 8)):
         N, H, W = batch, HW, HW
         Mpix = N * H * W
         per = Mpix * C * 4
-        nbuf = max(3, int(300e6 // per) + 1)
-        hd = LayerHandle(C, 3, 0.0, (1, 1), True, True, _abi.PRECISIONS[precision], _abi.LAYOUT_3BY3)
-        params = torch.randn(hd.num_params, device="cuda") * 0.05
-        _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(params), None, st))
-        xs = [torch.randn((N, H, W, C), device="cuda") for _ in range(nbuf)]
-        ys = [torch.empty((N, H, W, C), device="cuda") for _ in range(nbuf)]
-        ms = [torch.empty((N, H, W, C // 8), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
-        g = torch.empty(hd.num_params, device="cuda")
-        iters = 3 * nbuf
+        if not ChainHandle.supported(C, H, W, _abi.PRECISIONS[precision]):
+            continue
+        ch = ChainHandle(C, L, 0.0)
+        params = torch.randn(L * ch.num_params, device="cuda") * 0.05
+        ch.pack(params)
+        x0 = torch.relu(torch.randn((N, H, W, C), device="cuda"))
+        dy = torch.randn((N, H, W, C), device="cuda")
+        acts = torch.empty((L, N, H, W, C), device="cuda")
+        masks = torch.empty((L, N, H, W, C // 8), dtype=torch.uint8, device="cuda")
+        dz = torch.empty((L, N, H, W, C), device="cuda")
+        dx = torch.empty((N, H, W, C), device="cuda")
+        grad = torch.empty(L * ch.num_params, device="cuda")
 
-        def timeit(fn):
-            for i in range(nbuf):
-                fn(i)
+        def timeit(fn, iters=6):
+            for _ in range(3):
+                fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(iters):
-                fn(i % nbuf)
+            for _ in range(iters):
+                fn()
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) * 1e3 / iters  # us
 
-        def f_fwd(i):
-            _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(xs[i]), _ptr(ys[i]), _ptr(ms[i]), None, N, H, W, H_STEP, 15, st))
-
-        def f_dgrad(i):
-            _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(xs[i]), _ptr(ys[(i + 1) % nbuf]), _ptr(ys[i]), N, H, W, st))
-
-        def f_wgrad(i):
-            _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(xs[i]), _ptr(ys[i]), _ptr(g), None, N, H, W, 0, st))
-
-        for name, fn, nbytes, flops_mult in (("euler_conv_fwd", f_fwd, 2 * per + Mpix * C // 8, 1),
-                                             ("euler_conv_dgrad", f_dgrad, 3 * per, 1),
-                                             ("euler_conv_wgrad(+reduce,fold,bias colsum)", f_wgrad, 2 * per, 1)):
+        f_fwd = lambda: ch.forward(x0, H_STEP, acts=acts, masks=masks)
+        f_dgrad = lambda: ch.dgrad(dy, masks, dz, dx, H_STEP)
+        f_wgrad = lambda: ch.wgrad(x0, acts, dz, grad)
+        mask_b = Mpix * C // 8
+        for name, fn, nbytes in (("chain_fwd (36 Euler steps)", f_fwd, per + L * (per + mask_b)),
+                                 ("chain_dgrad (36 Euler steps)", f_dgrad, 2 * per + L * (per + mask_b)),
+                                 ("chain_wgrad (36 layers, +fold/reduce)", f_wgrad, 2 * L * per)):
             us = timeit(fn)
-            recs.append({"kernel": name, "shape": [N, H, W, C], "us": us, "launches_per_step": layers,
+            recs.append({"kernel": name, "shape": [N, H, W, C], "us": us, "launches_per_step": 1,
                          "algorithmic_bytes": nbytes, "GBps": nbytes / us * 1e-3,
-                         "algorithmic_TFLOPs": 2.0 * Mpix * 9 * C * C / us * 1e-6})
-        del xs, ys, ms
+                         "algorithmic_TFLOPs": 2.0 * Mpix * 9 * C * C * L / us * 1e-6})
+        del acts, dz, masks
         torch.cuda.empty_cache()
     return recs
 
@@ -336,8 +335,8 @@ def run_b200(args):
                                    "fwd+loss+bwd%s+Adam" % ("+allreduce" if world > 1 else ""),
                        "global_batch": world * B, "batch_per_gpu": B, "h": H_STEP, "gamma": 0.0,
                        "precision": args.precision, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
-                       "l2": "per-step working set (saved activations of 108 layers, >600 MB) exceeds the 126 MB L2; "
-                             "kernel microbench rotates >300 MB of buffers"},
+                       "l2": "per-step working set (saved activations + dZ of 108 layers, >1 GB) exceeds the 126 MB L2; "
+                             "each microbenchmarked chain launch streams 75-300 MB"},
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(img_h.numel() + lab_h.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches_per_step * K),

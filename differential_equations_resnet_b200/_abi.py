@@ -50,6 +50,17 @@ _SIGNATURES = {
     "b200ode_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_void_p]),
     "b200ode_increment": (c_int, [c_void_p, c_void_p]),
+    "b200ode_chain_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "b200ode_chain_create": (c_int, [c_int, c_int, c_float, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "b200ode_chain_destroy": (c_int, [c_void_p]),
+    "b200ode_chain_layer_params": (c_int64, [c_void_p]),
+    "b200ode_chain_pack": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200ode_chain_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                  c_int, c_void_p]),
+    "b200ode_chain_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                    c_void_p]),
+    "b200ode_chain_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                    c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

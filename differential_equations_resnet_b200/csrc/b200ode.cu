@@ -15,6 +15,7 @@
 
 #include "kernels_basic.cuh"
 #include "kernels_conv_tc.cuh"
+#include "kernels_chain_tc.cuh"
 #include "kernels_wgrad_tc.cuh"
 
 using namespace b200ode;
@@ -534,15 +535,19 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
 // ------------------------------------------------------------------------------------------------
 // tensor-core weight gradient planning + launch
 // ------------------------------------------------------------------------------------------------
-static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, int N, int H, int W, float* G, float* G_user,
-                        float* grad_params, int accumulate, cudaStream_t st) {
-  const int mode = L->mode_eff, C = L->g.C;
+// One launch computes the weight gradients of L layers of equal shape (L = 1: a single layer).
+// Layer 0 reads its input from x0, layer l >= 1 from xrest + (l-1)*N*H*W*C (the saved outputs of
+// a chain); dz of layer l is dz + l*N*H*W*C; gradients go to grad_params + l*grad_layer_stride.
+static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const void* xrest, const void* dz, int L, int N, int H,
+                        int W, float* G, float* G_user, float* grad_params, long long grad_layer_stride, int accumulate,
+                        cudaStream_t st) {
+  const int C = lg.C;
   const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
   const int eb = bf16 ? 2 : 4;
   const int UKP = bf16 ? 16 : 8;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L;
   if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
   p.CH = bf16 ? (C < 64 ? C : 64) : 32;
   p.RWB = p.CH * eb;
@@ -605,22 +610,26 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
   const size_t smem = (size_t)p.bar_off + 256 + 1024;
   p.total_tiles = N * p.tpi;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  int nparts = sms / ngroups;
+  int nparts = sms / (ngroups * L);
   if (nparts < 1) nparts = 1;
   if (nparts > p.total_tiles) nparts = p.total_tiles;
   p.nparts = nparts;
   const long long total = 9LL * C * C;
   float* ws = nullptr;
-  if (int rc = get_scratch(1, (size_t)nparts * (total + C) * sizeof(float), (void**)&ws)) return rc;
+  if (int rc = get_scratch(1, (size_t)L * nparts * (total + C) * sizeof(float), (void**)&ws)) return rc;
   p.partials = ws;
   p.trace = g_trace;
-  p.bias_partials = ws + (size_t)nparts * total;
-  CUtensorMap mx, md;
+  p.bias_partials = ws + (size_t)L * nparts * total;
+  p.part_layer_stride = (long long)nparts * total;
+  p.bias_layer_stride = (long long)nparts * C;
+  CUtensorMap mx0, mx, md;
   const CUtensorMapSwizzle sw = bf16 ? (p.RWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.RWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)
                                      : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (int rc = make_act_map(&mx, x, N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc;
-  if (int rc = make_act_map(&md, dz, N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
-  dim3 grid(nparts, ngroups);
+  if (int rc = make_act_map(&mx0, x0, N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc;
+  if (L > 1) { if (int rc = make_act_map(&mx, xrest, (L - 1) * N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc; }
+  else mx = mx0;
+  if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
+  dim3 grid(nparts, ngroups, L);
 #define WG_LAUNCH(M_)                                                                                          \
   do {                                                                                                         \
     static bool attr_set = false;                                                                              \
@@ -628,19 +637,21 @@ static int run_wgrad_tc(const b200ode_layer* L, const void* x, const void* dz, i
       CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    wgrad_tc_kernel<M_><<<grid, (M_ == MODE_STRICT ? 10 : 6) * 32, smem, st>>>(mx, md, p);                     \
+    wgrad_tc_kernel<M_><<<grid, (M_ == MODE_STRICT ? 10 : 6) * 32, smem, st>>>(mx0, mx, md, p);                \
   } while (0)
   if (mode == MODE_STRICT) WG_LAUNCH(MODE_STRICT);
   else if (mode == MODE_TF32) WG_LAUNCH(MODE_TF32);
   else WG_LAUNCH(MODE_BF16);
 #undef WG_LAUNCH
   LAUNCH_CHECK("wgrad_tc_kernel");
-  if (G_user) {   // dense gradient requested (tests / diagnostics)
+  if (G_user && L == 1) {   // dense gradient requested (tests / diagnostics)
     reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
     LAUNCH_CHECK("reduce_parts");
   }
-  const long long nout = (L->g.use_bias ? L->g.nparams : L->g.bias_off);
-  fold_reduce_kernel<<<blocks_for(nout * 16, 256), 256, 0, st>>>(L->g, ws, nparts, total, p.bias_partials, grad_params, accumulate);
+  const long long nout = (lg.use_bias ? lg.nparams : lg.bias_off);
+  dim3 fgrid(blocks_for(nout * 16, 256), L);
+  fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, total, p.bias_partials, grad_params, accumulate,
+                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride);
   LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }
@@ -653,7 +664,7 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long npix = (long long)N * g.Ho * g.Wo;
   if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
-    return run_wgrad_tc(L, x, dz, N, H, W, L->Gdense, G_dense, grad_params, accumulate, st);
+    return run_wgrad_tc(L->mode_eff, L->g, x, x, dz, 1, N, H, W, L->Gdense, G_dense, grad_params, 0, accumulate, st);
   } else {
     int parts = (int)(npix / 64);
     if (parts < 1) parts = 1;
@@ -744,4 +755,200 @@ extern "C" int b200ode_increment(int32_t* counter, void* stream) {
   increment_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter);
   LAUNCH_CHECK("increment_kernel");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent Euler-step chains (kernels_chain_tc.cuh): one launch per direction per residual stage
+// ------------------------------------------------------------------------------------------------
+struct b200ode_chain {
+  LayerGeom g;
+  int L;           // distinct weight layers
+  bool packed;
+  float* w_hi;     // [L][9][C][C] tf32-rounded, K-major B operand
+  float* bias;     // [L][C]
+};
+
+struct ChainPlan {
+  ChainParams p;
+  size_t smem;
+};
+
+static bool chain_channels_ok(int C) { return C == 16 || C == 32 || C == 64; }
+
+// Shared-memory plan of chain_tc_kernel; returns false when a whole image does not fit.
+static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
+  if (!chain_channels_ok(C)) return false;
+  const int rowb = C * 4 >= 128 ? 128 : C * 4;
+  const int nkb = C * 4 / rowb;
+  const int P = W + 1;
+  if (P > 256 || H + 2 > 256) return false;
+  const int maxseg = C == 16 ? 9 : C == 32 ? 5 : 2;
+  const int nseg = (H * P + 127) / 128;
+  if (nseg > maxseg || nseg * C > 512) return false;
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H; p.W = W; p.P = P; p.nseg = nseg;
+  p.plane_bytes = align_up((uint32_t)((H + 2) * P + 1) * rowb, 1024);
+  p.strip_stride = (uint32_t)nkb * p.plane_bytes;
+  p.x_bytes = (uint32_t)(H + 2) * P * rowb;
+  p.tw = taps_per_w_stage(MODE_TF32, C);
+  p.w_stage_bytes = (uint32_t)p.tw * C * rowb;
+  p.seg_outer = (nkb == 1 && p.tw == 9) ? 1 : 0;
+  p.e_off = 2 * p.strip_stride;
+  const uint32_t e_bytes = dir ? align_up((uint32_t)H * W * C * 4, 1024) : 0;
+  p.w_off = p.e_off + e_bytes;
+  const long long max_smem = 227 * 1024 - 1024 - 512;
+  const int per_layer = (9 / p.tw) * nkb;           // ring entries one layer consumes
+  int sw = 2 * per_layer;                            // ideally: the next layer fully prefetched
+  while (sw > 1 && (long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) --sw;
+  if ((long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) return false;
+  if (sw < 2 && per_layer > 1) return false;
+  p.sw = sw;
+  p.bar_off = p.w_off + (uint32_t)sw * p.w_stage_bytes;
+  // the MMAs of the last segment read (junk rows) up to 128*nseg + 2P + 2 positions of strip 1: keep that inside the allocation
+  const long long reach = (long long)p.strip_stride + (long long)(nkb - 1) * p.plane_bytes + (long long)(128 * nseg + 2 * P + 3) * rowb;
+  if (reach > (long long)p.bar_off) return false;
+  uint32_t cols = (uint32_t)nseg * C, pc = 32;
+  while (pc < cols) pc <<= 1;
+  p.tmem_cols = pc;
+  plan->p = p;
+  plan->smem = (size_t)p.bar_off + 512 + 1024;
+  return true;
+}
+
+extern "C" int b200ode_chain_supported(int channels, int H, int W, int precision_mode) {
+  if (precision_mode != B200ODE_PREC_FAST_TF32) return 0;
+  ChainPlan pl;
+  return plan_chain(channels, H, W, 0, &pl) && plan_chain(channels, H, W, 1, &pl) ? 1 : 0;
+}
+
+extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int use_bias, int precision_mode,
+                                    b200ode_chain_t** out) {
+  if (!out) return fail(B200ODE_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_layers < 1) return fail(B200ODE_ERR_INVALID, "n_layers must be >= 1");
+  if (precision_mode != B200ODE_PREC_FAST_TF32) return fail(B200ODE_ERR_UNSUPPORTED, "chains run in FAST_TF32 mode only");
+  if (!chain_channels_ok(channels)) return fail(B200ODE_ERR_UNSUPPORTED, "chains need C in {16,32,64} (got %d)", channels);
+  if (int rc = device_check()) return rc;
+  b200ode_chain* ch = new b200ode_chain();
+  memset(ch, 0, sizeof(*ch));
+  LayerGeom& g = ch->g;
+  g.C = channels; g.k = 3; g.layout = B200ODE_LAYOUT_3BY3; g.antisym = 1; g.use_bias = use_bias ? 1 : 0; g.gamma = gamma;
+  build_diag_tab(g);
+  g.bias_off = (long long)g.tab.nd * channels + 9LL * channels * (channels - 1) / 2;
+  g.nparams = g.bias_off + (use_bias ? channels : 0);
+  ch->L = n_layers;
+  cudaError_t e = cudaMalloc(&ch->w_hi, (size_t)n_layers * 9 * channels * channels * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ch->bias, (size_t)n_layers * channels * sizeof(float));
+  if (e != cudaSuccess) {
+    b200ode_chain_destroy(ch);
+    return fail(B200ODE_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = ch;
+  return 0;
+}
+
+extern "C" int b200ode_chain_destroy(b200ode_chain_t* ch) {
+  if (!ch) return 0;
+  cudaFree(ch->w_hi); cudaFree(ch->bias);
+  delete ch;
+  return 0;
+}
+extern "C" int64_t b200ode_chain_layer_params(const b200ode_chain_t* ch) { return ch ? ch->g.nparams : -1; }
+
+extern "C" int b200ode_chain_pack(b200ode_chain_t* ch, const float* params, int64_t param_layer_stride, void* stream) {
+  if (!ch || !params) return fail(B200ODE_ERR_INVALID, "chain/params is NULL");
+  const long long total = 9LL * ch->g.C * ch->g.C;
+  dim3 grid(blocks_for(total, 256), ch->L);
+  pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->bias);
+  LAUNCH_CHECK("pack_chain_kernel");
+  ch->packed = true;
+  return 0;
+}
+
+static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int C = ch->g.C;
+  const int rowb = C * 4 >= 128 ? 128 : C * 4;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)9 * ch->L};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)(rowb / 4), (cuuint32_t)C, (cuuint32_t)tw};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ch->w_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(chain weights) failed with %d", (int)r);
+  return 0;
+}
+
+template <int DIR>
+static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CUtensorMap& mx, const CUtensorMap& mw, int grid,
+                        cudaStream_t st) {
+#define CH_LAUNCH(C_)                                                                                              \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<C_, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    chain_tc_kernel<C_, DIR><<<grid, 192, plan.smem, st>>>(mx, mw, plan.p);                                        \
+  } while (0)
+  switch (ch->g.C) {
+    case 16: CH_LAUNCH(16); break;
+    case 32: CH_LAUNCH(32); break;
+    case 64: CH_LAUNCH(64); break;
+    default: return fail(B200ODE_ERR_UNSUPPORTED, "chain: unsupported channel count %d", ch->g.C);
+  }
+#undef CH_LAUNCH
+  LAUNCH_CHECK("chain_tc_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, float* acts, uint8_t* relu_masks, float* y_final, int N,
+                                 int H, int W, float h, int n_steps, void* stream) {
+  if (!ch || !x0) return fail(B200ODE_ERR_INVALID, "chain/x0 is NULL");
+  if (!ch->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_chain_pack must run before compute calls");
+  if (!acts && !y_final) return fail(B200ODE_ERR_INVALID, "need acts or y_final");
+  if (n_steps < 1 || N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape");
+  if (N == 0) return 0;
+  ChainPlan plan;
+  if (!plan_chain(ch->g.C, H, W, 0, &plan))
+    return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
+  ChainParams& p = plan.p;
+  p.N = N; p.L = n_steps; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
+  p.acts = acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias;
+  const int C = ch->g.C, rowb = C * 4 >= 128 ? 128 : C * 4;
+  CUtensorMap mx, mw;
+  CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (int rc = make_act_map(&mx, x0, N, H, W, C, 4, rowb / 4, p.P, H + 2, 1, sw)) return rc;
+  if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  return launch_chain<0>(ch, plan, mx, mw, N < sms ? N : sms, (cudaStream_t)stream);
+}
+
+extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, float* dz_all, float* dx,
+                                   int N, int H, int W, float h, void* stream) {
+  if (!ch || !dy || !relu_masks || !dz_all || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (!ch->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_chain_pack must run before compute calls");
+  if (N == 0) return 0;
+  ChainPlan plan;
+  if (!plan_chain(ch->g.C, H, W, 1, &plan))
+    return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
+  ChainParams& p = plan.p;
+  p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
+  p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = dz_all; p.dx = dx;
+  CUtensorMap mw;
+  if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  return launch_chain<1>(ch, plan, mw, mw, N < sms ? N : sms, (cudaStream_t)stream);
+}
+
+extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const float* acts, const float* dz_all,
+                                   float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream) {
+  if (!ch || !x0 || !dz_all || !grad_params) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
+  if (N == 0) return 0;
+  return run_wgrad_tc(MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params, grad_layer_stride, 0,
+                      (cudaStream_t)stream);
 }

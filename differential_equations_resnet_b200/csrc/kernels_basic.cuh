@@ -94,6 +94,21 @@ __global__ void pack_kernel(LayerGeom g, const float* __restrict__ params, float
   if (w_bf) w_bf[i] = __float2bfloat16_rn(v);
 }
 
+// Chain variant: blockIdx.y = layer; tf32-rounded staged weights [L][taps][o][ci] and biases [L][C].
+__global__ void pack_chain_kernel(LayerGeom g, const float* __restrict__ params, long long param_layer_stride,
+                                  float* __restrict__ w_hi, float* __restrict__ bias_out) {
+  const long long total = (long long)g.k * g.k * g.C * g.C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  params += (long long)l * param_layer_stride;
+  if (i < g.C) bias_out[(long long)l * g.C + i] = g.use_bias ? params[g.bias_off + i] : 0.0f;
+  if (i >= total) return;
+  const int ci = (int)(i % g.C);
+  const int o = (int)((i / g.C) % g.C);
+  const int tap = (int)(i / ((long long)g.C * g.C));
+  w_hi[(long long)l * total + i] = tf32_rna(kernel_entry(g, params, tap / g.k, tap % g.k, ci, o));
+}
+
 // ---------------------------------------------------------------------------------------------
 // SIMT convolution family (any C, odd k, any stride; TF SAME padding).  fp32.
 // ---------------------------------------------------------------------------------------------
@@ -251,8 +266,13 @@ __global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __res
 
 // Split-K reduction + fold + bias gradient in one launch: 16 lanes per output sum the partials
 // (lane l takes parts l, l+16, ...) and combine through a fixed-order shuffle tree -> deterministic.
+// blockIdx.y = layer of a batched (chain) weight gradient; the three layer strides are in floats.
 __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
-                                   const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate) {
+                                   const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate,
+                                   long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride) {
+  Gpart += (long long)blockIdx.y * part_layer_stride;
+  if (bias_part) bias_part += (long long)blockIdx.y * bias_layer_stride;
+  grad += (long long)blockIdx.y * grad_layer_stride;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = gid >> 4;
   const int l = (int)(gid & 15);

@@ -1,0 +1,407 @@
+// Persistent Euler-step chains: ALL consecutive Euler steps of one residual stage in one launch.
+//
+// Reference path replaced: the stage loop of models/tfkeras_resnets.py:575-593, which stacks
+// single_layer_identity_block (models/tfkeras_resnets.py:28-94: conv_K + bias -> relu -> h* -> +x)
+// n times on a tensor of constant shape, and its TF-autodiff backward sweep (training/training.py:300).
+//
+// One CTA owns one image for the whole chain.  The image lives in shared memory as a "padded linear"
+// halo strip (pitch P = W+1, see kernels_conv_tc.cuh) that the tcgen05 MMAs read as the A operand of
+// all nine taps; the epilogue warps write the next step's input back INTO shared memory in exactly
+// the swizzled K-major layout TMA would have produced, so step l+1 starts without touching L2/HBM.
+// Per step only the small weight tile streams in (TMA ring, prefetched one step ahead); to HBM go the
+// saved activation + 1-bit relu mask (forward) or dZ_l (backward), both needed by the weight gradient.
+//
+//   DIR 0 (forward):  x_{l+1} = x_l + h*relu(conv_{K_l}(x_l) + b_l)
+//   DIR 1 (backward): dZ_l = h*dY_l*mask_l ; dY_{l-1} = dY_l - conv_{K_l}(dZ_l) + 2*gamma*dZ_l
+//                     (the data gradient reuses the forward weights); dY stays in
+//                     a second, thread-private shared buffer E.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quarters).  When all nine
+// taps of a layer fit one ring stage (C <= 32) the MMAs are issued segment by segment with one commit
+// per 128-position segment, so the epilogue of segment s overlaps the MMAs of segments > s.
+#pragma once
+
+#include "kernels_conv_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200ode {
+
+constexpr int CHAIN_MAXSEG = 9;
+
+struct ChainParams {
+  int N, H, W, P;
+  int L;             // Euler steps to run
+  int Lw;            // distinct weight layers; step l uses weights l % Lw
+  int nseg;          // 128-position segments per image
+  int tw, sw;        // taps per weight ring stage, ring depth
+  int seg_outer;     // 1: all taps resident, per-segment commits
+  uint32_t plane_bytes;   // one K-block plane of a strip (1024-aligned)
+  uint32_t strip_stride;  // NKB * plane_bytes
+  uint32_t x_bytes;       // bytes one TMA plane load of x0 delivers
+  uint32_t e_off, w_off, w_stage_bytes, bar_off;
+  uint32_t tmem_cols;
+  float h, gamma;
+  // forward
+  float* acts;            // nullable [L][N,H,W,C]: output of every step
+  uint8_t* masks;         // nullable [L][N,H,W,C/8]
+  float* y_final;         // nullable [N,H,W,C]: output of the last step
+  const float* bias;      // [Lw][C]
+  // backward
+  const float* dy;        // [N,H,W,C] gradient w.r.t. the chain output
+  const uint8_t* masks_r; // [L][N,H,W,C/8]
+  float* dz_all;          // [L][N,H,W,C]
+  float* dx;              // [N,H,W,C] gradient w.r.t. the chain input
+};
+
+template <int C>
+struct ChainCfg {
+  static constexpr int ROWB = (C * 4 >= 128) ? 128 : C * 4;   // bytes per position row in one K-block plane
+  static constexpr int KB = ROWB / 4;                         // channels per plane
+  static constexpr int NKB = C / KB;
+  static constexpr int KS = ROWB / 32;                        // tf32 k-steps (8 channels) per plane
+  static constexpr int MW = (C + 31) / 32;                    // 32-bit mask words per pixel
+  static constexpr int MAXSEG = C == 16 ? 9 : C == 32 ? 5 : 2; // segments a whole image may need (host plan agrees)
+};
+
+// byte offset of 16-byte chunk `chunk` of position `pos` inside a swizzled plane
+template <int ROWB>
+__device__ __forceinline__ uint32_t strip_chunk_off(uint32_t pos, uint32_t chunk) {
+  return swizzle_addr(pos * ROWB + chunk * 16, ROWB);
+}
+// E buffer (thread-private rows, C*4 bytes per pixel) with an XOR swizzle that spreads a warp's
+// 16-byte accesses over all banks
+template <int C>
+__device__ __forceinline__ uint32_t e_chunk_off(uint32_t pix, uint32_t chunk) {
+  const uint32_t x = (C == 16) ? ((pix >> 1) & 3u) : (pix & 7u);
+  return pix * (C * 4) + ((chunk ^ x) << 4);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int C, int DIR>
+__global__ void __launch_bounds__(192, 1)
+chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ChainParams p) {
+  using Cfg = ChainCfg<C>;
+  constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG;
+  constexpr uint32_t LT = ROWB == 128 ? SWZ_128B : ROWB == 64 ? SWZ_64B : SWZ_32B;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr uint32_t RU = ROWB >> 4;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* x_full = bars;                    // [1]
+  uint64_t* layer_done = bars + 1;            // [1] count 4
+  uint64_t* img_done = bars + 2;              // [1] count 4
+  uint64_t* acc_full = bars + 3;              // [CHAIN_MAXSEG]
+  uint64_t* w_full = acc_full + CHAIN_MAXSEG; // [sw]
+  uint64_t* w_empty = w_full + p.sw;          // [sw]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + p.sw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0 && lane == 0) {
+    if (DIR == 0) tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    mbar_init(x_full, 1);
+    mbar_init(layer_done, 4);
+    mbar_init(img_done, 4);
+    for (int i = 0; i < CHAIN_MAXSEG; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  {
+    // both strips start as zeros: halo rows / the shared zero column are never written afterwards
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const uint32_t n16 = (2u * p.strip_stride) >> 4;
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long img_elems = (long long)p.H * p.W * C;
+  const long long layer_elems = (long long)p.N * img_elems;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t iw = 0, ic = 0;
+      for (int img = blockIdx.x; img < p.N; img += gridDim.x, ++ic) {
+        if (DIR == 0) {
+          if (ic > 0) mbar_wait(img_done, (ic - 1) & 1);
+          mbar_expect_tx(x_full, NKB * p.x_bytes);
+          for (int kb = 0; kb < NKB; ++kb) tma_load_4d(smem + kb * p.plane_bytes, &map_x, x_full, kb * KB, -1, -1, img);
+        }
+        for (int li = 0; li < p.L; ++li) {
+          const int l = DIR ? p.L - 1 - li : li;
+          const int lw = l % p.Lw;
+          for (int kb = 0; kb < NKB; ++kb)
+            for (int tg = 0; tg < 9; tg += p.tw) {
+              const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
+              mbar_wait(&w_empty[s], ph ^ 1);
+              mbar_expect_tx(&w_full[s], p.w_stage_bytes);
+              tma_load_3d(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg);
+              ++iw;
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) ==========
+    const bool leader = elect_one();
+    const uint32_t idesc = make_instr_desc(FMT_TF32, 128, C, 0, 0);
+    const uint32_t desc_hi32 = (SBO >> 4) | (1u << 14) | (LT << 29);
+    constexpr uint32_t LBO_FIELD = 1u << 16;
+    auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
+    constexpr uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;
+    uint32_t toff[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) toff[t] = (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
+    const uint32_t plane_units = p.plane_bytes >> 4;
+    uint32_t iw = 0, ic = 0, ld = 0;
+    for (int img = blockIdx.x; img < p.N; img += gridDim.x, ++ic) {
+      for (int li = 0; li < p.L; ++li) {
+        if (DIR == 0 && li == 0) mbar_wait(x_full, ic & 1);
+        else { mbar_wait(layer_done, ld & 1); ++ld; }
+        tc_fence_after_sync();
+        const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
+        if (p.seg_outer) {
+          const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
+          uint32_t a_sg = a_base, d = tmem_base;
+          for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint64_t da = mk(a_sg + toff[t] + 2 * ks), db = mk(b_base + t * tap_units + 2 * ks);
+                if (leader) umma_tf32(d, da, db, idesc, (t | ks) ? 1u : 0u);
+              }
+            }
+            if (leader) umma_commit(&acc_full[sg]);
+          }
+          if (leader) umma_commit(&w_empty[s]);
+          ++iw;
+        } else {
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t a_kb = a_base + kb * plane_units;
+            for (int tg = 0; tg < 9; tg += p.tw) {
+              const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
+              mbar_wait(&w_full[s], ph);
+              tc_fence_after_sync();
+              uint32_t b_units = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
+              for (int tt = 0; tt < p.tw; ++tt, b_units += tap_units) {
+                const int t = tg + tt;
+                const uint32_t a_tap = a_kb + (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
+                const uint32_t first = (kb | t) == 0 ? 0u : 1u;
+                uint32_t a_sg = a_tap, d = tmem_base;
+                for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks) {
+                    const uint64_t da = mk(a_sg + 2 * ks), db = mk(b_units + 2 * ks);
+                    if (leader) umma_tf32(d, da, db, idesc, ks ? 1u : first);
+                  }
+                }
+              }
+              if (leader) umma_commit(&w_empty[s]);
+              ++iw;
+            }
+          }
+          for (int sg = 0; sg < p.nseg; ++sg)
+            if (leader) umma_commit(&acc_full[sg]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 (TMEM lane quarters 2,3,0,1) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t e_base = smem_base + p.e_off;
+    const int groups = C / 8;   // mask bytes per pixel
+    uint32_t lc = 0;
+    for (int img = blockIdx.x; img < p.N; img += gridDim.x) {
+      const long long img_off = (long long)img * img_elems;
+      if (DIR == 1) {
+        // ---- init: E = dY_L, strip0 = dZ_{L-1} = h * dY_L * mask_{L-1} ----
+        const uint8_t* mk_l = p.masks_r + ((long long)(p.L - 1) * p.N + img) * (long long)p.H * p.W * groups;
+        float* dz_l = p.dz_all + (long long)(p.L - 1) * layer_elems + img_off;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const int q = sg * 128 + row;
+          const int yy = q / p.P, xq = q - yy * p.P;
+          if (yy < p.H && xq < p.W) {
+            const int pixl = yy * p.W + xq;
+            const uint32_t pos = (uint32_t)(q + p.P + 1);
+            const float* src = p.dy + img_off + (long long)pixl * C;
+#pragma unroll
+            for (int c0 = 0; c0 < C; c0 += 16) {
+              const uint32_t bits = *reinterpret_cast<const uint16_t*>(mk_l + (long long)pixl * groups + c0 / 8);
+              const uint32_t pl = smem_base + (uint32_t)(c0 / KB) * p.plane_bytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 d = *reinterpret_cast<const float4*>(src + c0 + 4 * j);
+                sts128(e_base + e_chunk_off<C>(pixl, c0 / 4 + j), d);
+                float4 z;
+                z.x = (bits >> (4 * j)) & 1u ? p.h * d.x : 0.0f;
+                z.y = (bits >> (4 * j + 1)) & 1u ? p.h * d.y : 0.0f;
+                z.z = (bits >> (4 * j + 2)) & 1u ? p.h * d.z : 0.0f;
+                z.w = (bits >> (4 * j + 3)) & 1u ? p.h * d.w : 0.0f;
+                sts128(pl + strip_chunk_off<ROWB>(pos, (c0 % KB) / 4 + j), z);
+                *reinterpret_cast<float4*>(dz_l + (long long)pixl * C + c0 + 4 * j) = z;
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(layer_done);
+      }
+      for (int li = 0; li < p.L; ++li, ++lc) {
+        const int l = DIR ? p.L - 1 - li : li;
+        const uint32_t cur = smem_base + (uint32_t)(li & 1) * p.strip_stride;
+        const uint32_t nxt = smem_base + (uint32_t)((li & 1) ^ 1) * p.strip_stride;
+        const bool last = li == p.L - 1;
+        // per-layer pointers
+        const float* bias_l = p.bias + (l % p.Lw) * C;
+        float* out_l = nullptr;        // global copy of this step's result
+        uint8_t* mask_w = nullptr;
+        uint32_t mkreg[MAXSEG][MW];
+        if (DIR == 0) {
+          if (p.acts) out_l = p.acts + (long long)l * layer_elems + img_off;
+          else if (last) out_l = p.y_final + img_off;
+          if (p.masks) mask_w = p.masks + ((long long)l * p.N + img) * (long long)p.H * p.W * groups;
+        } else {
+          if (!last) {
+            out_l = p.dz_all + (long long)(l - 1) * layer_elems + img_off;
+            // prefetch the relu masks of step l-1 for this thread's pixels (hidden behind the MMAs)
+            const uint8_t* mk_l = p.masks_r + ((long long)(l - 1) * p.N + img) * (long long)p.H * p.W * groups;
+#pragma unroll
+            for (int sg = 0; sg < MAXSEG; ++sg) {
+              if (sg < p.nseg) {
+                const int q = sg * 128 + row;
+                const int yy = q / p.P, xq = q - yy * p.P;
+                if (yy < p.H && xq < p.W) {
+                  const uint8_t* mp = mk_l + (long long)(yy * p.W + xq) * groups;
+                  if (C == 16) mkreg[sg][0] = *reinterpret_cast<const uint16_t*>(mp);
+                  else {
+#pragma unroll
+                    for (int w = 0; w < MW; ++w) mkreg[sg][w] = *reinterpret_cast<const uint32_t*>(mp + 4 * w);
+                  }
+                }
+              }
+            }
+          } else {
+            out_l = p.dx + img_off;
+          }
+        }
+#pragma unroll
+        for (int sg = 0; sg < MAXSEG; ++sg) {
+          if (sg < p.nseg) {
+            mbar_wait(&acc_full[sg], lc & 1);
+            tc_fence_after_sync();
+            const int q = sg * 128 + row;
+            const int yy = q / p.P, xq = q - yy * p.P;
+            const bool valid = (yy < p.H) && (xq < p.W);
+            const int pixl = yy * p.W + xq;
+            const uint32_t pos = (uint32_t)(q + p.P + 1);
+#pragma unroll
+            for (int c0 = 0; c0 < C; c0 += 16) {
+              uint32_t r[16];
+              tmem_ld_x16(tq + sg * C + c0, r);
+              tmem_ld_wait();
+              if (valid) {
+                const uint32_t plo = (uint32_t)(c0 / KB) * p.plane_bytes;
+                const uint32_t ch0 = (c0 % KB) / 4;
+                if (DIR == 0) {
+                  uint32_t bits = 0;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t so = plo + strip_chunk_off<ROWB>(pos, ch0 + j);
+                    const float4 xv = lds128(cur + so);
+                    float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                  __uint_as_float(r[4 * j + 3])};
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      float t = v[e] + __ldg(bias_l + c0 + 4 * j + e);
+                      bits |= (t > 0.0f ? 1u : 0u) << (4 * j + e);
+                      t = fmaxf(t, 0.0f);
+                      // Lambda(h*x) (only when h != 1, tfkeras_resnets.py:90) and add() are two layers in the
+                      // reference: two roundings, so no FMA contraction here
+                      if (p.h != 1.0f) t = __fmul_rn(p.h, t);
+                      v[e] = __fadd_rn(xs[e], t);
+                    }
+                    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+                    if (!last) sts128(nxt + so, o);
+                    if (out_l) *reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0 + 4 * j) = o;
+                  }
+                  if (mask_w) *reinterpret_cast<uint16_t*>(mask_w + (long long)pixl * groups + c0 / 8) = (uint16_t)bits;
+                } else {
+                  const uint32_t bits = last ? 0u : (mkreg[sg][c0 / 32] >> (c0 % 32)) & 0xFFFFu;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t so = plo + strip_chunk_off<ROWB>(pos, ch0 + j);
+                    const uint32_t eo = e_base + e_chunk_off<C>(pixl, c0 / 4 + j);
+                    const float4 dyv = lds128(eo);
+                    float v[4] = {-__uint_as_float(r[4 * j]), -__uint_as_float(r[4 * j + 1]), -__uint_as_float(r[4 * j + 2]),
+                                  -__uint_as_float(r[4 * j + 3])};
+                    if (p.gamma != 0.0f) {
+                      const float4 zv = lds128(cur + so);
+                      const float g2 = 2.0f * p.gamma;
+                      v[0] = fmaf(g2, zv.x, v[0]); v[1] = fmaf(g2, zv.y, v[1]);
+                      v[2] = fmaf(g2, zv.z, v[2]); v[3] = fmaf(g2, zv.w, v[3]);
+                    }
+                    v[0] += dyv.x; v[1] += dyv.y; v[2] += dyv.z; v[3] += dyv.w;
+                    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+                    if (!last) {
+                      sts128(eo, o);
+                      o.x = (bits >> (4 * j)) & 1u ? p.h * v[0] : 0.0f;
+                      o.y = (bits >> (4 * j + 1)) & 1u ? p.h * v[1] : 0.0f;
+                      o.z = (bits >> (4 * j + 2)) & 1u ? p.h * v[2] : 0.0f;
+                      o.w = (bits >> (4 * j + 3)) & 1u ? p.h * v[3] : 0.0f;
+                      sts128(nxt + so, o);
+                    }
+                    *reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0 + 4 * j) = o;
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        if (!last) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(layer_done);
+        } else if (DIR == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(img_done);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace b200ode

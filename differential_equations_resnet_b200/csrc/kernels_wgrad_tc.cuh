@@ -47,11 +47,16 @@ struct WgradParams {
   float* bias_partials;  // [nparts][C] column sums of dz (bias gradient), written by tap group 0
   uint32_t ent_off, bsum_off;  // smem offsets: per-entry A offsets (uint32[32]) and bias scratch (float[4][256])
   uint64_t* trace;             // nullable timeline buffer (debug)
+  // layer batching (blockIdx.z = layer): layer 0 reads its input through map_x0 (image n), layer l >= 1
+  // through map_x (image (l-1)*N + n: the saved outputs of the chain); dz image index is l*N + n.
+  int L;
+  long long part_layer_stride, bias_layer_stride;   // floats between consecutive layers' partials
 };
 
 template <int MODE>
 __global__ void __launch_bounds__((MODE == MODE_STRICT ? 10 : 6) * 32, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
   constexpr bool STRICT = MODE == MODE_STRICT;
   constexpr bool BF16 = MODE == MODE_BF16;
   constexpr int UKP = BF16 ? 16 : 8;  // positions per MMA
@@ -71,9 +76,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int group = blockIdx.y;
   const int tapgroup = group / p.nngroups, ngroup = group % p.nngroups;
   const int part = blockIdx.x;
+  const int layer = blockIdx.z;
+  const CUtensorMap* mx = layer == 0 ? &map_x0 : &map_x;
+  const int img_x0 = layer == 0 ? 0 : (layer - 1) * p.N;
+  const int img_d0 = layer * p.N;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(mx);
     tma_prefetch_desc(&map_d);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], group / p.nngroups == 0 ? 5 : 1); mbar_init(&conv[i], 4); }
     mbar_init(acc_full, 1);
@@ -97,9 +106,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
         for (int c = 0; c < p.xchunks; ++c)
-          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, &map_x, &full[s], c * p.CH, -1, row0 - 1, n);
+          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], c * p.CH, -1, row0 - 1, img_x0 + n);
         for (int c = 0; c < p.dchunks; ++c)
-          tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, n);
+          tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, img_d0 + n);
       }
     }
   } else if (warp == 1) {
@@ -141,6 +150,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
       uint32_t du = ((smem_base + s * p.stage_stride + p.d_off) >> 4) + off0;
+      if (p.trick && !STRICT) {
+        // beta trick: three M = 4*CH MMAs per k-step (one per kernel row), offsets held in registers
+        const uint32_t e1 = (uint32_t)p.P * RU, e2 = 2u * e1;
+        const uint32_t d0 = tmem_base, d1 = tmem_base + ACCW, d2 = tmem_base + 2 * ACCW;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+          const uint64_t dsc_b = mk(du, lbo_b);
+          const uint32_t accum = (it | ks) != 0;
+          const uint64_t a0 = mk(xu, lbo_a), a1 = mk(xu + e1, lbo_a), a2 = mk(xu + e2, lbo_a);
+          if (leader) {
+            if (BF16) { umma_f16(d0, a0, dsc_b, idesc, accum); umma_f16(d1, a1, dsc_b, idesc, accum); umma_f16(d2, a2, dsc_b, idesc, accum); }
+            else { umma_tf32(d0, a0, dsc_b, idesc, accum); umma_tf32(d1, a1, dsc_b, idesc, accum); umma_tf32(d2, a2, dsc_b, idesc, accum); }
+          }
+        }
+      } else
       for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
         const uint64_t dsc_b = mk(du, lbo_b);
         const uint32_t accum = (it | ks) != 0;
@@ -217,7 +241,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int ck = i / per_chunk_i, c = (i % per_chunk_i) * 32 + l;
         const int ch = ngroup * p.NT + ck * p.CH + c;
         if (ck < p.dchunks && c < p.CH && ch < p.C)
-          p.bias_partials[(size_t)part * p.C + ch] = bs[idx] + bs[256 + idx] + bs[512 + idx] + bs[768 + idx];
+          p.bias_partials[(size_t)layer * p.bias_layer_stride + (size_t)part * p.C + ch] = bs[idx] + bs[256 + idx] + bs[512 + idx] + bs[768 + idx];
       }
     }
     if (threadIdx.x == 64) tr.mark(5);
@@ -230,7 +254,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     bool row_ok;
     if (Mrows == 128) { m = quarter * 32 + lane; row_ok = true; }
     else { m = quarter * 16 + lane; row_ok = lane < 16; }   // M=64: 16 lanes per quarter
-    float* part_base = p.partials + (size_t)part * 9 * p.C * p.C;
+    float* part_base = p.partials + (size_t)layer * p.part_layer_stride + (size_t)part * 9 * p.C * p.C;
     for (int e = 0; e < nent; ++e) {
       int tap, ci;
       bool ok = row_ok;

@@ -109,6 +109,53 @@ class LayerHandle:
         return (g, G) if want_dense else g
 
 
+class ChainHandle:
+    """Owns one b200ode_chain_t: `n_layers` antisymmetric 3x3 Euler steps of equal shape run by the
+    persistent per-image kernels (one launch per direction).  Mirrors n stacked
+    single_layer_identity_block calls (models/tfkeras_resnets.py:28-94, stage loop :575-593)."""
+
+    def __init__(self, channels, n_layers, gamma, use_bias=True, precision=_abi.PREC_FAST_TF32):
+        _abi.require_device()
+        h = ctypes.c_void_p()
+        _abi.check(_abi.lib().b200ode_chain_create(int(channels), int(n_layers), float(gamma), int(bool(use_bias)),
+                                                   int(precision), ctypes.byref(h)))
+        self._h = h
+        self.channels, self.n_layers = int(channels), int(n_layers)
+        self.num_params = int(_abi.lib().b200ode_chain_layer_params(h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _abi.lib().b200ode_chain_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def supported(channels, H, W, precision=_abi.PREC_FAST_TF32):
+        return bool(_abi.lib().b200ode_chain_supported(int(channels), int(H), int(W), int(precision)))
+
+    def pack(self, params, layer_stride=None):
+        _abi.check(_abi.lib().b200ode_chain_pack(self._h, _ptr(params), int(layer_stride or self.num_params),
+                                                 _stream_ptr()))
+
+    def forward(self, x0, h, n_steps=None, acts=None, masks=None, y_final=None):
+        N, H, W, C = x0.shape
+        n_steps = self.n_layers if n_steps is None else int(n_steps)
+        _abi.check(_abi.lib().b200ode_chain_fwd(self._h, _ptr(x0), _ptr(acts), _ptr(masks), _ptr(y_final), N, H, W,
+                                                float(h), n_steps, _stream_ptr()))
+
+    def dgrad(self, dy, masks, dz_all, dx, h):
+        N, H, W, C = dy.shape
+        _abi.check(_abi.lib().b200ode_chain_dgrad(self._h, _ptr(dy), _ptr(masks), _ptr(dz_all), _ptr(dx), N, H, W,
+                                                  float(h), _stream_ptr()))
+
+    def wgrad(self, x0, acts, dz_all, grad, layer_stride=None):
+        N, H, W, C = x0.shape
+        _abi.check(_abi.lib().b200ode_chain_wgrad(self._h, _ptr(x0), _ptr(acts), _ptr(dz_all), _ptr(grad),
+                                                  int(layer_stride or self.num_params), N, H, W, _stream_ptr()))
+
+
 def relu_scale_bwd(dy, mask, h):
     dz = torch.empty_like(dy)
     C = dy.shape[-1]

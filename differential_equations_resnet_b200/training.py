@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _abi
-from .layers._base import LayerHandle, truncated_normal_, _ptr, _stream_ptr
+from .layers._base import ChainHandle, LayerHandle, truncated_normal_, _ptr, _stream_ptr
 from .parallel import allreduce_bucket
 
 
@@ -81,14 +81,43 @@ def conv2d_same_nhwc(x, w_hwio, bias, strides):
 class _Chain:
     """One run of consecutive Euler steps with equal shape: handles + saved activations."""
 
-    def __init__(self, C, n_layers, gamma, precision, offset):
-        self.C, self.n = C, n_layers
-        self.handles = [LayerHandle(C, 3, gamma, (1, 1), True, True, _abi.PRECISIONS[precision], _abi.LAYOUT_3BY3)
-                        for _ in range(n_layers)]
-        self.np_layer = self.handles[0].num_params
+    def __init__(self, C, n_layers, gamma, precision, offset, persistent=True):
+        self.C, self.n, self.gamma, self.precision = C, n_layers, gamma, precision
+        self.persistent = persistent and precision == "fast_tf32"
+        self._handles = None
+        self.fused = None                         # ChainHandle once a shape that fits shared memory is seen
+        self.np_layer = 4 * C + 9 * C * (C - 1) // 2 + C
         self.offset = offset                      # offset of layer 0 in the flat Euler bucket
         self.acts = None
         self.masks = None
+        self._fshape = None
+
+    @property
+    def handles(self):
+        """Per-layer handles (fallback path: strict mode, or images too large for shared memory)."""
+        if self._handles is None:
+            self._handles = [LayerHandle(self.C, 3, self.gamma, (1, 1), True, True, _abi.PRECISIONS[self.precision],
+                                         _abi.LAYOUT_3BY3) for _ in range(self.n)]
+            assert self._handles[0].num_params == self.np_layer
+        return self._handles
+
+    def use_fused(self, shape):
+        if not self.persistent or not ChainHandle.supported(self.C, shape[1], shape[2]):
+            return False
+        if self.fused is None:
+            self.fused = ChainHandle(self.C, self.n, self.gamma)
+            assert self.fused.num_params == self.np_layer
+        return True
+
+    def ensure_fused_buffers(self, shape, device):
+        if self._fshape == shape:
+            return
+        N, H, W, C = shape
+        self.f_acts = torch.empty((self.n,) + shape, dtype=torch.float32, device=device)
+        self.f_masks = torch.empty((self.n, N, H, W, C // 8), dtype=torch.uint8, device=device)
+        self.f_dz = torch.empty((self.n,) + shape, dtype=torch.float32, device=device)
+        self.f_dx = torch.empty(shape, dtype=torch.float32, device=device)
+        self._fshape = shape
 
     def ensure_buffers(self, shape, device):
         if self.acts is not None and self.acts[1].shape == shape:
@@ -109,6 +138,15 @@ class _ChainFn(torch.autograd.Function):
         lib, st = _abi.lib(), _stream_ptr()
         x = x.contiguous()
         N, H, W, C = x.shape
+        ctx.chain, ctx.net, ctx.shape = chain, net, (N, H, W, C)
+        ctx.fused = chain.use_fused(tuple(x.shape))
+        if ctx.fused:
+            # persistent path: pack all layers, then ONE launch runs every Euler step of the chain
+            chain.ensure_fused_buffers(tuple(x.shape), x.device)
+            chain.x0 = x.detach()
+            chain.fused.pack(net.theta_euler[chain.offset:], chain.np_layer)
+            chain.fused.forward(chain.x0, net.spec.h, acts=chain.f_acts, masks=chain.f_masks)
+            return chain.f_acts[chain.n - 1].view(N, H, W, C)
         chain.ensure_buffers(tuple(x.shape), x.device)
         chain.acts[0] = x.detach()                # layer 0 reads the caller's tensor (no copy, no graph reference)
         for l, hd in enumerate(chain.handles):
@@ -116,7 +154,6 @@ class _ChainFn(torch.autograd.Function):
             _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(net.theta_euler[off:]), None, st))
             _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(chain.acts[l]), _ptr(chain.acts[l + 1]), _ptr(chain.masks[l]),
                                              None, N, H, W, net.spec.h, _abi.F_EULER, st))
-        ctx.chain, ctx.net, ctx.shape = chain, net, (N, H, W, C)
         return chain.acts[chain.n].view(N, H, W, C)
 
     @staticmethod
@@ -125,6 +162,11 @@ class _ChainFn(torch.autograd.Function):
         N, H, W, C = ctx.shape
         lib, st = _abi.lib(), _stream_ptr()
         dy = dy.contiguous()
+        if ctx.fused:
+            # backward sweep (one launch) + weight gradients of all layers (one launch + one fold)
+            chain.fused.dgrad(dy, chain.f_masks, chain.f_dz, chain.f_dx, net.spec.h)
+            chain.fused.wgrad(chain.x0, chain.f_acts, chain.f_dz, net.grad_euler[chain.offset:], chain.np_layer)
+            return chain.f_dx.view(N, H, W, C), None, None
         cur = dy
         for l in range(chain.n - 1, -1, -1):
             hd = chain.handles[l]
@@ -145,7 +187,7 @@ class EulerNet:
     precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1):
+                 world_size=1, persistent=True):
         _abi.require_device()
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
         self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
@@ -161,7 +203,7 @@ class EulerNet:
                 j = i
                 while j < len(plan) and plan[j][0] == "euler" and plan[j][2] == co:
                     j += 1
-                ch = _Chain(co, j - i, spec.gamma, precision, off)
+                ch = _Chain(co, j - i, spec.gamma, precision, off, persistent)
                 off += ch.np_layer * ch.n
                 self.segments.append(("chain", ch))
                 i = j

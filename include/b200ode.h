@@ -139,6 +139,36 @@ int b200ode_adam_step(float* params, const float* grads, float* m, float* v, int
                       float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 int b200ode_increment(int32_t* counter, void* stream);
 
+/* ---- persistent Euler-step chains: the stage loop of models/tfkeras_resnets.py:575-593
+ *      (n x single_layer_identity_block, :28-94, on a tensor of constant shape) forward and its
+ *      TF-autodiff backward sweep (training/training.py:300) in ONE launch per direction.  One CTA
+ *      keeps one image in shared memory across all steps.  FAST_TF32 only; shapes whose image does
+ *      not fit shared memory are refused (b200ode_chain_supported == 0): use the per-layer calls. ---- */
+typedef struct b200ode_chain b200ode_chain_t;
+int b200ode_chain_supported(int channels, int H, int W, int precision_mode);
+/* n_layers distinct antisymmetric 3x3 layers (LAYOUT_3BY3 parameters, strides (1,1)) */
+int b200ode_chain_create(int channels, int n_layers, float gamma, int use_bias, int precision_mode,
+                         b200ode_chain_t** out);
+int b200ode_chain_destroy(b200ode_chain_t* chain);
+int64_t b200ode_chain_layer_params(const b200ode_chain_t* chain);
+/* K1 for all layers at once: params + l*param_layer_stride = packed parameters of layer l */
+int b200ode_chain_pack(b200ode_chain_t* chain, const float* params, int64_t param_layer_stride, void* stream);
+/* n_steps Euler steps x_{l+1} = x_l + h*relu(conv_{K_l}(x_l)+b_l); step l uses layer l % n_layers
+ * (n_layers == 1: the long-horizon integration through one block).  acts: nullable fp32
+ * [n_steps][N,H,W,C] receiving every x_{l+1}; relu_masks: nullable [n_steps][N,H,W,C/8];
+ * y_final: nullable [N,H,W,C] (required when acts is NULL). */
+int b200ode_chain_fwd(b200ode_chain_t* chain, const float* x0, float* acts, uint8_t* relu_masks, float* y_final, int N,
+                      int H, int W, float h, int n_steps, void* stream);
+/* backward sweep over the n_layers steps: dy = dL/dx_L -> dx = dL/dx_0; dz_all: fp32
+ * [n_layers][N,H,W,C] receives dZ_l = h*dY_l*mask_l (input of the weight gradient). */
+int b200ode_chain_dgrad(b200ode_chain_t* chain, const float* dy, const uint8_t* relu_masks, float* dz_all, float* dx,
+                        int N, int H, int W, float h, void* stream);
+/* weight + bias gradients of all layers in one launch (+ one fold/reduce launch):
+ * layer l reads x_l (x0 for l = 0, acts[l-1] otherwise) and dz_all[l];
+ * result at grad_params + l*grad_layer_stride. */
+int b200ode_chain_wgrad(b200ode_chain_t* chain, const float* x0, const float* acts, const float* dz_all,
+                        float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream);
+
 /* test hook: number of kernel launches issued by this library in this process */
 int64_t b200ode_launch_count(void);
 /* debug hook: device buffer of uint64 [ctas][16] that the tensor-core kernels fill with a per-CTA

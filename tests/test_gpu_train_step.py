@@ -59,3 +59,8 @@ def test_train_step_fast_tf32_matches_oracle():
 
 def test_train_step_cuda_graph_matches_oracle():
     _run("strict", 1e-5, 2e-4, graph=True)
+
+
+def test_train_step_fast_tf32_cuda_graph_matches_oracle():
+    """fast_tf32 takes the persistent chain kernels (one launch per stage and direction)."""
+    _run("fast_tf32", 2e-3, 3e-2, graph=True)
