@@ -595,6 +595,12 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   if (KT > Q) KT = (int)((Q + UKP - 1) / UKP * UKP);
   p.tpi = (int)((Q + KT - 1) / KT);
   KT = (int)(((Q + p.tpi - 1) / p.tpi + UKP - 1) / UKP * UKP);
+  {  // small tiles (small images): deepen the TMA pipeline with the shared memory that is left
+    const int RBx = (p.P - 1 + KT + 2 * p.P + 4 + p.P - 1) / p.P, RBd = (p.P - 1 + KT + p.P - 1) / p.P;
+    const uint32_t xs = align_up((uint32_t)RBx * p.P * p.RWB, 1024), ds = align_up((uint32_t)RBd * p.P * p.RWB, 1024);
+    const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
+    while (stages < 6 && stage * (stages + 1) + 1024 + 4608 <= max_smem) ++stages;
+  }
   p.KT = KT; p.stages = stages;
   p.RBx = (p.P - 1 + KT + 2 * p.P + 4 + p.P - 1) / p.P;
   p.RBd = (p.P - 1 + KT + p.P - 1) / p.P;
@@ -649,9 +655,11 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     LAUNCH_CHECK("reduce_parts");
   }
   const long long nout = (lg.use_bias ? lg.nparams : lg.bias_off);
-  dim3 fgrid(blocks_for(nout * 16, 256), L);
+  int fl = 1;                                   // lanes per output: power of two >= nparts, at most 16
+  while (fl < 16 && fl < nparts) fl <<= 1;
+  dim3 fgrid(blocks_for(nout * fl, 256), L);
   fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, total, p.bias_partials, grad_params, accumulate,
-                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride);
+                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl);
   LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }
@@ -892,7 +900,7 @@ static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CU
       CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<C_, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    chain_tc_kernel<C_, DIR><<<grid, 192, plan.smem, st>>>(mx, mw, plan.p);                                        \
+    chain_tc_kernel<C_, DIR><<<grid, 320, plan.smem, st>>>(mx, mw, plan.p);                                        \
   } while (0)
   switch (ch->g.C) {
     case 16: CH_LAUNCH(16); break;
@@ -917,7 +925,7 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, float* ac
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = n_steps; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
-  p.acts = acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias;
+  p.acts = acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias; p.trace = g_trace;
   const int C = ch->g.C, rowb = C * 4 >= 128 ? 128 : C * 4;
   CUtensorMap mx, mw;
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -937,7 +945,7 @@ extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const u
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
-  p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = dz_all; p.dx = dx;
+  p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = dz_all; p.dx = dx; p.trace = g_trace;
   CUtensorMap mw;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;

@@ -264,18 +264,20 @@ __global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __res
   grad[i] = accumulate ? grad[i] + val : val;
 }
 
-// Split-K reduction + fold + bias gradient in one launch: 16 lanes per output sum the partials
-// (lane l takes parts l, l+16, ...) and combine through a fixed-order shuffle tree -> deterministic.
+// Split-K reduction + fold + bias gradient in one launch: `lanes` (1,2,4,8,16) threads per output
+// sum the partials (lane l takes parts l, l+lanes, ...) and combine through a fixed-order shuffle
+// tree -> deterministic.
 // blockIdx.y = layer of a batched (chain) weight gradient; the three layer strides are in floats.
 __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
                                    const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate,
-                                   long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride) {
+                                   long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride,
+                                   int lanes) {
   Gpart += (long long)blockIdx.y * part_layer_stride;
   if (bias_part) bias_part += (long long)blockIdx.y * bias_layer_stride;
   grad += (long long)blockIdx.y * grad_layer_stride;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long i = gid >> 4;
-  const int l = (int)(gid & 15);
+  const long long i = gid / lanes;
+  const int l = (int)(gid % lanes);
   const long long nfree = g.use_bias ? g.bias_off : g.nparams;
   const long long total = nfree + ((g.use_bias && bias_part) ? g.C : 0);
   if (i >= total) return;
@@ -284,18 +286,15 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
   if (i < nfree) {
     long long e1, e2; float s1, s2;
     param_entries(g, i, e1, s1, e2, s2);
-    for (int p = l; p < nparts; p += 16) {
+    for (int p = l; p < nparts; p += lanes) {
       const float* Gp = Gpart + (long long)p * part_stride;
       val += s1 * Gp[e1] + s2 * Gp[e2];
     }
   } else {
     const int c = (int)(i - nfree);
-    for (int p = l; p < nparts; p += 16) val += bias_part[(long long)p * g.C + c];
+    for (int p = l; p < nparts; p += lanes) val += bias_part[(long long)p * g.C + c];
   }
-  val += __shfl_xor_sync(mask, val, 8, 16);
-  val += __shfl_xor_sync(mask, val, 4, 16);
-  val += __shfl_xor_sync(mask, val, 2, 16);
-  val += __shfl_xor_sync(mask, val, 1, 16);
+  for (int off = lanes >> 1; off > 0; off >>= 1) val += __shfl_xor_sync(mask, val, off, 32);
   if (l == 0) grad[i] = accumulate ? grad[i] + val : val;
 }
 

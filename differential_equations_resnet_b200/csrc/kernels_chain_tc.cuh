@@ -16,7 +16,7 @@
 //                     (the data gradient reuses the forward weights); dY stays in
 //                     a second, thread-private shared buffer E.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quarters).  When all nine
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two warps per TMEM lane quarter).  When all nine
 // taps of a layer fit one ring stage (C <= 32) the MMAs are issued segment by segment with one commit
 // per 128-position segment, so the epilogue of segment s overlaps the MMAs of segments > s.
 #pragma once
@@ -51,6 +51,7 @@ struct ChainParams {
   const uint8_t* masks_r; // [L][N,H,W,C/8]
   float* dz_all;          // [L][N,H,W,C]
   float* dx;              // [N,H,W,C] gradient w.r.t. the chain input
+  uint64_t* trace;        // nullable per-CTA timeline (debug)
 };
 
 template <int C>
@@ -86,7 +87,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
 }
 
 template <int C, int DIR>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ChainParams p) {
   using Cfg = ChainCfg<C>;
   constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG;
@@ -108,13 +109,17 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
+  Trace tr;
+  tr.begin(p.trace);
+  if (threadIdx.x == 0) tr.wall(0);
+  constexpr int TL = 4;   // traced (steady-state) step
 
   if (warp == 0 && lane == 0) {
     if (DIR == 0) tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     mbar_init(x_full, 1);
-    mbar_init(layer_done, 4);
-    mbar_init(img_done, 4);
+    mbar_init(layer_done, 8);
+    mbar_init(img_done, 8);
     for (int i = 0; i < CHAIN_MAXSEG; ++i) mbar_init(&acc_full[i], 1);
     for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_mbar_init();
@@ -134,6 +139,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tr.mark(1);
   const long long img_elems = (long long)p.H * p.W * C;
   const long long layer_elems = (long long)p.N * img_elems;
 
@@ -179,11 +185,13 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (DIR == 0 && li == 0) mbar_wait(x_full, ic & 1);
         else { mbar_wait(layer_done, ld & 1); ++ld; }
         tc_fence_after_sync();
+        if (ic == 0 && lane == 0) { if (li == TL) tr.mark(2); if (li == TL + 1) tr.mark(5); }
         const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
         if (p.seg_outer) {
           const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
           mbar_wait(&w_full[s], ph);
           tc_fence_after_sync();
+          if (ic == 0 && li == TL && lane == 0) tr.mark(3);
           const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
           uint32_t a_sg = a_base, d = tmem_base;
           for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
@@ -227,16 +235,22 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           for (int sg = 0; sg < p.nseg; ++sg)
             if (leader) umma_commit(&acc_full[sg]);
         }
+        if (ic == 0 && li == TL && lane == 0) tr.mark(4);
         __syncwarp();
       }
     }
+    if (lane == 0) tr.mark(10);
   } else {
-    // ===================== epilogue warps 2..5 (TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue warps 2..9 =====================
+    // Two warps per TMEM lane quarter (hardware: warp w reads lanes 32*(w%4)..+31); the (segment,
+    // 16-channel group) work items of a layer alternate between the two.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t e_base = smem_base + p.e_off;
-    const int groups = C / 8;   // mask bytes per pixel
+    constexpr int groups = C / 8;   // mask bytes per pixel
+    constexpr int NG = C / 16;      // 16-channel groups per pixel
     uint32_t lc = 0;
     for (int img = blockIdx.x; img < p.N; img += gridDim.x) {
       const long long img_off = (long long)img * img_elems;
@@ -252,18 +266,22 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint32_t pos = (uint32_t)(q + p.P + 1);
             const float* src = p.dy + img_off + (long long)pixl * C;
 #pragma unroll
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int cg = 0; cg < NG; ++cg) {
+              if (((sg * NG + cg) & 1) != half) continue;
+              const int c0 = cg * 16;
               const uint32_t bits = *reinterpret_cast<const uint16_t*>(mk_l + (long long)pixl * groups + c0 / 8);
               const uint32_t pl = smem_base + (uint32_t)(c0 / KB) * p.plane_bytes;
+              float4 d[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d[j] = *reinterpret_cast<const float4*>(src + c0 + 4 * j);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float4 d = *reinterpret_cast<const float4*>(src + c0 + 4 * j);
-                sts128(e_base + e_chunk_off<C>(pixl, c0 / 4 + j), d);
+                sts128(e_base + e_chunk_off<C>(pixl, c0 / 4 + j), d[j]);
                 float4 z;
-                z.x = (bits >> (4 * j)) & 1u ? p.h * d.x : 0.0f;
-                z.y = (bits >> (4 * j + 1)) & 1u ? p.h * d.y : 0.0f;
-                z.z = (bits >> (4 * j + 2)) & 1u ? p.h * d.z : 0.0f;
-                z.w = (bits >> (4 * j + 3)) & 1u ? p.h * d.w : 0.0f;
+                z.x = (bits >> (4 * j)) & 1u ? p.h * d[j].x : 0.0f;
+                z.y = (bits >> (4 * j + 1)) & 1u ? p.h * d[j].y : 0.0f;
+                z.z = (bits >> (4 * j + 2)) & 1u ? p.h * d[j].z : 0.0f;
+                z.w = (bits >> (4 * j + 3)) & 1u ? p.h * d[j].w : 0.0f;
                 sts128(pl + strip_chunk_off<ROWB>(pos, (c0 % KB) / 4 + j), z);
                 *reinterpret_cast<float4*>(dz_l + (long long)pixl * C + c0 + 4 * j) = z;
               }
@@ -280,7 +298,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t nxt = smem_base + (uint32_t)((li & 1) ^ 1) * p.strip_stride;
         const bool last = li == p.L - 1;
         // per-layer pointers
-        const float* bias_l = p.bias + (l % p.Lw) * C;
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + (l % p.Lw) * C);
         float* out_l = nullptr;        // global copy of this step's result
         uint8_t* mask_w = nullptr;
         uint32_t mkreg[MAXSEG][MW];
@@ -314,34 +332,51 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
 #pragma unroll
         for (int sg = 0; sg < MAXSEG; ++sg) {
-          if (sg < p.nseg) {
+          // Every warp waits for the LAST segment's commit even when it owns no item of it: that gates
+          // it to the MMA warp's progress, so no warp can arrive twice in one layer_done phase.
+          if (sg < p.nseg && (NG > 1 || (sg & 1) == half || sg == p.nseg - 1)) {
             mbar_wait(&acc_full[sg], lc & 1);
             tc_fence_after_sync();
+            if (threadIdx.x == 64 && lc == TL && sg == 0) tr.mark(6);
+            if (threadIdx.x == 64 && lc == TL + 1 && sg == 0) tr.mark(9);
+            if (threadIdx.x == 64 && lc == TL && sg == 2) tr.mark(7);
             const int q = sg * 128 + row;
             const int yy = q / p.P, xq = q - yy * p.P;
             const bool valid = (yy < p.H) && (xq < p.W);
             const int pixl = yy * p.W + xq;
             const uint32_t pos = (uint32_t)(q + p.P + 1);
 #pragma unroll
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int cg = 0; cg < NG; ++cg) {
+              if (((sg * NG + cg) & 1) != half) continue;
+              const int c0 = cg * 16;
               uint32_t r[16];
               tmem_ld_x16(tq + sg * C + c0, r);
-              tmem_ld_wait();
-              if (valid) {
-                const uint32_t plo = (uint32_t)(c0 / KB) * p.plane_bytes;
-                const uint32_t ch0 = (c0 % KB) / 4;
-                if (DIR == 0) {
+              const uint32_t plo = (uint32_t)(c0 / KB) * p.plane_bytes;
+              const uint32_t ch0 = (c0 % KB) / 4;
+              uint32_t so[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) so[j] = plo + strip_chunk_off<ROWB>(pos, ch0 + j);
+              if (DIR == 0) {
+                float4 bv[4], xv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = __ldg(bias4 + c0 / 4 + j);
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) xv[j] = lds128(cur + so[j]);
+                }
+                tmem_ld_wait();
+                if (valid) {
                   uint32_t bits = 0;
+                  float4 o[4];
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const uint32_t so = plo + strip_chunk_off<ROWB>(pos, ch0 + j);
-                    const float4 xv = lds128(cur + so);
                     float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                   __uint_as_float(r[4 * j + 3])};
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float bs[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
+                    const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                      float t = v[e] + __ldg(bias_l + c0 + 4 * j + e);
+                      float t = v[e] + bs[e];
                       bits |= (t > 0.0f ? 1u : 0u) << (4 * j + e);
                       t = fmaxf(t, 0.0f);
                       // Lambda(h*x) (only when h != 1, tfkeras_resnets.py:90) and add() are two layers in the
@@ -349,37 +384,61 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                       if (p.h != 1.0f) t = __fmul_rn(p.h, t);
                       v[e] = __fadd_rn(xs[e], t);
                     }
-                    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-                    if (!last) sts128(nxt + so, o);
-                    if (out_l) *reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0 + 4 * j) = o;
+                    o[j] = make_float4(v[0], v[1], v[2], v[3]);
+                  }
+                  if (!last) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sts128(nxt + so[j], o[j]);
+                  }
+                  if (out_l) {
+                    float4* op = reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = o[j];
                   }
                   if (mask_w) *reinterpret_cast<uint16_t*>(mask_w + (long long)pixl * groups + c0 / 8) = (uint16_t)bits;
-                } else {
-                  const uint32_t bits = last ? 0u : (mkreg[sg][c0 / 32] >> (c0 % 32)) & 0xFFFFu;
+                }
+              } else {
+                const uint32_t bits = last ? 0u : (mkreg[sg][c0 / 32] >> (c0 % 32)) & 0xFFFFu;
+                uint32_t eo[4];
+                float4 dyv[4], zv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) eo[j] = e_base + e_chunk_off<C>(pixl, c0 / 4 + j);
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) dyv[j] = lds128(eo[j]);
+                  if (p.gamma != 0.0f) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) zv[j] = lds128(cur + so[j]);
+                  }
+                }
+                tmem_ld_wait();
+                if (valid) {
+                  float4 o[4], z[4];
+                  const float g2 = 2.0f * p.gamma;
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const uint32_t so = plo + strip_chunk_off<ROWB>(pos, ch0 + j);
-                    const uint32_t eo = e_base + e_chunk_off<C>(pixl, c0 / 4 + j);
-                    const float4 dyv = lds128(eo);
                     float v[4] = {-__uint_as_float(r[4 * j]), -__uint_as_float(r[4 * j + 1]), -__uint_as_float(r[4 * j + 2]),
                                   -__uint_as_float(r[4 * j + 3])};
                     if (p.gamma != 0.0f) {
-                      const float4 zv = lds128(cur + so);
-                      const float g2 = 2.0f * p.gamma;
-                      v[0] = fmaf(g2, zv.x, v[0]); v[1] = fmaf(g2, zv.y, v[1]);
-                      v[2] = fmaf(g2, zv.z, v[2]); v[3] = fmaf(g2, zv.w, v[3]);
+                      v[0] = fmaf(g2, zv[j].x, v[0]); v[1] = fmaf(g2, zv[j].y, v[1]);
+                      v[2] = fmaf(g2, zv[j].z, v[2]); v[3] = fmaf(g2, zv[j].w, v[3]);
                     }
-                    v[0] += dyv.x; v[1] += dyv.y; v[2] += dyv.z; v[3] += dyv.w;
-                    float4 o = make_float4(v[0], v[1], v[2], v[3]);
-                    if (!last) {
-                      sts128(eo, o);
-                      o.x = (bits >> (4 * j)) & 1u ? p.h * v[0] : 0.0f;
-                      o.y = (bits >> (4 * j + 1)) & 1u ? p.h * v[1] : 0.0f;
-                      o.z = (bits >> (4 * j + 2)) & 1u ? p.h * v[2] : 0.0f;
-                      o.w = (bits >> (4 * j + 3)) & 1u ? p.h * v[3] : 0.0f;
-                      sts128(nxt + so, o);
-                    }
-                    *reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0 + 4 * j) = o;
+                    v[0] += dyv[j].x; v[1] += dyv[j].y; v[2] += dyv[j].z; v[3] += dyv[j].w;
+                    o[j] = make_float4(v[0], v[1], v[2], v[3]);
+                    z[j].x = (bits >> (4 * j)) & 1u ? p.h * v[0] : 0.0f;
+                    z[j].y = (bits >> (4 * j + 1)) & 1u ? p.h * v[1] : 0.0f;
+                    z[j].z = (bits >> (4 * j + 2)) & 1u ? p.h * v[2] : 0.0f;
+                    z[j].w = (bits >> (4 * j + 3)) & 1u ? p.h * v[3] : 0.0f;
+                  }
+                  float4* op = reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0);
+                  if (!last) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { sts128(eo[j], o[j]); sts128(nxt + so[j], z[j]); }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = z[j];
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = o[j];
                   }
                 }
               }
@@ -387,6 +446,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
         tc_fence_before_sync();
+        if (threadIdx.x == 64 && lc == TL) tr.mark(8);
         if (!last) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -399,9 +459,11 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   }
 
+  if (threadIdx.x == 64) tr.mark(11);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) { tr.mark(12); tr.wall(15); }
 }
 
 }  // namespace b200ode

@@ -138,6 +138,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       ent[lane] = (uint32_t)shift * RU + (a_off >> 4);
     }
     __syncwarp();
+    uint32_t entr[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
     const int ksteps = p.KT / UKP;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
     uint32_t it = 0;
@@ -162,6 +165,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           if (leader) {
             if (BF16) { umma_f16(d0, a0, dsc_b, idesc, accum); umma_f16(d1, a1, dsc_b, idesc, accum); umma_f16(d2, a2, dsc_b, idesc, accum); }
             else { umma_tf32(d0, a0, dsc_b, idesc, accum); umma_tf32(d1, a1, dsc_b, idesc, accum); umma_tf32(d2, a2, dsc_b, idesc, accum); }
+          }
+        }
+      } else if (nent <= 16) {
+        // general tiling: per-entry A offsets held in registers (static unroll), no smem reads in the loop
+        for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+          const uint64_t dsc_b = mk(du, lbo_b);
+          const uint64_t dsc_b_lo = mk(du + lo_d, lbo_b);
+          const uint32_t accum = (it | ks) != 0;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (e < nent) {
+              const uint32_t au = xu + entr[e];
+              const uint32_t d_tmem = tmem_base + e * ACCW;
+              const uint64_t dsc_a = mk(au, lbo_a);
+              if (leader) {
+                if (BF16) umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum);
+                else {
+                  umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
+                  if (STRICT) {
+                    umma_tf32(d_tmem + p.NT, dsc_a, dsc_b_lo, idesc, accum);
+                    umma_tf32(d_tmem + p.NT, mk(au + lo_x, lbo_a), dsc_b, idesc, 1);
+                  }
+                }
+              }
+            }
           }
         }
       } else
