@@ -346,9 +346,16 @@ def run_b200(args):
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
+        # All ranks meet once more, then leave without tearing the communicator down: destroying NCCL
+        # communicators whose collectives were captured into a (still alive) CUDA graph blocked the
+        # process on this stack (torch 2.11 / NCCL 2.28.9); the processes are finished anyway.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -544,17 +545,24 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int C = lg.C;
   const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
   const int eb = bf16 ? 2 : 4;
-  const int UKP = bf16 ? 16 : 8;
+  int UKP = bf16 ? 16 : 8;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L;
   if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
+  static const int pair_env = getenv("B200ODE_WGRAD_PAIR") ? atoi(getenv("B200ODE_WGRAD_PAIR")) : 1;   // debug switch
+  p.pair = (!bf16 && !strict && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
+  if (p.pair) p.P = W + 2;
   p.CH = bf16 ? (C < 64 ? C : 64) : 32;
   p.RWB = p.CH * eb;
+  p.PB = p.RWB;
+  if (p.pair) { p.CH = 16; p.RWB = 128; p.PB = 64; UKP = 16; }
   const int Cpad = C > p.CH ? C : p.CH;
   p.xchunks = Cpad / p.CH;
-  p.trick = (p.xchunks == 1 && 4 * p.CH <= 128) ? 1 : 0;
-  if (p.trick) {
+  p.trick = (p.pair || (p.xchunks == 1 && 4 * p.CH <= 128)) ? 1 : 0;
+  if (p.pair) {
+    p.TG = 9; p.NT = 32; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 128; p.dchunks = 1;
+  } else if (p.trick) {
     p.TG = 9; p.NT = p.CH; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 4 * p.CH; p.dchunks = 1;
   } else {
     p.Mblk = Cpad < 128 ? Cpad : 128;
@@ -581,13 +589,14 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // positions per tile: as large as fits two stages (one as a fallback)
   const long long Q = (long long)H * p.P;
   const int max_smem = 227 * 1024 - 2048;
+  const int off_max = p.P - 1;   // largest offset of a tile start inside its strip
   int KT = 0, stages = 0;
   for (int st_try = 2; st_try >= 1 && !KT; --st_try) {
-    for (int kt = 512; kt >= UKP; kt -= UKP) {
-      const int RBx = (p.P - 1 + kt + 2 * p.P + 4 + p.P - 1) / p.P, RBd = (p.P - 1 + kt + p.P - 1) / p.P;
+    for (int kt = p.pair ? 1024 : 512; kt >= UKP; kt -= UKP) {
+      const int RBx = (off_max + kt + 2 * p.P + 8 + p.P - 1) / p.P, RBd = (off_max + kt + p.P - 1) / p.P;
       if (RBx > 256) continue;
-      const uint32_t xs = align_up((uint32_t)RBx * p.P * p.RWB, 1024), ds = align_up((uint32_t)RBd * p.P * p.RWB, 1024);
-      const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
+      const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
+      const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
       if (stage * st_try + 1024 + 4608 <= max_smem) { KT = kt; stages = st_try; break; }
     }
   }
@@ -596,17 +605,17 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.tpi = (int)((Q + KT - 1) / KT);
   KT = (int)(((Q + p.tpi - 1) / p.tpi + UKP - 1) / UKP * UKP);
   {  // small tiles (small images): deepen the TMA pipeline with the shared memory that is left
-    const int RBx = (p.P - 1 + KT + 2 * p.P + 4 + p.P - 1) / p.P, RBd = (p.P - 1 + KT + p.P - 1) / p.P;
-    const uint32_t xs = align_up((uint32_t)RBx * p.P * p.RWB, 1024), ds = align_up((uint32_t)RBd * p.P * p.RWB, 1024);
-    const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
+    const int RBx = (off_max + KT + 2 * p.P + 8 + p.P - 1) / p.P, RBd = (off_max + KT + p.P - 1) / p.P;
+    const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
+    const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
     while (stages < 6 && stage * (stages + 1) + 1024 + 4608 <= max_smem) ++stages;
   }
   p.KT = KT; p.stages = stages;
-  p.RBx = (p.P - 1 + KT + 2 * p.P + 4 + p.P - 1) / p.P;
-  p.RBd = (p.P - 1 + KT + p.P - 1) / p.P;
-  p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.RWB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.RWB;
+  p.RBx = (off_max + KT + 2 * p.P + 8 + p.P - 1) / p.P;
+  p.RBd = (off_max + KT + p.P - 1) / p.P;
+  p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.PB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.PB;
   p.x_chunk_stride = align_up(p.x_chunk_bytes, 1024); p.d_chunk_stride = align_up(p.d_chunk_bytes, 1024);
-  p.x_off = 0; p.d_off = p.xchunks * p.x_chunk_stride;
+  p.x_off = p.pair ? 1024 : 0; p.d_off = p.x_off + p.xchunks * p.x_chunk_stride;
   const uint32_t hi_bytes = p.d_off + p.dchunks * p.d_chunk_stride;
   p.x_lo_off = hi_bytes; p.d_lo_off = hi_bytes + p.d_off;
   p.stage_stride = strict ? 2 * hi_bytes : hi_bytes;
@@ -621,20 +630,30 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   if (nparts > p.total_tiles) nparts = p.total_tiles;
   p.nparts = nparts;
   const long long total = 9LL * C * C;
+  const long long pstride = p.pair ? 3LL * 128 * 32 : total;   // floats per partial
+  p.part_stride = pstride;
   float* ws = nullptr;
-  if (int rc = get_scratch(1, (size_t)L * nparts * (total + C) * sizeof(float), (void**)&ws)) return rc;
+  if (int rc = get_scratch(1, (size_t)L * nparts * (pstride + C) * sizeof(float), (void**)&ws)) return rc;
   p.partials = ws;
   p.trace = g_trace;
-  p.bias_partials = ws + (size_t)L * nparts * total;
-  p.part_layer_stride = (long long)nparts * total;
+  p.bias_partials = ws + (size_t)L * nparts * pstride;
+  p.part_layer_stride = (long long)nparts * pstride;
   p.bias_layer_stride = (long long)nparts * C;
   CUtensorMap mx0, mx, md;
   const CUtensorMapSwizzle sw = bf16 ? (p.RWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.RWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)
                                      : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (int rc = make_act_map(&mx0, x0, N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc;
-  if (L > 1) { if (int rc = make_act_map(&mx, xrest, (L - 1) * N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc; }
-  else mx = mx0;
-  if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
+  if (p.pair) {
+    // pixel-pair view: [images, H, W/2, 32 floats]; the box is P/2 = W/2+1 pairs wide (last pair out of bounds -> zeros)
+    if (int rc = make_act_map(&mx0, x0, N, H, W / 2, 32, eb, 32, p.P / 2, p.RBx, 1, sw)) return rc;
+    if (L > 1) { if (int rc = make_act_map(&mx, xrest, (L - 1) * N, H, W / 2, 32, eb, 32, p.P / 2, p.RBx, 1, sw)) return rc; }
+    else mx = mx0;
+    if (int rc = make_act_map(&md, dz, L * N, H, W / 2, 32, eb, 32, p.P / 2, p.RBd, 1, sw)) return rc;
+  } else {
+    if (int rc = make_act_map(&mx0, x0, N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc;
+    if (L > 1) { if (int rc = make_act_map(&mx, xrest, (L - 1) * N, H, W, C, eb, p.CH, p.P, p.RBx, 1, sw)) return rc; }
+    else mx = mx0;
+    if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
+  }
   dim3 grid(nparts, ngroups, L);
 #define WG_LAUNCH(M_)                                                                                          \
   do {                                                                                                         \
@@ -651,15 +670,16 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
 #undef WG_LAUNCH
   LAUNCH_CHECK("wgrad_tc_kernel");
   if (G_user && L == 1) {   // dense gradient requested (tests / diagnostics)
-    reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
+    if (p.pair) reduce_parts_pair<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, pstride, total, G, G_user, p.P);
+    else reduce_parts<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, total, G, G_user);
     LAUNCH_CHECK("reduce_parts");
   }
   const long long nout = (lg.use_bias ? lg.nparams : lg.bias_off);
   int fl = 1;                                   // lanes per output: power of two >= nparts, at most 16
   while (fl < 16 && fl < nparts) fl <<= 1;
   dim3 fgrid(blocks_for(nout * fl, 256), L);
-  fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, total, p.bias_partials, grad_params, accumulate,
-                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl);
+  fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, pstride, p.bias_partials, grad_params, accumulate,
+                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl, p.pair ? p.P : 0);
   LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }

@@ -209,6 +209,11 @@ __global__ void reduce_parts(const float* __restrict__ Gpart, int nparts, long l
   if (G_user) G_user[e] = acc;
 }
 
+__device__ __forceinline__ float pair_gather(const float* __restrict__ Gp, long long e, int P);
+// dense G from the raw pixel-pair partials of wgrad_tc_kernel (tests / diagnostics)
+__global__ void reduce_parts_pair(const float* __restrict__ Gpart, int nparts, long long part_stride, long long total,
+                                  float* __restrict__ G, float* __restrict__ G_user, int P);
+
 // Which kernel entries a free scalar feeds: every free scalar appears in exactly
 // two entries of K (one for a trainable centre); dL/dparam = s1*G[e1] + s2*G[e2].
 __device__ __forceinline__ void param_entries(const LayerGeom& g, long long i, long long& e1, float& s1, long long& e2,
@@ -268,10 +273,35 @@ __global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __res
 // sum the partials (lane l takes parts l, l+lanes, ...) and combine through a fixed-order shuffle
 // tree -> deterministic.
 // blockIdx.y = layer of a batched (chain) weight gradient; the three layer strides are in floats.
+// pair != 0: the partials are the raw pixel-pair accumulators of wgrad_tc_kernel
+// ([3 kernel rows][128 lanes (c,px,ci)][32 cols (pd,o)], C = 16): with t = beta - 1 + pd,
+// G[alpha,beta,ci,o] = sum over pd of lane (c = floor(t/2) + 1, px = t & 1, ci), col (pd, o).
+__device__ __forceinline__ float pair_gather(const float* __restrict__ Gp, long long e, int) {
+  const int o = (int)(e & 15), ci = (int)((e >> 4) & 15), tap = (int)(e >> 8);
+  const int alpha = tap / 3, beta = tap - 3 * alpha;
+  const float* base = Gp + (long long)alpha * 128 * 32;
+  float acc = 0.0f;
+#pragma unroll
+  for (int pd = 0; pd < 2; ++pd) {
+    const int t = beta + pd + 1;                 // (beta - 1 + pd) + 2, so that >> and & act on a non-negative value
+    const int c = (t >> 1), px = t & 1;          // c = floor((beta-1+pd)/2) + 1
+    acc += base[(c * 32 + px * 16 + ci) * 32 + pd * 16 + o];
+  }
+  return acc;
+}
+__global__ void reduce_parts_pair(const float* __restrict__ Gpart, int nparts, long long part_stride, long long total,
+                                  float* __restrict__ G, float* __restrict__ G_user, int P) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float acc = 0.0f;
+  for (int p = 0; p < nparts; ++p) acc += pair_gather(Gpart + (long long)p * part_stride, e, P);
+  G[e] = acc;
+  if (G_user) G_user[e] = acc;
+}
 __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
                                    const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate,
                                    long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride,
-                                   int lanes) {
+                                   int lanes, int pair_P) {
   Gpart += (long long)blockIdx.y * part_layer_stride;
   if (bias_part) bias_part += (long long)blockIdx.y * bias_layer_stride;
   grad += (long long)blockIdx.y * grad_layer_stride;
@@ -288,7 +318,8 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
     param_entries(g, i, e1, s1, e2, s2);
     for (int p = l; p < nparts; p += lanes) {
       const float* Gp = Gpart + (long long)p * part_stride;
-      val += s1 * Gp[e1] + s2 * Gp[e2];
+      if (pair_P) val += s1 * pair_gather(Gp, e1, pair_P) + s2 * pair_gather(Gp, e2, pair_P);
+      else val += s1 * Gp[e1] + s2 * Gp[e2];
     }
   } else {
     const int c = (int)(i - nfree);

@@ -51,6 +51,20 @@ struct WgradParams {
   // through map_x (image (l-1)*N + n: the saved outputs of the chain); dz image index is l*N + n.
   int L;
   long long part_layer_stride, bias_layer_stride;   // floats between consecutive layers' partials
+  // Pixel-pair mode (tf32, C = 16, W even).  The TMA maps view the activations as pixel PAIRS
+  // ([.., W/2, 32 floats]; csrc/tma_layout_probe.cu: a 64-byte inner box would be padded to a 128-byte
+  // pitch), the padded pitch is P = W+2 (two zero slots = one out-of-bounds pair at the end of every
+  // row) and one 128-byte MN-major operand row holds two positions: M = (kernel row alpha, parity px,
+  // row holds two positions: M = (row copy c, parity px, ci), N = (parity pd, o).  With the x strip
+  // starting one image row above the dz strip, tap (alpha, beta) is the position shift
+  // alpha*P + beta - 1 = 2*(alpha*P/2 + j) + px - pd with j = floor((beta-1+pd)/2) in {-1,0,1}: per
+  // kernel row ONE M=128 MMA (four row copies c = j+1 through LBO = one row, start row alpha*P/2 - 1)
+  // covers 16 positions of all three beta taps -- three MMAs per 16 positions instead of per 8, and no
+  // zero-padded channels.  The row before each x strip is a zeroed 1 KB pad (x_off = 1024).
+  // The accumulators are written raw ([3][128 lanes][32 cols] per part) and gathered by fold_reduce_kernel.
+  int pair;
+  int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
+  long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
 };
 
 template <int MODE>
@@ -77,6 +91,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   const int tapgroup = group / p.nngroups, ngroup = group % p.nngroups;
   const int part = blockIdx.x;
   const int layer = blockIdx.z;
+  const int ukp = p.pair ? 16 : UKP;    // positions per k-step
   const CUtensorMap* mx = layer == 0 ? &map_x0 : &map_x;
   const int img_x0 = layer == 0 ? 0 : (layer - 1) * p.N;
   const int img_d0 = layer * p.N;
@@ -89,6 +104,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  if (p.pair) {   // zero the 1 KB pad in front of every stage's x strip (row -1 of the first kernel row)
+    for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem + (i >> 6) * p.stage_stride)[i & 63] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -100,13 +120,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
-        const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.KT, row0 = q0 / p.P;
+        const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.KT;
+        const int row0 = q0 / p.P;
+        const int xc0 = p.pair ? 0 : -1;    // pair mode: the zero slots sit at the END of every row
         const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
         for (int c = 0; c < p.xchunks; ++c)
-          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], c * p.CH, -1, row0 - 1, img_x0 + n);
+          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], c * p.CH, xc0, row0 - 1, img_x0 + n);
         for (int c = 0; c < p.dchunks; ++c)
           tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, img_d0 + n);
       }
@@ -114,15 +136,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   } else if (warp == 1) {
     // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
     const bool leader = elect_one();
-    const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
+    const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
     const uint32_t idesc = make_instr_desc(BF16 ? FMT_BF16 : FMT_TF32, Mrows, p.NT, 1, 1);
     const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
     const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
     const uint32_t hi32 = (sbo >> 4) | (1u << 14) | (lt << 29);
+    // M-chunk stride: pair mode = one kernel row (P/2 operand rows); beta trick = one position; else one channel chunk
     const uint32_t lbo_a = (((p.trick ? (uint32_t)p.RWB : p.x_chunk_stride) >> 4) & 0x3FFF) << 16;
     const uint32_t lbo_b = ((p.d_chunk_stride >> 4) & 0x3FFF) << 16;
     auto mk = [&](uint32_t lo, uint32_t lbo) -> uint64_t { return (static_cast<uint64_t>(hi32) << 32) | (lo | lbo); };
-    const uint32_t RU = (uint32_t)p.RWB >> 4;
+    const uint32_t RU = (uint32_t)p.PB >> 4;           // 16-byte units per position
     const uint32_t smem_base = smem_u32(smem);
     const int nent = p.trick ? 3 : p.TG * p.MB;
     const int ACCW = STRICT ? 2 * p.NT : p.NT;   // strict: main + correction accumulators (see conv kernel)
@@ -141,7 +164,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     uint32_t entr[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
-    const int ksteps = p.KT / UKP;
+    const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
     uint32_t it = 0;
     for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
@@ -155,13 +178,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       uint32_t du = ((smem_base + s * p.stage_stride + p.d_off) >> 4) + off0;
       if (p.trick && !STRICT) {
         // beta trick: three M = 4*CH MMAs per k-step (one per kernel row), offsets held in registers
-        const uint32_t e1 = (uint32_t)p.P * RU, e2 = 2u * e1;
+        // start row of kernel row alpha: alpha*P positions; pair mode: alpha*P/2 - 1 operand rows (8 units each)
+        const uint32_t e0 = p.pair ? 0u - 8u : 0u;
+        const uint32_t e1 = p.pair ? (uint32_t)(p.P >> 1) * 8u - 8u : (uint32_t)p.P * RU;
+        const uint32_t e2 = p.pair ? (uint32_t)p.P * 8u - 8u : 2u * e1;
         const uint32_t d0 = tmem_base, d1 = tmem_base + ACCW, d2 = tmem_base + 2 * ACCW;
 #pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+        for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
           const uint64_t dsc_b = mk(du, lbo_b);
           const uint32_t accum = (it | ks) != 0;
-          const uint64_t a0 = mk(xu, lbo_a), a1 = mk(xu + e1, lbo_a), a2 = mk(xu + e2, lbo_a);
+          const uint64_t a0 = mk(xu + e0, lbo_a), a1 = mk(xu + e1, lbo_a), a2 = mk(xu + e2, lbo_a);
           if (leader) {
             if (BF16) { umma_f16(d0, a0, dsc_b, idesc, accum); umma_f16(d1, a1, dsc_b, idesc, accum); umma_f16(d2, a2, dsc_b, idesc, accum); }
             else { umma_tf32(d0, a0, dsc_b, idesc, accum); umma_tf32(d1, a1, dsc_b, idesc, accum); umma_tf32(d2, a2, dsc_b, idesc, accum); }
@@ -169,7 +195,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         }
       } else if (nent <= 16) {
         // general tiling: per-entry A offsets held in registers (static unroll), no smem reads in the loop
-        for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+        for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
           const uint64_t dsc_b = mk(du, lbo_b);
           const uint64_t dsc_b_lo = mk(du + lo_d, lbo_b);
           const uint32_t accum = (it | ks) != 0;
@@ -193,7 +219,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           }
         }
       } else
-      for (int ks = 0; ks < ksteps; ++ks, xu += UKP * RU, du += UKP * RU) {
+      for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
         const uint64_t dsc_b = mk(du, lbo_b);
         const uint32_t accum = (it | ks) != 0;
         uint32_t d_tmem = tmem_base;
@@ -244,7 +270,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
             const uint8_t* cb = dbase + ck * p.d_chunk_stride;
             float acc = 0.0f;
             for (int pos = w4; pos < p.KT; pos += 4) {
-              uint32_t a = (uint32_t)(off0 + pos) * p.RWB + c * (BF16 ? 2 : 4);
+              uint32_t a = (uint32_t)(off0 + pos) * p.PB + c * (BF16 ? 2 : 4);
               if (BF16) {
                 a = swizzle_addr(a, p.RWB);
                 acc += __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(cb + a)) << 16);
@@ -276,13 +302,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     mbar_wait(acc_full, 0);
     if (threadIdx.x == 64) tr.mark(6);
     tc_fence_after_sync();
-    const int Mrows = p.trick ? 4 * p.CH : p.Mblk;
+    const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
     const int nent = p.trick ? 3 : p.TG * p.MB;
     int m;  // accumulator row held by this thread's TMEM lane
     bool row_ok;
     if (Mrows == 128) { m = quarter * 32 + lane; row_ok = true; }
     else { m = quarter * 16 + lane; row_ok = lane < 16; }   // M=64: 16 lanes per quarter
-    float* part_base = p.partials + (size_t)layer * p.part_layer_stride + (size_t)part * 9 * p.C * p.C;
+    float* part_base = p.partials + (size_t)layer * p.part_layer_stride + (size_t)part * p.part_stride;
+    if (p.pair) {
+      // raw accumulators [alpha][lane (c,px,ci)][col (pd,o)]
+      for (int e = 0; e < 3; ++e) {
+        float* dst = part_base + ((size_t)e * 128 + m) * 32;
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * ACCW + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    } else
     for (int e = 0; e < nent; ++e) {
       int tap, ci;
       bool ok = row_ok;
