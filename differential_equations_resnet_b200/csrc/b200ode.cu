@@ -830,7 +830,7 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
   int sw = 2 * per_layer;                            // ideally: the next layer fully prefetched
   while (sw > 1 && (long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) --sw;
   if ((long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) return false;
-  if (sw < 2 && per_layer > 1) return false;
+  if (sw < per_layer) return false;                  // the MMA warp waits for a whole layer's entries up front
   p.sw = sw;
   p.bar_off = p.w_off + (uint32_t)sw * p.w_stage_bytes;
   // the MMAs of the last segment read (junk rows) up to 128*nseg + 2P + 2 positions of strip 1: keep that inside the allocation
@@ -910,6 +910,21 @@ static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw) {
   return 0;
 }
 
+// Grid and cluster size: one CTA per image (up to the SM count); clusters share the weight stream.
+static int chain_grid(ChainParams& p, int C, int N) {
+  static const int cs_env = getenv("B200ODE_CHAIN_CLUSTER") ? atoi(getenv("B200ODE_CHAIN_CLUSTER")) : 0;   // debug override
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int cs = cs_env > 0 ? cs_env : (C >= 32 ? 4 : 1);   // 8 halves the resident CTAs (measured); 2/4 cost nothing and cut L2 reads
+  while (cs > 1 && cs > N) cs >>= 1;
+  int grid = N < sms ? N : sms;
+  grid = (grid + cs - 1) / cs * cs;
+  if (grid > sms) grid = sms / cs * cs;
+  p.cs = cs;
+  p.dbg_skip_w = getenv("B200ODE_CHAIN_SKIPW") ? 1 : 0;
+  p.iters = (N + grid - 1) / grid;
+  return grid;
+}
+
 template <int DIR>
 static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CUtensorMap& mx, const CUtensorMap& mw, int grid,
                         cudaStream_t st) {
@@ -920,7 +935,14 @@ static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CU
       CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<C_, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    chain_tc_kernel<C_, DIR><<<grid, 320, plan.smem, st>>>(mx, mw, plan.p);                                        \
+    cudaLaunchConfig_t cfg;                                                                                        \
+    memset(&cfg, 0, sizeof(cfg));                                                                                  \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;          \
+    cudaLaunchAttribute attr[1];                                                                                   \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+    attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;              \
+    cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;                                                         \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_tc_kernel<C_, DIR>, mx, mw, plan.p));                                   \
   } while (0)
   switch (ch->g.C) {
     case 16: CH_LAUNCH(16); break;
@@ -951,8 +973,7 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, float* ac
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (int rc = make_act_map(&mx, x0, N, H, W, C, 4, rowb / 4, p.P, H + 2, 1, sw)) return rc;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
-  const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  return launch_chain<0>(ch, plan, mx, mw, N < sms ? N : sms, (cudaStream_t)stream);
+  return launch_chain<0>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
 }
 
 extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, float* dz_all, float* dx,
@@ -968,8 +989,7 @@ extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const u
   p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = dz_all; p.dx = dx; p.trace = g_trace;
   CUtensorMap mw;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
-  const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  return launch_chain<1>(ch, plan, mw, mw, N < sms ? N : sms, (cudaStream_t)stream);
+  return launch_chain<1>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream);
 }
 
 extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const float* acts, const float* dz_all,

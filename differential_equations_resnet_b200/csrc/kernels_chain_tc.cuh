@@ -52,6 +52,11 @@ struct ChainParams {
   float* dz_all;          // [L][N,H,W,C]
   float* dx;              // [N,H,W,C] gradient w.r.t. the chain input
   uint64_t* trace;        // nullable per-CTA timeline (debug)
+  // Thread-block cluster: all CTAs of a cluster run the same layer schedule on different images, so
+  // the per-layer weight tiles are loaded ONCE per cluster by a TMA multicast of the rank-0 CTA.
+  int cs;                 // cluster size (1 = no cluster)
+  int dbg_skip_w;         // debug: do not load weights (timing experiments only)
+  int iters;              // images per CTA = ceil(N / gridDim.x); CTAs whose image index is >= N run as ghosts
 };
 
 template <int C>
@@ -62,6 +67,8 @@ struct ChainCfg {
   static constexpr int KS = ROWB / 32;                        // tf32 k-steps (8 channels) per plane
   static constexpr int MW = (C + 31) / 32;                    // 32-bit mask words per pixel
   static constexpr int MAXSEG = C == 16 ? 9 : C == 32 ? 5 : 2; // segments a whole image may need (host plan agrees)
+  // taps per weight ring stage (same rule as taps_per_w_stage() on the host)
+  static constexpr int TW = (C * ROWB * 9 <= 40 * 1024) ? 9 : (C * ROWB * 3 <= 56 * 1024) ? 3 : 1;
 };
 
 // byte offset of 16-byte chunk `chunk` of position `pos` inside a swizzled plane
@@ -90,7 +97,7 @@ template <int C, int DIR>
 __global__ void __launch_bounds__(320, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ChainParams p) {
   using Cfg = ChainCfg<C>;
-  constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG;
+  constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG, TW = Cfg::TW;
   constexpr uint32_t LT = ROWB == 128 ? SWZ_128B : ROWB == 64 ? SWZ_64B : SWZ_32B;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr uint32_t RU = ROWB >> 4;
@@ -104,7 +111,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   uint64_t* acc_full = bars + 3;              // [CHAIN_MAXSEG]
   uint64_t* w_full = acc_full + CHAIN_MAXSEG; // [sw]
   uint64_t* w_empty = w_full + p.sw;          // [sw]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + p.sw);
+  uint64_t* w_empty_cl = w_empty + p.sw;      // [sw] rank 0 only: the other CTAs of the cluster released the stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty_cl + p.sw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,7 +129,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     mbar_init(layer_done, 8);
     mbar_init(img_done, 8);
     for (int i = 0; i < CHAIN_MAXSEG; ++i) mbar_init(&acc_full[i], 1);
-    for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < p.sw; ++i) {
+      mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty_cl[i], p.cs > 1 ? p.cs - 1 : 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -137,6 +148,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tr.mark(1);
@@ -146,23 +158,40 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t iw = 0, ic = 0;
-      for (int img = blockIdx.x; img < p.N; img += gridDim.x, ++ic) {
+      uint32_t iw = 0, ws = 0, wph = 0;
+      const uint32_t crank = p.cs > 1 ? cluster_ctarank() : 0u;
+      const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+      for (uint32_t ic = 0; ic < (uint32_t)p.iters; ++ic) {
+        const int img = blockIdx.x + ic * gridDim.x;   // >= N: ghost (TMA zero-fills the out-of-bounds box)
         if (DIR == 0) {
-          if (ic > 0) mbar_wait(img_done, (ic - 1) & 1);
+          if (ic > 0) mbar_wait_sleep(img_done, (ic - 1) & 1);
           mbar_expect_tx(x_full, NKB * p.x_bytes);
           for (int kb = 0; kb < NKB; ++kb) tma_load_4d(smem + kb * p.plane_bytes, &map_x, x_full, kb * KB, -1, -1, img);
         }
         for (int li = 0; li < p.L; ++li) {
           const int l = DIR ? p.L - 1 - li : li;
           const int lw = l % p.Lw;
+          if (ic == 0 && li == TL + 1) tr.mark(13);
+          if (ic == 0 && li == TL + 2) tr.mark(14);
           for (int kb = 0; kb < NKB; ++kb)
             for (int tg = 0; tg < 9; tg += p.tw) {
-              const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
-              mbar_wait(&w_empty[s], ph ^ 1);
-              mbar_expect_tx(&w_full[s], p.w_stage_bytes);
-              tma_load_3d(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg);
+              const uint32_t s = ws, ph = wph;
+              mbar_wait_sleep(&w_empty[s], ph ^ 1);           // this CTA's MMAs are done with the stage's previous contents
+              if (p.dbg_skip_w && iw >= (uint32_t)p.sw) {
+                mbar_arrive(&w_full[s]);
+              } else if (p.cs == 1) {
+                mbar_expect_tx(&w_full[s], p.w_stage_bytes);
+                tma_load_3d(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg);
+              } else if (crank != 0) {
+                if (iw >= (uint32_t)p.sw) mbar_arrive_cluster(&w_empty_cl[s], 0);   // tell rank 0 the stage is free here
+                mbar_expect_tx(&w_full[s], p.w_stage_bytes);                        // rank 0's multicast completes it
+              } else {
+                if (iw >= (uint32_t)p.sw) mbar_wait_sleep(&w_empty_cl[s], ph ^ 1);
+                mbar_expect_tx(&w_full[s], p.w_stage_bytes);
+                tma_load_3d_mc(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg, cmask);
+              }
               ++iw;
+              if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
             }
         }
       }
@@ -179,8 +208,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
     for (int t = 0; t < 9; ++t) toff[t] = (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
     const uint32_t plane_units = p.plane_bytes >> 4;
-    uint32_t iw = 0, ic = 0, ld = 0;
-    for (int img = blockIdx.x; img < p.N; img += gridDim.x, ++ic) {
+    uint32_t ws = 0, wph = 0, ld = 0;   // weight ring position kept incrementally (no integer division in the loop)
+    for (uint32_t ic = 0; ic < (uint32_t)p.iters; ++ic) {
       for (int li = 0; li < p.L; ++li) {
         if (DIR == 0 && li == 0) mbar_wait(x_full, ic & 1);
         else { mbar_wait(layer_done, ld & 1); ++ld; }
@@ -188,8 +217,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (ic == 0 && lane == 0) { if (li == TL) tr.mark(2); if (li == TL + 1) tr.mark(5); }
         const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
         if (p.seg_outer) {
-          const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
-          mbar_wait(&w_full[s], ph);
+          const uint32_t s = ws;
+          mbar_wait(&w_full[s], wph);
           tc_fence_after_sync();
           if (ic == 0 && li == TL && lane == 0) tr.mark(3);
           const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
@@ -206,34 +235,50 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (leader) umma_commit(&acc_full[sg]);
           }
           if (leader) umma_commit(&w_empty[s]);
-          ++iw;
+          if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
         } else {
+          // All ring entries of the layer are normally prefetched while the previous layer ran: wait for
+          // them up front, then issue the layer's MMAs as one unrolled stream (no wait bubbles in between).
+          long long wstall = 0;
+          constexpr int NENT = NKB * (9 / TW);
+          {
+            const long long tw0 = clock64();
+#pragma unroll
+            uint32_t s2 = ws, ph2 = wph;
+#pragma unroll
+            for (int e = 0; e < NENT; ++e) {
+              mbar_wait(&w_full[s2], ph2);
+              if (++s2 == (uint32_t)p.sw) { s2 = 0; ph2 ^= 1; }
+            }
+            wstall = clock64() - tw0;
+            tc_fence_after_sync();
+          }
+#pragma unroll
           for (int kb = 0; kb < NKB; ++kb) {
             const uint32_t a_kb = a_base + kb * plane_units;
-            for (int tg = 0; tg < 9; tg += p.tw) {
-              const uint32_t s = iw % p.sw, ph = (iw / p.sw) & 1;
-              mbar_wait(&w_full[s], ph);
-              tc_fence_after_sync();
-              uint32_t b_units = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
-              for (int tt = 0; tt < p.tw; ++tt, b_units += tap_units) {
-                const int t = tg + tt;
-                const uint32_t a_tap = a_kb + (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
-                const uint32_t first = (kb | t) == 0 ? 0u : 1u;
-                uint32_t a_sg = a_tap, d = tmem_base;
-                for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+#pragma unroll
+            for (int tg = 0; tg < 9; tg += TW) {
+              const uint32_t s = ws;
+              const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
+              // taps and k-steps fully unrolled (descriptor arithmetic overlaps across MMAs); segments outermost
+              uint32_t a_sg = a_kb, d = tmem_base;
+              for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+#pragma unroll
+                for (int tt = 0; tt < TW; ++tt) {
 #pragma unroll
                   for (int ks = 0; ks < KS; ++ks) {
-                    const uint64_t da = mk(a_sg + 2 * ks), db = mk(b_units + 2 * ks);
-                    if (leader) umma_tf32(d, da, db, idesc, ks ? 1u : first);
+                    const uint64_t da = mk(a_sg + toff[tg + tt] + 2 * ks), db = mk(b_base + tt * tap_units + 2 * ks);
+                    if (leader) umma_tf32(d, da, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
                   }
                 }
               }
               if (leader) umma_commit(&w_empty[s]);
-              ++iw;
+              if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
             }
           }
           for (int sg = 0; sg < p.nseg; ++sg)
             if (leader) umma_commit(&acc_full[sg]);
+          if (ic == 0 && li == TL && lane == 0 && tr.buf) tr.buf[3] = (uint64_t)wstall;
         }
         if (ic == 0 && li == TL && lane == 0) tr.mark(4);
         __syncwarp();
@@ -252,7 +297,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     constexpr int groups = C / 8;   // mask bytes per pixel
     constexpr int NG = C / 16;      // 16-channel groups per pixel
     uint32_t lc = 0;
-    for (int img = blockIdx.x; img < p.N; img += gridDim.x) {
+    for (int ic = 0; ic < p.iters; ++ic) {
+      const int img = blockIdx.x + ic * gridDim.x;
+      const bool active = img < p.N;     // ghosts keep the barrier protocol but touch no global memory
       const long long img_off = (long long)img * img_elems;
       if (DIR == 1) {
         // ---- init: E = dY_L, strip0 = dZ_{L-1} = h * dY_L * mask_{L-1} ----
@@ -261,7 +308,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int sg = 0; sg < p.nseg; ++sg) {
           const int q = sg * 128 + row;
           const int yy = q / p.P, xq = q - yy * p.P;
-          if (yy < p.H && xq < p.W) {
+          if (active && yy < p.H && xq < p.W) {
             const int pixl = yy * p.W + xq;
             const uint32_t pos = (uint32_t)(q + p.P + 1);
             const float* src = p.dy + img_off + (long long)pixl * C;
@@ -316,7 +363,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               if (sg < p.nseg) {
                 const int q = sg * 128 + row;
                 const int yy = q / p.P, xq = q - yy * p.P;
-                if (yy < p.H && xq < p.W) {
+                if (active && yy < p.H && xq < p.W) {
                   const uint8_t* mp = mk_l + (long long)(yy * p.W + xq) * groups;
                   if (C == 16) mkreg[sg][0] = *reinterpret_cast<const uint16_t*>(mp);
                   else {
@@ -335,14 +382,14 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           // Every warp waits for the LAST segment's commit even when it owns no item of it: that gates
           // it to the MMA warp's progress, so no warp can arrive twice in one layer_done phase.
           if (sg < p.nseg && (NG > 1 || (sg & 1) == half || sg == p.nseg - 1)) {
-            mbar_wait(&acc_full[sg], lc & 1);
+            mbar_wait_sleep(&acc_full[sg], lc & 1);
             tc_fence_after_sync();
             if (threadIdx.x == 64 && lc == TL && sg == 0) tr.mark(6);
             if (threadIdx.x == 64 && lc == TL + 1 && sg == 0) tr.mark(9);
             if (threadIdx.x == 64 && lc == TL && sg == 2) tr.mark(7);
             const int q = sg * 128 + row;
             const int yy = q / p.P, xq = q - yy * p.P;
-            const bool valid = (yy < p.H) && (xq < p.W);
+            const bool valid = active && (yy < p.H) && (xq < p.W);
             const int pixl = yy * p.W + xq;
             const uint32_t pos = (uint32_t)(q + p.P + 1);
 #pragma unroll
@@ -462,6 +509,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (threadIdx.x == 64) tr.mark(11);
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
   if (threadIdx.x == 0) { tr.mark(12); tr.wall(15); }
 }

@@ -19,19 +19,22 @@ struct RateCase {
   uint32_t a_step, b_step;  // bytes added per MMA (cycled over `span` steps)
   int span;
   int nacc;                 // accumulators cycled through (N columns each)
+  uint32_t a_off;           // bytes added to the A start address (row-shifted taps of the conv kernels)
+  int commit_every;         // 0: never; k: tcgen05.commit to a scratch mbarrier after every k MMAs
 };
 
 template <int VARIANT, int BF16 = -1>
 __global__ void __launch_bounds__(128, 1) rate_kernel(RateCase c, int reps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_base_s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
   for (int i = threadIdx.x * 16; i < 192 * 1024; i += blockDim.x * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   const int warp = threadIdx.x / 32;
   if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
-  if (threadIdx.x == 32) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 32) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_mbar_init(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateCase c, int reps, long
     const bool leader = elect_one();
     const uint32_t b32 = smem_u32(base);
     const uint32_t idesc = make_instr_desc(c.bf16 ? FMT_BF16 : FMT_TF32, c.M, c.N, c.a_mn, c.b_mn);
-    const uint64_t da0 = make_smem_desc(b32, c.a_lbo, c.a_sbo, c.a_lt);
+    const uint64_t da0 = make_smem_desc(b32 + c.a_off, c.a_lbo, c.a_sbo, c.a_lt);
     const uint64_t db0 = make_smem_desc(b32 + 100 * 1024, c.b_lbo, c.b_sbo, c.b_lt);
     long long t0 = 0, t1 = 0, t2 = 0;
     for (int pass = 0; pass < 2; ++pass) {   // pass 0 warms up
@@ -76,12 +79,21 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateCase c, int reps, long
             dbs[j] = db0 + ((uint64_t)((j % c.span) * c.b_step) >> 4);
             dd[j] = tmem + (j % c.nacc) * c.N;
           }
+          if (c.span > 8) {   // long walks: descriptors computed on the fly
+            int sidx = 0;
+            for (int r = 0; r < reps; ++r) {
+              const uint64_t da = da0 + ((uint64_t)(sidx * c.a_step) >> 4), db = db0 + ((uint64_t)((sidx % 9) * c.b_step) >> 4);
+              umma_tf32(tmem, da, db, idesc, 1);
+              if (++sidx == c.span) sidx = 0;
+            }
+          } else
           for (int r = 0; r < reps; r += 8) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (BF16) umma_f16(dd[j], das[j], dbs[j], idesc, 1);
               else      umma_tf32(dd[j], das[j], dbs[j], idesc, 1);
             }
+            if (c.commit_every && ((r + 8) % c.commit_every) == 0) umma_commit(&bar2);
           }
         }
         __syncwarp();
@@ -129,6 +141,38 @@ int main(int argc, char** argv) {
         cases.push_back({nm, bf, 128, N, 0, 0, lt, lt, 16, (uint32_t)8 * rowb, 16, (uint32_t)8 * rowb, 32u, 32u, rowb / 32,
                          512 / N > 8 ? 8 : 512 / N});
       }
+  // ---- conv-kernel conditions: row-shifted A start (a tap shift is a whole number of position rows) and
+  //      ONE accumulator (every MMA of a segment accumulates into the same TMEM columns)
+  for (int rowb : {64, 128})
+    for (int N : {16, 32, 64})
+      for (int shift_rows : {0, 1})
+        for (int nacc : {1, 2, 4}) {
+          if (rowb == 64 && N != 16) continue;
+          if (rowb == 128 && N == 16) continue;
+          const uint32_t lt = rowb == 128 ? SWZ_128B : SWZ_64B;
+          char* nm = new char[96];
+          snprintf(nm, 96, "conv tf32 rowB=%3d N=%3d A shifted %d rows, %d accumulators", rowb, N, shift_rows, nacc);
+          cases.push_back({nm, 0, 128, N, 0, 0, lt, lt, 16, (uint32_t)8 * rowb, 16, (uint32_t)8 * rowb, 32u, 32u, rowb / 32, nacc,
+                           (uint32_t)(shift_rows * rowb), 0});
+        }
+  for (int N : {16, 32, 64, 128})
+    for (int ce : {8, 16, 32}) {
+      const int rowb = N == 16 ? 64 : 128;
+      const uint32_t lt = rowb == 128 ? SWZ_128B : SWZ_64B;
+      char* nm = new char[96];
+      snprintf(nm, 96, "commit tf32 rowB=%3d N=%3d commit every %2d MMAs", rowb, N, ce);
+      cases.push_back({nm, 0, 128, N, 0, 0, lt, lt, 16, (uint32_t)8 * rowb, 16, (uint32_t)8 * rowb, 32u, 32u, rowb / 32, 1, 0u, ce});
+    }
+  // ---- many distinct operand tiles (the conv kernels walk 9 taps x k-steps of A windows and weight tiles)
+  for (int N : {32, 64})
+    for (int mode = 0; mode < 3; ++mode) {
+      char* nm = new char[96];
+      snprintf(nm, 96, "walk tf32 rowB=128 N=%3d %s", N, mode == 0 ? "A walks 36 windows" : mode == 1 ? "B walks 36 tiles" : "A and B walk");
+      // A: +1 row and +1 k-step per MMA (160 B); B: next weight tile (N*128 B) every MMA
+      cases.push_back({nm, 0, 128, N, 0, 0, SWZ_128B, SWZ_128B, 16, 1024, 16, 1024, mode == 1 ? 32u : 160u,
+                       mode == 0 ? 32u : (uint32_t)(N * 128), mode == 1 ? 4 : 36, 1, 0u, 0});
+      if (mode == 1) cases.back().span = 36;
+    }
   // ---- MN-major tf32 (wgrad): 128B swizzle / 32B atoms, 32-channel chunks, SBO=512, LBO = chunk stride
   for (int N : {32, 64, 128, 256})
     for (int M : {64, 128}) {

@@ -7,8 +7,8 @@ import torch
 from differential_equations_resnet_b200 import _abi
 from differential_equations_resnet_b200.layers._base import ChainHandle
 
-NAMES = {1: "setup", 2: "mma:L4 start", 3: "mma:L4 w_full", 4: "mma:L4 issued", 5: "mma:L5 start", 6: "epi:L4 seg0 rdy",
-         7: "epi:L4 seg1 rdy", 8: "epi:L4 done", 9: "epi:L5 seg0 rdy", 10: "mma:end", 11: "epi:end", 12: "end"}
+NAMES = {1: "setup", 2: "mma:L4 start", 3: "mma:L4 w_full|wstall", 4: "mma:L4 issued", 5: "mma:L5 start", 6: "epi:L4 seg0 rdy",
+         7: "epi:L4 seg1 rdy", 8: "epi:L4 done", 9: "epi:L5 seg0 rdy", 10: "mma:end", 11: "epi:end", 12: "end", 13: "tma:L5 first issue", 14: "tma:L6 first issue"}
 
 
 def main():
