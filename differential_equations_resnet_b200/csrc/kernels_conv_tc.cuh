@@ -63,7 +63,7 @@ struct ConvTcCfg {
   static constexpr int NKB = C / KB;
   static constexpr int KS = ROWB / 32;                             // 32-byte k-steps per K-block
   static constexpr bool STRICT = MODE == MODE_STRICT;
-  static constexpr int NWARPS = STRICT ? 10 : 6;                   // TMA, MMA, 4 epilogue (+4 converter)
+  static constexpr int NWARPS = STRICT ? 14 : 10;                  // TMA, MMA, 8 epilogue (+4 converter)
 };
 
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
@@ -104,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (STRICT) tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_conv[i], 4); }
     for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -126,25 +126,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0;
+      uint32_t as_ = 0, aph = 0, ws = 0, wph = 0;   // ring positions kept incrementally (no integer division per entry)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n0 = (tile / p.tpi) * p.nimg;
         const int q0 = (tile % p.tpi) * T;
         const int row0 = q0 / p.P;  // first halo row of the strip (halo row r <-> image row r-1)
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
-          mbar_wait(&a_empty[s], ph ^ 1);
+          const uint32_t s = as_, ph = aph;
+          mbar_wait_sleep(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], p.a_bytes);
           tma_load_4d(smem + p.a_off + s * p.a_stride, &map_a, &a_full[s], kb * KB, -1, row0 - 1, n0);
-          ++ia;
+          if (++as_ == (uint32_t)p.sa) { as_ = 0; aph ^= 1; }
           for (int tg = 0; tg < 9; tg += p.tw) {
-            const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
-            mbar_wait(&w_empty[sw_], phw ^ 1);
+            const uint32_t sw_ = ws, phw = wph;
+            mbar_wait_sleep(&w_empty[sw_], phw ^ 1);
             mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
             uint8_t* wdst = smem + p.w_off + sw_ * p.w_stride;
             tma_load_3d(wdst, &map_w, &w_full[sw_], kb * KB, 0, tg);
             if (STRICT) tma_load_3d(wdst + p.w_bytes, &map_w_lo, &w_full[sw_], kb * KB, 0, tg);
-            ++iw;
+            if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
           }
         }
       }
@@ -164,22 +164,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t a_lo_units = p.a_lo_off >> 4, w_lo_units = p.w_bytes >> 4;
     const uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;               // one tap's weight tile
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
-    uint32_t ia = 0, iw = 0, it = 0;
+    uint32_t as_ = 0, aph_ = 0, ws = 0, wph = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int q0 = (tile % p.tpi) * T;
       const uint32_t off0_units = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
-      const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
+      const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(&acc_empty[as], aph ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tile = tmem_base + as * mt * ACCW;
       for (int kb = 0; kb < NKB; ++kb) {
-        const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
+        const uint32_t s = as_, ph = aph_;
         mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
         if (it == 0 && kb == 0 && lane == 0) tr.mark(2);
         const uint32_t a_units = ((smem_base + p.a_off + s * p.a_stride) >> 4) + off0_units;
         int alpha = 0, beta = 0;
         for (int tg = 0; tg < 9; tg += p.tw) {
-          const uint32_t sw_ = iw % p.sw, phw = (iw / p.sw) & 1;
+          const uint32_t sw_ = ws, phw = wph;
           mbar_wait(&w_full[sw_], phw);
           if (it == 0 && kb == 0 && tg == 0 && lane == 0) tr.mark(3);
           tc_fence_after_sync();
@@ -212,20 +212,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++beta == 3) { beta = 0; ++alpha; }
           }
           if (leader) umma_commit(&w_empty[sw_]);
-          ++iw;
+          if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
         }
         if (leader) umma_commit(&a_empty[s]);
-        ++ia;
+        if (++as_ == (uint32_t)p.sa) { as_ = 0; aph_ ^= 1; }
       }
       if (leader) umma_commit(&acc_full[as]);
       if (it == 0 && lane == 0) tr.mark(4);
       __syncwarp();
     }
     if (lane == 0) tr.mark(5);
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+  } else if (warp < 10) {
+    // ===================== epilogue warps 2..9: two warps per TMEM lane quarter =====================
+    // Work item = (segment, G-channel group); the items of a tile alternate between the two warps of a
+    // quarter.  Every global load of an item (residual input, skip) is issued before the TMEM wait.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
+    constexpr int G = C < 32 ? C : 32;        // channels per work item
+    constexpr int NGR = C / G;
     uint32_t it = 0;
     using IoT = typename std::conditional<MODE == MODE_BF16, __nv_bfloat16, float>::type;
     const IoT* in = reinterpret_cast<const IoT*>(p.in);
@@ -234,8 +239,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n0 = (tile / p.tpi) * p.nimg;
       const int q0 = (tile % p.tpi) * T;
-      const uint32_t as = it % acc_stages, aph = (it / acc_stages) & 1;
-      mbar_wait(&acc_full[as], aph);
+      const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait_sleep(&acc_full[as], aph);
       if (it == 0 && threadIdx.x == 64) tr.mark(6);
       tc_fence_after_sync();
       for (int sg = 0; sg < mt; ++sg) {
@@ -246,105 +251,140 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool valid = (n < p.N) && (y < p.H) && (xq < p.W);
         const long long pix = ((long long)n * p.H + y) * p.W + xq;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * ACCW;
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld_x16(taddr + c0, r);
-          if (STRICT) {
-            uint32_t r2[16];
-            tmem_ld_x16(taddr + C + c0, r2);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-          } else {
-            tmem_ld_wait();
+        for (int gi = 0; gi < NGR; ++gi) {
+          if (((sg * NGR + gi) & 1) != half) continue;
+          const int c0 = gi * G;
+          uint32_t r[G];
+          {
+            uint32_t t16[16];
+            tmem_ld_x16(taddr + c0, t16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = t16[j];
+            if (G == 32) {
+              uint32_t u16[16];
+              tmem_ld_x16(taddr + c0 + 16, u16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[16 + (j & 15)] = u16[j];
+            }
           }
+          uint32_t r2[STRICT ? G : 1];
+          if (STRICT) {
+            uint32_t t16[16];
+            tmem_ld_x16(taddr + C + c0, t16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r2[j] = t16[j];
+            if (G == 32) {
+              uint32_t u16[16];
+              tmem_ld_x16(taddr + C + c0 + 16, u16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r2[16 + (j & 15)] = u16[j];
+            }
+          }
+          // operands from global memory, all in flight before the TMEM wait
+          float xin[G], xsk[G], bs[G];
+          const bool has_in = in != nullptr, has_skip = skip != nullptr, has_bias = p.bias != nullptr;
           if (valid) {
-            float v[16];
+            if (MODE == MODE_BF16) {
+              if (has_in) {
+                const uint4* ip = reinterpret_cast<const uint4*>(in + pix * C + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = p.acc_scale * __uint_as_float(r[j]);
-            if (p.bias) {
+                for (int j = 0; j < G / 8; ++j) {
+                  const uint4 u = ip[j];
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+                  for (int e = 0; e < 4; ++e) {
+                    xin[8 * j + 2 * e] = __uint_as_float(w[e] << 16);
+                    xin[8 * j + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                  }
+                }
+              }
+              if (has_skip) {
+                const uint4* sp = reinterpret_cast<const uint4*>(skip + pix * C + c0);
+#pragma unroll
+                for (int j = 0; j < G / 8; ++j) {
+                  const uint4 u = sp[j];
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    xsk[8 * j + 2 * e] = __uint_as_float(w[e] << 16);
+                    xsk[8 * j + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                  }
+                }
+              }
+            } else {
+              if (has_in) {
+                const float4* ip = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + pix * C + c0);
+#pragma unroll
+                for (int j = 0; j < G / 4; ++j) {
+                  const float4 u = ip[j];
+                  xin[4 * j] = u.x; xin[4 * j + 1] = u.y; xin[4 * j + 2] = u.z; xin[4 * j + 3] = u.w;
+                }
+              }
+              if (has_skip) {
+                const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(skip) + pix * C + c0);
+#pragma unroll
+                for (int j = 0; j < G / 4; ++j) {
+                  const float4 u = sp[j];
+                  xsk[4 * j] = u.x; xsk[4 * j + 1] = u.y; xsk[4 * j + 2] = u.z; xsk[4 * j + 3] = u.w;
+                }
+              }
+            }
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < G / 4; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+              bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+            }
+          }
+          tmem_ld_wait();
+          if (valid) {
+            float v[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+              float a = __uint_as_float(r[j]);
+              if (STRICT) a += __uint_as_float(r2[j]);
+              v[j] = p.acc_scale * a;
+              if (has_bias) v[j] += bs[j];
             }
             if (p.z_out) {
               float4* zp = reinterpret_cast<float4*>(p.z_out + pix * C + c0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < G / 4; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (p.mask) {
               uint32_t bits = 0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
-              *reinterpret_cast<uint16_t*>(p.mask + pix * (C / 8) + c0 / 8) = static_cast<uint16_t>(bits);
+              for (int j = 0; j < G; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
+              if (G == 32) *reinterpret_cast<uint32_t*>(p.mask + pix * (C / 8) + c0 / 8) = bits;
+              else *reinterpret_cast<uint16_t*>(p.mask + pix * (C / 8) + c0 / 8) = static_cast<uint16_t>(bits);
             }
             if (out) {
-              if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-              }
-              if (p.scale_h) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = p.h * v[j];
+              for (int j = 0; j < G; ++j) {
+                if (p.relu) v[j] = fmaxf(v[j], 0.0f);
+                if (p.scale_h) v[j] = __fmul_rn(p.h, v[j]);      // Lambda(h*x): own rounding (two layers in the reference)
+                // c_in == 1 in the forward pass: plain add of x (the reference's add layer)
+                if (has_in) v[j] = fmaf(p.c_in, xin[j], v[j]);
+                if (has_skip) v[j] += xsk[j];
               }
               if (MODE == MODE_BF16) {
-                if (in) {
-                  const uint4* ip = reinterpret_cast<const uint4*>(in + pix * C + c0);
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const uint4 u = ip[j];
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      v[8 * j + 2 * e] += p.c_in * __uint_as_float(w[e] << 16);
-                      v[8 * j + 2 * e + 1] += p.c_in * __uint_as_float(w[e] & 0xFFFF0000u);
-                    }
-                  }
-                }
-                if (skip) {
-                  const uint4* sp = reinterpret_cast<const uint4*>(skip + pix * C + c0);
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const uint4 u = sp[j];
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      v[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
-                      v[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                    }
-                  }
-                }
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                  pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-                }
                 uint4* op = reinterpret_cast<uint4*>(out + pix * C + c0);
-                op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+                for (int j = 0; j < G / 8; ++j) {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                    pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  }
+                  op[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
               } else {
-                if (in) {
-                  const float4* ip = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + pix * C + c0);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float4 u = ip[j];
-                    // c_in == 1 in the forward pass: plain add of x (the reference's add layer)
-                    v[4 * j] = fmaf(p.c_in, u.x, v[4 * j]); v[4 * j + 1] = fmaf(p.c_in, u.y, v[4 * j + 1]);
-                    v[4 * j + 2] = fmaf(p.c_in, u.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(p.c_in, u.w, v[4 * j + 3]);
-                  }
-                }
-                if (skip) {
-                  const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(skip) + pix * C + c0);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float4 u = sp[j];
-                    v[4 * j] += u.x; v[4 * j + 1] += u.y; v[4 * j + 2] += u.z; v[4 * j + 3] += u.w;
-                  }
-                }
                 float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * C + c0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < G / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
             }
           }
@@ -357,14 +397,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (threadIdx.x == 64) tr.mark(8);
   } else {
-    // ===================== strict-mode converter warps 6..9 =====================
+    // ===================== strict-mode converter warps 10..13 =====================
     if (STRICT) {
-      const int ctid = threadIdx.x - 6 * 32;  // 0..127
+      const int ctid = threadIdx.x - 10 * 32;  // 0..127
       uint32_t ia = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < NKB; ++kb) {
           const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
-          mbar_wait(&a_full[s], ph);
+          mbar_wait_sleep(&a_full[s], ph);
           const uint4* src = reinterpret_cast<const uint4*>(smem + p.a_off + s * p.a_stride);
           uint4* dst = reinterpret_cast<uint4*>(smem + p.a_off + s * p.a_stride + p.a_lo_off);
           const int n16 = p.a_bytes / 16;

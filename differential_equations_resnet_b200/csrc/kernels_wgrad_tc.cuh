@@ -118,13 +118,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, rs = 0, rph = 0;   // ring position kept incrementally
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
         const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.KT;
         const int row0 = q0 / p.P;
         const int xc0 = p.pair ? 0 : -1;    // pair mode: the zero slots sit at the END of every row
-        const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        const uint32_t s = rs, ph = rph;
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
+        mbar_wait_sleep(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
         for (int c = 0; c < p.xchunks; ++c)
@@ -166,11 +167,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
     const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
-    uint32_t it = 0;
+    uint32_t it = 0, rs = 0, rph = 0;
     for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
       const int q0 = (tile % p.tpi) * p.KT;
       const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
-      const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+      const uint32_t s = rs, ph = rph;
+      if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
       mbar_wait(STRICT ? &conv[s] : &full[s], ph);
       if (it == 0 && lane == 0) tr.mark(2);
       tc_fence_after_sync();
@@ -256,12 +258,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
       const int per_chunk = (p.CH + 31) / 32;
-      uint32_t it = 0;
+      uint32_t it = 0, rs = 0, rph = 0;
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
         const int q0 = (tile % p.tpi) * p.KT;
         const int off0 = q0 - (q0 / p.P) * p.P;
-        const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-        mbar_wait(&full[s], ph);
+        const uint32_t s = rs, ph = rph;
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
+        mbar_wait_sleep(&full[s], ph);
         const uint8_t* dbase = smem + s * p.stage_stride + p.d_off;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -299,7 +302,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       }
     }
     if (threadIdx.x == 64) tr.mark(5);
-    mbar_wait(acc_full, 0);
+    mbar_wait_sleep(acc_full, 0);
     if (threadIdx.x == 64) tr.mark(6);
     tc_fence_after_sync();
     const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
