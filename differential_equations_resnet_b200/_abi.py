@@ -50,6 +50,15 @@ _SIGNATURES = {
     "b200ode_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_void_p]),
     "b200ode_increment": (c_int, [c_void_p, c_void_p]),
+    "b200ode_stem_fwd": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "b200ode_stem_wgrad": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_int, c_int, c_void_p]),
+    "b200ode_transition_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "b200ode_transition_dgrad": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "b200ode_transition_wgrad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "b200ode_head_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_int, c_void_p]),
     "b200ode_chain_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "b200ode_chain_create": (c_int, [c_int, c_int, c_float, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "b200ode_chain_destroy": (c_int, [c_void_p]),

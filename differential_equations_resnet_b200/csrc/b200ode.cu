@@ -17,6 +17,7 @@
 #include "kernels_basic.cuh"
 #include "kernels_conv_tc.cuh"
 #include "kernels_chain_tc.cuh"
+#include "kernels_glue.cuh"
 #include "kernels_wgrad_tc.cuh"
 
 using namespace b200ode;
@@ -92,7 +93,7 @@ struct Scratch {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-static Scratch g_scratch[2];
+static Scratch g_scratch[3];
 static std::mutex g_scratch_mu;
 static int get_scratch(int slot, size_t bytes, void** out) {
   std::lock_guard<std::mutex> lk(g_scratch_mu);
@@ -577,6 +578,10 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
         const double t = (load > mma ? load : mma) * (9 / TG) * (C / NT);
         if (t < best - 1e-9) { best = t; p.TG = TG; p.NT = NT; }
       }
+    if (getenv("B200ODE_WGRAD_TG") && getenv("B200ODE_WGRAD_NT")) {   // debug override of the tiling search
+      const int tg = atoi(getenv("B200ODE_WGRAD_TG")), nt = atoi(getenv("B200ODE_WGRAD_NT"));
+      if (tg * p.MB * nt * (strict ? 2 : 1) <= 512 && nt >= p.CH && nt <= C) { p.TG = tg; p.NT = nt; best = 0; }
+    }
     if (best > 1e29) return fail(B200ODE_ERR_UNSUPPORTED, "no wgrad tiling for C=%d", C);
     p.ntapgroups = 9 / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
   }
@@ -999,4 +1004,187 @@ extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const f
   if (N == 0) return 0;
   return run_wgrad_tc(MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params, grad_layer_stride, 0,
                       (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// stem / transition / head layers (kernels_glue.cuh)
+// ------------------------------------------------------------------------------------------------
+static int reduce_rows(const float* ws, int R, long long stride, long long n, float* out, cudaStream_t st);
+
+static GlueConv glue_geom(int N, int H, int W, int Cin, int Cout, int sh, int sw) {
+  GlueConv g;
+  g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.sh = sh; g.sw = sw;
+  g.Ho = (H + sh - 1) / sh; g.Wo = (W + sw - 1) / sw;
+  const int ph = (g.Ho - 1) * sh + 3 - H, pw = (g.Wo - 1) * sw + 3 - W;
+  g.pt = (ph > 0 ? ph : 0) / 2; g.pl = (pw > 0 ? pw : 0) / 2;   // TF SAME: pad_before = total // 2
+  return g;
+}
+
+extern "C" int b200ode_stem_fwd(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
+                                const float* kernel_hwio, const float* bias, float* out, int N, int H, int W, int Cin, int Cout,
+                                void* stream) {
+  if (!images || !kernel_hwio || !bias || !out) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (Cout % 4) return fail(B200ODE_ERR_UNSUPPORTED, "stem: filters must be a multiple of 4 (got %d)", Cout);
+  if (int rc = device_check()) return rc;
+  if (N == 0) return 0;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, 1, 1);
+  const long long total = (long long)N * H * W * (Cout / 4);
+  stem_fwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev,
+                                                                           normalize, kernel_hwio, bias, out);
+  LAUNCH_CHECK("stem_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_stem_wgrad(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
+                                  const float* out, const float* dout, float* dparams, int N, int H, int W, int Cin, int Cout,
+                                  void* stream) {
+  if (!images || !out || !dout || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (N == 0) return 0;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, 1, 1);
+  const int rows = 8, bands = (H + rows - 1) / rows;
+  const long long nout = 9LL * Cin * Cout + Cout;
+  float* ws = nullptr;
+  if (int rc = get_scratch(2, (size_t)N * bands * nout * sizeof(float), (void**)&ws)) return rc;
+  const size_t smem = ((size_t)rows * W * Cout + (size_t)(rows + 2) * (W + 2) * Cin) * sizeof(float);
+  if (smem > 48 * 1024) return fail(B200ODE_ERR_UNSUPPORTED, "stem_wgrad: image too wide (W=%d, filters=%d)", W, Cout);
+  stem_wgrad_partial<<<dim3(N, bands), 256, smem, (cudaStream_t)stream>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev,
+                                                                         normalize, out, dout, ws, rows);
+  LAUNCH_CHECK("stem_wgrad_partial");
+  return reduce_rows(ws, N * bands, nout, nout, dparams, (cudaStream_t)stream);
+}
+
+static int transition_check(int Cin, int Cout) {
+  if (Cin % 4 || Cout % 8) return fail(B200ODE_ERR_UNSUPPORTED, "transition: Cin %% 4 and Cout %% 8 must be 0 (got %d -> %d)", Cin, Cout);
+  if (Cout > 256 || 256 % Cout || Cin % (256 / Cout) || Cin / (256 / Cout) > 16)
+    return fail(B200ODE_ERR_UNSUPPORTED, "transition: unsupported channel pair %d -> %d", Cin, Cout);
+  return 0;
+}
+
+// reduction of per-block partials: 8 row lanes per output when there are many rows
+static int reduce_rows(const float* ws, int R, long long stride, long long n, float* out, cudaStream_t st) {
+  if (R >= 32 && (n * 8) % 32 == 0) {
+    reduce_rows_wide_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>(ws, R, stride, n, out);
+    LAUNCH_CHECK("reduce_rows_wide_kernel");
+  } else {
+    reduce_rows_kernel<<<blocks_for(n, 128), 128, 0, st>>>(ws, R, stride, n, out);
+    LAUNCH_CHECK("reduce_rows_kernel");
+  }
+  return 0;
+}
+
+#define GLUE_SMEM_LAUNCH(kern, grid, block, smem, st, ...)                                                       \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));             \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                                \
+  } while (0)
+
+extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                                      const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
+                                      int Cout, int stride_h, int stride_w, void* stream) {
+  if (!x || !main_kernel || !main_bias || !short_kernel || !short_bias || !out || !relu_mask) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (int rc = transition_check(Cin, Cout)) return rc;
+  if (int rc = device_check()) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  // bands of ~128 output pixels (4 per lane); each warp of a block owns one 8-channel slice
+  constexpr int COT = 8, PT = 4;
+  int orows = (128 + g.Wo - 1) / g.Wo;
+  if (orows > g.Ho) orows = g.Ho;
+  int G = Cout / COT < 4 ? Cout / COT : 4;
+  while ((Cout / COT) % G) --G;
+  size_t smem = 0;
+  for (; orows >= 1; orows >>= 1) {
+    smem = ((size_t)((orows - 1) * stride_h + 3) * W * (Cin + 4) + (size_t)G * 10 * Cin * COT) * sizeof(float);
+    if (smem <= 160 * 1024) break;
+  }
+  if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_fwd: rows too wide (W=%d, Cin=%d)", W, Cin);
+  const int bands = (g.Ho + orows - 1) / orows;
+  GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, PT>), dim3(N, bands, Cout / COT / G), 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
+  LAUNCH_CHECK("transition_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                                        const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                                        int stride_w, void* stream) {
+  if (!dout || !relu_mask || !main_kernel || !short_kernel || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (int rc = transition_check(Cin, Cout)) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  // band height: the staged output rows (dout + masked copy) and the weight slice must fit shared memory
+  constexpr int CIT = 8, PT = 4;
+  if (Cin % CIT) return fail(B200ODE_ERR_UNSUPPORTED, "transition_dgrad: Cin must be a multiple of %d (got %d)", CIT, Cin);
+  int rows = H < 16 ? H : 16;
+  size_t smem = 0;
+  for (; rows >= 1; rows >>= 1) {
+    const int nor = (rows - 1 + 2) / stride_h + 2;
+    smem = ((size_t)2 * nor * g.Wo * (Cout + 4) + (size_t)10 * CIT * Cout) * sizeof(float);
+    if (smem <= 160 * 1024) break;
+  }
+  if (rows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_dgrad: rows too wide (Wo=%d, Cout=%d)", g.Wo, Cout);
+  const int bands = (H + rows - 1) / rows;
+  GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, PT>), dim3(N, bands, Cin / CIT), 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
+  LAUNCH_CHECK("transition_dgrad_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
+                                        int W, int Cin, int Cout, int stride_h, int stride_w, void* stream) {
+  if (!x || !dout || !relu_mask || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (int rc = transition_check(Cin, Cout)) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  const long long nout = 9LL * Cin * Cout + Cout + (long long)Cin * Cout + Cout;
+  const int ntile = (Cin / 4) * (Cout / 4);
+  if (ntile > 256 || 256 % ntile) return fail(B200ODE_ERR_UNSUPPORTED, "transition_wgrad: unsupported channel pair %d -> %d", Cin, Cout);
+  const int ngroups = 256 / ntile > 10 ? 10 : 256 / ntile;
+  const int tpg = (10 + ngroups - 1) / ngroups;
+  // band of output rows per block: dout + masked copy + the input rows they touch
+  int orows = g.Ho < 4 ? g.Ho : 4;
+  size_t smem = 0;
+  for (; orows >= 1; orows >>= 1) {
+    const int nir = (orows - 1) * stride_h + 3;
+    smem = ((size_t)2 * orows * g.Wo * Cout + (size_t)nir * W * Cin) * sizeof(float);
+    if (smem <= 100 * 1024) break;
+  }
+  if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_wgrad: rows too wide (W=%d)", W);
+  const int bands = (g.Ho + orows - 1) / orows;
+  float* ws = nullptr;
+  if (int rc = get_scratch(2, (size_t)N * bands * nout * sizeof(float), (void**)&ws)) return rc;
+  switch (tpg) {
+    case 1: GLUE_SMEM_LAUNCH(transition_wgrad_partial<1>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
+    case 2: GLUE_SMEM_LAUNCH(transition_wgrad_partial<2>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
+    case 3: case 4: case 5: GLUE_SMEM_LAUNCH(transition_wgrad_partial<5>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
+    default: GLUE_SMEM_LAUNCH(transition_wgrad_partial<10>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
+  }
+  LAUNCH_CHECK("transition_wgrad_partial");
+  return reduce_rows(ws, N * bands, nout, nout, dparams, st);
+}
+
+extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
+                                    float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* stream) {
+  if (!x || !fc_kernel || !fc_bias || !onehot || !loss) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (K > 32 || K > C || C > 1024 || (C % 32)) return fail(B200ODE_ERR_UNSUPPORTED, "head: need classes <= 32 <= channels (multiple of 32, <= 1024)");
+  if (int rc = device_check()) return rc;
+  if (N == 0) return 0;
+  const long long nout = (long long)C * K + K + 1;
+  float* ws = nullptr;
+  if (int rc = get_scratch(2, (size_t)N * nout * sizeof(float), (void**)&ws)) return rc;
+  head_kernel<<<N, C, (C + 33) * sizeof(float), (cudaStream_t)stream>>>(x, HW, C, K, fc_kernel, fc_bias, onehot, eps, N, probs, dx, ws);
+  LAUNCH_CHECK("head_kernel");
+  if (dparams) {
+    reduce_rows_kernel<<<blocks_for(nout - 1, 128), 128, 0, (cudaStream_t)stream>>>(ws, N, nout, nout - 1, dparams);
+    LAUNCH_CHECK("reduce_rows_kernel");
+  }
+  reduce_rows_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws + (nout - 1), N, nout, 1, loss);
+  LAUNCH_CHECK("reduce_rows_kernel");
+  return 0;
 }

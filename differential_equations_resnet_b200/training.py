@@ -187,7 +187,7 @@ class EulerNet:
     precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1, persistent=True):
+                 world_size=1, persistent=True, native_glue=True):
         _abi.require_device()
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
         self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
@@ -260,6 +260,8 @@ class EulerNet:
         self._leaf_grad_views = [self.grad[a:a + math.prod(shape)].view(shape) for a, shape in self.torch_params.values()]
         self._graph = None
         self._static_in = None
+        self.native_glue = native_glue
+        self._nb = None
 
     # ----------------------------------------------------------------------------------------------
     def forward(self, images):
@@ -293,7 +295,116 @@ class EulerNet:
         p = torch.clamp(p, eps, 1.0 - eps)
         return -(onehot * torch.log(p)).sum(dim=-1).mean()
 
+    # ----------------------------------------------------------------------------------------------
+    # all-native step: stem / transition / head kernels of libb200ode (include/b200ode.h) around the
+    # persistent Euler chains; no torch autograd, ~25 launches per step
+    # ----------------------------------------------------------------------------------------------
+    def _native_plan(self, shape, device):
+        """Per-input-shape buffers of the native path, or None when some layer cannot take it."""
+        if self._nb is not None and self._nb["shape"] == tuple(shape):
+            return self._nb
+        spec = self.spec
+        N, H, W, Cin = shape
+        ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32
+        plan, h, w, c = [], H, W, Cin
+        for seg in self.segments:
+            if not ok:
+                break
+            if seg[0] == "stem":
+                _, ci, co, st, name = seg
+                ok = ok and tuple(st) == (1, 1) and co % 4 == 0 and ci == c
+                plan.append(dict(kind="stem", name=name, ci=ci, co=co, h=h, w=w,
+                                 out=torch.empty((N, h, w, co), dtype=torch.float32, device=device)))
+                c = co
+            elif seg[0] == "transition":
+                _, ci, co, st, name = seg
+                ho, wo = -(-h // st[0]), -(-w // st[1])
+                lanes = 256 // co if co and 256 % co == 0 else 0
+                ok = ok and ci % 4 == 0 and co % 8 == 0 and lanes > 0 and ci % lanes == 0 and ci // lanes <= 16
+                plan.append(dict(kind="transition", name=name, ci=ci, co=co, h=h, w=w, st=tuple(st),
+                                 out=torch.empty((N, ho, wo, co), dtype=torch.float32, device=device),
+                                 mask=torch.empty((N, ho, wo, co // 8), dtype=torch.uint8, device=device),
+                                 dx=torch.empty((N, h, w, ci), dtype=torch.float32, device=device)))
+                h, w, c = ho, wo, co
+            else:
+                ch = seg[1]
+                ok = ok and ch.use_fused((N, h, w, c))
+                if ok:
+                    ch.ensure_fused_buffers((N, h, w, c), device)
+                plan.append(dict(kind="chain", chain=ch, h=h, w=w, c=c))
+        ok = ok and c % 32 == 0 and c <= 1024 and spec.num_classes <= c
+        if not ok:
+            self._nb = dict(shape=tuple(shape), plan=None)
+            return self._nb
+        self._nb = dict(shape=tuple(shape), plan=plan, hw=h * w, c=c,
+                        head_dx=torch.empty((N, h, w, c), dtype=torch.float32, device=device),
+                        loss=torch.zeros(1, dtype=torch.float32, device=device))
+        return self._nb
+
+    def _off(self, name):
+        return self.torch_params[name][0]
+
+    def _fwd_bwd_native(self, images, onehot, nb):
+        lib, st, spec = _abi.lib(), _stream_ptr(), self.spec
+        N, H, W, _ = images.shape
+        is_u8 = images.dtype == torch.uint8
+        images = images.contiguous() if is_u8 else images.contiguous().float()
+        onehot = onehot.contiguous().float()
+        norm = spec.subtract_mean is not None or spec.divide_by_stddev is not None
+        sub = float(spec.subtract_mean or 0.0)
+        div = float(spec.divide_by_stddev if spec.divide_by_stddev is not None else 1.0)
+        th, gr = self.theta, self.grad
+        cur = images
+        for e in nb["plan"]:
+            if e["kind"] == "stem":
+                ko = self._off(e["name"] + "/kernel")
+                _abi.check(lib.b200ode_stem_fwd(_ptr(cur), int(is_u8), sub, div, int(norm), _ptr(th[ko:]),
+                                                _ptr(th[self._off(e["name"] + "/bias"):]), _ptr(e["out"]), N, e["h"], e["w"],
+                                                e["ci"], e["co"], st))
+                cur = e["out"]
+            elif e["kind"] == "transition":
+                nm = e["name"]
+                e["x"] = cur
+                _abi.check(lib.b200ode_transition_fwd(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                      _ptr(th[self._off(nm + "2/bias"):]), _ptr(th[self._off(nm + "1/kernel"):]),
+                                                      _ptr(th[self._off(nm + "1/bias"):]), _ptr(e["out"]), _ptr(e["mask"]),
+                                                      N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                cur = e["out"]
+            else:
+                ch = e["chain"]
+                ch.x0 = cur
+                ch.fused.pack(self.theta_euler[ch.offset:], ch.np_layer)
+                ch.fused.forward(cur, spec.h, acts=ch.f_acts, masks=ch.f_masks)
+                cur = ch.f_acts[ch.n - 1]
+        fo = self._off("fc/kernel")
+        _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
+                                            _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
+                                            spec.num_classes, st))
+        d = nb["head_dx"]
+        for e in reversed(nb["plan"]):
+            if e["kind"] == "chain":
+                ch = e["chain"]
+                ch.fused.dgrad(d, ch.f_masks, ch.f_dz, ch.f_dx, spec.h)
+                ch.fused.wgrad(ch.x0, ch.f_acts, ch.f_dz, self.grad_euler[ch.offset:], ch.np_layer)
+                d = ch.f_dx
+            elif e["kind"] == "transition":
+                nm = e["name"]
+                _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
+                                                        N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                _abi.check(lib.b200ode_transition_dgrad(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                        _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
+                                                        e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                d = e["dx"]
+            else:
+                _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
+                                                  _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
+                                                  e["co"], st))
+        return nb["loss"].view(())
+
     def _fwd_bwd(self, images, onehot):
+        nb = self._native_plan(images.shape, images.device)
+        if nb["plan"] is not None:
+            return self._fwd_bwd_native(images, onehot, nb)
         # strict mode: the few torch-op layers (stem / transitions / head) must not use TF32 either
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "strict"):
             return self._fwd_bwd_inner(images, onehot)

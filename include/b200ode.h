@@ -169,6 +169,35 @@ int b200ode_chain_dgrad(b200ode_chain_t* chain, const float* dy, const uint8_t* 
 int b200ode_chain_wgrad(b200ode_chain_t* chain, const float* x0, const float* acts, const float* dz_all,
                         float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream);
 
+/* ---- stem / transition / head of the single-block ResNet, fp32 CUDA-core kernels.
+ *      All tensors NHWC fp32 (images: uint8 or fp32); kernels in the Keras HWIO layout. ---- */
+/* input Lambda layers + conv1 + relu (models/tfkeras_resnets.py:555-572), 3x3, strides (1,1):
+ * out = relu(conv_SAME((images - subtract_mean) / divide_by_stddev) + bias)   [normalize == 0: raw images] */
+int b200ode_stem_fwd(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
+                     const float* kernel_hwio, const float* bias, float* out, int N, int H, int W, int Cin, int Cout,
+                     void* stream);
+/* dparams = [dkernel (3,3,Cin,Cout) | dbias (Cout)] from dout = dL/dout and the saved stem output */
+int b200ode_stem_wgrad(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
+                       const float* out, const float* dout, float* dparams, int N, int H, int W, int Cin, int Cout,
+                       void* stream);
+/* single_layer_conv_block (models/tfkeras_resnets.py:204-269): out = relu(conv3x3_s(x)+bm) + conv1x1_s(x)+bs,
+ * TF SAME padding (pad_before = total/2); relu_mask: 1 bit per output element ((main > 0), as euler_fwd). */
+int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                           const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin, int Cout,
+                           int stride_h, int stride_w, void* stream);
+int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                             const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                             int stride_w, void* stream);
+/* dparams = [dmain_kernel (3,3,Cin,Cout) | dmain_bias | dshort_kernel (Cin,Cout) | dshort_bias] */
+int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H, int W,
+                             int Cin, int Cout, int stride_h, int stride_w, void* stream);
+/* GlobalAveragePooling2D -> Dense(softmax) (models/tfkeras_resnets.py:595-597) -> mean
+ * K.categorical_crossentropy(onehot, probs) with clipping eps (training/training.py:295), forward and
+ * backward in one call: loss (1 float), dx = dL/dx [N,HW,C] (nullable), dparams = [dfc_kernel (C,K) | dfc_bias]
+ * (nullable), probs [N,K] (nullable). */
+int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
+                         float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* stream);
+
 /* test hook: number of kernel launches issued by this library in this process */
 int64_t b200ode_launch_count(void);
 /* debug hook: device buffer of uint64 [ctas][16] that the tensor-core kernels fill with a per-CTA

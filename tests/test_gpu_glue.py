@@ -1,0 +1,113 @@
+"""GPU parity of the stem / transition / head kernels (b200ode_stem_*, b200ode_transition_*,
+b200ode_head_fwd_bwd; reference: models/tfkeras_resnets.py:204-269, 555-572, 595-597 and
+training/training.py:295) against the O1 oracle's torch-CPU fp32 ops with autograd.
+Tolerance: fp32 FMA kernels vs fp32 oneDNN: 1e-5 relative (summation order only)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import antisym_torch as O1
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def _lib():
+    from differential_equations_resnet_b200 import _abi
+    return _abi, _abi.lib()
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("u8", [True, False])
+def test_stem_matches_oracle(u8):
+    _abi, lib = _lib()
+    N, H, W, Ci, Co = 5, 12, 10, 3, 16
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (N, H, W, Ci), generator=g, dtype=torch.uint8)
+    if not u8:
+        img = img.float() + 0.25
+    K = (torch.randn((3, 3, Ci, Co), generator=g) * 0.2).requires_grad_(True)
+    b = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    dout = torch.randn((N, H, W, Co), generator=g)
+    x = (img.float() - 127.5) / 127.5
+    ref = torch.relu(O1.conv2d_same_nhwc(x, K, (1, 1)) + b)
+    ref.backward(dout)
+    out = torch.empty((N, H, W, Co), device="cuda")
+    imgd, Kd, bd, dd = img.cuda(), K.detach().cuda(), b.detach().cuda(), dout.cuda()   # keep the device copies alive
+    _abi.check(lib.b200ode_stem_fwd(P(imgd), int(u8), 127.5, 127.5, 1, P(Kd), P(bd), P(out), N, H, W, Ci, Co, None))
+    dp = torch.empty(27 * Co + Co, device="cuda")
+    _abi.check(lib.b200ode_stem_wgrad(P(imgd), int(u8), 127.5, 127.5, 1, P(out), P(dd), P(dp), N, H, W, Ci, Co, None))
+    torch.cuda.synchronize()
+    assert rel(out, ref) <= 1e-5
+    assert rel(dp[:27 * Co].view(3, 3, Ci, Co), K.grad) <= 1e-5
+    assert rel(dp[27 * Co:], b.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("Ci,Co,H,W,st", [(16, 32, 32, 32, (2, 2)), (32, 64, 16, 16, (2, 2)), (16, 32, 9, 11, (2, 2)),
+                                          (32, 64, 8, 8, (1, 1))])
+def test_transition_matches_oracle(Ci, Co, H, W, st):
+    _abi, lib = _lib()
+    N = 3
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((N, H, W, Ci), generator=g).requires_grad_(True)
+    Wm = (torch.randn((3, 3, Ci, Co), generator=g) * 0.1).requires_grad_(True)
+    bm = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    Ws = (torch.randn((1, 1, Ci, Co), generator=g) * 0.1).requires_grad_(True)
+    bs = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
+    main = O1.conv2d_same_nhwc(x, Wm, st) + bm
+    ref = torch.relu(main) + O1.conv2d_same_nhwc(x, Ws, st) + bs
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    out = torch.empty((N, Ho, Wo, Co), device="cuda")
+    mask = torch.empty((N, Ho, Wo, Co // 8), dtype=torch.uint8, device="cuda")
+    xd, Wmd, Wsd, bmd, bsd = x.detach().cuda(), Wm.detach().cuda(), Ws.detach().cuda(), bm.detach().cuda(), bs.detach().cuda()
+    _abi.check(lib.b200ode_transition_fwd(P(xd), P(Wmd), P(bmd), P(Wsd), P(bsd), P(out), P(mask),
+                                          N, H, W, Ci, Co, st[0], st[1], None))
+    dx = torch.empty((N, H, W, Ci), device="cuda")
+    dd = dout.cuda()
+    _abi.check(lib.b200ode_transition_dgrad(P(dd), P(mask), P(Wmd), P(Wsd), P(dx), N, H, W, Ci, Co, st[0], st[1], None))
+    nm = 9 * Ci * Co
+    dp = torch.empty(nm + Co + Ci * Co + Co, device="cuda")
+    _abi.check(lib.b200ode_transition_wgrad(P(xd), P(dd), P(mask), P(dp), N, H, W, Ci, Co, st[0], st[1], None))
+    torch.cuda.synchronize()
+    assert rel(out, ref) <= 1e-5
+    bits = np.unpackbits(mask.cpu().numpy(), axis=-1, bitorder="little").astype(bool)
+    assert np.array_equal(bits, (main.detach().numpy() > 0))
+    assert rel(dx, x.grad) <= 1e-5
+    assert rel(dp[:nm].view(3, 3, Ci, Co), Wm.grad) <= 1e-5
+    assert rel(dp[nm:nm + Co], bm.grad) <= 1e-5
+    assert rel(dp[nm + Co:nm + Co + Ci * Co].view(1, 1, Ci, Co), Ws.grad) <= 1e-5
+    assert rel(dp[nm + Co + Ci * Co:], bs.grad) <= 1e-5
+
+
+def test_head_matches_oracle():
+    _abi, lib = _lib()
+    N, H, W, C, K = 7, 8, 8, 64, 10
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((N, H, W, C), generator=g).requires_grad_(True)
+    Wfc = (torch.randn((C, K), generator=g) * 0.5).requires_grad_(True)
+    bfc = (torch.randn(K, generator=g) * 0.1).requires_grad_(True)
+    onehot = torch.nn.functional.one_hot(torch.randint(0, K, (N,), generator=g), K).float()
+    probs_ref = torch.softmax(x.mean(dim=(1, 2)) @ Wfc + bfc, dim=-1)
+    loss_ref = O1.loss_fn(probs_ref, onehot)
+    loss_ref.backward()
+    probs = torch.empty((N, K), device="cuda"); loss = torch.zeros(1, device="cuda")
+    dx = torch.empty((N, H, W, C), device="cuda"); dp = torch.empty(C * K + K, device="cuda")
+    xd, Wd, bd, od = x.detach().cuda(), Wfc.detach().cuda(), bfc.detach().cuda(), onehot.cuda()   # keep alive
+    _abi.check(lib.b200ode_head_fwd_bwd(P(xd), P(Wd), P(bd), P(od), 1e-7, P(probs), P(loss), P(dx), P(dp), N, H * W, C, K, None))
+    torch.cuda.synchronize()
+    assert rel(probs, probs_ref) <= 1e-5
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel(dx, x.grad) <= 1e-4
+    assert rel(dp[:C * K].view(C, K), Wfc.grad) <= 1e-4
+    assert rel(dp[C * K:], bfc.grad) <= 1e-4
