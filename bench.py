@@ -310,11 +310,23 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         recs = kernel_microbench(torch, args.precision, B)
         dom = max(recs, key=lambda r: r["us"] * r["launches_per_step"])
+        # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+        traffic, ncu_extra = None, {}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            rec = tj["kernels"].get("%s|%d" % (dom["kernel"], dom["shape"][3]))
+            if rec and B == BATCH_PER_GPU:
+                traffic = rec["dram_bytes_per_launch"]
+                ncu_extra = {"ncu_tensor_pipe_active_pct": rec["tensor_pipe_active_pct"],
+                             "ncu_dram_throughput_pct": rec["dram_throughput_pct"], "ncu_source": "profiles/r01_ncu_traffic.json"}
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dom["GBps"] / hbm_peak, "traffic": None, "kernel": dom["kernel"], "shape": dom["shape"],
+                    "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "kernel": dom["kernel"], "shape": dom["shape"],
                     "us_per_launch": dom["us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                     "peak_source": peak_src,
                     "share_of_step": dom["us"] * dom["launches_per_step"] / (1e3 * ms_dev / K)}
+        roofline.update(ncu_extra)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
