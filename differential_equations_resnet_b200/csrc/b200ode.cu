@@ -583,7 +583,9 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
       if (tg * p.MB * nt * (strict ? 2 : 1) <= 512 && nt >= p.CH && nt <= C) { p.TG = tg; p.NT = nt; best = 0; }
     }
     if (best > 1e29) return fail(B200ODE_ERR_UNSUPPORTED, "no wgrad tiling for C=%d", C);
-    p.ntapgroups = 9 / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
+    // five taps per CTA when TMEM allows: two tap groups (5 + 4) re-read the strips twice instead of three times
+    if (p.TG == 3 && 5 * p.MB * p.NT * (strict ? 2 : 1) <= 512) p.TG = 5;
+    p.ntapgroups = (9 + p.TG - 1) / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
   }
   const int ngroups = p.ntapgroups * p.nngroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;

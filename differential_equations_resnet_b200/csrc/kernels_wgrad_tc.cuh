@@ -19,6 +19,8 @@
 
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "kernels_conv_tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -196,14 +198,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           }
         }
       } else if (nent <= 16) {
-        // general tiling: per-entry A offsets held in registers (static unroll), no smem reads in the loop
-        for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
-          const uint64_t dsc_b = mk(du, lbo_b);
-          const uint64_t dsc_b_lo = mk(du + lo_d, lbo_b);
-          const uint32_t accum = (it | ks) != 0;
+        // general tiling: per-entry A offsets held in registers; the entry count is made a compile-time
+        // constant (switch below) so the MMAs of a k-step form one straight-line stream -- with a guarded
+        // 16-way unroll the dependent IMAD/R2UR chain per MMA cost ~100 cycles (3x the hardware rate)
+        auto run = [&](auto ne_c) {
+          constexpr int NE = decltype(ne_c)::value;
+#pragma unroll 2
+          for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
+            const uint64_t dsc_b = mk(du, lbo_b);
+            const uint64_t dsc_b_lo = mk(du + lo_d, lbo_b);
+            const uint32_t accum = (it | ks) != 0;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (e < nent) {
+            for (int e = 0; e < NE; ++e) {
               const uint32_t au = xu + entr[e];
               const uint32_t d_tmem = tmem_base + e * ACCW;
               const uint64_t dsc_a = mk(au, lbo_a);
@@ -219,6 +225,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
               }
             }
           }
+        };
+        switch (nent) {
+          case 1: run(std::integral_constant<int, 1>{}); break;
+          case 2: run(std::integral_constant<int, 2>{}); break;
+          case 3: run(std::integral_constant<int, 3>{}); break;
+          case 4: run(std::integral_constant<int, 4>{}); break;
+          case 5: run(std::integral_constant<int, 5>{}); break;
+          case 6: run(std::integral_constant<int, 6>{}); break;
+          case 9: run(std::integral_constant<int, 9>{}); break;
+          case 10: run(std::integral_constant<int, 10>{}); break;
+          default:   // entry counts the planner does not produce today: generic loop
+            for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
+              const uint64_t dsc_b = mk(du, lbo_b);
+              const uint32_t accum = (it | ks) != 0;
+              for (int e = 0; e < nent; ++e) {
+                const uint32_t au = xu + ent[e];
+                const uint64_t dsc_a = mk(au, lbo_a);
+                if (leader) {
+                  if (BF16) umma_f16(tmem_base + e * ACCW, dsc_a, dsc_b, idesc, accum);
+                  else {
+                    umma_tf32(tmem_base + e * ACCW, dsc_a, dsc_b, idesc, accum);
+                    if (STRICT) {
+                      umma_tf32(tmem_base + e * ACCW + p.NT, dsc_a, mk(du + lo_d, lbo_b), idesc, accum);
+                      umma_tf32(tmem_base + e * ACCW + p.NT, mk(au + lo_x, lbo_a), dsc_b, idesc, 1);
+                    }
+                  }
+                }
+              }
+            }
+            break;
         }
       } else
       for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
