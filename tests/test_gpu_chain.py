@@ -116,9 +116,12 @@ def test_chain_equals_per_layer_kernels(C, H, W):
     assert torch.equal(dx, d)
 
 
-def test_chain_long_horizon_shared_weights():
-    """BASELINE cfg5 shape: one block applied n times with shared weights (n_layers == 1, n_steps = n)."""
-    C, N, H, W, h, gamma, n = 16, 8, 32, 32, 0.01, -0.1, 200
+@pytest.mark.parametrize("C,H,W,h,gamma,n", [(16, 32, 32, 0.01, -0.1, 200), (16, 32, 32, 0.125, 0.0, 1000),
+                                             (64, 8, 8, 0.01, -0.1, 1000)])
+def test_chain_long_horizon_shared_weights(C, H, W, h, gamma, n):
+    """BASELINE cfg5: one block applied n times with shared weights (n_layers == 1, n_steps = n), ONE launch.
+    Reports the free-running norm drift ratio against the float64 oracle."""
+    N = 8
     ch, flats, theta = _setup(C, 1, gamma, seed=5)
     g = torch.Generator().manual_seed(1)
     x = torch.randn((N, H, W, C), generator=g)
@@ -129,7 +132,17 @@ def test_chain_long_horizon_shared_weights():
     cur = x.numpy().astype(np.float64)
     for _ in range(n):
         cur, _ = O0.euler_step_fwd(cur, K, flats[0, -C:].astype(np.float64), h)
-    assert rel(y.cpu().numpy(), cur) <= 2e-3
+    err = rel(y.cpu().numpy(), cur)
+    print("cfg5 C=%d h=%g gamma=%g n=%d: |x_n| oracle %.4e gpu %.4e rel err %.2e" % (
+        C, h, gamma, n, np.linalg.norm(cur), float(y.double().norm()), err))
+    # free-running norm drift ratio (BASELINE cfg5): always; state error: where the dynamics are contractive
+    # (gamma < 0, small h).  With gamma = 0 and h = 0.125 the state grows 1e3-fold over 1000 steps and the
+    # per-step tf32 error (~3e-4 of the conv term) is amplified with it: the states decorrelate (~1e-1)
+    # while the norms still agree to < 1 %.
+    drift = float(y.double().norm()) / np.linalg.norm(cur)
+    assert abs(drift - 1.0) <= 2e-2, drift
+    if gamma < 0 and h <= 0.01:
+        assert err <= 2e-3
 
 
 def test_chain_refuses_what_does_not_fit():
