@@ -71,9 +71,15 @@ __global__ void stem_wgrad_partial(GlueConv g, const void* __restrict__ img, int
   const int PW = g.W + 2;
   float* dz = sm;                                   // [rows*W][Cout]
   float* xin = sm + rows * g.W * g.Cout;            // [rows+2][W+2][Cin]
-  for (int i = threadIdx.x; i < nr * g.W * g.Cout; i += blockDim.x) {
-    const long long op = ((long long)n * g.H + y0) * g.W * g.Cout + i;
-    dz[i] = out[op] > 0.0f ? dout[op] : 0.0f;
+  {
+    const float4* o4 = reinterpret_cast<const float4*>(out + ((long long)n * g.H + y0) * g.W * g.Cout);
+    const float4* d4 = reinterpret_cast<const float4*>(dout + ((long long)n * g.H + y0) * g.W * g.Cout);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nr * g.W * g.Cout / 4; i += blockDim.x) {
+      const float4 o = o4[i], d = d4[i];
+      reinterpret_cast<float4*>(dz)[i] = make_float4(o.x > 0.0f ? d.x : 0.0f, o.y > 0.0f ? d.y : 0.0f,
+                                                     o.z > 0.0f ? d.z : 0.0f, o.w > 0.0f ? d.w : 0.0f);
+    }
   }
   for (int i = threadIdx.x; i < (nr + 2) * PW * g.Cin; i += blockDim.x) {
     const int ci = i % g.Cin, px = (i / g.Cin) % PW - 1, py = i / (g.Cin * PW) + y0 - 1;
@@ -136,11 +142,13 @@ __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, c
   const int PS = g.Cin + 4;                          // padded pixel stride (floats)
   float* xs = sm;
   float* wsm = sm + ((orows - 1) * g.sh + 3) * g.W * PS + warp * 10 * g.Cin * COT;    // this warp's weight slice
+#pragma unroll 4
   for (int i = threadIdx.x; i < (i1 - i0) * g.W * (g.Cin / 4); i += blockDim.x) {
     const int c4 = i % (g.Cin / 4), pix = i / (g.Cin / 4);
     *reinterpret_cast<float4*>(xs + pix * PS + c4 * 4) =
         *reinterpret_cast<const float4*>(x + (((long long)n * g.H + i0) * g.W + pix) * g.Cin + c4 * 4);
   }
+#pragma unroll 4
   for (int i = lane; i < 10 * g.Cin * (COT / 4); i += 32) {
     const int j = i % (COT / 4), ci = (i / (COT / 4)) % g.Cin, t = i / ((COT / 4) * g.Cin);
     const float* src = t == 9 ? Ws + (long long)ci * g.Cout : Wm + (long long)(t * g.Cin + ci) * g.Cout;
@@ -236,13 +244,20 @@ __global__ void transition_dgrad_kernel(GlueConv g, const float* __restrict__ do
   float* dO = sm;                                    // [nor*Wo][Cout+4]
   float* dM = sm + (long long)nor_max * g.Wo * PS;   // masked
   float* wsm = dM + (long long)nor_max * g.Wo * PS;  // [10][CIT][Cout]
-  for (int i = threadIdx.x; i < nor * g.Wo * g.Cout; i += blockDim.x) {
-    const long long op = ((long long)n * g.Ho + o0) * g.Wo * g.Cout + i;
-    const float d = dout[op];
-    const int si = (i / g.Cout) * PS + i % g.Cout;
-    dO[si] = d;
-    dM[si] = (mask[op >> 3] >> (op & 7)) & 1u ? d : 0.0f;      // Cout % 8 == 0: bit index = element index
+  {
+    const long long base = ((long long)n * g.Ho + o0) * g.Wo * g.Cout;       // multiple of 8 (Cout % 8 == 0)
+    const float4* d4 = reinterpret_cast<const float4*>(dout + base);
+#pragma unroll 4
+    for (int i4 = threadIdx.x; i4 < nor * g.Wo * g.Cout / 4; i4 += blockDim.x) {
+      const int i = 4 * i4;
+      const float4 d = d4[i4];
+      const uint32_t mb = mask[(base + i) >> 3] >> (i & 4);                  // bit index = element index
+      const int si = (i / g.Cout) * PS + i % g.Cout;
+      *reinterpret_cast<float4*>(dO + si) = d;
+      *reinterpret_cast<float4*>(dM + si) = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
+    }
   }
+#pragma unroll 4
   for (int i = threadIdx.x; i < 10 * CIT * (g.Cout / 4); i += blockDim.x) {
     const int c4 = i % (g.Cout / 4), k = (i / (g.Cout / 4)) % CIT, t = i / ((g.Cout / 4) * CIT);
     const float* src = t == 9 ? Ws + (long long)(ci0 + k) * g.Cout : Wm + (long long)(t * g.Cin + ci0 + k) * g.Cout;
@@ -333,12 +348,18 @@ __global__ void transition_wgrad_partial(GlueConv g, const float* __restrict__ x
   float* dO = sm;                                    // [nor*Wo][Cout]
   float* dM = dO + orows * g.Wo * g.Cout;
   float* xs = dM + orows * g.Wo * g.Cout;            // [nir][W][Cin]
-  for (int i = threadIdx.x; i < nor * g.Wo * g.Cout; i += blockDim.x) {
-    const long long op = ((long long)n * g.Ho + o0) * g.Wo * g.Cout + i;
-    const float d = dout[op];
-    dO[i] = d;
-    dM[i] = (mask[op >> 3] >> (op & 7)) & 1u ? d : 0.0f;
+  {
+    const long long base = ((long long)n * g.Ho + o0) * g.Wo * g.Cout;
+    const float4* d4 = reinterpret_cast<const float4*>(dout + base);
+#pragma unroll 4
+    for (int i4 = threadIdx.x; i4 < nor * g.Wo * g.Cout / 4; i4 += blockDim.x) {
+      const float4 d = d4[i4];
+      const uint32_t mb = mask[(base + 4 * i4) >> 3] >> ((4 * i4) & 4);
+      reinterpret_cast<float4*>(dO)[i4] = d;
+      reinterpret_cast<float4*>(dM)[i4] = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
+    }
   }
+#pragma unroll 4
   for (int i = threadIdx.x; i < nir * g.W * g.Cin / 4; i += blockDim.x)
     reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x + ((long long)n * g.H + i0) * g.W * g.Cin)[i];
   __syncthreads();
