@@ -211,6 +211,17 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t ws = 0, wph = 0, ld = 0;   // weight ring position kept incrementally (no integer division in the loop)
     for (uint32_t ic = 0; ic < (uint32_t)p.iters; ++ic) {
       for (int li = 0; li < p.L; ++li) {
+        // The step's weight entries are awaited FIRST: they were prefetched a step ahead, and this warp is
+        // idle while the previous step's epilogue runs, so the ~140 cycles per mbarrier wait are hidden there
+        // instead of sitting between the strip hand-over and the first MMA.
+        {
+          uint32_t s2 = ws, ph2 = wph;
+          const int nent = p.seg_outer ? 1 : NKB * (9 / TW);
+          for (int e = 0; e < nent; ++e) {
+            mbar_wait(&w_full[s2], ph2);
+            if (++s2 == (uint32_t)p.sw) { s2 = 0; ph2 ^= 1; }
+          }
+        }
         if (DIR == 0 && li == 0) mbar_wait(x_full, ic & 1);
         else { mbar_wait(layer_done, ld & 1); ++ld; }
         tc_fence_after_sync();
@@ -218,8 +229,6 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
         if (p.seg_outer) {
           const uint32_t s = ws;
-          mbar_wait(&w_full[s], wph);
-          tc_fence_after_sync();
           if (ic == 0 && li == TL && lane == 0) tr.mark(3);
           const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
           uint32_t a_sg = a_base, d = tmem_base;
@@ -240,19 +249,6 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           // All ring entries of the layer are normally prefetched while the previous layer ran: wait for
           // them up front, then issue the layer's MMAs as one unrolled stream (no wait bubbles in between).
           long long wstall = 0;
-          constexpr int NENT = NKB * (9 / TW);
-          {
-            const long long tw0 = clock64();
-#pragma unroll
-            uint32_t s2 = ws, ph2 = wph;
-#pragma unroll
-            for (int e = 0; e < NENT; ++e) {
-              mbar_wait(&w_full[s2], ph2);
-              if (++s2 == (uint32_t)p.sw) { s2 = 0; ph2 ^= 1; }
-            }
-            wstall = clock64() - tw0;
-            tc_fence_after_sync();
-          }
 #pragma unroll
           for (int kb = 0; kb < NKB; ++kb) {
             const uint32_t a_kb = a_base + kb * plane_units;
@@ -392,12 +388,19 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const bool valid = active && (yy < p.H) && (xq < p.W);
             const int pixl = yy * p.W + xq;
             const uint32_t pos = (uint32_t)(q + p.P + 1);
+            // all TMEM loads of this warp's items of the segment are issued up front (one wait covers them)
+            constexpr int NGI = NG > 1 ? NG / 2 : 1;
+            uint32_t rr[NGI][16];
+#pragma unroll
+            for (int gj = 0; gj < NGI; ++gj) {
+              const int cgw = NG > 1 ? half + 2 * gj : 0;
+              if (NG > 1 || (sg & 1) == half) tmem_ld_x16(tq + sg * C + cgw * 16, rr[gj]);
+            }
 #pragma unroll
             for (int cg = 0; cg < NG; ++cg) {
               if (((sg * NG + cg) & 1) != half) continue;
               const int c0 = cg * 16;
-              uint32_t r[16];
-              tmem_ld_x16(tq + sg * C + c0, r);
+              uint32_t (&r)[16] = rr[NG > 1 ? cg / 2 : 0];
               const uint32_t plo = (uint32_t)(c0 / KB) * p.plane_bytes;
               const uint32_t ch0 = (c0 % KB) / 4;
               uint32_t so[4];
