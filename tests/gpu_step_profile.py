@@ -19,7 +19,7 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     prec = sys.argv[2] if len(sys.argv) > 2 else "fast_tf32"
     blocks = int(sys.argv[3]) if len(sys.argv) > 3 else 36
-    spec = NetSpec(blocks_per_stage=(blocks, blocks + 1, blocks + 1), filters_per_block=(16, 32, 64), h=8.0 / 108.0)
+    spec = NetSpec(blocks_per_stage=(blocks, blocks + 1, blocks + 1), filters_per_block=(16, 32, 64), h=2.0 / 108.0)
     net = EulerNet(spec, precision=prec, seed=1236)
     g = torch.Generator().manual_seed(1236)
     img = torch.randint(0, 256, (128, 32, 32, 3), generator=g, dtype=torch.uint8).cuda()
