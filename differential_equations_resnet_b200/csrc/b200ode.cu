@@ -358,7 +358,19 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
         while (pc < cols) pc <<= 1;
         p.tmem_cols = pc;
         best.smem = (size_t)p.bar_off + 512 + 1024;
-        best.grid = (int)(tiles < sms ? tiles : sms);
+        // Cluster multicast of the weight stream (B200ODE_CONV_CLUSTER=2|4) is implemented but OFF by default:
+        // measured at C = 128/256 it does not help (the limit is the shared-memory port: TMA stage writes +
+        // MMA operand reads, which multicast does not reduce) and clusters of 4 CTAs of ~220 KB do not all fit
+        // one wave on 148 SMs (2x slower).  Ghost tiles pad the last round when a cluster is used.
+        static const int cs_env = getenv("B200ODE_CONV_CLUSTER") ? atoi(getenv("B200ODE_CONV_CLUSTER")) : 0;
+        int cs = cs_env > 0 ? cs_env : 1;
+        while (cs > 1 && (cs > tiles || sms % cs)) cs >>= 1;
+        int grid = (int)(tiles < sms ? tiles : sms);
+        grid = (grid + cs - 1) / cs * cs;
+        if (grid > sms) grid = sms / cs * cs;
+        p.cs = cs;
+        p.iters = (int)((tiles + grid - 1) / grid);
+        best.grid = grid;
         best.box_rows = RB; best.box_imgs = nimg;
       }
     }
@@ -394,7 +406,14 @@ static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CU
   }
   const CUtensorMap& mw = MODE == MODE_BF16 ? L->map_w_bf : L->map_w_hi;
   const CUtensorMap& mwl = MODE == MODE_STRICT ? L->map_w_lo : mw;
-  kern<<<plan.grid, ConvTcCfg<MODE, C>::NWARPS * 32, plan.smem, st>>>(map_a, mw, mwl, plan.p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(ConvTcCfg<MODE, C>::NWARPS * 32); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, mw, mwl, plan.p));
   LAUNCH_CHECK("conv_tc_kernel");
   return 0;
 }

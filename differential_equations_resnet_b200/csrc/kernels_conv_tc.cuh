@@ -53,6 +53,11 @@ struct ConvTcParams {
   float acc_scale, c_in, h;
   int relu, scale_h;
   uint64_t* trace;     // nullable timeline buffer (debug)
+  // Thread-block cluster: the CTAs of a cluster walk their tiles in lockstep on the weight ring, so each
+  // weight stage is fetched from L2 ONCE per cluster (TMA multicast by rank 0).  At C >= 128 every 256-position
+  // tile re-streams all 9*C*C weights: unicast that is ~32 B/clk per SM, more than L2 delivers to 148 SMs.
+  int cs;              // cluster size (1 = no cluster)
+  int iters;           // tiles per CTA = ceil(total_tiles / gridDim.x); tile indices >= total_tiles are ghosts
 };
 
 template <int MODE, int C>
@@ -64,6 +69,9 @@ struct ConvTcCfg {
   static constexpr int KS = ROWB / 32;                             // 32-byte k-steps per K-block
   static constexpr bool STRICT = MODE == MODE_STRICT;
   static constexpr int NWARPS = STRICT ? 14 : 10;                  // TMA, MMA, 8 epilogue (+4 converter)
+  // taps per weight ring stage (same rule as taps_per_w_stage() on the host)
+  static constexpr int PER_TAP = C * ROWB * (STRICT ? 2 : 1);
+  static constexpr int TW = PER_TAP * 9 <= 40 * 1024 ? 9 : PER_TAP * 3 <= 56 * 1024 ? 3 : 1;
 };
 
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
@@ -86,7 +94,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* a_conv = a_empty + p.sa;       // [sa] (strict)
   uint64_t* w_full = a_conv + p.sa;        // [sw]
   uint64_t* w_empty = w_full + p.sw;       // [sw]
-  uint64_t* acc_full = w_empty + p.sw;     // [2]
+  uint64_t* w_empty_cl = w_empty + p.sw;   // [sw] rank 0 only: the other CTAs of the cluster released the stage
+  uint64_t* acc_full = w_empty_cl + p.sw;  // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -103,7 +112,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_w);
     if (STRICT) tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_conv[i], 4); }
-    for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&w_empty_cl[i], p.cs > 1 ? p.cs - 1 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_mbar_init();
   }
@@ -113,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tr.mark(1);
@@ -127,7 +137,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t as_ = 0, aph = 0, ws = 0, wph = 0;   // ring positions kept incrementally (no integer division per entry)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      uint32_t iw = 0;
+      const uint32_t crank = p.cs > 1 ? cluster_ctarank() : 0u;
+      const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+      for (int itile = 0; itile < p.iters; ++itile) {
+        const int tile = blockIdx.x + itile * gridDim.x;   // >= total_tiles: ghost (TMA zero-fills the out-of-bounds strip)
         const int n0 = (tile / p.tpi) * p.nimg;
         const int q0 = (tile % p.tpi) * T;
         const int row0 = q0 / p.P;  // first halo row of the strip (halo row r <-> image row r-1)
@@ -139,11 +153,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++as_ == (uint32_t)p.sa) { as_ = 0; aph ^= 1; }
           for (int tg = 0; tg < 9; tg += p.tw) {
             const uint32_t sw_ = ws, phw = wph;
-            mbar_wait_sleep(&w_empty[sw_], phw ^ 1);
-            mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
+            mbar_wait_sleep(&w_empty[sw_], phw ^ 1);     // this CTA's MMAs are done with the stage's previous contents
             uint8_t* wdst = smem + p.w_off + sw_ * p.w_stride;
-            tma_load_3d(wdst, &map_w, &w_full[sw_], kb * KB, 0, tg);
-            if (STRICT) tma_load_3d(wdst + p.w_bytes, &map_w_lo, &w_full[sw_], kb * KB, 0, tg);
+            if (p.cs == 1) {
+              mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
+              tma_load_3d(wdst, &map_w, &w_full[sw_], kb * KB, 0, tg);
+              if (STRICT) tma_load_3d(wdst + p.w_bytes, &map_w_lo, &w_full[sw_], kb * KB, 0, tg);
+            } else if (crank != 0) {
+              if (iw >= (uint32_t)p.sw) mbar_arrive_cluster(&w_empty_cl[sw_], 0);   // tell rank 0 the stage is free here
+              mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);     // rank 0's multicast completes it
+            } else {
+              if (iw >= (uint32_t)p.sw) mbar_wait_sleep(&w_empty_cl[sw_], phw ^ 1);
+              mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
+              tma_load_3d_mc(wdst, &map_w, &w_full[sw_], kb * KB, 0, tg, cmask);
+              if (STRICT) tma_load_3d_mc(wdst + p.w_bytes, &map_w_lo, &w_full[sw_], kb * KB, 0, tg, cmask);
+            }
+            ++iw;
             if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
           }
         }
@@ -164,37 +189,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t a_lo_units = p.a_lo_off >> 4, w_lo_units = p.w_bytes >> 4;
     const uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;               // one tap's weight tile
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
+    auto toff_of = [&](int t) -> uint32_t { return (uint32_t)((t / 3) * p.P + (t % 3)) * RU; };
     uint32_t as_ = 0, aph_ = 0, ws = 0, wph = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    long long st_a = 0, st_w = 0, st_acc = 0;   // cycles this warp spent waiting for strips / weights / free accumulators (trace)
+    for (int itile = 0; itile < p.iters; ++itile, ++it) {
+      const int tile = blockIdx.x + itile * gridDim.x;
       const int q0 = (tile % p.tpi) * T;
       const uint32_t off0_units = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
-      mbar_wait(&acc_empty[as], aph ^ 1);
+      { const long long t0 = clock64(); mbar_wait(&acc_empty[as], aph ^ 1); st_acc += clock64() - t0; }
       tc_fence_after_sync();
       const uint32_t d_tile = tmem_base + as * mt * ACCW;
       for (int kb = 0; kb < NKB; ++kb) {
         const uint32_t s = as_, ph = aph_;
-        mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph);
+        { const long long t0 = clock64(); mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph); st_a += clock64() - t0; }
         if (it == 0 && kb == 0 && lane == 0) tr.mark(2);
         const uint32_t a_units = ((smem_base + p.a_off + s * p.a_stride) >> 4) + off0_units;
-        int alpha = 0, beta = 0;
-        for (int tg = 0; tg < 9; tg += p.tw) {
+        // Taps-per-stage and k-steps are compile-time: per segment the stage's MMAs form one straight-line
+        // stream (runtime tap loops left a dependent IMAD/R2UR chain of ~130 cycles per MMA, twice the
+        // hardware time of an N = 128 MMA).  Per accumulator the order (kb, tap, k-step) is unchanged.
+        constexpr int TW = Cfg::TW;
+#pragma unroll 1
+        for (int tg = 0; tg < 9; tg += TW) {
           const uint32_t sw_ = ws, phw = wph;
-          mbar_wait(&w_full[sw_], phw);
+          { const long long t0 = clock64(); mbar_wait(&w_full[sw_], phw); st_w += clock64() - t0; }
           if (it == 0 && kb == 0 && tg == 0 && lane == 0) tr.mark(3);
           tc_fence_after_sync();
-          uint32_t b_units = (smem_base + p.w_off + sw_ * p.w_stride) >> 4;
-          for (int tt = 0; tt < p.tw; ++tt, b_units += tap_units) {
-            const uint32_t a_tap = a_units + (uint32_t)(alpha * p.P + beta) * RU;
-            const uint32_t first = (kb | tg | tt) == 0 ? 0u : 1u;
-            uint32_t a_img = a_tap, d_seg = d_tile;
-            for (int im = 0; im < p.nimg; ++im, a_img += seg_img_step) {
-              uint32_t a_sg = a_img;
-              for (int j = 0; j < p.spi; ++j, a_sg += 128 * RU, d_seg += ACCW) {
+          const uint32_t b_base = (smem_base + p.w_off + sw_ * p.w_stride) >> 4;
+          uint32_t a_img = a_units, d_seg = d_tile;
+          for (int im = 0; im < p.nimg; ++im, a_img += seg_img_step) {
+            uint32_t a_sg = a_img;
+            for (int j = 0; j < p.spi; ++j, a_sg += 128 * RU, d_seg += ACCW) {
+#pragma unroll
+              for (int tt = 0; tt < TW; ++tt) {
+                const uint32_t a_tap = a_sg + toff_of(tg + tt);
+                const uint32_t b_units = b_base + tt * tap_units;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                  const uint64_t da = mk(a_sg + 2 * ks), db = mk(b_units + 2 * ks);
-                  const uint32_t acc = ks ? 1u : first;
+                  const uint64_t da = mk(a_tap + 2 * ks), db = mk(b_units + 2 * ks);
+                  const uint32_t acc = (tg | tt | ks) ? 1u : (kb ? 1u : 0u);
                   if (leader) {
                     if (MODE == MODE_BF16) {
                       umma_f16(d_seg, da, db, idesc, acc);
@@ -202,14 +235,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                       umma_tf32(d_seg, da, db, idesc, acc);
                       if (STRICT) {
                         umma_tf32(d_seg + C, da, mk(b_units + w_lo_units + 2 * ks), idesc, acc);
-                        umma_tf32(d_seg + C, mk(a_sg + a_lo_units + 2 * ks), db, idesc, 1);
+                        umma_tf32(d_seg + C, mk(a_tap + a_lo_units + 2 * ks), db, idesc, 1);
                       }
                     }
                   }
                 }
               }
             }
-            if (++beta == 3) { beta = 0; ++alpha; }
           }
           if (leader) umma_commit(&w_empty[sw_]);
           if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
@@ -222,6 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
     }
     if (lane == 0) tr.mark(5);
+    if (lane == 0 && tr.buf) { tr.buf[10] = (uint64_t)st_a; tr.buf[11] = (uint64_t)st_w; tr.buf[12] = (uint64_t)st_acc; }
   } else if (warp < 10) {
     // ===================== epilogue warps 2..9: two warps per TMEM lane quarter =====================
     // Work item = (segment, G-channel group); the items of a tile alternate between the two warps of a
@@ -236,7 +269,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const IoT* in = reinterpret_cast<const IoT*>(p.in);
     const IoT* skip = reinterpret_cast<const IoT*>(p.skip);
     IoT* out = reinterpret_cast<IoT*>(p.out);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int itile = 0; itile < p.iters; ++itile, ++it) {
+      const int tile = blockIdx.x + itile * gridDim.x;   // ghost tiles: n0 >= N, nothing is stored
       const int n0 = (tile / p.tpi) * p.nimg;
       const int q0 = (tile % p.tpi) * T;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
@@ -401,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (STRICT) {
       const int ctid = threadIdx.x - 10 * 32;  // 0..127
       uint32_t ia = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int itile = 0; itile < p.iters; ++itile) {
         for (int kb = 0; kb < NKB; ++kb) {
           const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
           mbar_wait_sleep(&a_full[s], ph);
@@ -428,6 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
   if (threadIdx.x == 0) { tr.mark(9); tr.wall(15); }
 }

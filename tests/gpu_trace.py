@@ -50,6 +50,9 @@ def main():
                   + "  wall=%.2fus" % ((row[15].item() - row[0].item()) / 1e3))
         med = t[:, 1:10].float().median(dim=0).values
         print("  median : " + "  ".join("%s=%d" % (nm[i], med[i - 1].item()) for i in range(1, 10) if nm[i] != "-"))
+        if kind != "wgrad":
+            w = t[:, 10:13].float().median(dim=0).values
+            print("  MMA warp waits (cycles, median): strips %d  weights %d  free accumulators %d" % (w[0].item(), w[1].item(), w[2].item()))
     for kind in ("fwd", "dgrad", "wgrad"):
         run(kind)
 
