@@ -26,6 +26,14 @@ def allreduce_bucket(flat_grad: torch.Tensor, world_size: int):
     return flat_grad
 
 
+def allreduce_async(flat_slice: torch.Tensor):
+    """Start the sum all-reduce of one contiguous slice of the gradient bucket and return the work handle;
+    the collective runs on the backend's own stream, so kernels launched afterwards on the caller's stream
+    overlap it (the exchange is hidden behind the remaining backward pass).  Call
+    `.wait()` on the handle before the optimiser reads the slice."""
+    return dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, async_op=True)
+
+
 def adam_reference_step(theta, grad_sum, m, v, t, world_size, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
     """Host restatement of b200ode_adam_step (tf.train.AdamOptimizer form) used by the CPU tests."""
     g = grad_sum / world_size

@@ -16,13 +16,14 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn.functional as F
 
 from . import _abi
 from .layers._base import ChainHandle, LayerHandle, truncated_normal_, _ptr, _stream_ptr
-from .parallel import allreduce_bucket
+from .parallel import allreduce_async, allreduce_bucket
 
 
 class NetSpec:
@@ -262,6 +263,7 @@ class EulerNet:
         self._static_in = None
         self.native_glue = native_glue
         self._nb = None
+        self._pending, self._reduced_upto = [], self.n_euler_params     # overlapped all-reduces of this step
 
     # ----------------------------------------------------------------------------------------------
     def forward(self, images):
@@ -386,6 +388,12 @@ class EulerNet:
                 ch = e["chain"]
                 ch.fused.dgrad(d, ch.f_masks, ch.f_dz, ch.f_dx, spec.h)
                 ch.fused.wgrad(ch.x0, ch.f_acts, ch.f_dz, self.grad_euler[ch.offset:], ch.np_layer)
+                if self.world_size > 1 and not os.environ.get("B200ODE_NO_OVERLAP"):
+                    # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
+                    # overlaps the rest of the backward pass; joined in _optimizer before Adam
+                    lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
+                    self._pending.append(allreduce_async(self.grad_euler[lo:hi]))
+                    self._reduced_upto = min(self._reduced_upto, lo)
                 d = ch.f_dx
             elif e["kind"] == "transition":
                 nm = e["name"]
@@ -418,7 +426,17 @@ class EulerNet:
         return loss
 
     def _optimizer(self):
-        allreduce_bucket(self.grad, self.world_size)
+        if self._pending:
+            # chains were reduced stage by stage (they sit at the front of the flat bucket in forward order,
+            # i.e. [reduced_upto, n_euler) is done); reduce what is left, then join the overlapped collectives
+            if self._reduced_upto > 0:
+                allreduce_bucket(self.grad[:self._reduced_upto], self.world_size)
+            allreduce_bucket(self.grad[self.n_euler_params:], self.world_size)
+            for w in self._pending:
+                w.wait()
+            self._pending, self._reduced_upto = [], self.n_euler_params
+        else:
+            allreduce_bucket(self.grad, self.world_size)
         lib, st = _abi.lib(), _stream_ptr()
         _abi.check(lib.b200ode_adam_step(_ptr(self.theta), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
                                          self.n_params, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,
