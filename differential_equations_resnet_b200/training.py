@@ -409,6 +409,50 @@ class EulerNet:
                                                   e["co"], st))
         return nb["loss"].view(())
 
+    def predict(self, images):
+        """Inference (softmax probabilities [N, classes]) through the native kernels: stem, one persistent
+        chain launch per stage that keeps every intermediate activation in shared memory (nothing but the
+        stage output is written), transitions, head.  Falls back to `forward` for shapes / modes the native
+        path does not take."""
+        nb = self._native_plan(images.shape, images.device)
+        if nb["plan"] is None:
+            with torch.no_grad():
+                return self.forward(images)
+        lib, st, spec = _abi.lib(), _stream_ptr(), self.spec
+        N = images.shape[0]
+        is_u8 = images.dtype == torch.uint8
+        images = images.contiguous() if is_u8 else images.contiguous().float()
+        norm = spec.subtract_mean is not None or spec.divide_by_stddev is not None
+        sub = float(spec.subtract_mean or 0.0)
+        div = float(spec.divide_by_stddev if spec.divide_by_stddev is not None else 1.0)
+        th = self.theta
+        cur = images
+        for e in nb["plan"]:
+            if e["kind"] == "stem":
+                _abi.check(lib.b200ode_stem_fwd(_ptr(cur), int(is_u8), sub, div, int(norm), _ptr(th[self._off(e["name"] + "/kernel"):]),
+                                                _ptr(th[self._off(e["name"] + "/bias"):]), _ptr(e["out"]), N, e["h"], e["w"],
+                                                e["ci"], e["co"], st))
+                cur = e["out"]
+            elif e["kind"] == "transition":
+                nm = e["name"]
+                _abi.check(lib.b200ode_transition_fwd(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                      _ptr(th[self._off(nm + "2/bias"):]), _ptr(th[self._off(nm + "1/kernel"):]),
+                                                      _ptr(th[self._off(nm + "1/bias"):]), _ptr(e["out"]), _ptr(e["mask"]),
+                                                      N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                cur = e["out"]
+            else:
+                ch = e["chain"]
+                ch.fused.pack(self.theta_euler[ch.offset:], ch.np_layer)
+                ch.fused.forward(cur, spec.h, y_final=ch.f_dx)      # f_dx doubles as the stage output buffer
+                cur = ch.f_dx
+        probs = torch.empty((N, spec.num_classes), dtype=torch.float32, device=images.device)
+        zeros = torch.zeros((N, spec.num_classes), dtype=torch.float32, device=images.device)
+        fo = self._off("fc/kernel")
+        _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(zeros), 1e-7,
+                                            _ptr(probs), _ptr(nb["loss"]), None, None, N, nb["hw"], nb["c"],
+                                            spec.num_classes, st))
+        return probs
+
     def _fwd_bwd(self, images, onehot):
         nb = self._native_plan(images.shape, images.device)
         if nb["plan"] is not None:

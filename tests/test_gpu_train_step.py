@@ -64,3 +64,21 @@ def test_train_step_cuda_graph_matches_oracle():
 def test_train_step_fast_tf32_cuda_graph_matches_oracle():
     """fast_tf32 takes the persistent chain kernels (one launch per stage and direction)."""
     _run("fast_tf32", 2e-3, 3e-2, graph=True)
+
+
+def test_native_predict_matches_oracle():
+    """Inference through stem + one chain launch per stage (activations never leave shared memory inside a
+    stage) + transitions + head against the O1 forward pass; fast_tf32 tolerance on probabilities."""
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    kw = dict(blocks_per_stage=(4, 5, 3), filters_per_block=(16, 32, 64), h=0.125, gamma=-0.05)
+    ospec = O1.NetSpec(**kw)
+    P = O1.init_net_params(ospec, seed=9)
+    net = EulerNet(NetSpec(**kw), precision="fast_tf32", seed=0)
+    net.import_params(P)
+    gen = torch.Generator().manual_seed(4)
+    for N in (1, 9):
+        img = torch.randint(0, 256, (N, 32, 32, 3), generator=gen, dtype=torch.uint8)
+        ref = O1.net_forward(ospec, P, img)
+        got = net.predict(img.cuda()).cpu()
+        assert float((got - ref).abs().max()) <= 5e-3, float((got - ref).abs().max())
+        assert torch.equal(got.argmax(-1), ref.argmax(-1))
