@@ -124,10 +124,11 @@ class _Chain:
         if self.acts is not None and self.acts[1].shape == shape:
             return
         N, H, W, C = shape
-        self.acts = [None] + [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(self.n)]
+        dt = self.handles[0].io_dtype                 # fp32, or bf16 in fast_bf16 mode
+        self.acts = [None] + [torch.empty(shape, dtype=dt, device=device) for _ in range(self.n)]
         self.masks = [torch.empty((N, H, W, C // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
-        self.dz = torch.empty(shape, dtype=torch.float32, device=device)
-        self.dx = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self.dz = torch.empty(shape, dtype=dt, device=device)
+        self.dx = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]
 
 
 class _ChainFn(torch.autograd.Function):
@@ -149,13 +150,15 @@ class _ChainFn(torch.autograd.Function):
             chain.fused.forward(chain.x0, net.spec.h, acts=chain.f_acts, masks=chain.f_masks)
             return chain.f_acts[chain.n - 1].view(N, H, W, C)
         chain.ensure_buffers(tuple(x.shape), x.device)
-        chain.acts[0] = x.detach()                # layer 0 reads the caller's tensor (no copy, no graph reference)
+        dt = chain.handles[0].io_dtype
+        ctx.in_dtype = x.dtype
+        chain.acts[0] = x.detach().to(dt)         # layer 0 reads the caller's tensor (no copy when dtypes agree)
         for l, hd in enumerate(chain.handles):
             off = chain.offset + l * chain.np_layer
             _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(net.theta_euler[off:]), None, st))
             _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(chain.acts[l]), _ptr(chain.acts[l + 1]), _ptr(chain.masks[l]),
                                              None, N, H, W, net.spec.h, _abi.F_EULER, st))
-        return chain.acts[chain.n].view(N, H, W, C)
+        return chain.acts[chain.n].view(N, H, W, C).to(ctx.in_dtype)
 
     @staticmethod
     def backward(ctx, dy):
@@ -168,24 +171,26 @@ class _ChainFn(torch.autograd.Function):
             chain.fused.dgrad(dy, chain.f_masks, chain.f_dz, chain.f_dx, net.spec.h)
             chain.fused.wgrad(chain.x0, chain.f_acts, chain.f_dz, net.grad_euler[chain.offset:], chain.np_layer)
             return chain.f_dx.view(N, H, W, C), None, None
-        cur = dy
+        dt = chain.handles[0].io_dtype
+        cur = dy.to(dt)
         for l in range(chain.n - 1, -1, -1):
             hd = chain.handles[l]
             off = chain.offset + l * chain.np_layer
             _abi.check(lib.b200ode_relu_scale_bwd(_ptr(cur), _ptr(chain.masks[l]), _ptr(chain.dz), N * H * W, C,
-                                                  net.spec.h, 0, st))
+                                                  net.spec.h, int(dt == torch.bfloat16), st))
             nxt = chain.dx[l & 1]
             _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(chain.dz), _ptr(cur), _ptr(nxt), N, H, W, st))
             _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(chain.acts[l]), _ptr(chain.dz), _ptr(net.grad_euler[off:]),
                                                None, N, H, W, 0, st))
             cur = nxt
-        return cur.view(N, H, W, C), None, None
+        return cur.view(N, H, W, C).to(ctx.in_dtype), None, None
 
 
 class EulerNet:
     """Antisymmetric single-block ResNet with a fused train step.
 
-    precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', or 'simt'."""
+    precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', 'fast_bf16' (bf16 operands and activations,
+    fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
                  world_size=1, persistent=True, native_glue=True):
