@@ -580,6 +580,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int Cpad = C > p.CH ? C : p.CH;
   p.xchunks = Cpad / p.CH;
   p.trick = (p.pair || (p.xchunks == 1 && 4 * p.CH <= 128)) ? 1 : 0;
+  p.mgroups = 1;
   if (p.pair) {
     p.TG = 9; p.NT = 32; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 128; p.dchunks = 1;
   } else if (p.trick) {
@@ -587,14 +588,22 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   } else {
     p.Mblk = Cpad < 128 ? Cpad : 128;
     p.MB = Cpad / p.Mblk;
+    // More than one M block (C = 256): deal the blocks to different CTAs.  Staging all C input channels leaves
+    // room for only ~64 positions per stage (3x halo over-read, L2-bound); one 128-channel block per CTA fits
+    // four times as many and lets a CTA keep 3 taps x 128 output channels in TMEM.
+    // Measured (N=256, C=256): bf16 32x32 841 -> 670 us; tf32 1303 -> 1653 us and bf16 64x64 702 -> 1106 us get
+    // worse (row-granular strips at P = 65 over-read 3-5x for short tiles), so it is on for bf16 at W <= 32 only.
+    static const int mg_env = getenv("B200ODE_WGRAD_MGROUPS") ? atoi(getenv("B200ODE_WGRAD_MGROUPS")) : -1;   // debug override
+    const bool use_mg = mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 32);
+    if (p.MB > 1 && use_mg) { p.mgroups = p.MB; p.MB = 1; p.xchunks = p.Mblk / p.CH; }
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
       for (int TG : {9, 3, 1}) {
         if (TG * p.MB * NT * (strict ? 2 : 1) > 512) continue;
-        const double load = (double)(C + NT) * UKP * eb / 40.0;
+        const double load = (double)(p.Mblk * p.MB + NT) * UKP * eb / 40.0;     // channels staged per position
         const double per = (double)(NT / 2 > p.Mblk / 4 ? NT / 2 : p.Mblk / 4);
         const double mma = (double)TG * p.MB * per * (strict ? 3 : 1);
-        const double t = (load > mma ? load : mma) * (9 / TG) * (C / NT);
+        const double t = (load > mma ? load : mma) * (9 / TG) * (C / NT) * p.mgroups;
         if (t < best - 1e-9) { best = t; p.TG = TG; p.NT = NT; }
       }
     if (getenv("B200ODE_WGRAD_TG") && getenv("B200ODE_WGRAD_NT")) {   // debug override of the tiling search
@@ -606,7 +615,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     if (p.TG == 3 && 5 * p.MB * p.NT * (strict ? 2 : 1) <= 512) p.TG = 5;
     p.ntapgroups = (9 + p.TG - 1) / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
   }
-  const int ngroups = p.ntapgroups * p.nngroups;
+  const int ngroups = p.ntapgroups * p.nngroups * p.mgroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;
   if (p.trick && strict && 3 * p.NT * 2 > 512) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad TMEM");
   uint32_t cols = (uint32_t)nent * p.NT * (strict ? 2 : 1), pc = 32;

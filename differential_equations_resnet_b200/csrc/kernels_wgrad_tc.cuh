@@ -40,6 +40,7 @@ struct WgradParams {
   int TG;            // taps per CTA group (normal mode)
   int NT;            // output channels per CTA group
   int ntapgroups, nngroups;
+  int mgroups;       // M blocks (of Mblk input channels) dealt to different CTAs; each CTA stages only its block's x chunks
   int MB, Mblk;      // M blocks per tap and rows per block (normal mode)
   uint32_t x_chunk_bytes, d_chunk_bytes, x_chunk_stride, d_chunk_stride;
   uint32_t x_off, d_off, x_lo_off, d_lo_off, stage_stride, bar_off;
@@ -90,7 +91,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   tr.begin(p.trace);
   if (threadIdx.x == 0) tr.wall(0);
   const int group = blockIdx.y;
-  const int tapgroup = group / p.nngroups, ngroup = group % p.nngroups;
+  const int mgroup = group % p.mgroups;
+  const int tapgroup = (group / p.mgroups) / p.nngroups, ngroup = (group / p.mgroups) % p.nngroups;
+  const bool do_bias = tapgroup == 0 && mgroup == 0;   // the dz column sums (bias gradient) are produced once per N range
   const int part = blockIdx.x;
   const int layer = blockIdx.z;
   const int ukp = p.pair ? 16 : UKP;    // positions per k-step
@@ -101,7 +104,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(mx);
     tma_prefetch_desc(&map_d);
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], group / p.nngroups == 0 ? 5 : 1); mbar_init(&conv[i], 4); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], do_bias ? 5 : 1); mbar_init(&conv[i], 4); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -131,7 +134,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
         for (int c = 0; c < p.xchunks; ++c)
-          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], c * p.CH, xc0, row0 - 1, img_x0 + n);
+          tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk * (p.mgroups > 1) + c * p.CH, xc0, row0 - 1, img_x0 + n);
         for (int c = 0; c < p.dchunks; ++c)
           tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, img_d0 + n);
       }
@@ -289,7 +292,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     const int quarter = warp & 3;
     const int w4 = warp - 2;
     const int ACCW = STRICT ? 2 * p.NT : p.NT;
-    if (tapgroup == 0) {
+    if (do_bias) {
       float bsum[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
@@ -367,7 +370,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       int tap, ci;
       bool ok = row_ok;
       if (p.trick) { const int beta = m / p.CH; tap = e * 3 + beta; ci = m % p.CH; ok = ok && beta < 3; }
-      else { tap = tapgroup * p.TG + e / p.MB; ci = (e % p.MB) * p.Mblk + m; }
+      else { tap = tapgroup * p.TG + e / p.MB; ci = (e % p.MB) * p.Mblk + m + (p.mgroups > 1 ? mgroup * p.Mblk : 0); }
       ok = ok && ci < p.C && tap < 9;
       float* dst = part_base + ((size_t)tap * p.C + ci) * p.C + ngroup * p.NT;
       for (int c0 = 0; c0 < p.NT; c0 += 16) {
