@@ -594,7 +594,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     // Measured (N=256, C=256): bf16 32x32 841 -> 670 us; tf32 1303 -> 1653 us and bf16 64x64 702 -> 1106 us get
     // worse (row-granular strips at P = 65 over-read 3-5x for short tiles), so it is on for bf16 at W <= 32 only.
     static const int mg_env = getenv("B200ODE_WGRAD_MGROUPS") ? atoi(getenv("B200ODE_WGRAD_MGROUPS")) : -1;   // debug override
-    const bool use_mg = mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 32);
+    const bool use_mg = mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 64);
     if (p.MB > 1 && use_mg) { p.mgroups = p.MB; p.MB = 1; p.xchunks = p.Mblk / p.CH; }
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
@@ -621,9 +621,48 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   uint32_t cols = (uint32_t)nent * p.NT * (strict ? 2 : 1), pc = 32;
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
-  // positions per tile: as large as fits two stages (one as a fallback)
   const long long Q = (long long)H * p.P;
   const int max_smem = 227 * 1024 - 2048;
+  // Row-aligned tiles (bf16, 128-channel operand blocks): a tile is R whole image rows, so the strips hold exactly
+  // R+2 / R rows (x over-read (R+2)/R instead of the ~3x of position-granular tiles on row-granular strips) and
+  // the k-steps run into a zeroed pad up to the next multiple of 16 positions.
+  static const int rows_env = getenv("B200ODE_WGRAD_ROWS") ? atoi(getenv("B200ODE_WGRAD_ROWS")) : -1;   // debug override (0 = off)
+  int rows = 0;
+  if (bf16 && !p.trick && !p.pair && p.Mblk == 128 && rows_env != 0) {
+    auto stage_bytes = [&](int R) -> long long {
+      const int kt = (R * p.P + UKP - 1) / UKP * UKP;
+      const uint32_t xs = align_up((uint32_t)(kt + 2 * p.P + 3) * p.PB, 1024), ds = align_up((uint32_t)kt * p.PB, 1024);
+      return (long long)p.xchunks * xs + (long long)p.dchunks * ds;
+    };
+    if (rows_env > 0) rows = rows_env;
+    else {   // most rows that still leave two stages; prefer a row count with little k-step padding
+      double best_cost = 1e30;
+      for (int R = 1; R <= H && R <= 64; ++R) {
+        if (stage_bytes(R) * 2 + 1024 + 4608 > max_smem) break;
+        const int kt = (R * p.P + UKP - 1) / UKP * UKP;
+        const int tpi = (H + R - 1) / R;
+        // bytes staged per useful position (x rows R+2, dz padded) and MMA k-steps per useful position
+        const double bytes = ((double)p.xchunks * (R + 2) * p.P + (double)p.dchunks * R * p.P) * tpi / (double)(H * p.P);
+        const double mma = (double)kt * tpi / (double)(H * p.P);
+        const double cost = bytes * 0.5 + mma * (p.xchunks + p.dchunks);
+        if (cost < best_cost - 1e-9) { best_cost = cost; rows = R; }
+      }
+    }
+    if (rows > 0 && (stage_bytes(rows) + 1024 + 4608 > max_smem || rows + 2 > 256)) rows = 0;
+  }
+  if (rows > 0) {
+    p.rowtiles = 1;
+    p.KT = (rows * p.P + UKP - 1) / UKP * UKP;
+    p.tstride = rows * p.P;
+    p.tpi = (H + rows - 1) / rows;
+    p.RBx = rows + 2; p.RBd = rows;
+    p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.PB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.PB;
+    p.x_chunk_stride = align_up((uint32_t)(p.KT + 2 * p.P + 3) * p.PB, 1024); p.d_chunk_stride = align_up((uint32_t)p.KT * p.PB, 1024);
+    const long long stage = (long long)p.xchunks * p.x_chunk_stride + (long long)p.dchunks * p.d_chunk_stride;
+    p.stages = 1;
+    while (p.stages < 6 && stage * (p.stages + 1) + 1024 + 4608 <= max_smem) ++p.stages;
+  } else {
+  // positions per tile: as large as fits two stages (one as a fallback)
   const int off_max = p.P - 1;   // largest offset of a tile start inside its strip
   int KT = 0, stages = 0;
   for (int st_try = 2; st_try >= 1 && !KT; --st_try) {
@@ -645,16 +684,17 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
     while (stages < 6 && stage * (stages + 1) + 1024 + 4608 <= max_smem) ++stages;
   }
-  p.KT = KT; p.stages = stages;
+  p.KT = KT; p.tstride = KT; p.stages = stages;
   p.RBx = (off_max + KT + 2 * p.P + 8 + p.P - 1) / p.P;
   p.RBd = (off_max + KT + p.P - 1) / p.P;
   p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.PB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.PB;
   p.x_chunk_stride = align_up(p.x_chunk_bytes, 1024); p.d_chunk_stride = align_up(p.d_chunk_bytes, 1024);
+  }
   p.x_off = p.pair ? 1024 : 0; p.d_off = p.x_off + p.xchunks * p.x_chunk_stride;
   const uint32_t hi_bytes = p.d_off + p.dchunks * p.d_chunk_stride;
   p.x_lo_off = hi_bytes; p.d_lo_off = hi_bytes + p.d_off;
   p.stage_stride = strict ? 2 * hi_bytes : hi_bytes;
-  p.ent_off = p.stage_stride * stages;
+  p.ent_off = p.stage_stride * p.stages;
   p.bsum_off = p.ent_off + 128;
   p.bar_off = p.bsum_off + 4096;
   const size_t smem = (size_t)p.bar_off + 256 + 1024;
@@ -712,9 +752,22 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const long long nout = (lg.use_bias ? lg.nparams : lg.bias_off);
   int fl = 1;                                   // lanes per output: power of two >= nparts, at most 16
   while (fl < 16 && fl < nparts) fl <<= 1;
-  dim3 fgrid(blocks_for(nout * fl, 256), L);
+  // Off-diagonal blocks through the coalesced tile kernel when it has enough blocks to fill the GPU and few partials per
+  // entry (it sums them serially); otherwise the per-parameter kernel with up to 16 lanes per output.
+  // Measured: C=256 / 12 partials 88 -> ~10 us; C=32 / 148 partials (9 blocks) 10 -> 110 us, hence the gate.
+  const int T = (C + 31) / 32;
+  const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && nparts <= 16 &&
+                     (long long)T * (T + 1) / 2 * lg.k * lg.k * L >= 148;
+  if (tiled) {
+    fold_reduce_tiled_kernel<<<dim3(T * (T + 1) / 2, lg.k * lg.k, L), 256, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate,
+                                                                                   p.part_layer_stride, grad_layer_stride);
+    LAUNCH_CHECK("fold_reduce_tiled_kernel");
+  }
+  const long long nfold = tiled ? 4LL * C + (lg.use_bias ? C : 0) : nout;
+  dim3 fgrid(blocks_for(nfold * fl, 256), L);
   fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, pstride, p.bias_partials, grad_params, accumulate,
-                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl, p.pair ? p.P : 0);
+                                            p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl, p.pair ? p.P : 0,
+                                            tiled ? 1 : 0);
   LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }

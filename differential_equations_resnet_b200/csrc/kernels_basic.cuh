@@ -301,15 +301,18 @@ __global__ void reduce_parts_pair(const float* __restrict__ Gpart, int nparts, l
 __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
                                    const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate,
                                    long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride,
-                                   int lanes, int pair_P) {
+                                   int lanes, int pair_P, int diag_only) {
   Gpart += (long long)blockIdx.y * part_layer_stride;
   if (bias_part) bias_part += (long long)blockIdx.y * bias_layer_stride;
   grad += (long long)blockIdx.y * grad_layer_stride;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long i = gid / lanes;
+  long long i = gid / lanes;
   const int l = (int)(gid % lanes);
   const long long nfree = g.use_bias ? g.bias_off : g.nparams;
   const long long total = nfree + ((g.use_bias && bias_part) ? g.C : 0);
+  // diag_only (3By3 layout): the off-diagonal blocks are folded by fold_reduce_tiled_kernel; this launch covers
+  // the 4C diagonal scalars [0, 4C) and the bias [nfree, total) only
+  if (diag_only && i >= 4LL * g.C) i += nfree - 4LL * g.C;
   if (i >= total) return;
   const unsigned mask = __activemask();
   float val = 0.0f;
@@ -327,6 +330,49 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
   }
   for (int off = lanes >> 1; off > 0; off >>= 1) val += __shfl_xor_sync(mask, val, off, 32);
   if (l == 0) grad[i] = accumulate ? grad[i] + val : val;
+}
+
+// Off-diagonal free parameters in 32x32 (ci, o) tiles:
+//   dL/dW_o[tap][ci-o-1] = sum_p G_p[tap][ci][o] - sum_p G_p[kk-1-tap][o][ci]        
+// The first term is read coalesced along o and transposed through shared memory, the second term and the
+// write are coalesced along ci (the per-parameter kernel gathers the first term with a stride of C floats:
+// 80 us for C = 256 / 12 partials where the partials are 28 MB).  Fixed summation order -> deterministic.
+// grid: (tile pairs to <= tc, taps, layers).
+__global__ void __launch_bounds__(256) fold_reduce_tiled_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts,
+                                                                long long part_stride, float* __restrict__ grad, int accumulate,
+                                                                long long part_layer_stride, long long grad_layer_stride) {
+  __shared__ float t1[32][33];
+  Gpart += (long long)blockIdx.z * part_layer_stride;
+  grad += (long long)blockIdx.z * grad_layer_stride;
+  int tc = 0;
+  while ((tc + 1) * (tc + 2) / 2 <= (int)blockIdx.x) ++tc;
+  const int to = (int)blockIdx.x - tc * (tc + 1) / 2;
+  const int tap = blockIdx.y, rt = g.k * g.k - 1 - tap;
+  const int C = g.C, ci0 = tc * 32, o0 = to * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, o = o0 + tx;
+    float a = 0.0f;
+    if (ci < C && o < C) {
+      const float* src = Gpart + ((long long)tap * C + ci) * C + o;
+      for (int p = 0; p < nparts; ++p) a += src[(long long)p * part_stride];
+    }
+    t1[r][tx] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, ci = ci0 + tx;
+    if (o < C && ci < C && ci > o) {
+      const float* src = Gpart + ((long long)rt * C + o) * C + ci;
+      float b = 0.0f;
+      for (int p = 0; p < nparts; ++p) b += src[(long long)p * part_stride];
+      const float val = t1[tx][r] - b;
+      const long long i = w_block_off(g, o) + (long long)tap * (C - o - 1) + (ci - o - 1);
+      grad[i] = accumulate ? grad[i] + val : val;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

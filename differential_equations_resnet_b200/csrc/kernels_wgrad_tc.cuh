@@ -29,6 +29,9 @@ namespace b200ode {
 struct WgradParams {
   int N, H, W, C, P;
   int KT;            // positions per tile (multiple of the MMA K extent)
+  int tstride;       // positions between consecutive tile starts (= KT, or rows*P for row-aligned tiles)
+  int rowtiles;      // row-aligned tiles: a tile is `rows` whole image rows; strips hold exactly the rows needed and
+                     // the k-steps run over a zeroed pad up to the next multiple of the MMA K extent
   int tpi;           // tiles per image
   int total_tiles, nparts;
   int RBx, RBd;      // strip rows of x (halo) and dz
@@ -48,7 +51,7 @@ struct WgradParams {
   uint32_t tmem_cols;
   float* partials;   // [nparts][9][C][C]
   float* bias_partials;  // [nparts][C] column sums of dz (bias gradient), written by tap group 0
-  uint32_t ent_off, bsum_off;  // smem offsets: per-entry A offsets (uint32[32]) and bias scratch (float[4][256])
+  uint32_t ent_off, bsum_off;  // smem offsets: per-entry A offsets (uint32[32]) and bias scratch (float[128][8])
   uint64_t* trace;             // nullable timeline buffer (debug)
   // layer batching (blockIdx.z = layer): layer 0 reads its input through map_x0 (image n), layer l >= 1
   // through map_x (image (l-1)*N + n: the saved outputs of the chain); dz image index is l*N + n.
@@ -93,7 +96,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   const int group = blockIdx.y;
   const int mgroup = group % p.mgroups;
   const int tapgroup = (group / p.mgroups) / p.nngroups, ngroup = (group / p.mgroups) % p.nngroups;
-  const bool do_bias = tapgroup == 0 && mgroup == 0;   // the dz column sums (bias gradient) are produced once per N range
+  // The dz column sums (bias gradient) of an N range are dealt over the CTAs that stage the same dz strip (all tap
+  // groups and M blocks): each sums its share of the strip's 16-byte column units, so no role is slower than the others.
+  const int b_upr = p.RWB >> 4;                    // 16-byte units per operand row
+  const int b_units = p.dchunks * b_upr;           // column units of this CTA's dz strip (power of two, <= 64)
+  const int b_roles = p.trick ? 1 : p.ntapgroups * p.mgroups, b_rid = p.trick ? 0 : tapgroup * p.mgroups + mgroup;
+  const int b_lo = b_rid * b_units / b_roles, b_n = (b_rid + 1) * b_units / b_roles - b_lo;
+  const bool do_bias = b_n > 0;
   const int part = blockIdx.x;
   const int layer = blockIdx.z;
   const int ukp = p.pair ? 16 : UKP;    // positions per k-step
@@ -114,6 +123,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       reinterpret_cast<uint4*>(smem + (i >> 6) * p.stage_stride)[i & 63] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
+  if (p.rowtiles) {   // zero what TMA never writes between a chunk's rows and its stride: the k-steps past the last row read it
+    const uint32_t xpad = (p.x_chunk_stride - p.x_chunk_bytes) >> 4, dpad = (p.d_chunk_stride - p.d_chunk_bytes) >> 4;
+    const uint32_t per_stage = p.xchunks * xpad + p.dchunks * dpad;
+    for (uint32_t i = threadIdx.x; i < p.stages * per_stage; i += blockDim.x) {
+      const uint32_t s = i / per_stage, r = i % per_stage;
+      uint8_t* dst;
+      if (r < p.xchunks * xpad) dst = smem + s * p.stage_stride + p.x_off + (r / xpad) * p.x_chunk_stride + p.x_chunk_bytes + ((r % xpad) << 4);
+      else { const uint32_t r2 = r - p.xchunks * xpad; dst = smem + s * p.stage_stride + p.d_off + (r2 / dpad) * p.d_chunk_stride + p.d_chunk_bytes + ((r2 % dpad) << 4); }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -125,7 +146,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0, rs = 0, rph = 0;   // ring position kept incrementally
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
-        const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.KT;
+        const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.tstride;
         const int row0 = q0 / p.P;
         const int xc0 = p.pair ? 0 : -1;    // pair mode: the zero slots sit at the END of every row
         const uint32_t s = rs, ph = rph;
@@ -172,13 +193,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
     const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
+    long long mma_wait = 0;   // trace: cycles spent waiting for operand stages
     uint32_t it = 0, rs = 0, rph = 0;
     for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
-      const int q0 = (tile % p.tpi) * p.KT;
+      const int q0 = (tile % p.tpi) * p.tstride;
       const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t s = rs, ph = rph;
       if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
+      const long long tw0 = tr.buf ? clock64() : 0;
       mbar_wait(STRICT ? &conv[s] : &full[s], ph);
+      if (tr.buf) mma_wait += clock64() - tw0;
       if (it == 0 && lane == 0) tr.mark(2);
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
@@ -285,6 +309,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     }
     if (leader) umma_commit(acc_full);
     if (lane == 0) tr.mark(4);
+    if (lane == 0 && tr.buf) tr.buf[10] = (uint64_t)mma_wait;
   } else if (warp < 6) {
     // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
     // to accumulate the bias gradient sum_q dz[q, o] from the dz strips already in shared memory
@@ -293,51 +318,70 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     const int w4 = warp - 2;
     const int ACCW = STRICT ? 2 * p.NT : p.NT;
     if (do_bias) {
-      float bsum[8];
+      // Column sums of the dz strips with 16-byte shared-memory loads: thread t owns one 16-byte unit (8 bf16 / 4 fp32
+      // channels) of the operand rows r = k0, k0 + tpu, ... (a per-element loop with one dependent 2-byte load per
+      // position made the bias CTAs 2.4x slower than the rest of the grid: ncu sm__cycles_active avg 0.5 of max).
+      const int t = threadIdx.x - 64;
+      const int upr = b_upr, units = b_n;
+      const int tpu = 128 / units;                 // threads per unit (the last 128 - tpu*units threads idle)
+      const int unit = b_lo + t % units, k0 = t / units;
+      const int ck = unit / upr, u = unit % upr;
+      const int ppr = p.RWB / p.PB;                // positions per operand row (2 in pixel-pair mode)
+      const int nr = p.KT / ppr;
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
-      const int per_chunk = (p.CH + 31) / 32;
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
       uint32_t it = 0, rs = 0, rph = 0;
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
-        const int q0 = (tile % p.tpi) * p.KT;
-        const int off0 = q0 - (q0 / p.P) * p.P;
+        const int q0 = (tile % p.tpi) * p.tstride;
+        const int r0 = (q0 - (q0 / p.P) * p.P) / ppr;
         const uint32_t s = rs, ph = rph;
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
         mbar_wait_sleep(&full[s], ph);
-        const uint8_t* dbase = smem + s * p.stage_stride + p.d_off;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ck = i / per_chunk, c = (i % per_chunk) * 32 + lane;
-          if (ck < p.dchunks && c < p.CH) {
-            const uint8_t* cb = dbase + ck * p.d_chunk_stride;
-            float acc = 0.0f;
-            for (int pos = w4; pos < p.KT; pos += 4) {
-              uint32_t a = (uint32_t)(off0 + pos) * p.PB + c * (BF16 ? 2 : 4);
-              if (BF16) {
-                a = swizzle_addr(a, p.RWB);
-                acc += __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(cb + a)) << 16);
-              } else {
-                a ^= ((a >> 7) & 3u) << 5;
-                acc += *reinterpret_cast<const float*>(cb + a);
-              }
-            }
-            bsum[i] += acc;
+        const uint8_t* cb = smem + s * p.stage_stride + p.d_off + ck * p.d_chunk_stride;
+#pragma unroll 4
+        for (int r = k0 < tpu ? k0 : nr; r < nr; r += tpu) {
+          uint32_t a = (uint32_t)(r0 + r) * p.RWB + (u << 4);
+          a = BF16 ? swizzle_addr(a, p.RWB) : a ^ (((a >> 7) & 3u) << 5);
+          const uint4 v = *reinterpret_cast<const uint4*>(cb + a);
+          if (BF16) {
+            acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xFFFF0000u);
+            acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xFFFF0000u);
+            acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xFFFF0000u);
+            acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
+          } else {
+            acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+            acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
       }
-      float* bs = reinterpret_cast<float*>(smem + p.bsum_off);
+      float* bs = reinterpret_cast<float*>(smem + p.bsum_off);   // [128 threads][8]
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bs[w4 * 256 + i * 32 + lane] = bsum[i];
+      for (int i = 0; i < 8; ++i) bs[t * 8 + i] = acc[i];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int per_chunk_i = per_chunk;
-      for (int idx = threadIdx.x - 64; idx < 256; idx += 128) {
-        const int i = idx / 32, l = idx % 32;
-        const int ck = i / per_chunk_i, c = (i % per_chunk_i) * 32 + l;
-        const int ch = ngroup * p.NT + ck * p.CH + c;
-        if (ck < p.dchunks && c < p.CH && ch < p.C)
-          p.bias_partials[(size_t)layer * p.bias_layer_stride + (size_t)part * p.C + ch] = bs[idx] + bs[256 + idx] + bs[512 + idx] + bs[768 + idx];
+      const int epu = BF16 ? 8 : 4;                // channels per unit
+      float* out = p.bias_partials + (size_t)layer * p.bias_layer_stride + (size_t)part * p.C;
+      if (p.pair) {
+        // operand row = [parity][16 channels]: unit = parity*4 + c/4; fixed summation order (parity, then k)
+        if (t < 16) {
+          float sum = 0.0f;
+          for (int par = 0; par < 2; ++par)
+            for (int k = 0; k < tpu; ++k) sum += bs[(k * units + par * 4 + (t >> 2)) * 8 + (t & 3)];
+          out[t] = sum;
+        }
+      } else {
+        for (int idx = t; idx < units * epu; idx += 128) {
+          const int ul = idx / epu, jj = idx % epu, un = b_lo + ul;
+          const int c = (un % upr) * epu + jj;
+          const int ch = ngroup * p.NT + (un / upr) * p.CH + c;
+          if (c < p.CH && ch < p.C) {
+            float sum = 0.0f;
+            for (int k = 0; k < tpu; ++k) sum += bs[(k * units + ul) * 8 + jj];
+            out[ch] = sum;
+          }
+        }
       }
     }
     if (threadIdx.x == 64) tr.mark(5);
