@@ -330,6 +330,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
       int sa = 2;
       long long need = (long long)sa * a_stride + (long long)sw * w_stride + 1024;
       if (need > max_smem) { sa = 1; need = (long long)sa * a_stride + (long long)sw * w_stride + 1024; }
+      if (need > max_smem && sw > 2) { sw = 2; need = (long long)sa * a_stride + (long long)sw * w_stride + 1024; }   // strict C = 256
       if (need > max_smem) continue;
       while (sw < 6 && tw == 1 && need + w_stride <= max_smem) { ++sw; need += w_stride; }
       if (nkb > 1 || true) while (sa < 3 && need + a_stride <= max_smem) { ++sa; need += a_stride; }
@@ -561,7 +562,7 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
 // a chain); dz of layer l is dz + l*N*H*W*C; gradients go to grad_params + l*grad_layer_stride.
 static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const void* xrest, const void* dz, int L, int N, int H,
                         int W, float* G, float* G_user, float* grad_params, long long grad_layer_stride, int accumulate,
-                        cudaStream_t st) {
+                        cudaStream_t st, int force_mgroups = 0) {
   const int C = lg.C;
   const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
   const int eb = bf16 ? 2 : 4;
@@ -594,7 +595,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     // Measured (N=256, C=256): bf16 32x32 841 -> 670 us; tf32 1303 -> 1653 us and bf16 64x64 702 -> 1106 us get
     // worse (row-granular strips at P = 65 over-read 3-5x for short tiles), so it is on for bf16 at W <= 32 only.
     static const int mg_env = getenv("B200ODE_WGRAD_MGROUPS") ? atoi(getenv("B200ODE_WGRAD_MGROUPS")) : -1;   // debug override
-    const bool use_mg = mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 64);
+    const bool use_mg = force_mgroups || (mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 64));
     if (p.MB > 1 && use_mg) { p.mgroups = p.MB; p.MB = 1; p.xchunks = p.Mblk / p.CH; }
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
@@ -674,6 +675,8 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
       if (stage * st_try + 1024 + 4608 <= max_smem) { KT = kt; stages = st_try; break; }
     }
   }
+  if (!KT && p.MB > 1 && !force_mgroups)   // all-channel strips do not fit (strict C = 256, tf32 C = 256 at W = 64): one M block per CTA
+    return run_wgrad_tc(mode, lg, x0, xrest, dz, L, N, H, W, G, G_user, grad_params, grad_layer_stride, accumulate, st, 1);
   if (!KT) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad strips do not fit shared memory (C=%d W=%d)", C, W);
   if (KT > Q) KT = (int)((Q + UKP - 1) / UKP * UKP);
   p.tpi = (int)((Q + KT - 1) / KT);

@@ -131,6 +131,7 @@ def test_conv_known_answer_on_gpu(golden_dir):
 SHAPES = [
     (2, 8, 8, 16), (3, 12, 10, 32), (2, 32, 32, 64), (5, 16, 16, 32), (9, 8, 8, 64),
     (2, 16, 16, 128), (2, 8, 8, 256), (1, 33, 17, 16), (3, 7, 5, 5), (2, 4, 4, 64),
+    (1, 32, 32, 256),   # BASELINE cfg2's widest layer at its real 32x32 extent (strict: two weight stages, M-block wgrad)
 ]
 
 
