@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "torch"), choices=["torch", "abi"],
+                    help="gradient exchange: torch.distributed NCCL, or NCCL bound by libb200ode (b200ode_comm_*)")
     return ap.parse_args()
 
 
@@ -239,7 +241,11 @@ def run_b200(args):
     from differential_equations_resnet_b200.training import EulerNet, NetSpec
 
     spec = NetSpec(blocks_per_stage=BLOCKS, filters_per_block=FILTERS, h=H_STEP, gamma=0.0)
-    net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world)
+    comm = None
+    if world > 1 and args.comm == "abi":
+        from differential_equations_resnet_b200.parallel import AbiComm
+        comm = AbiComm(rank, world)
+    net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
     B = args.batch
     g = torch.Generator().manual_seed(1236 + rank)
     img_h = torch.randint(0, 256, (B, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory()

@@ -28,6 +28,10 @@ _SIGNATURES = {
     "b200ode_last_error": (ctypes.c_char_p, []),
     "b200ode_device_ok": (c_int, []),
     "b200ode_launch_count": (c_int64, []),
+    "b200ode_comm_unique_id": (c_int, [c_void_p]),
+    "b200ode_comm_init": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(c_void_p)]),
+    "b200ode_comm_allreduce_bucket": (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "b200ode_comm_destroy": (c_int, [c_void_p]),
     "b200ode_debug_set_trace": (c_int, [c_void_p]),
     "b200ode_layer_create": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                      ctypes.POINTER(c_void_p)]),

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cmath>
@@ -197,6 +198,76 @@ static int taps_per_w_stage(int mode, int C) {
 extern "C" int b200ode_version(void) { return B200ODE_VERSION; }
 extern "C" const char* b200ode_last_error(void) { return g_err.c_str(); }
 extern "C" int b200ode_device_ok(void) { return device_check() == 0 ? 1 : 0; }
+// ------------------------------------------------------------------------------------------------
+// gradient exchange: NCCL bound at run time
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };          // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+  if (g_nccl.lib) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(B200ODE_ERR_UNSUPPORTED, "cannot load libnccl.so.2: %s", dlerror());
+  NcclApi a;
+  a.lib = h;
+  a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+    return fail(B200ODE_ERR_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
+  g_nccl = a;
+  return 0;
+}
+}  // namespace
+struct b200ode_comm { void* nccl; int nranks, rank; };
+#define NCCL_TRY(x)                                                                                          \
+  do {                                                                                                       \
+    int e__ = (x);                                                                                           \
+    if (e__ != 0) return fail(B200ODE_ERR_CUDA, "%s failed: %s", #x, g_nccl.GetErrorString(e__));            \
+  } while (0)
+
+extern "C" int b200ode_comm_unique_id(void* id_out) {
+  if (!id_out) return fail(B200ODE_ERR_INVALID, "id_out is NULL");
+  if (int rc = load_nccl()) return rc;
+  NCCL_TRY(g_nccl.GetUniqueId(reinterpret_cast<NcclId*>(id_out)));
+  return 0;
+}
+extern "C" int b200ode_comm_init(int nranks, int rank, const void* nccl_unique_id, b200ode_comm_t** out) {
+  if (!out || !nccl_unique_id) return fail(B200ODE_ERR_INVALID, "unique id / out is NULL");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(B200ODE_ERR_INVALID, "rank %d of %d", rank, nranks);
+  if (int rc = device_check()) return rc;
+  if (int rc = load_nccl()) return rc;
+  NcclId id;
+  memcpy(&id, nccl_unique_id, sizeof(id));
+  void* c = nullptr;
+  NCCL_TRY(g_nccl.CommInitRank(&c, nranks, id, rank));
+  *out = new b200ode_comm{c, nranks, rank};
+  return 0;
+}
+extern "C" int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, size_t n, void* stream) {
+  if (!comm || !buf) return fail(B200ODE_ERR_INVALID, "comm/buf is NULL");
+  if (n == 0) return 0;
+  NCCL_TRY(g_nccl.AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->nccl, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int b200ode_comm_destroy(b200ode_comm_t* comm) {
+  if (!comm) return 0;
+  int e = g_nccl.CommDestroy ? g_nccl.CommDestroy(comm->nccl) : 0;
+  delete comm;
+  return e ? fail(B200ODE_ERR_CUDA, "ncclCommDestroy failed: %s", g_nccl.GetErrorString(e)) : 0;
+}
+
 extern "C" int64_t b200ode_launch_count(void) { return g_launches.load(); }
 
 extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h, int stride_w, int use_bias,

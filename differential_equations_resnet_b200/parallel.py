@@ -34,6 +34,63 @@ def allreduce_async(flat_slice: torch.Tensor):
     return dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, async_op=True)
 
 
+class _AbiWork:
+    """Handle of an all-reduce queued on the communicator's side stream (same `.wait()` as a torch work handle)."""
+
+    def __init__(self, done):
+        self._done = done
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self._done)
+
+
+class AbiComm:
+    """Gradient exchange through the C ABI (`b200ode_comm_*`, include/b200ode.h): libb200ode binds NCCL itself, the
+    all-reduce runs on a dedicated stream ordered against the caller's stream with events (capturable in a CUDA
+    graph).  The 128-byte unique id travels from rank 0 through the already initialised `torch.distributed` group
+    (any backend; only a broadcast of 128 bytes) or, without one, through `id_bytes` supplied by the launcher."""
+
+    def __init__(self, rank: int, world_size: int, id_bytes: bytes = None):
+        import ctypes
+        from . import _abi
+        lib = _abi.lib()
+        self._lib, self._abi = lib, _abi
+        self.rank, self.world_size = rank, world_size
+        if id_bytes is None:
+            buf = ctypes.create_string_buffer(128)
+            if rank == 0:
+                _abi.check(lib.b200ode_comm_unique_id(buf))
+            box = [bytes(buf.raw)]
+            if world_size > 1:
+                dist.broadcast_object_list(box, src=0)
+            id_bytes = box[0]
+        self._id = ctypes.create_string_buffer(id_bytes, 128)
+        h = ctypes.c_void_p()
+        _abi.check(lib.b200ode_comm_init(world_size, rank, self._id, ctypes.byref(h)))
+        self._h = h
+        self.stream = torch.cuda.Stream()
+
+    def allreduce_async(self, flat_slice: torch.Tensor):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.stream.wait_event(ready)
+        self._abi.check(self._lib.b200ode_comm_allreduce_bucket(self._h, flat_slice.data_ptr(), flat_slice.numel(),
+                                                                self.stream.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        return _AbiWork(done)
+
+    def allreduce_bucket(self, flat_grad: torch.Tensor):
+        if self.world_size > 1:
+            self.allreduce_async(flat_grad).wait()
+        return flat_grad
+
+    def close(self):
+        if self._h:
+            self._lib.b200ode_comm_destroy(self._h)
+            self._h = None
+
+
 def adam_reference_step(theta, grad_sum, m, v, t, world_size, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
     """Host restatement of b200ode_adam_step (tf.train.AdamOptimizer form) used by the CPU tests."""
     g = grad_sum / world_size

@@ -193,10 +193,12 @@ class EulerNet:
     fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1, persistent=True, native_glue=True):
+                 world_size=1, persistent=True, native_glue=True, comm=None):
         _abi.require_device()
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
         self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
+        # gradient exchange: torch.distributed (default) or a parallel.AbiComm (NCCL bound by libb200ode itself)
+        self.comm = comm
         gen = torch.Generator().manual_seed(seed)
         plan = spec.plan()
         # ---- flat Euler bucket -------------------------------------------------------------------
@@ -397,7 +399,7 @@ class EulerNet:
                     # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
                     # overlaps the rest of the backward pass; joined in _optimizer before Adam
                     lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
-                    self._pending.append(allreduce_async(self.grad_euler[lo:hi]))
+                    self._pending.append(self._ar_async(self.grad_euler[lo:hi]))
                     self._reduced_upto = min(self._reduced_upto, lo)
                 d = ch.f_dx
             elif e["kind"] == "transition":
@@ -474,18 +476,24 @@ class EulerNet:
         torch._foreach_copy_(self._leaf_grad_views, list(grads))
         return loss
 
+    def _ar_async(self, t):
+        return self.comm.allreduce_async(t) if self.comm is not None else allreduce_async(t)
+
+    def _ar(self, t):
+        return self.comm.allreduce_bucket(t) if self.comm is not None else allreduce_bucket(t, self.world_size)
+
     def _optimizer(self):
         if self._pending:
             # chains were reduced stage by stage (they sit at the front of the flat bucket in forward order,
             # i.e. [reduced_upto, n_euler) is done); reduce what is left, then join the overlapped collectives
             if self._reduced_upto > 0:
-                allreduce_bucket(self.grad[:self._reduced_upto], self.world_size)
-            allreduce_bucket(self.grad[self.n_euler_params:], self.world_size)
+                self._ar(self.grad[:self._reduced_upto])
+            self._ar(self.grad[self.n_euler_params:])
             for w in self._pending:
                 w.wait()
             self._pending, self._reduced_upto = [], self.n_euler_params
         else:
-            allreduce_bucket(self.grad, self.world_size)
+            self._ar(self.grad)
         lib, st = _abi.lib(), _stream_ptr()
         _abi.check(lib.b200ode_adam_step(_ptr(self.theta), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
                                          self.n_params, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,

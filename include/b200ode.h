@@ -198,6 +198,19 @@ int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* r
 int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
                          float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* stream);
 
+/* ---- gradient exchange ------------------------------------------------------------
+ * The reference has no collective (single tf.Session, training/training.py:132); data parallel training sums
+ * the flat packed-gradient bucket over ranks.  NCCL is bound at run time (dlopen of libnccl.so.2, the copy the
+ * process already holds if a framework loaded one), so the library itself has no link-time NCCL dependency.
+ * One process per GPU; the caller distributes the 128-byte unique id (rank 0 creates it) out of band. */
+typedef struct b200ode_comm b200ode_comm_t;
+#define B200ODE_UNIQUE_ID_BYTES 128
+int b200ode_comm_unique_id(void* id_out /* B200ODE_UNIQUE_ID_BYTES bytes */);
+int b200ode_comm_init(int nranks, int rank, const void* nccl_unique_id, b200ode_comm_t** out);
+/* in-place sum of buf[0..n) (device pointer, fp32) over all ranks, stream ordered, graph capturable */
+int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, size_t n, void* stream);
+int b200ode_comm_destroy(b200ode_comm_t* comm);
+
 /* test hook: number of kernel launches issued by this library in this process */
 int64_t b200ode_launch_count(void);
 /* debug hook: device buffer of uint64 [ctas][16] that the tensor-core kernels fill with a per-CTA
