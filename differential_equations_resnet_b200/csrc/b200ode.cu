@@ -510,6 +510,7 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   ConvTcParams& p = plan.p;
   p.in = epi.in; p.skip = epi.skip; p.out = epi.out; p.z_out = epi.z_out; p.mask = epi.mask; p.bias = epi.bias;
   p.acc_scale = epi.acc_scale; p.c_in = epi.c_in; p.h = epi.h; p.relu = epi.relu; p.scale_h = epi.scale_h;
+  p.mask2 = epi.mask2; p.out2 = epi.out2; p.h2 = epi.h2;
   p.trace = g_trace;
   const int eb = mode == MODE_BF16 ? 2 : 4;
   const int rowb = C * eb >= 128 ? 128 : C * eb;
@@ -604,6 +605,27 @@ extern "C" int b200ode_euler_dgrad(b200ode_layer_t* L, const void* dz, const voi
   simt_conv_dgrad<<<blocks_for(total, 256), 256, 0, st>>>(g, (const float*)dz, L->Kdense, (const float*)dy_skip, (float*)dx);
   LAUNCH_CHECK("simt_conv_dgrad");
   return 0;
+}
+
+// Data gradient of one Euler step fused with the relu/h backward of the step below it:
+//   dx = dy_skip - conv_K(dz) + 2*gamma*dz          (= dY of the previous step)
+//   dz_prev = h * dx * prev_relu_mask                (= the dz input of the previous step's dgrad / wgrad)
+extern "C" int b200ode_euler_dgrad_fused(b200ode_layer_t* L, const void* dz, const void* dy_skip, void* dx,
+                                         const uint8_t* prev_relu_mask, void* dz_prev, float h, int N, int H, int W, void* stream) {
+  if (!L || !dz || !dx || !prev_relu_mask || !dz_prev) return fail(B200ODE_ERR_INVALID, "layer/dz/dx/prev_relu_mask/dz_prev is NULL");
+  if (!L->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_pack_kernel must run before compute calls");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    ConvTcParams e;
+    memset(&e, 0, sizeof(e));
+    e.in = L->g.gamma != 0.0f ? dz : nullptr; e.skip = dy_skip; e.out = dx;
+    e.acc_scale = -1.0f; e.c_in = 2.0f * L->g.gamma; e.h = 1.0f;
+    e.mask2 = prev_relu_mask; e.out2 = dz_prev; e.h2 = h;
+    return run_conv_tc(L, dz, N, H, W, e, st);
+  }
+  if (int rc = b200ode_euler_dgrad(L, dz, dy_skip, dx, N, H, W, stream)) return rc;
+  return b200ode_relu_scale_bwd(dx, prev_relu_mask, dz_prev, (int64_t)N * H * W, L->g.C, h, 0, stream);
 }
 
 static int colsum_impl(ColsumArgs A, float* out0, float* out1, float* ws, long long pixels, int C, cudaStream_t st) {

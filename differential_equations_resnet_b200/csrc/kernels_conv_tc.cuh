@@ -52,6 +52,12 @@ struct ConvTcParams {
   const float* bias;   // nullable
   float acc_scale, c_in, h;
   int relu, scale_h;
+  // fused backward tail (data-gradient launches): out2 = h2 * out * mask2, i.e. dZ_{l-1} = h * dY_{l-1} * relu mask_{l-1}
+  // written in the same pass as dY_{l-1} (saves relu_scale_bwd_kernel's re-read of dY); computed from the value as
+  // stored (bf16-rounded in bf16 mode) so the result is bit-identical to the two-kernel sequence
+  const uint8_t* mask2;  // nullable [pixels][C/8]
+  void* out2;            // nullable
+  float h2;
   uint64_t* trace;     // nullable timeline buffer (debug)
   // Thread-block cluster: the CTAs of a cluster walk their tiles in lockstep on the weight ring, so each
   // weight stage is fetched from L2 ONCE per cluster (TMA multicast by rank 0).  At C >= 128 every 256-position
@@ -419,6 +425,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * C + c0);
 #pragma unroll
                 for (int j = 0; j < G / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+              if (p.out2) {
+                uint32_t bits2;
+                if (G == 32) bits2 = *reinterpret_cast<const uint32_t*>(p.mask2 + pix * (C / 8) + c0 / 8);
+                else bits2 = *reinterpret_cast<const uint16_t*>(p.mask2 + pix * (C / 8) + c0 / 8);
+                if (MODE == MODE_BF16) {
+                  uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < G / 8; ++j) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const int j0 = 8 * j + 2 * e;
+                      const float a0 = __bfloat162float(__float2bfloat16_rn(v[j0])), a1 = __bfloat162float(__float2bfloat16_rn(v[j0 + 1]));
+                      __nv_bfloat162 b2 = __floats2bfloat162_rn((bits2 >> j0) & 1u ? p.h2 * a0 : 0.0f,
+                                                                (bits2 >> (j0 + 1)) & 1u ? p.h2 * a1 : 0.0f);
+                      pk[e] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    op2[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  }
+                } else {
+                  float4* op2 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + pix * C + c0);
+#pragma unroll
+                  for (int j = 0; j < G / 4; ++j)
+                    op2[j] = make_float4((bits2 >> (4 * j)) & 1u ? p.h2 * v[4 * j] : 0.0f, (bits2 >> (4 * j + 1)) & 1u ? p.h2 * v[4 * j + 1] : 0.0f,
+                                         (bits2 >> (4 * j + 2)) & 1u ? p.h2 * v[4 * j + 2] : 0.0f, (bits2 >> (4 * j + 3)) & 1u ? p.h2 * v[4 * j + 3] : 0.0f);
+                }
               }
             }
           }

@@ -127,7 +127,7 @@ class _Chain:
         dt = self.handles[0].io_dtype                 # fp32, or bf16 in fast_bf16 mode
         self.acts = [None] + [torch.empty(shape, dtype=dt, device=device) for _ in range(self.n)]
         self.masks = [torch.empty((N, H, W, C // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
-        self.dz = torch.empty(shape, dtype=dt, device=device)
+        self.dz = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]   # dZ_l lives in dz[l & 1]
         self.dx = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]
 
 
@@ -173,14 +173,21 @@ class _ChainFn(torch.autograd.Function):
             return chain.f_dx.view(N, H, W, C), None, None
         dt = chain.handles[0].io_dtype
         cur = dy.to(dt)
-        for l in range(chain.n - 1, -1, -1):
+        is_bf16 = int(dt == torch.bfloat16)
+        top = chain.n - 1
+        _abi.check(lib.b200ode_relu_scale_bwd(_ptr(cur), _ptr(chain.masks[top]), _ptr(chain.dz[top & 1]), N * H * W, C,
+                                              net.spec.h, is_bf16, st))
+        for l in range(top, -1, -1):
             hd = chain.handles[l]
             off = chain.offset + l * chain.np_layer
-            _abi.check(lib.b200ode_relu_scale_bwd(_ptr(cur), _ptr(chain.masks[l]), _ptr(chain.dz), N * H * W, C,
-                                                  net.spec.h, int(dt == torch.bfloat16), st))
             nxt = chain.dx[l & 1]
-            _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(chain.dz), _ptr(cur), _ptr(nxt), N, H, W, st))
-            _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(chain.acts[l]), _ptr(chain.dz), _ptr(net.grad_euler[off:]),
+            if l > 0:
+                # dY_{l-1} and dZ_{l-1} = h * dY_{l-1} * mask_{l-1} in ONE pass (the epilogue of the data-gradient kernel)
+                _abi.check(lib.b200ode_euler_dgrad_fused(hd._h, _ptr(chain.dz[l & 1]), _ptr(cur), _ptr(nxt), _ptr(chain.masks[l - 1]),
+                                                         _ptr(chain.dz[(l - 1) & 1]), net.spec.h, N, H, W, st))
+            else:
+                _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(chain.dz[0]), _ptr(cur), _ptr(nxt), N, H, W, st))
+            _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(chain.acts[l]), _ptr(chain.dz[l & 1]), _ptr(net.grad_euler[off:]),
                                                None, N, H, W, 0, st))
             cur = nxt
         return cur.view(N, H, W, C).to(ctx.in_dtype), None, None

@@ -96,6 +96,12 @@ int b200ode_euler_fwd(b200ode_layer_t* layer, const void* x, void* y, uint8_t* r
  *      dz: [N,Ho,Wo,C]; dy_skip: nullable [N,H,W,C] added to the result; dx: [N,H,W,C]. ---- */
 int b200ode_euler_dgrad(b200ode_layer_t* layer, const void* dz, const void* dy_skip, void* dx, int N, int H, int W,
                         void* stream);
+/* The same data gradient fused with the relu/h backward of the step BELOW it in a chain of Euler steps (the TF autodiff
+ * of models/tfkeras_resnets.py:89-92 for the previous block): in one pass
+ *   dx      = dy_skip - conv_K(dz) + 2*gamma*dz
+ *   dz_prev = h * dx * prev_relu_mask          (bit-identical to b200ode_euler_dgrad followed by b200ode_relu_scale_bwd) */
+int b200ode_euler_dgrad_fused(b200ode_layer_t* layer, const void* dz, const void* dy_skip, void* dx,
+                              const uint8_t* prev_relu_mask, void* dz_prev, float h, int N, int H, int W, void* stream);
 
 /* ---- K4 weight gradient (Conv2DBackpropFilter + backprop through the assembly graph):
  *      dense G = sum_pixels x^T dz, folded onto the free parameters

@@ -252,3 +252,32 @@ def test_linearity_and_antisymmetry_at_full_size():
     assert float(lin) <= 2e-5
     quad = (x.double() * kx.double()).sum() / (x.double() * x.double()).sum()
     assert abs(float(quad) - gamma) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["strict", "fast_tf32", "fast_bf16", "simt"])
+@pytest.mark.parametrize("shape", [(2, 8, 8, 16), (3, 12, 10, 32), (2, 16, 16, 128), (1, 9, 64, 256)])
+def test_dgrad_fused_tail_bit_identical(shape, precision):
+    """b200ode_euler_dgrad_fused == b200ode_euler_dgrad followed by b200ode_relu_scale_bwd, bit for bit."""
+    import ctypes
+    from differential_equations_resnet_b200 import _abi
+    N, H, W, C = shape
+    if precision == "simt" and C > 32:
+        pytest.skip("CUDA-core path: small shapes only")
+    layer = make_layer(C, precision, gamma=-0.1)
+    hd = layer._handle
+    hd.pack(layer.packed.detach())
+    dz, _ = rand_x(shape, 31, precision)
+    dy, _ = rand_x(shape, 32, precision)
+    mask = torch.randint(0, 256, (N, H, W, C // 8), dtype=torch.uint8, device="cuda")
+    lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    dx_a, dx_b, dzp_a, dzp_b = (torch.empty_like(dz) for _ in range(4))
+    h = 0.37
+    _abi.check(lib.b200ode_euler_dgrad(hd._h, P(dz), P(dy), P(dx_a), N, H, W, st))
+    _abi.check(lib.b200ode_relu_scale_bwd(P(dx_a), P(mask), P(dzp_a), N * H * W, C, h, int(dz.dtype == torch.bfloat16), st))
+    _abi.check(lib.b200ode_euler_dgrad_fused(hd._h, P(dz), P(dy), P(dx_b), P(mask), P(dzp_b), h, N, H, W, st))
+    torch.cuda.synchronize()
+    assert torch.equal(dx_a, dx_b)
+    assert torch.equal(dzp_a.view(torch.int16 if dz.dtype == torch.bfloat16 else torch.int32),
+                       dzp_b.view(torch.int16 if dz.dtype == torch.bfloat16 else torch.int32))
+    assert float(dzp_a.float().abs().sum()) > 0
