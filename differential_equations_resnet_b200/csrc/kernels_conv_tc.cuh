@@ -74,7 +74,15 @@ struct ConvTcCfg {
   static constexpr int NKB = C / KB;
   static constexpr int KS = ROWB / 32;                             // 32-byte k-steps per K-block
   static constexpr bool STRICT = MODE == MODE_STRICT;
-  static constexpr int NWARPS = STRICT ? 14 : 10;                  // TMA, MMA, 8 epilogue (+4 converter)
+  // Epilogue warps per TMEM lane quarter.  At C = 256 (bf16) the two 256-column accumulators of a tile fill TMEM, so
+  // the next tile's MMAs wait for the drain (~22k cycles per 256x256 tile against 37k cycles of MMAs; one 32x32
+  // item takes a warp ~3000 cycles).  Measured at C = 256: four warps per quarter on 16-channel items are SLOWER
+  // (348 vs 318 us); staggering odd CTAs by half a tile, or removing the drain's loads, stores or TMEM reads: no
+  // change.  The drain is bound by the instruction throughput of its ~20 integer/convert/compare operations per
+  // element (bf16 unpack, relu, mask bits, pack), not by memory.  Left at two.
+  static constexpr int EPQ = 2;
+  static constexpr int G = EPQ == 4 ? 16 : (C < 32 ? C : 32);      // channels per epilogue work item
+  static constexpr int NWARPS = STRICT ? 14 : 2 + 4 * EPQ;         // TMA, MMA, epilogue (+4 converter)
   // taps per weight ring stage (same rule as taps_per_w_stage() on the host)
   static constexpr int PER_TAP = C * ROWB * (STRICT ? 2 : 1);
   static constexpr int TW = PER_TAP * 9 <= 40 * 1024 ? 9 : PER_TAP * 3 <= 56 * 1024 ? 3 : 1;
@@ -119,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (STRICT) tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_conv[i], 4); }
     for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&w_empty_cl[i], p.cs > 1 ? p.cs - 1 : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * Cfg::EPQ); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -261,14 +269,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (lane == 0) tr.mark(5);
     if (lane == 0 && tr.buf) { tr.buf[10] = (uint64_t)st_a; tr.buf[11] = (uint64_t)st_w; tr.buf[12] = (uint64_t)st_acc; }
-  } else if (warp < 10) {
+  } else if (warp < 2 + 4 * Cfg::EPQ) {
     // ===================== epilogue warps 2..9: two warps per TMEM lane quarter =====================
     // Work item = (segment, G-channel group); the items of a tile alternate between the two warps of a
     // quarter.  Every global load of an item (residual input, skip) is issued before the TMEM wait.
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    constexpr int G = C < 32 ? C : 32;        // channels per work item
+    constexpr int G = Cfg::G;                 // channels per work item
     constexpr int NGR = C / G;
     uint32_t it = 0;
     using IoT = typename std::conditional<MODE == MODE_BF16, __nv_bfloat16, float>::type;
@@ -280,6 +288,149 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n0 = (tile / p.tpi) * p.nimg;
       const int q0 = (tile % p.tpi) * T;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+      if constexpr (MODE == MODE_BF16 && NGR >= 2) {
+        // bf16, C >= 64: software-pipelined items.  The epilogue is bound by global-load latency x bytes in flight
+        // (ncu: the epilogue warps' samples sit on the first use of the residual loads; 16 warps on half-size items
+        // changed nothing), and at C = 256 it cannot overlap the next tile's MMAs (two 256-column accumulators fill
+        // TMEM).  So: the raw operands of item k+1 are requested before item k is processed, and those of the
+        // tile's first item before the wait for the accumulators.
+        constexpr int IPS = NGR / Cfg::EPQ;   // items per segment for this warp: channel groups gi = EPQ*j + half
+        constexpr int UV = G / 8;             // 16-byte vectors per operand per item
+        const int nit = mt * IPS;
+        const bool has_in = in != nullptr, has_skip = skip != nullptr, has_bias = p.bias != nullptr;
+        auto geom = [&](int k, bool& valid, long long& pix, int& c0, int& sg) {
+          sg = k / IPS;
+          c0 = (Cfg::EPQ * (k - sg * IPS) + half) * G;
+          const int n = n0 + sg / p.spi;
+          const int q = q0 + (sg % p.spi) * 128 + row;
+          const int y = q / p.P, xq = q - y * p.P;
+          valid = (n < p.N) && (y < p.H) && (xq < p.W);
+          pix = ((long long)n * p.H + y) * p.W + xq;
+        };
+        auto request = [&](bool valid, long long pix, int c0, uint4 (&a)[UV], uint4 (&b)[UV]) {
+          if (valid) {
+            if (has_in) {
+              const uint4* ip = reinterpret_cast<const uint4*>(in + pix * C + c0);
+#pragma unroll
+              for (int j = 0; j < UV; ++j) a[j] = ip[j];
+            }
+            if (has_skip) {
+              const uint4* sp = reinterpret_cast<const uint4*>(skip + pix * C + c0);
+#pragma unroll
+              for (int j = 0; j < UV; ++j) b[j] = sp[j];
+            }
+          }
+        };
+        uint4 cin[UV], csk[UV], nin[UV], nsk[UV];
+#pragma unroll
+        for (int j = 0; j < UV; ++j) cin[j] = csk[j] = nin[j] = nsk[j] = make_uint4(0u, 0u, 0u, 0u);
+        // The per-element arithmetic is branch-free: the optional stages are folded into operands that make them
+        // identities (relu floor -inf, scale 1, centre coefficient 0, zeroed operand registers).  With `if (flag)` per
+        // element the compiler emitted ~2300 instructions per 32x32 item and the drain of a tile took 22k cycles of
+        // pure ALU work (measured with every memory and TMEM access disabled).
+        const float relu_floor = p.relu ? 0.0f : -__int_as_float(0x7f800000);
+        const float hs = p.scale_h ? p.h : 1.0f;
+        const float cin_c = has_in ? p.c_in : 0.0f;
+        const bool want2 = p.out2 != nullptr;
+        bool valid, nvalid = false; long long pix, npix = 0; int c0, nc0 = 0, sg, nsg = 0;
+        geom(0, valid, pix, c0, sg);
+        request(valid, pix, c0, cin, csk);
+        mbar_wait_sleep(&acc_full[as], aph);
+        if (it == 0 && threadIdx.x == 64) tr.mark(6);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int k = 0; k < nit; ++k) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * ACCW + c0;
+          uint32_t r[G];
+          {
+            uint32_t t16[16];
+            tmem_ld_x16(taddr, t16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = t16[j];
+            if (G == 32) {
+              uint32_t u16[16];
+              tmem_ld_x16(taddr + 16, u16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[16 + (j & 15)] = u16[j];
+            }
+          }
+          if (k + 1 < nit) {
+            geom(k + 1, nvalid, npix, nc0, nsg);
+            request(nvalid, npix, nc0, nin, nsk);
+          }
+          float bs[G];
+#pragma unroll
+          for (int j = 0; j < G / 4; ++j) {
+            float4 b4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+            bs[4 * j] = b4.x; bs[4 * j + 1] = b4.y; bs[4 * j + 2] = b4.z; bs[4 * j + 3] = b4.w;
+          }
+          uint32_t bits2 = 0;
+          if (want2 && valid) {
+            if (G == 32) bits2 = *reinterpret_cast<const uint32_t*>(p.mask2 + pix * (C / 8) + c0 / 8);
+            else bits2 = *reinterpret_cast<const uint16_t*>(p.mask2 + pix * (C / 8) + c0 / 8);
+          }
+          tmem_ld_wait();
+          if (valid) {
+            float v[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = fmaf(p.acc_scale, __uint_as_float(r[j]), bs[j]);
+            if (p.z_out) {
+              float4* zp = reinterpret_cast<float4*>(p.z_out + pix * C + c0);
+#pragma unroll
+              for (int j = 0; j < G / 4; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.mask) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int j = 0; j < G; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
+              if (G == 32) *reinterpret_cast<uint32_t*>(p.mask + pix * (C / 8) + c0 / 8) = bits;
+              else *reinterpret_cast<uint16_t*>(p.mask + pix * (C / 8) + c0 / 8) = static_cast<uint16_t>(bits);
+            }
+            if (out) {
+              uint32_t pk[G / 2];
+#pragma unroll
+              for (int j = 0; j < UV; ++j) {
+                const uint32_t wi[4] = {cin[j].x, cin[j].y, cin[j].z, cin[j].w};
+                const uint32_t ws_[4] = {csk[j].x, csk[j].y, csk[j].z, csk[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j0 = 8 * j + 2 * e;
+                  // relu -> Lambda(h*x) (own rounding) -> + c_in * x -> + skip; disabled stages are identities
+                  float a0 = __fmul_rn(hs, fmaxf(v[j0], relu_floor)), a1 = __fmul_rn(hs, fmaxf(v[j0 + 1], relu_floor));
+                  a0 = fmaf(cin_c, __uint_as_float(wi[e] << 16), a0) + __uint_as_float(ws_[e] << 16);
+                  a1 = fmaf(cin_c, __uint_as_float(wi[e] & 0xFFFF0000u), a1) + __uint_as_float(ws_[e] & 0xFFFF0000u);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+                  pk[4 * j + e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+              }
+              uint4* op = reinterpret_cast<uint4*>(out + pix * C + c0);
+#pragma unroll
+              for (int j = 0; j < UV; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              if (want2) {   // dZ of the step below from the value as stored (see ConvTcParams::out2)
+                uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + pix * C + c0);
+#pragma unroll
+                for (int j = 0; j < UV; ++j) {
+                  uint32_t pk2[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j0 = 8 * j + 2 * e;
+                    const uint32_t w = pk[4 * j + e];
+                    const float s0 = (bits2 >> j0) & 1u ? p.h2 * __uint_as_float(w << 16) : 0.0f;
+                    const float s1 = (bits2 >> (j0 + 1)) & 1u ? p.h2 * __uint_as_float(w & 0xFFFF0000u) : 0.0f;
+                    __nv_bfloat162 z2 = __floats2bfloat162_rn(s0, s1);
+                    pk2[e] = *reinterpret_cast<uint32_t*>(&z2);
+                  }
+                  op2[j] = make_uint4(pk2[0], pk2[1], pk2[2], pk2[3]);
+                }
+              }
+            }
+          }
+          valid = nvalid; pix = npix; c0 = nc0; sg = nsg;
+#pragma unroll
+          for (int j = 0; j < UV; ++j) { cin[j] = nin[j]; csk[j] = nsk[j]; }
+        }
+      } else {
       mbar_wait_sleep(&acc_full[as], aph);
       if (it == 0 && threadIdx.x == 64) tr.mark(6);
       tc_fence_after_sync();
@@ -293,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * mt + sg) * ACCW;
 #pragma unroll
         for (int gi = 0; gi < NGR; ++gi) {
-          if (((sg * NGR + gi) & 1) != half) continue;
+          if (((sg * NGR + gi) & (Cfg::EPQ - 1)) != half) continue;
           const int c0 = gi * G;
           uint32_t r[G];
           {
@@ -457,6 +608,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      }   // per-item path (fp32 modes, C < 64)
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
