@@ -685,10 +685,11 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     // More than one M block (C = 256): deal the blocks to different CTAs.  Staging all C input channels leaves
     // room for only ~64 positions per stage (3x halo over-read, L2-bound); one 128-channel block per CTA fits
     // four times as many and lets a CTA keep 3 taps x 128 output channels in TMEM.
-    // Measured (N=256, C=256): bf16 32x32 841 -> 670 us; tf32 1303 -> 1653 us and bf16 64x64 702 -> 1106 us get
-    // worse (row-granular strips at P = 65 over-read 3-5x for short tiles), so it is on for bf16 at W <= 32 only.
+    // Measured (N=256, C=256) together with the row-aligned tiles below: bf16 32x32 841 -> 283 us, bf16 64x64
+    // 702 -> 285 us, tf32 32x32 1264 -> 527 us.  tf32 at W = 64 leaves room for one stage only (position-granular
+    // tiles stay), strict doubles every strip (hi + lo).
     static const int mg_env = getenv("B200ODE_WGRAD_MGROUPS") ? atoi(getenv("B200ODE_WGRAD_MGROUPS")) : -1;   // debug override
-    const bool use_mg = force_mgroups || (mg_env >= 0 ? mg_env != 0 : (bf16 && W <= 64));
+    const bool use_mg = force_mgroups || (mg_env >= 0 ? mg_env != 0 : ((bf16 && W <= 64) || (!strict && W <= 32)));
     if (p.MB > 1 && use_mg) { p.mgroups = p.MB; p.MB = 1; p.xchunks = p.Mblk / p.CH; }
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
@@ -717,12 +718,12 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.tmem_cols = pc;
   const long long Q = (long long)H * p.P;
   const int max_smem = 227 * 1024 - 2048;
-  // Row-aligned tiles (bf16, 128-channel operand blocks): a tile is R whole image rows, so the strips hold exactly
+  // Row-aligned tiles (bf16 / tf32, 128-channel operand blocks): a tile is R whole image rows, so the strips hold exactly
   // R+2 / R rows (x over-read (R+2)/R instead of the ~3x of position-granular tiles on row-granular strips) and
   // the k-steps run into a zeroed pad up to the next multiple of 16 positions.
   static const int rows_env = getenv("B200ODE_WGRAD_ROWS") ? atoi(getenv("B200ODE_WGRAD_ROWS")) : -1;   // debug override (0 = off)
   int rows = 0;
-  if (bf16 && !p.trick && !p.pair && p.Mblk == 128 && rows_env != 0) {
+  if (!strict && !p.trick && !p.pair && p.Mblk == 128 && rows_env != 0) {
     auto stage_bytes = [&](int R) -> long long {
       const int kt = (R * p.P + UKP - 1) / UKP * UKP;
       const uint32_t xs = align_up((uint32_t)(kt + 2 * p.P + 3) * p.PB, 1024), ds = align_up((uint32_t)kt * p.PB, 1024);
