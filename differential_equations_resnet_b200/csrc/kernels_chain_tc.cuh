@@ -297,16 +297,27 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int img = blockIdx.x + ic * gridDim.x;
       const bool active = img < p.N;     // ghosts keep the barrier protocol but touch no global memory
       const long long img_off = (long long)img * img_elems;
+      // Per-thread geometry of every segment (layer invariant): pixel index, strip position and validity are computed
+      // ONCE per image.  They used to be recomputed per (layer, segment) between the accumulator barrier and the TMEM
+      // load -- ~90 of the ~240 instructions of an item, on the critical path of the layer hand-over.
+      int pixl_s[MAXSEG];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int sg = 0; sg < MAXSEG; ++sg) {
+        const int q = sg * 128 + row;
+        const int yy = q / p.P, xq = q - yy * p.P;
+        pixl_s[sg] = yy * p.W + xq;
+        if (sg < p.nseg && active && yy < p.H && xq < p.W) vmask |= 1u << sg;
+      }
       if (DIR == 1) {
         // ---- init: E = dY_L, strip0 = dZ_{L-1} = h * dY_L * mask_{L-1} ----
         const uint8_t* mk_l = p.masks_r + ((long long)(p.L - 1) * p.N + img) * (long long)p.H * p.W * groups;
         float* dz_l = p.dz_all + (long long)(p.L - 1) * layer_elems + img_off;
-        for (int sg = 0; sg < p.nseg; ++sg) {
-          const int q = sg * 128 + row;
-          const int yy = q / p.P, xq = q - yy * p.P;
-          if (active && yy < p.H && xq < p.W) {
-            const int pixl = yy * p.W + xq;
-            const uint32_t pos = (uint32_t)(q + p.P + 1);
+#pragma unroll
+        for (int sg = 0; sg < MAXSEG; ++sg) {
+          if ((vmask >> sg) & 1u) {
+            const int pixl = pixl_s[sg];
+            const uint32_t pos = (uint32_t)(sg * 128 + row + p.P + 1);
             const float* src = p.dy + img_off + (long long)pixl * C;
 #pragma unroll
             for (int cg = 0; cg < NG; ++cg) {
@@ -356,11 +367,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint8_t* mk_l = p.masks_r + ((long long)(l - 1) * p.N + img) * (long long)p.H * p.W * groups;
 #pragma unroll
             for (int sg = 0; sg < MAXSEG; ++sg) {
-              if (sg < p.nseg) {
-                const int q = sg * 128 + row;
-                const int yy = q / p.P, xq = q - yy * p.P;
-                if (active && yy < p.H && xq < p.W) {
-                  const uint8_t* mp = mk_l + (long long)(yy * p.W + xq) * groups;
+              {
+                if ((vmask >> sg) & 1u) {
+                  const uint8_t* mp = mk_l + (long long)pixl_s[sg] * groups;
                   if (C == 16) mkreg[sg][0] = *reinterpret_cast<const uint16_t*>(mp);
                   else {
 #pragma unroll
@@ -383,11 +392,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (threadIdx.x == 64 && lc == TL && sg == 0) tr.mark(6);
             if (threadIdx.x == 64 && lc == TL + 1 && sg == 0) tr.mark(9);
             if (threadIdx.x == 64 && lc == TL && sg == 2) tr.mark(7);
-            const int q = sg * 128 + row;
-            const int yy = q / p.P, xq = q - yy * p.P;
-            const bool valid = active && (yy < p.H) && (xq < p.W);
-            const int pixl = yy * p.W + xq;
-            const uint32_t pos = (uint32_t)(q + p.P + 1);
+            const bool valid = (vmask >> sg) & 1u;
+            const int pixl = pixl_s[sg];
+            const uint32_t pos = (uint32_t)(sg * 128 + row + p.P + 1);
             // all TMEM loads of this warp's items of the segment are issued up front (one wait covers them)
             constexpr int NGI = NG > 1 ? NG / 2 : 1;
             uint32_t rr[NGI][16];
