@@ -1,6 +1,6 @@
 """BASELINE.json configs[3]: wide antisymmetric ResNet -- stem 3->256 at 64x64, 8 Euler steps with 256 channels,
 GAP + FC, bf16 fast mode; one full train step (forward, loss, backward, Adam).  Not a pytest.
-usage: python tests/gpu_cfg4.py [batch=512] [precision=fast_bf16] [steps=5]"""
+usage: python tools/gpu_cfg4.py [batch=512] [precision=fast_bf16] [steps=5]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,5 +1,5 @@
 """2-GPU check of the C-ABI gradient exchange (b200ode_comm_*): not a pytest, run under torchrun:
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_comm_abi.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/gpu_comm_abi.py
 (1) the ABI all-reduce of a bucket equals torch.distributed's; (2) three train steps with comm=AbiComm give the
 same losses and parameters as with torch.distributed, eagerly and replayed from a CUDA graph."""
 import os, sys

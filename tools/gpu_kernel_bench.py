@@ -1,5 +1,5 @@
 """Micro-benchmark / profiling driver for the three tensor-core kernels (not a pytest).
-usage: python tests/gpu_kernel_bench.py N H W C precision [iters]"""
+usage: python tools/gpu_kernel_bench.py N H W C precision [iters]"""
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

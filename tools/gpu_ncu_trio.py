@@ -1,5 +1,5 @@
 """One forward, data-gradient and weight-gradient launch of a single Euler layer (for `ncu --set full`).  Not a pytest.
-usage: python tests/gpu_ncu_trio.py N H W C precision"""
+usage: python tools/gpu_ncu_trio.py N H W C precision"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch

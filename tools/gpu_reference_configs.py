@@ -2,7 +2,7 @@
   * train throughput, antisymmetric net: stem + 64 single-layer Euler blocks, 16 channels, 32x32, h = 8/64, no BN,
     batch 32, Adam(1e-3, eps 1e-7)  -- experiments_antisymmetric_resnet_v6.ipynb:362 (1.46 it/s = 46.7 img/s)
   * inference latency at batch 1 of the same net -- experiments_antisymmetric_resnet_v7.ipynb:650-651 (199.3 ms, 5.02 FPS)
-Not a pytest.  usage: python tests/gpu_reference_configs.py"""
+Not a pytest.  usage: python tools/gpu_reference_configs.py"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

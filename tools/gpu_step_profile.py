@@ -1,7 +1,7 @@
 """Run a few EAGER cfg3 train steps (no CUDA graph) so that `ncu --metrics gpu__time_duration.sum`
 lists every launch of one step.  Not a pytest.
 
-usage: python tests/gpu_step_profile.py [steps] [precision] [blocks]
+usage: python tools/gpu_step_profile.py [steps] [precision] [blocks]
 Prints the number of libb200ode launches per step (use it for ncu's -s / -c).
 """
 import os

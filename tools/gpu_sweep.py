@@ -2,7 +2,7 @@
 every tensor-core precision mode.  Not a pytest; prints one line per (kernel, shape, mode) and writes
 JSON lines to the path given by --out.
 
-usage: python tests/gpu_sweep.py [--batch 256] [--hw 32] [--channels 16,32,64,128,256]
+usage: python tools/gpu_sweep.py [--batch 256] [--hw 32] [--channels 16,32,64,128,256]
                                  [--modes fast_tf32,fast_bf16,strict] [--out gpurun_out/sweep.jsonl]
 """
 import argparse

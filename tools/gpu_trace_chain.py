@@ -1,5 +1,5 @@
 """Per-CTA timeline of the persistent chain kernels (debug hook b200ode_debug_set_trace).  Not a pytest.
-usage: python tests/gpu_trace_chain.py N H W C [L]"""
+usage: python tools/gpu_trace_chain.py N H W C [L]"""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

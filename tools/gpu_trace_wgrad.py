@@ -1,5 +1,5 @@
 """Per-role timeline of the tensor-core weight-gradient kernel (debug hook b200ode_debug_set_trace).  Not a pytest.
-usage: python tests/gpu_trace_wgrad.py N H W C precision"""
+usage: python tools/gpu_trace_wgrad.py N H W C precision"""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
