@@ -56,6 +56,7 @@ _SIGNATURES = {
     "b200ode_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_void_p]),
     "b200ode_increment": (c_int, [c_void_p, c_void_p]),
+    "b200ode_gradient_mean_norms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "b200ode_stem_fwd": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "b200ode_stem_wgrad": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -963,6 +963,17 @@ extern "C" int b200ode_adam_step(float* params, const float* grads, float* m, fl
   return 0;
 }
 
+extern "C" int b200ode_gradient_mean_norms(const float* grads, const int64_t* offsets, const int64_t* sizes, int n_slices,
+                                           float grad_scale, float* out, void* stream) {
+  if (!grads || !offsets || !sizes || !out) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (n_slices <= 0) return 0;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+  segment_mean_norm_kernel<<<n_slices, 256, 0, (cudaStream_t)stream>>>(grads, reinterpret_cast<const long long*>(offsets),
+                                                                       reinterpret_cast<const long long*>(sizes), grad_scale, out);
+  LAUNCH_CHECK("segment_mean_norm_kernel");
+  return 0;
+}
+
 extern "C" int b200ode_increment(int32_t* counter, void* stream) {
   if (!counter) return fail(B200ODE_ERR_INVALID, "NULL argument");
   increment_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter);

@@ -546,4 +546,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void increment_kernel(int* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
 
+// Per-layer gradient metric of the reference trainer (training/training.py:385-407): ||g||_2 / size over the slice
+// [offset, offset + size) of the flat gradient bucket, one block per slice, fixed summation order (deterministic).
+// `scale` = 1/world_size turns the all-reduced sum into the mean gradient first.
+__global__ void __launch_bounds__(256) segment_mean_norm_kernel(const float* __restrict__ g, const long long* __restrict__ offsets,
+                                                                const long long* __restrict__ sizes, float scale,
+                                                                float* __restrict__ out) {
+  __shared__ float red[256];
+  const long long off = offsets[blockIdx.x], n = sizes[blockIdx.x];
+  float acc = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += 256) { const float v = g[off + i] * scale; acc = fmaf(v, v, acc); }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = n > 0 ? sqrtf(red[0]) / (float)n : 0.0f;
+}
+
 }  // namespace b200ode

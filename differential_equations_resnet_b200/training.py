@@ -577,10 +577,37 @@ class EulerNet:
                 idx += 1
         return out
 
+    def gradient_metric_names(self):
+        """Column names of the reference's gradient history (`training/training.py:385-407`; header of
+        numerical_results/csv/*_gradient_history.csv): conv1 first, then every Euler layer in graph order."""
+        return ["conv1_kernel_gradient_mean_norm"] + [name + "_kernel_gradient_mean_norm" for name, _, _, _ in self.layer_param_slices()]
+
     def gradient_mean_norms(self):
-        """Per-layer ||g||_2 / size over the kernel variables (training/training.py:385-407)."""
-        res = {}
-        for name, off, n, C in self.layer_param_slices():
-            g = self.grad[off:off + n - C]
-            res[name] = float(g.norm() / g.numel())
-        return res
+        """Per-layer ||g||_2 / size over the kernel variables (training/training.py:385-407): the stem kernel and, per
+        antisymmetric layer, its C+3 kernel variables a,b,c,d,W_o merged (bias excluded) -- ONE launch over the flat
+        gradient bucket (`b200ode_gradient_mean_norms`).  Returns an OrderedDict name -> float."""
+        from collections import OrderedDict
+        if getattr(self, "_gm_tables", None) is None:
+            a, shape = self.torch_params["conv1/kernel"]
+            offs, sizes = [a], [math.prod(shape)]
+            for _, off, n, C in self.layer_param_slices():
+                offs.append(off); sizes.append(n - C)
+            self._gm_tables = (torch.tensor(offs, dtype=torch.int64, device=self.device),
+                               torch.tensor(sizes, dtype=torch.int64, device=self.device),
+                               torch.empty(len(offs), dtype=torch.float32, device=self.device))
+        offs, sizes, out = self._gm_tables
+        _abi.check(_abi.lib().b200ode_gradient_mean_norms(_ptr(self.grad), _ptr(offs), _ptr(sizes), offs.numel(),
+                                                          1.0 / self.world_size, _ptr(out), _stream_ptr()))
+        return OrderedDict(zip(self.gradient_metric_names(), out.cpu().tolist()))
+
+    def history_row(self, loss, probs=None, onehot=None):
+        """One row of the reference's gradient-history CSV: `global_step mean_loss accuracy <layer>_kernel_gradient_mean_norm ...`
+        (space separated; `header=True` rows via gradient_history_header())."""
+        acc = float("nan")
+        if probs is not None and onehot is not None:
+            acc = float((probs.argmax(dim=1) == onehot.argmax(dim=1)).float().mean())
+        step = int(self.step_counter) - 1
+        return " ".join([str(step), repr(float(loss)), repr(acc)] + [repr(v) for v in self.gradient_mean_norms().values()])
+
+    def gradient_history_header(self):
+        return " ".join(["global_step", "mean_loss", "accuracy"] + self.gradient_metric_names())

@@ -144,6 +144,11 @@ int b200ode_bn_bwd_apply(const float* dy, const float* z, const float* scale, co
 int b200ode_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int32_t* step_counter,
                       float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 int b200ode_increment(int32_t* counter, void* stream);
+/* The reference trainer's gradient metric (training/training.py:385-407, `<layer>_kernel_gradient_mean_norm`):
+ * out[i] = || grad_scale * grads[offsets[i] .. offsets[i]+sizes[i]) ||_2 / sizes[i], one launch for all layers
+ * (offsets / sizes are DEVICE arrays of n_slices int64). */
+int b200ode_gradient_mean_norms(const float* grads, const int64_t* offsets, const int64_t* sizes, int n_slices,
+                                float grad_scale, float* out, void* stream);
 
 /* ---- persistent Euler-step chains: the stage loop of models/tfkeras_resnets.py:575-593
  *      (n x single_layer_identity_block, :28-94, on a tensor of constant shape) forward and its

@@ -88,3 +88,28 @@ def test_native_predict_matches_oracle():
         got = net.predict(img.cuda()).cpu()
         assert float((got - ref).abs().max()) <= 5e-3, float((got - ref).abs().max())
         assert torch.equal(got.argmax(-1), ref.argmax(-1))
+
+
+def test_gradient_history_metrics():
+    """Reference trainer metrics (training/training.py:385-407): per-layer ||g||_2/size in one native launch, and the
+    column layout of numerical_results/csv/*_gradient_history.csv."""
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    net = EulerNet(NetSpec(blocks_per_stage=(3, 2, 2), filters_per_block=(16, 32, 64), h=0.25, gamma=-0.05), seed=2)
+    gen = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (8, 32, 32, 3), generator=gen, dtype=torch.uint8).cuda()
+    lab = torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=gen), 10).float().cuda()
+    loss = net.train_step(img, lab)
+    norms = net.gradient_mean_norms()
+    names = list(norms.keys())
+    assert names[:3] == ["conv1_kernel_gradient_mean_norm", "res2_0_branch2_kernel_gradient_mean_norm",
+                         "res2_1_branch2_kernel_gradient_mean_norm"]
+    assert net.gradient_history_header().split(" ")[:4] == ["global_step", "mean_loss", "accuracy", "conv1_kernel_gradient_mean_norm"]
+    g = net.grad.detach().double().cpu()
+    a, shape = net.torch_params["conv1/kernel"]
+    n = int(np.prod(shape))
+    assert abs(norms[names[0]] - float(g[a:a + n].norm() / n)) <= 1e-6 * float(g[a:a + n].norm() / n)
+    for (name, off, size, C), key in zip(net.layer_param_slices(), names[1:]):
+        ref = float(g[off:off + size - C].norm() / (size - C))     # 19 kernel variables of a 16-channel layer, bias excluded
+        assert abs(norms[key] - ref) <= 1e-5 * ref, key
+    row = net.history_row(loss, net.predict(img), lab).split(" ")
+    assert len(row) == 3 + len(names) and int(row[0]) == 1 and abs(float(row[1]) - float(loss)) < 1e-6
