@@ -378,6 +378,8 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
   for (int whole = 0; whole < 2; ++whole) {
     for (int a = 1; a <= 32; ++a) {
       int spi, nimg, tpi, RB;
+      static const int spi_env = getenv("B200ODE_CONV_SPI") ? atoi(getenv("B200ODE_CONV_SPI")) : 0;   // debug: force segments per tile
+      if (spi_env > 0 && (whole || a != spi_env)) continue;
       if (whole) {
         // H+2 halo rows plus one: tap (2,2) of the last pixel reads the first pixel of halo row H+2
         // (the shared zero column), which must come from TMA zero fill, not stale shared memory
@@ -406,18 +408,28 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
       while (sw < 6 && tw == 1 && need + w_stride <= max_smem) { ++sw; need += w_stride; }
       if (nkb > 1 || true) while (sa < 3 && need + a_stride <= max_smem) { ++sa; need += a_stride; }
       const long long tiles = whole ? (N + nimg - 1) / nimg : (long long)N * tpi;
-      // rough per-tile cycle model: tensor issue vs L2->smem fill vs epilogue traffic
-      const double per_mma = (C / 2 > 32 ? C / 2 : 32) * (strict ? 3.0 : 1.0);
+      // Per-tile cycle model, calibrated on per-CTA timelines (tools/gpu_trace.py): MMA issue (M = 128: 40 cycles up
+      // to N = 32, 48 at N = 64, N/2 above), L2 -> smem fill at ~40 B/clk, and the drain of the accumulators at ~48
+      // cycles per (segment, channel) (C = 16: 7.8k cycles for 9 segments, C = 256 bf16: 22k for 2).  With double-
+      // buffered accumulators the drain overlaps the next tile's MMAs; one tile's worth of the shorter phase is
+      // exposed as pipeline fill/drain, which is what favours more, smaller tiles at small C.
+      static const int model_env = getenv("B200ODE_CONV_COSTMODEL") ? atoi(getenv("B200ODE_CONV_COSTMODEL")) : 1;   // 0: previous model (A/B runs)
+      const double per_mma = model_env ? (C >= 128 ? C / 2 : C == 64 ? 48 : 40) * (strict ? 3.0 : 1.0)
+                                       : (C / 2 > 32 ? C / 2 : 32) * (strict ? 3.0 : 1.0);
       const double mma_clk = (double)mt * nkb * 9 * (rowb / 32) * per_mma;
       const double load_clk = ((double)nimg * RB * P * C * eb + 9.0 * C * C * eb * (strict ? 2 : 1)) / 40.0;
-      const double epi_clk = (double)mt * 128 * C * 4 * 2 / 40.0;
+      const double epi_clk = model_env ? (double)mt * C * 48.0 : (double)mt * 128 * C * 4 * 2 / 40.0;
       double tile_clk = mma_clk > load_clk ? mma_clk : load_clk;
       if (acc_stages == 1) tile_clk += epi_clk; else if (epi_clk > tile_clk) tile_clk = epi_clk;
+      // single-buffered accumulators serialise MMAs and drain; measured tiles (C = 256: 125k cycles tf32, 61k bf16) run
+      // ~25 % over the sum of the two phases
+      if (model_env && acc_stages == 1) tile_clk *= 1.25;
       if (sa == 1) tile_clk = mma_clk + load_clk + (acc_stages == 1 ? epi_clk : 0);
       tile_clk += 600;
       const int sms = g_num_sms > 0 ? g_num_sms : 148;
       const double waves = std::ceil((double)tiles / sms);
-      const double cost = waves * tile_clk;
+      double cost = waves * tile_clk;
+      if (model_env && acc_stages == 2) cost += mma_clk < epi_clk ? mma_clk : epi_clk;
       if (cost < best_cost) {
         best_cost = cost; found = true;
         memset(&best, 0, sizeof(best));
@@ -448,6 +460,11 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
     }
   }
   if (!found) return fail(B200ODE_ERR_UNSUPPORTED, "no tensor-core tiling fits shared memory for C=%d H=%d W=%d", C, H, W);
+  static const bool plan_dbg = getenv("B200ODE_PLAN_DEBUG") != nullptr;
+  if (plan_dbg)
+    fprintf(stderr, "[b200ode] conv plan mode=%d C=%d N=%d %dx%d: nimg=%d spi=%d tpi=%d tiles=%d grid=%d iters=%d sa=%d sw=%d tw=%d tmem=%u smem=%zu cost=%.0f\n",
+            mode, C, N, H, W, best.p.nimg, best.p.spi, best.p.tpi, best.p.total_tiles, best.grid, best.p.iters, best.p.sa, best.p.sw,
+            best.p.tw, best.p.tmem_cols, best.smem, best_cost);
   *plan = best;
   return 0;
 }
