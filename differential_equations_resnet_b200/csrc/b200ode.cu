@@ -866,15 +866,19 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const long long nout = (lg.use_bias ? lg.nparams : lg.bias_off);
   int fl = 1;                                   // lanes per output: power of two >= nparts, at most 16
   while (fl < 16 && fl < nparts) fl <<= 1;
-  // Off-diagonal blocks through the coalesced tile kernel when it has enough blocks to fill the GPU and few partials per
-  // entry (it sums them serially); otherwise the per-parameter kernel with up to 16 lanes per output.
-  // Measured: C=256 / 12 partials 88 -> ~10 us; C=32 / 148 partials (9 blocks) 10 -> 110 us, hence the gate.
+  // Off-diagonal blocks through the coalesced tile kernel when it has enough threads to fill the GPU; PZ lanes per
+  // block share the partials (1 / 2 / 4 for <= 4 / <= 16 / more partials).  Otherwise the per-parameter kernel with up
+  // to 16 lanes per output.  Measured: C=256 / 12 partials 88 -> ~10 us; C=32 / 148 partials (9 blocks) stays on the
+  // per-parameter kernel (10 us there, 110 us tiled).
   const int T = (C + 31) / 32;
-  const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && nparts <= 16 &&
-                     (long long)T * (T + 1) / 2 * lg.k * lg.k * L >= 148;
+  const int PZ = nparts <= 4 ? 1 : nparts <= 16 ? 2 : 4;
+  const long long tblocks = (long long)T * (T + 1) / 2 * lg.k * lg.k * L;
+  const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && nparts <= 16 * PZ && tblocks * PZ >= 296;
   if (tiled) {
-    fold_reduce_tiled_kernel<<<dim3(T * (T + 1) / 2, lg.k * lg.k, L), 256, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate,
-                                                                                   p.part_layer_stride, grad_layer_stride);
+    const dim3 tgrid(T * (T + 1) / 2, lg.k * lg.k, L), tblock(32, 8, PZ);
+    if (PZ == 1) fold_reduce_tiled_kernel<1><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
+    else if (PZ == 2) fold_reduce_tiled_kernel<2><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
+    else fold_reduce_tiled_kernel<4><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
     LAUNCH_CHECK("fold_reduce_tiled_kernel");
   }
   const long long nfold = tiled ? 4LL * C + (lg.use_bias ? C : 0) : nout;

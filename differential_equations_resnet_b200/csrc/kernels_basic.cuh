@@ -337,11 +337,15 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
 // The first term is read coalesced along o and transposed through shared memory, the second term and the
 // write are coalesced along ci (the per-parameter kernel gathers the first term with a stride of C floats:
 // 80 us for C = 256 / 12 partials where the partials are 28 MB).  Fixed summation order -> deterministic.
-// grid: (tile pairs to <= tc, taps, layers).
-__global__ void __launch_bounds__(256) fold_reduce_tiled_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts,
-                                                                long long part_stride, float* __restrict__ grad, int accumulate,
-                                                                long long part_layer_stride, long long grad_layer_stride) {
-  __shared__ float t1[32][33];
+// grid: (tile pairs to <= tc, taps, layers); PZ lanes over the partials per block.
+template <int PZ>
+__global__ void __launch_bounds__(256 * PZ) fold_reduce_tiled_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts,
+                                                                     long long part_stride, float* __restrict__ grad, int accumulate,
+                                                                     long long part_layer_stride, long long grad_layer_stride) {
+  // blockDim = (32, 8, PZ): threadIdx.z deals the partials (part p goes to lane p % PZ); the PZ partial sums are
+  // combined in a fixed order through shared memory.
+  __shared__ float t1[PZ][32][33];
+  __shared__ float t2[PZ][32][33];
   Gpart += (long long)blockIdx.z * part_layer_stride;
   grad += (long long)blockIdx.z * grad_layer_stride;
   int tc = 0;
@@ -349,28 +353,40 @@ __global__ void __launch_bounds__(256) fold_reduce_tiled_kernel(LayerGeom g, con
   const int to = (int)blockIdx.x - tc * (tc + 1) / 2;
   const int tap = blockIdx.y, rt = g.k * g.k - 1 - tap;
   const int C = g.C, ci0 = tc * 32, o0 = to * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {
-    const int ci = ci0 + r, o = o0 + tx;
-    float a = 0.0f;
-    if (ci < C && o < C) {
-      const float* src = Gpart + ((long long)tap * C + ci) * C + o;
-      for (int p = 0; p < nparts; ++p) a += src[(long long)p * part_stride];
+    float a = 0.0f, b = 0.0f;
+    {
+      const int ci = ci0 + r, o = o0 + tx;      // first term: row ci, contiguous along o
+      if (ci < C && o < C) {
+        const float* src = Gpart + ((long long)tap * C + ci) * C + o;
+        for (int p = tz; p < nparts; p += PZ) a += src[(long long)p * part_stride];
+      }
     }
-    t1[r][tx] = a;
+    {
+      const int o = o0 + r, ci = ci0 + tx;      // second term: row o, contiguous along ci
+      if (o < C && ci < C && ci > o) {
+        const float* src = Gpart + ((long long)rt * C + o) * C + ci;
+        for (int p = tz; p < nparts; p += PZ) b += src[(long long)p * part_stride];
+      }
+    }
+    t1[tz][r][tx] = a;
+    t2[tz][r][tx] = b;
   }
   __syncthreads();
+  if (tz == 0) {
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int o = o0 + r, ci = ci0 + tx;
-    if (o < C && ci < C && ci > o) {
-      const float* src = Gpart + ((long long)rt * C + o) * C + ci;
-      float b = 0.0f;
-      for (int p = 0; p < nparts; ++p) b += src[(long long)p * part_stride];
-      const float val = t1[tx][r] - b;
-      const long long i = w_block_off(g, o) + (long long)tap * (C - o - 1) + (ci - o - 1);
-      grad[i] = accumulate ? grad[i] + val : val;
+    for (int r = ty; r < 32; r += 8) {
+      const int o = o0 + r, ci = ci0 + tx;
+      if (o < C && ci < C && ci > o) {
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int z = 0; z < PZ; ++z) { a += t1[z][tx][r]; b += t2[z][r][tx]; }
+        const float val = a - b;
+        const long long i = w_block_off(g, o) + (long long)tap * (C - o - 1) + (ci - o - 1);
+        grad[i] = accumulate ? grad[i] + val : val;
+      }
     }
   }
 }
