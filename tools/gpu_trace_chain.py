@@ -37,7 +37,7 @@ def main():
         w0, w1 = t[:, 0].min().item(), t[:, 15].max().item()
         print("%s %s L=%d: %d CTAs, wall span %.2f us" % (kind, (N, H, W, C), L, t.shape[0], (w1 - w0) / 1e3))
         if kind == "wgrad":
-            nm = {1: "setup", 2: "mma:full0", 3: "mma:tile0 issued", 4: "mma:all issued", 5: "epi:bias done", 6: "epi:acc_full", 7: "epi:done", 9: "end"}
+            nm = {1: "setup", 2: "mma:full0", 3: "mma:tile0 issued", 4: "mma:all issued", 5: "epi:bias done", 6: "epi:acc_full", 7: "epi:done", 9: "end", 10: "mma wait on stages"}
         else:
             nm = NAMES
         for cta in (0, t.shape[0] // 2, t.shape[0] - 1):
