@@ -1273,10 +1273,14 @@ static int transition_check(int Cin, int Cout) {
   return 0;
 }
 
-// reduction of per-block partials: 8 row lanes per output when there are many rows
+// reduction of per-block partials: 32 / 8 row lanes per output when there are many rows (whole warps only: the
+// combine is a warp shuffle, so n * LANES must fill the last warp)
 static int reduce_rows(const float* ws, int R, long long stride, long long n, float* out, cudaStream_t st) {
-  if (R >= 32 && (n * 8) % 32 == 0) {
-    reduce_rows_wide_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>(ws, R, stride, n, out);
+  if (R >= 64 && n <= 2048) {   // few outputs: 32 row lanes (a warp's lanes read 32 different rows: 4 useful bytes per sector, only worth it when the launch is latency-bound)
+    reduce_rows_wide_kernel<32><<<blocks_for(n * 32, 256), 256, 0, st>>>(ws, R, stride, n, out);
+    LAUNCH_CHECK("reduce_rows_wide_kernel");
+  } else if (R >= 32 && (n * 8) % 32 == 0) {
+    reduce_rows_wide_kernel<8><<<blocks_for(n * 8, 256), 256, 0, st>>>(ws, R, stride, n, out);
     LAUNCH_CHECK("reduce_rows_wide_kernel");
   } else {
     reduce_rows_kernel<<<blocks_for(n, 128), 128, 0, st>>>(ws, R, stride, n, out);
@@ -1392,11 +1396,7 @@ extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, cons
   if (int rc = get_scratch(2, (size_t)N * nout * sizeof(float), (void**)&ws)) return rc;
   head_kernel<<<N, C, (C + 33) * sizeof(float), (cudaStream_t)stream>>>(x, HW, C, K, fc_kernel, fc_bias, onehot, eps, N, probs, dx, ws);
   LAUNCH_CHECK("head_kernel");
-  if (dparams) {
-    reduce_rows_kernel<<<blocks_for(nout - 1, 128), 128, 0, (cudaStream_t)stream>>>(ws, N, nout, nout - 1, dparams);
-    LAUNCH_CHECK("reduce_rows_kernel");
-  }
-  reduce_rows_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws + (nout - 1), N, nout, 1, loss);
-  LAUNCH_CHECK("reduce_rows_kernel");
-  return 0;
+  if (dparams)
+    if (int rc = reduce_rows(ws, N, nout, nout - 1, dparams, (cudaStream_t)stream)) return rc;
+  return reduce_rows(ws + (nout - 1), N, nout, 1, loss, (cudaStream_t)stream);
 }

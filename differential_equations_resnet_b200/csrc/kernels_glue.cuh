@@ -418,17 +418,20 @@ __global__ void transition_wgrad_partial(GlueConv g, const float* __restrict__ x
   }
 }
 
-// out[o] = sum_r part[r*stride + o] for many rows: 8 row lanes per output, fixed-order combine (deterministic)
+// out[o] = sum_r part[r*stride + o] for many rows: LANES (8 or 32) row lanes per output, fixed-order combine
+// (deterministic).  A single thread per output walked R = 128..512 rows serially (8-11 us per launch for a few
+// hundred outputs).
+template <int LANES>
 __global__ void reduce_rows_wide_kernel(const float* __restrict__ part, int R, long long stride, long long n, float* __restrict__ out) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long o = gid >> 3;
-  const int l = (int)(gid & 7);
+  const long long o = gid / LANES;
+  const int l = (int)(gid % LANES);
   if (o >= n) return;
   float acc = 0.0f;
-  for (int r = l; r < R; r += 8) acc += part[(long long)r * stride + o];
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4, 8);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2, 8);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1, 8);
+#pragma unroll 4
+  for (int r = l; r < R; r += LANES) acc += part[(long long)r * stride + o];
+#pragma unroll
+  for (int off = LANES >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, LANES);
   if (l == 0) out[o] = acc;
 }
 

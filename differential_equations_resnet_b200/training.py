@@ -371,6 +371,21 @@ class EulerNet:
         div = float(spec.divide_by_stddev if spec.divide_by_stddev is not None else 1.0)
         th, gr = self.theta, self.grad
         cur = images
+        # The chains' weight staging (K1, one small launch per stage) only depends on the parameters: it runs on a side
+        # stream under the stem / first stages instead of in front of every chain launch (fork / join, graph capturable).
+        if getattr(self, "_pack_stream", None) is None:
+            self._pack_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        overlap_pack = not os.environ.get("B200ODE_NO_PACK_OVERLAP")
+        if overlap_pack:
+            self._pack_stream.wait_stream(main)
+        with torch.cuda.stream(self._pack_stream if overlap_pack else main):
+            for e in nb["plan"]:
+                if e["kind"] == "chain":
+                    e["chain"].fused.pack(self.theta_euler[e["chain"].offset:], e["chain"].np_layer)
+            packed = torch.cuda.Event()
+            packed.record(self._pack_stream if overlap_pack else main)
+        joined = False
         for e in nb["plan"]:
             if e["kind"] == "stem":
                 ko = self._off(e["name"] + "/kernel")
@@ -389,9 +404,13 @@ class EulerNet:
             else:
                 ch = e["chain"]
                 ch.x0 = cur
-                ch.fused.pack(self.theta_euler[ch.offset:], ch.np_layer)
+                if not joined:
+                    main.wait_event(packed)
+                    joined = True
                 ch.fused.forward(cur, spec.h, acts=ch.f_acts, masks=ch.f_masks)
                 cur = ch.f_acts[ch.n - 1]
+        if not joined:
+            main.wait_event(packed)
         fo = self._off("fc/kernel")
         _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
                                             _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
