@@ -33,6 +33,7 @@ _SIGNATURES = {
     "b200ode_comm_allreduce_bucket": (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "b200ode_comm_destroy": (c_int, [c_void_p]),
     "b200ode_debug_set_trace": (c_int, [c_void_p]),
+    "b200ode_debug_conv_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
     "b200ode_layer_create": (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                      ctypes.POINTER(c_void_p)]),
     "b200ode_layer_destroy": (c_int, [c_void_p]),

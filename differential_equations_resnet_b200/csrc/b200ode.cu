@@ -984,6 +984,20 @@ extern "C" int b200ode_adam_step(float* params, const float* grads, float* m, fl
   return 0;
 }
 
+// Host-only view of the tile planner (no device needed): lets the CPU test-suite pin the tiling decisions the
+// measurements in DESIGN.md rest on.  out = {nimg, spi, tpi, total_tiles, grid, sa, sw, accumulator stages}.
+extern "C" int b200ode_debug_conv_plan(int precision_mode, int channels, int N, int H, int W, int* out8) {
+  if (!out8) return fail(B200ODE_ERR_INVALID, "out8 is NULL");
+  if (precision_mode < 0 || precision_mode > 2 || !tc_channels_ok(channels))
+    return fail(B200ODE_ERR_UNSUPPORTED, "tensor-core plans exist for STRICT / FAST_TF32 / FAST_BF16 and C in {16,32,64,128,256}");
+  TcPlan plan;
+  if (int rc = plan_conv_tc(precision_mode, channels, N, H, W, &plan)) return rc;
+  const int accw = precision_mode == MODE_STRICT ? 2 * channels : channels, mt = plan.p.nimg * plan.p.spi;
+  out8[0] = plan.p.nimg; out8[1] = plan.p.spi; out8[2] = plan.p.tpi; out8[3] = plan.p.total_tiles; out8[4] = plan.grid;
+  out8[5] = plan.p.sa; out8[6] = plan.p.sw; out8[7] = 2 * mt * accw <= 512 ? 2 : 1;
+  return 0;
+}
+
 extern "C" int b200ode_gradient_mean_norms(const float* grads, const int64_t* offsets, const int64_t* sizes, int n_slices,
                                            float grad_scale, float* out, void* stream) {
   if (!grads || !offsets || !sizes || !out) return fail(B200ODE_ERR_INVALID, "NULL argument");

@@ -224,6 +224,10 @@ int b200ode_comm_destroy(b200ode_comm_t* comm);
 
 /* test hook: number of kernel launches issued by this library in this process */
 int64_t b200ode_launch_count(void);
+/* debug hook, host only (no device needed): the tile plan the per-layer convolution would use;
+ * out8 = {images per tile, 128-position segments per image per tile, tiles per image, total tiles, grid, A stages,
+ * weight stages, accumulator stages (2 = the drain of a tile overlaps the next tile's MMAs)}. */
+int b200ode_debug_conv_plan(int precision_mode, int channels, int N, int H, int W, int* out8);
 /* debug hook: device buffer of uint64 [ctas][16] that the tensor-core kernels fill with a per-CTA
  * timeline (slot 0/15: %globaltimer ns at CTA start/end; others: SM clock deltas); NULL disables. */
 int b200ode_debug_set_trace(void* device_buffer);

@@ -75,3 +75,28 @@ def test_netspec_plan_matches_oracle_plan():
     assert NetSpec(**kw).plan() == O1.NetSpec(**kw).plan()
     kinds = [p[0] for p in NetSpec(**kw).plan()]
     assert kinds.count("euler") == 108 and kinds.count("transition") == 2
+
+
+def test_conv_tile_planner_decisions():
+    """The tile planner runs on the host: pin the decisions DESIGN.md's measurements rest on (no GPU needed).
+    C >= 128 (and bf16 C = 64) at cfg2's 256x32x32 takes 128-position tiles with DOUBLE-buffered accumulators (the drain of a tile
+    overlaps the next tile's MMAs: bf16 C=256 forward 316 -> 279 us); every plan covers all positions."""
+    import ctypes
+    from differential_equations_resnet_b200 import _abi
+    lib = _abi.lib()
+    out = (ctypes.c_int * 8)()
+    for mode, name in ((1, "fast_tf32"), (2, "fast_bf16")):
+        for C in (64, 128, 256):
+            assert lib.b200ode_debug_conv_plan(mode, C, 256, 32, 32, out) == 0
+            nimg, spi, tpi, tiles, grid, sa, sw, acc = list(out)
+            assert nimg == 1 and acc == 2, (name, C, list(out))
+            assert spi == 1 or (name == "fast_tf32" and C == 64 and spi <= 3), (name, C, list(out))
+            assert tiles == 256 * tpi and tpi * spi * 128 >= 32 * 33 and 1 <= grid <= 148 and sa >= 2 and sw >= 2
+    # small images: whole images per tile
+    assert lib.b200ode_debug_conv_plan(1, 64, 128, 8, 8, out) == 0
+    assert out[2] == 1 and out[0] >= 1
+    # strict mode at C = 256 fits (two weight stages) instead of being refused
+    assert lib.b200ode_debug_conv_plan(0, 256, 256, 32, 32, out) == 0 and out[6] == 2
+    # unsupported requests fail with a message instead of planning nonsense
+    assert lib.b200ode_debug_conv_plan(1, 48, 8, 8, 8, out) < 0
+    assert b"tensor-core plans" in lib.b200ode_last_error()
