@@ -12,8 +12,11 @@
 // ("beta trick") the M-chunk stride (LBO) is set to ONE position so a single M=4*chunk MMA covers
 // the three taps beta=0,1,2 of a kernel row (4th chunk is junk) -- 3 instead of 9 MMAs per k-step.
 // The junk padded column of dZ is zero (TMA OOB), so junk positions add nothing.
-// Each CTA owns (tap group, N range, slice of positions), keeps its accumulators in TMEM for its
+// Each CTA owns (tap group, N range, M block, slice of positions), keeps its accumulators in TMEM for its
 // whole slice and writes ONE fp32 partial; partials are reduced deterministically afterwards.
+// Tiles are either position-granular (KT positions from row-granular strips) or, for 128-channel operand
+// blocks, ROW-ALIGNED (R whole image rows: strips hold exactly R+2 / R rows, the k-steps run into a zeroed
+// pad); the dz column sums (bias gradient) are dealt over all CTAs that stage the same dz strip.
 // Strict mode = 3xTF32: x_hi*dz_hi + x_hi*dz_lo + x_lo*dz_hi with lo strips produced by converter warps.
 #pragma once
 
