@@ -336,6 +336,20 @@ def run_b200(args):
                     "peak_source": peak_src,
                     "share_of_step": dom["us"] * dom["launches_per_step"] / (1e3 * ms_dev / K)}
         roofline.update(ncu_extra)
+        if dom["kernel"].startswith(("chain_fwd", "chain_dgrad")):
+            # Context for the HBM fraction: the persistent chains are not HBM-bound by design (one image stays in shared
+            # memory for all steps); what binds them is the tcgen05 issue / operand-read rate at N = C <= 64 columns
+            # (measured 39 / 40 / 48 cycles per 128 x C x 8 tf32 MMA, profiles/r01_umma_rate_v3.log).  issue_bound_frac =
+            # (MMAs of the launch at that rate, one image per SM) / measured time.
+            Nn, Hh, Ww, Cc = dom["shape"]
+            nseg = (Hh * (Ww + 1) + 127) // 128
+            mmas = BLOCKS[0] * nseg * 9 * (Cc * 4 // 32)
+            cyc = {16: 39.0, 32: 40.0, 64: 48.0}.get(Cc, Cc / 2.0)
+            sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+            waves = -(-Nn // 148)
+            roofline["issue_bound_frac"] = waves * mmas * cyc / sm_hz / (dom["us"] * 1e-6)
+            roofline["note"] = ("chain kernels are bound by the tcgen05 issue rate at N=C columns, not by HBM: "
+                                "issue_bound_frac = MMA count x measured cycles per MMA / time")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
