@@ -12,6 +12,8 @@ Sources (raw notebook outputs; TF 1.12.0 per antisymmetric_conv_kernel.ipynb cel
     of the assembly loop (512 channels): six printed 3x3 blocks.
   * experiments_antisymmetric_resnet_v6.ipynb cell 35: 7x7 anti-centrosymmetric
     integer matrix printed by the general-k prototype.
+  * antisymmetric_conv_kernel.ipynb / experiments_antisymmetric_resnet_v2.0.ipynb:
+    printed diagonal blocks K[:,:,1,1] of trained antisymmetric layers.
 """
 import json
 import os
@@ -75,6 +77,20 @@ def main():
     json.dump({"source": "experiments_antisymmetric_resnet_v6.ipynb cell 35 (7x7 anti-centrosymmetric prototype)",
                "matrix_7x7": m},
               open(os.path.join(HERE, "centrosymmetric_7x7_v6_cell35.json"), "w"), indent=1)
+    # Diagonal blocks K[:,:,1,1] of trained antisymmetric layers printed by two notebooks (gamma = 0): every cell that
+    # prints `res2a_branch2_kernel[:,:,1,1]` / `res2d_branch2_kernel[:,:,1,1]`.
+    diag = []
+    for fn in ("antisymmetric_conv_kernel.ipynb", "experiments_antisymmetric_resnet_v2.0.ipynb"):
+        nbx = json.load(open(os.path.join(REF, fn)))
+        for i, c in enumerate(nbx["cells"]):
+            src = "".join(c.get("source", []))
+            if c.get("cell_type") == "code" and "res2a_branch2_kernel[:,:,1,1]" in src and "res2d_branch2_kernel[:,:,1,1]" in src:
+                bl = blocks(cell_text(nbx, i))
+                if len(bl) == 2 and all(len(x) == 9 for x in bl):
+                    diag.append({"source": "%s cell %d" % (fn, i), "res2a_K_1_1": bl[0], "res2d_K_1_1": bl[1]})
+    assert len(diag) >= 2
+    json.dump({"source": "printed get_kernel()[:,:,1,1] / layer.kernel[:,:,1,1] of trained Conv2DAntisymmetric layers (gamma = 0)",
+               "cells": diag}, open(os.path.join(HERE, "diagonal_blocks.json"), "w"), indent=1)
     print("golden fixtures written to", HERE)
 
 

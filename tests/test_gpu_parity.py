@@ -91,6 +91,29 @@ def test_kernel_structure_golden_on_gpu(golden_dir):
     assert np.array_equal(K[:, :, 4, 4], d)
 
 
+def test_diagonal_blocks_golden_on_gpu(golden_dir):
+    """Printed K[:,:,1,1] of trained antisymmetric layers (antisymmetric_conv_kernel.ipynb cell 15, v2.0 cell 16)
+    through the CUDA pack kernel, for both layer classes (3By3: d at (1,0); general k=3: free scalar at (1,2))."""
+    g = json.load(open(os.path.join(golden_dir, "diagonal_blocks.json")))
+    pkg = _pkg()
+    for cell in g["cells"]:
+        for key in ("res2a_K_1_1", "res2d_K_1_1"):
+            B = np.array(cell[key], np.float32).reshape(3, 3)
+            layer = make_layer(16, "strict", gamma=0.0, bias_std=0)
+            w = layer.get_weights()
+            w[0][0, 0, 0, 1], w[1][0, 0, 0, 1], w[2][0, 0, 0, 1], w[3][0, 0, 0, 1] = B[0, 0], B[0, 1], B[0, 2], B[1, 0]
+            layer.set_weights(w)
+            assert np.array_equal(layer.get_kernel()[:, :, 1, 1], B), (cell["source"], key)
+            lg = pkg.Conv2DAntisymmetric(3, gamma=0.0, antisymmetric=True, precision="strict", seed=1)
+            lg.build((None, 8, 8, 16))
+            wg = lg.get_weights()
+            scal = [i for i, a in enumerate(wg) if a.size == 1][4:8]      # the four diagonal scalars of output channel 1
+            for slot, val in zip(scal, (B[0, 0], B[0, 1], B[0, 2], B[1, 2])):
+                wg[slot][...] = val
+            lg.set_weights(wg)
+            assert np.array_equal(lg.get_kernel()[:, :, 1, 1], B), (cell["source"], key, "general class")
+
+
 @pytest.mark.parametrize("k,anti,C", [(3, True, 5), (3, False, 4), (5, True, 3), (3, True, 16)])
 def test_general_layer_pack(k, anti, C):
     pkg = _pkg()

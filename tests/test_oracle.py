@@ -216,3 +216,33 @@ def test_adam_tf1_matches_torch_formula():
     th1, m1, v1 = O0.adam_step_tf1(th, g, m, v, 1)
     # first step of Adam moves each coordinate by ~lr*sign(g)
     assert np.allclose(th - th1, 1e-3 * np.sign(g), rtol=1e-5)
+
+
+def test_diagonal_blocks_golden(golden_dir):
+    """Printed K[:,:,1,1] of trained antisymmetric layers (antisymmetric_conv_kernel.ipynb cell 15,
+    experiments_antisymmetric_resnet_v2.0.ipynb cell 16): both layer classes must rebuild every printed block exactly
+    from its four free scalars -- pins the position and sign of every dependent entry of the diagonal law."""
+    g = _load(golden_dir, "diagonal_blocks.json")
+    assert len(g["cells"]) >= 2
+    rng = np.random.default_rng(0)
+    for cell in g["cells"]:
+        for key in ("res2a_K_1_1", "res2d_K_1_1"):
+            B = np.array(cell[key], np.float64).reshape(3, 3)
+            C = 3
+            # 3By3 class: a,b,c at (0,0),(0,1),(0,2), d at (1,0)   (tfkeras_layer_Conv2DAntisymmetric3By3.py:262-275)
+            flat = rng.standard_normal(O0.num_params_3by3(C)).astype(np.float64)
+            v = O0.split_params_3by3(flat, C)
+            v[0][..., 1], v[1][..., 1], v[2][..., 1], v[3][..., 1] = B[0, 0], B[0, 1], B[0, 2], B[1, 0]
+            flat = O0.join_params(v)
+            for K in (O0.assemble_kernel_3by3_literal(O0.split_params_3by3(flat, C), C, 0.0),
+                      O0.assemble_kernel_3by3_closed(flat, C, 0.0)):
+                assert np.array_equal(K[:, :, 1, 1], B), (cell["source"], key)
+            # general class at k = 3: free scalars at (0,0),(0,1),(0,2),(1,2); (1,0) = -v   (tfkeras_layer_Conv2DAntisymmetric.py:231-249)
+            flat = rng.standard_normal(O0.num_params_general(C, 3)).astype(np.float64)
+            vg = O0.split_params_general(flat, C, 3)
+            idx = [i for i, a in enumerate(vg) if a.size == 1]      # diagonal scalars, 4 per output channel in creation order
+            o1 = idx[4:8]
+            for slot, val in zip(o1, (B[0, 0], B[0, 1], B[0, 2], B[1, 2])):
+                vg[slot][...] = val
+            Kg = O0.assemble_kernel_general_literal(vg, C, 3, 0.0)
+            assert np.array_equal(Kg[:, :, 1, 1], B), (cell["source"], key)
