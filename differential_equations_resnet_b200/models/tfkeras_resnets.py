@@ -14,6 +14,7 @@ section 2, row 6).
 from __future__ import annotations
 
 import math
+import zlib
 
 import numpy as np
 import torch
@@ -41,6 +42,13 @@ class _Scope:
             self.layers[name] = factory()
             self.order.append(name)
         return self.layers[name]
+
+    def seed_for(self, name):
+        """Per-layer seed derived from (model seed, layer name): same-shape layers must not start as copies of each
+        other (the reference draws every he_normal variable independently)."""
+        if self.seed is None:
+            return None
+        return (int(self.seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 31 - 1)
 
 
 def _scope():
@@ -166,18 +174,21 @@ def single_layer_identity_block(input_tensor,
     if antisymmetric:
         layer = sc.get(conv_name_base + '2', lambda: Conv2DAntisymmetric3By3(
             gamma=gamma, strides=(1, 1), use_bias=True, kernel_initializer='he_normal',
-            kernel_regularizer=kernel_regularizer, name=conv_name_base + '2', precision=sc.precision, seed=sc.seed))
+            kernel_regularizer=kernel_regularizer, name=conv_name_base + '2', precision=sc.precision, seed=sc.seed_for(conv_name_base + '2')))
         if not use_batch_norm:
             return layer.euler_step(x, h)                       # one fused kernel
         if not layer.built:
             layer.build(tuple(x.shape))
         bn = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2'))
         bn.ensure(x.shape[-1], x.device)
+        if layer._handle.io_dtype != torch.float32:
+            raise ValueError("use_batch_norm=True needs fp32 activations: the BatchNorm tail kernels are fp32-only "
+                             "(precision=%r computes with %s I/O)" % (sc.precision, layer._handle.io_dtype))
         if sc.training:
             return _EulerBNFn.apply(layer._check_input(x), layer.packed, bn.gamma, bn.beta, layer, bn, float(h))
         y = bn.torch_apply(layer(x), False)
     else:
-        conv = sc.get(conv_name_base + '2', lambda: _RegularConv(int(x.shape[-1]), kernel_size, (1, 1), conv_name_base + '2', sc.seed))
+        conv = sc.get(conv_name_base + '2', lambda: _RegularConv(int(x.shape[-1]), kernel_size, (1, 1), conv_name_base + '2', sc.seed_for(conv_name_base + '2')))
         y = conv(x)
         if use_batch_norm:
             y = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2')).torch_apply(y, sc.training)
@@ -202,8 +213,8 @@ def single_layer_conv_block(input_tensor,
     x = as_torch(input_tensor)
     conv_name_base = 'res' + str(stage) + '_' + str(block) + '_branch'
     bn_name_base = 'bn' + str(stage) + '_' + str(block) + '_branch'
-    main = sc.get(conv_name_base + '2', lambda: _RegularConv(num_filters, kernel_size, strides, conv_name_base + '2', sc.seed))(x)
-    short = sc.get(conv_name_base + '1', lambda: _RegularConv(num_filters, 1, strides, conv_name_base + '1', sc.seed))(x)
+    main = sc.get(conv_name_base + '2', lambda: _RegularConv(num_filters, kernel_size, strides, conv_name_base + '2', sc.seed_for(conv_name_base + '2')))(x)
+    short = sc.get(conv_name_base + '1', lambda: _RegularConv(num_filters, 1, strides, conv_name_base + '1', sc.seed_for(conv_name_base + '1')))(x)
     if use_batch_norm:
         main = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2')).torch_apply(main, sc.training)
         short = sc.get(bn_name_base + '1', lambda: _BatchNorm(bn_name_base + '1')).torch_apply(short, sc.training)
@@ -281,7 +292,7 @@ def get_single_block_resnet_build_function(kernel_type='antisymmetric',
             x = x - torch.as_tensor(np.array(subtract_mean), dtype=torch.float32, device=x.device)
         if divide_by_stddev is not None:
             x = x / torch.as_tensor(np.array(divide_by_stddev), dtype=torch.float32, device=x.device)
-        x = sc.get('conv1', lambda: _RegularConv(filters_per_block[0], kernel_size, strides[0], 'conv1', sc.seed))(x)
+        x = sc.get('conv1', lambda: _RegularConv(filters_per_block[0], kernel_size, strides[0], 'conv1', sc.seed_for('conv1')))(x)
         if use_batch_norm:
             x = sc.get('bn_conv1', lambda: _BatchNorm('bn_conv1')).torch_apply(x, sc.training)
         x = torch.relu(x)
@@ -299,7 +310,7 @@ def get_single_block_resnet_build_function(kernel_type='antisymmetric',
                     x = single_layer_identity_block(x, kernel_size, antisymmetric, use_batch_norm, stage=s + 2, block=b, h=h, gamma=gamma)
         if include_top:
             x = x.mean(dim=(1, 2))
-            fc = sc.get('fc', lambda: _Dense(num_classes, fc_activation, sc.seed))
+            fc = sc.get('fc', lambda: _Dense(num_classes, fc_activation, sc.seed_for('fc')))
             x = fc(x)
         return x
 

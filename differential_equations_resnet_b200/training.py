@@ -92,6 +92,9 @@ class _Chain:
         self.acts = None
         self.masks = None
         self._fshape = None
+        self._fbufs = {}                          # shape -> buffer set (kept: a captured CUDA graph holds their addresses)
+        self._last_fused = False
+        self.generation = 0                       # bumped by every forward: a stale backward must not read newer state
 
     @property
     def handles(self):
@@ -111,14 +114,24 @@ class _Chain:
         return True
 
     def ensure_fused_buffers(self, shape, device):
+        """Buffer sets are keyed by shape and never replaced: a CUDA graph captured at one batch size keeps valid
+        addresses when an eager call with another shape (a partial eval batch) comes in between replays."""
         if self._fshape == shape:
             return
-        N, H, W, C = shape
-        self.f_acts = torch.empty((self.n,) + shape, dtype=torch.float32, device=device)
-        self.f_masks = torch.empty((self.n, N, H, W, C // 8), dtype=torch.uint8, device=device)
-        self.f_dz = torch.empty((self.n,) + shape, dtype=torch.float32, device=device)
-        self.f_dx = torch.empty(shape, dtype=torch.float32, device=device)
+        if shape not in self._fbufs:
+            N, H, W, C = shape
+            self._fbufs[shape] = dict(
+                f_acts=torch.empty((self.n,) + shape, dtype=torch.float32, device=device),
+                f_masks=torch.empty((self.n, N, H, W, (C + 7) // 8), dtype=torch.uint8, device=device),
+                f_dz=torch.empty((self.n,) + shape, dtype=torch.float32, device=device),
+                f_dx=torch.empty(shape, dtype=torch.float32, device=device))
+        for k, v in self._fbufs[shape].items():
+            setattr(self, k, v)
         self._fshape = shape
+
+    def saved_mask(self, l):
+        """relu bit mask [N,H,W,C/8] of Euler step l as saved by the last forward pass"""
+        return self.f_masks[l] if self._last_fused else self.masks[l]
 
     def ensure_buffers(self, shape, device):
         if self.acts is not None and self.acts[1].shape == shape:
@@ -126,7 +139,7 @@ class _Chain:
         N, H, W, C = shape
         dt = self.handles[0].io_dtype                 # fp32, or bf16 in fast_bf16 mode
         self.acts = [None] + [torch.empty(shape, dtype=dt, device=device) for _ in range(self.n)]
-        self.masks = [torch.empty((N, H, W, C // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
+        self.masks = [torch.empty((N, H, W, (C + 7) // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
         self.dz = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]   # dZ_l lives in dz[l & 1]
         self.dx = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]
 
@@ -141,7 +154,9 @@ class _ChainFn(torch.autograd.Function):
         x = x.contiguous()
         N, H, W, C = x.shape
         ctx.chain, ctx.net, ctx.shape = chain, net, (N, H, W, C)
-        ctx.fused = chain.use_fused(tuple(x.shape))
+        chain.generation += 1                     # saved state lives in per-chain buffers: ONE forward in flight
+        ctx.generation = chain.generation
+        ctx.fused = chain._last_fused = chain.use_fused(tuple(x.shape))
         if ctx.fused:
             # persistent path: pack all layers, then ONE launch runs every Euler step of the chain
             chain.ensure_fused_buffers(tuple(x.shape), x.device)
@@ -163,6 +178,9 @@ class _ChainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         chain, net = ctx.chain, ctx.net
+        if ctx.generation != chain.generation:
+            raise RuntimeError("EulerNet chains keep the saved activations of ONE forward pass: another forward ran "
+                               "before this backward (gradient accumulation / interleaved eval needs a second EulerNet)")
         N, H, W, C = ctx.shape
         lib, st = _abi.lib(), _stream_ptr()
         dy = dy.contiguous()
@@ -277,6 +295,7 @@ class EulerNet:
         self._static_in = None
         self.native_glue = native_glue
         self._nb = None
+        self._nb_cache = {}
         self._pending, self._reduced_upto = [], self.n_euler_params     # overlapped all-reduces of this step
 
     # ----------------------------------------------------------------------------------------------
@@ -319,6 +338,12 @@ class EulerNet:
         """Per-input-shape buffers of the native path, or None when some layer cannot take it."""
         if self._nb is not None and self._nb["shape"] == tuple(shape):
             return self._nb
+        if tuple(shape) in self._nb_cache:         # kept per shape (CUDA graphs hold the addresses of their set)
+            self._nb = self._nb_cache[tuple(shape)]
+            for e in self._nb["plan"] or []:
+                if e["kind"] == "chain":
+                    e["chain"].ensure_fused_buffers((shape[0], e["h"], e["w"], e["c"]), device)
+            return self._nb
         spec = self.spec
         N, H, W, Cin = shape
         ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32
@@ -351,10 +376,11 @@ class EulerNet:
         ok = ok and c % 32 == 0 and c <= 1024 and spec.num_classes <= c
         if not ok:
             self._nb = dict(shape=tuple(shape), plan=None)
-            return self._nb
-        self._nb = dict(shape=tuple(shape), plan=plan, hw=h * w, c=c,
-                        head_dx=torch.empty((N, h, w, c), dtype=torch.float32, device=device),
-                        loss=torch.zeros(1, dtype=torch.float32, device=device))
+        else:
+            self._nb = dict(shape=tuple(shape), plan=plan, hw=h * w, c=c,
+                            head_dx=torch.empty((N, h, w, c), dtype=torch.float32, device=device),
+                            loss=torch.zeros(1, dtype=torch.float32, device=device))
+        self._nb_cache[tuple(shape)] = self._nb
         return self._nb
 
     def _off(self, name):
@@ -404,6 +430,7 @@ class EulerNet:
             else:
                 ch = e["chain"]
                 ch.x0 = cur
+                ch._last_fused = True
                 if not joined:
                     main.wait_event(packed)
                     joined = True
@@ -534,8 +561,11 @@ class EulerNet:
 
     # ----------------------------------------------------------------------------------------------
     def capture(self, images, onehot, warmup=3):
-        """Capture the whole train step in a CUDA graph (inputs are copied into static buffers)."""
+        """Capture the whole train step in a CUDA graph (inputs are copied into static buffers).  The warm-up
+        steps run on the static batch but leave no trace: parameters, Adam moments and the step counter are
+        snapshotted before and restored after them (capture itself executes nothing)."""
         self._static_in = (images.clone(), onehot.clone())
+        snap = (self.theta.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_counter.clone())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -543,6 +573,8 @@ class EulerNet:
                 self.train_step(*self._static_in)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        for dst, src in zip((self.theta, self.adam_m, self.adam_v, self.step_counter), snap):
+            dst.copy_(src)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self.train_step(*self._static_in)

@@ -132,12 +132,14 @@ def batch_norm_train(z, bn_gamma, bn_beta, eps=O0.BN_EPS):
     return bn_gamma * (z - mu) / torch.sqrt(var + eps) + bn_beta
 
 
-def euler_step(x, K, bias, h=1.0, bn=None):
-    """models/tfkeras_resnets.py:69-92."""
+def euler_step(x, K, bias, h=1.0, bn=None, forced_mask=None):
+    """models/tfkeras_resnets.py:69-92.  `forced_mask` (bool, optional; parity tests only) replaces relu's own
+    branch decision: relu(z) -> z*mask, so that a backward pass can be compared element by element with an
+    implementation whose pre-activations differ from this one at rounding level (relu' is discontinuous at 0)."""
     z = conv2d_same_nhwc(x, K) + bias
     if bn is not None:
         z = batch_norm_train(z, bn[0], bn[1])
-    r = torch.relu(z)
+    r = torch.relu(z) if forced_mask is None else z * forced_mask.to(z.dtype)
     if h != 1.0:
         r = h * r
     return r + x
@@ -224,8 +226,10 @@ def init_net_params(spec: NetSpec, seed=0):
     return P
 
 
-def net_forward(spec: NetSpec, P, images_u8_or_f32, assembly="closed"):
-    """images [N,H,W,3] (uint8 or float) -> softmax probabilities [N,num_classes]."""
+def net_forward(spec: NetSpec, P, images_u8_or_f32, assembly="closed", forced_masks=None, record_z=None):
+    """images [N,H,W,3] (uint8 or float) -> softmax probabilities [N,num_classes].
+    forced_masks: optional dict layer name -> bool mask for Euler layers (see euler_step);
+    record_z: optional dict filled with the sign of every Euler layer's pre-activation (z > 0)."""
     x = images_u8_or_f32.to(torch.float32)
     if spec.subtract_mean is not None:
         x = x - spec.subtract_mean
@@ -248,7 +252,11 @@ def net_forward(spec: NetSpec, P, images_u8_or_f32, assembly="closed"):
             if spec.use_batch_norm:
                 b = name.replace("res", "bn")
                 bn = (P[b + "/gamma"], P[b + "/beta"])
-            x = euler_step(x, K, bias, spec.h, bn)
+            if record_z is not None:
+                with torch.no_grad():
+                    zz = conv2d_same_nhwc(x, K) + bias
+                    record_z[name] = (zz > 0, zz.abs())
+            x = euler_step(x, K, bias, spec.h, bn, None if forced_masks is None else forced_masks.get(name))
         else:
             main = conv2d_same_nhwc(x, P[name + "2/kernel"], st) + P[name + "2/bias"]
             short = conv2d_same_nhwc(x, P[name + "1/kernel"], st) + P[name + "1/bias"]
@@ -269,13 +277,13 @@ def loss_fn(probs, onehot, eps=1e-7):
     return -(onehot * torch.log(p)).sum(dim=-1).mean()
 
 
-def train_step(spec, P, M, V, t, images, onehot, lr=1e-3, assembly="closed"):
+def train_step(spec, P, M, V, t, images, onehot, lr=1e-3, assembly="closed", forced_masks=None, record_z=None):
     """One reference train step: fwd, loss, autodiff, tf.train.AdamOptimizer(eps=1e-7).
     P, M, V are dicts updated in place; returns (loss, grads)."""
     names = list(P.keys())
     leaves = [P[n].detach().requires_grad_(True) for n in names]
     Pl = dict(zip(names, leaves))
-    loss = loss_fn(net_forward(spec, Pl, images, assembly), onehot)
+    loss = loss_fn(net_forward(spec, Pl, images, assembly, forced_masks, record_z), onehot)
     grads = torch.autograd.grad(loss, leaves)
     lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
     out_g = {}

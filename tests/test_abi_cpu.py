@@ -100,3 +100,33 @@ def test_conv_tile_planner_decisions():
     # unsupported requests fail with a message instead of planning nonsense
     assert lib.b200ode_debug_conv_plan(1, 48, 8, 8, 8, out) < 0
     assert b"tensor-core plans" in lib.b200ode_last_error()
+
+
+@pytest.mark.parametrize("size", [3, 5, 7])
+@pytest.mark.parametrize("anti", [True, False])
+def test_get_centrosymmetric_matrix_package_function(size, anti):
+    """The package's free function (reference layers/antisymmetric_conv2d_utils.py:23-75): free scalars at (i,j) for
+    j > i or (j == i, i <= size//2 - 1) in creation order, the mirror (size-1-i, size-1-j) gets -v (anti) / +v, the
+    centre of an anti-centrosymmetric block is a constant zero; rank reshapes with trailing singleton axes.
+    Checked against the oracle's literal builder fed with the scalars the function drew."""
+    import math
+    import numpy as np
+    from oracle import antisym_numpy as O0
+    from differential_equations_resnet_b200.layers.antisymmetric_conv2d_utils import get_centrosymmetric_matrix
+    C = 4
+    g = torch.Generator().manual_seed(size * 2 + int(anti))
+    m4 = get_centrosymmetric_matrix(size, C, rank=4, anti=anti, generator=g)
+    assert tuple(m4.shape) == (size, size, 1, 1)
+    m = m4.reshape(size, size).numpy()
+    slots = O0.diag_slots_general(size, anti)
+    want = O0._centrosymmetric_matrix([m[i, j] for i, j in slots], size, 0.0, anti, np.float32)
+    assert np.array_equal(m, want)
+    sign = -1.0 if anti else 1.0
+    assert np.array_equal(m, sign * m[::-1, ::-1])
+    if anti:
+        assert m[size // 2, size // 2] == 0.0
+    assert len(slots) == (size * size - 1) // 2 + (0 if anti else 1)
+    assert float(np.abs(m).max()) <= 2.0 * math.sqrt(2.0 / (size * size * C)) + 1e-7     # truncated normal, +-2 sigma
+    assert float(np.abs(m).max()) > 0.0
+    m2 = get_centrosymmetric_matrix(size, C, rank=2, anti=anti, generator=torch.Generator().manual_seed(size * 2 + int(anti)))
+    assert tuple(m2.shape) == (size, size) and np.array_equal(m2.numpy(), m)

@@ -23,6 +23,7 @@ def _run(precision, tol_loss, tol_grad, graph=False):
             P[k][-C:] = torch.randn(C, generator=gen) * 0.05
     net = EulerNet(NetSpec(**kw), precision=precision, seed=0)
     net.import_params(P)
+    P0 = {k: v.clone() for k, v in P.items()}
     img = torch.randint(0, 256, (8, 32, 32, 3), generator=gen, dtype=torch.uint8)
     lab = torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=gen), 10).float()
     M = {k: torch.zeros_like(v) for k, v in P.items()}
@@ -45,8 +46,19 @@ def _run(precision, tol_loss, tol_grad, graph=False):
     for a, b in zip(losses, losses_ref):
         assert abs(a - b) <= tol_loss * max(1.0, abs(b)), (losses, losses_ref)
     th = net.export_params()
-    for k in P:   # after 3 Adam steps the parameters moved by ~3e-3; compare the updates
-        assert float((th[k] - P[k]).abs().max()) <= (2e-4 if precision == "strict" else 4e-3), k   # Adam steps are ~1e-3
+    # After 3 Adam steps compare the UPDATES relatively.  At step t <= 3 Adam moves every element by ~lr*sign(g)
+    # (|g| >> eps), so the update's relative error is sqrt(4 * fraction of elements whose gradient sign differs):
+    # a gradient relative error e flips about a fraction e of the signs -> strict (1e-5) ~ 6e-3, fast (1e-2) ~ 0.2;
+    # an unrelated update scores sqrt(2).
+    tol_upd = 2e-2 if precision == "strict" else 0.35
+    num = den = 0.0
+    for k in P:
+        du, du_ref = (th[k] - P0[k]).double(), (P[k] - P0[k]).double()
+        num += float((du - du_ref).pow(2).sum()); den += float(du_ref.pow(2).sum())
+        if k.endswith("/packed") or k.endswith("/kernel"):
+            e = float((du - du_ref).norm() / du_ref.norm())
+            assert e <= 2 * tol_upd, (k, e)
+    assert (num / den) ** 0.5 <= tol_upd, (num / den) ** 0.5
 
 
 def test_train_step_strict_matches_oracle():
