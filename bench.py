@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the antisymmetric-ResNet train step (BASELINE.json metric: train images/sec).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fast_tf32|strict]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fast_f16|fast_tf32|strict]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
 
@@ -40,10 +40,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fast_tf32", choices=["fast_tf32", "strict"])
+    ap.add_argument("--precision", default="fast_f16", choices=["fast_f16", "fast_tf32", "strict"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode (fp32-grade) measurement of the same step")
     ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "torch"), choices=["torch", "abi"],
                     help="gradient exchange: torch.distributed NCCL, or NCCL bound by libb200ode (b200ode_comm_*)")
     return ap.parse_args()
@@ -187,17 +188,20 @@ def kernel_microbench(torch, precision, batch):
         N, H, W = batch, HW, HW
         Mpix = N * H * W
         per = Mpix * C * 4
-        if not ChainHandle.supported(C, H, W, _abi.PRECISIONS[precision]):
+        cprec = _abi.CHAIN_PRECISIONS.get(precision)
+        if cprec is None or not ChainHandle.supported(C, H, W, cprec):
             continue
-        ch = ChainHandle(C, L, 0.0)
+        ch = ChainHandle(C, L, 0.0, precision=cprec)
+        sdt, sb = ch.saved_dtype, (2 if ch.f16 else 4)
         params = torch.randn(L * ch.num_params, device="cuda") * 0.05
         ch.pack(params)
         x0 = torch.relu(torch.randn((N, H, W, C), device="cuda"))
         dy = torch.randn((N, H, W, C), device="cuda")
-        acts = torch.empty((L, N, H, W, C), device="cuda")
+        acts = torch.empty((L, N, H, W, C), device="cuda", dtype=sdt)
         masks = torch.empty((L, N, H, W, C // 8), dtype=torch.uint8, device="cuda")
-        dz = torch.empty((L, N, H, W, C), device="cuda")
+        dz = torch.empty((L, N, H, W, C), device="cuda", dtype=sdt)
         dx = torch.empty((N, H, W, C), device="cuda")
+        yfin = torch.empty((N, H, W, C), device="cuda") if ch.f16 else None
         grad = torch.empty(L * ch.num_params, device="cuda")
 
         def timeit(fn, iters=6):
@@ -212,13 +216,15 @@ def kernel_microbench(torch, precision, batch):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) * 1e3 / iters  # us
 
-        f_fwd = lambda: ch.forward(x0, H_STEP, acts=acts, masks=masks)
+        f_fwd = lambda: ch.forward(x0, H_STEP, acts=acts, masks=masks, y_final=yfin)
         f_dgrad = lambda: ch.dgrad(dy, masks, dz, dx, H_STEP)
         f_wgrad = lambda: ch.wgrad(x0, acts, dz, grad)
         mask_b = Mpix * C // 8
-        for name, fn, nbytes in (("chain_fwd (36 Euler steps)", f_fwd, per + L * (per + mask_b)),
-                                 ("chain_dgrad (36 Euler steps)", f_dgrad, 2 * per + L * (per + mask_b)),
-                                 ("chain_wgrad (36 layers, +fold/reduce)", f_wgrad, 2 * L * per)):
+        sav = Mpix * C * sb          # one saved weight-gradient operand (fp32, or fp16 in fast_f16 mode)
+        # algorithmic bytes: chain input (+ fp32 output in fp16 mode) + per step the saved operand and the relu mask
+        for name, fn, nbytes in (("chain_fwd (36 Euler steps)", f_fwd, per + (per if ch.f16 else 0) + L * (sav + mask_b)),
+                                 ("chain_dgrad (36 Euler steps)", f_dgrad, 2 * per + L * (sav + mask_b)),
+                                 ("chain_wgrad (36 layers, +fold/reduce)", f_wgrad, 2 * L * sav)):
             us = timeit(fn)
             recs.append({"kernel": name, "shape": [N, H, W, C], "us": us, "launches_per_step": 1,
                          "algorithmic_bytes": nbytes, "GBps": nbytes / us * 1e-3,
@@ -303,8 +309,34 @@ def run_b200(args):
             loss_h.copy_(out.reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
     ms_e2e = timed(step_e2e, K, W, after=read_loss)
-    clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss_h.item())
+
+    # The same step in the fp32-grade mode (strict: 3xTF32 operands, fp32 accumulate, <= 1e-5 of the float64 oracle),
+    # reported next to the fast-mode headline inside the same JSON line.
+    strict = None
+    if args.precision != "strict" and not args.no_strict and world == 1:
+        del step, step_e2e
+        net_s = EulerNet(spec, precision="strict", seed=1236, world_size=world, comm=comm)
+        net_s.train_step(img_d, lab_d)
+        l1 = _abi.launch_count()
+        net_s.train_step(img_d, lab_d)
+        strict_launches = _abi.launch_count() - l1
+        if use_graph:
+            net_s.capture(img_d, lab_d)
+            s_step = lambda: net_s.train_step_graph()
+            s_e2e = lambda: net_s.train_step_graph(img_h, lab_h)
+        else:
+            s_step = lambda: net_s.train_step(img_d, lab_d)
+            s_e2e = lambda: net_s.train_step(img_h.cuda(non_blocking=True), lab_h.cuda(non_blocking=True))
+        Ks = max(3, min(K, 10))
+        ms_s = timed(s_step, Ks, 3)
+        ms_se = timed(s_e2e, Ks, 3, after=read_loss)
+        strict = {"dtype": "f32 (3xTF32 operands, fp32 accumulate; <= 1e-5 rel. of the float64 oracle)",
+                  "value": world * B * Ks / (ms_s * 1e-3), "unit": "images/s", "ms_per_step": ms_s / Ks, "steps": Ks,
+                  "e2e": {"value": world * B * Ks / (ms_se * 1e-3), "unit": "images/s", "ms_per_step": ms_se / Ks},
+                  "gpu_launches_per_step": int(strict_launches), "final_loss": float(loss_h.item())}
+        del net_s
+    clocks = sampler.stop() if rank == 0 else None
 
     ips = world * B * K / (ms_dev * 1e-3)
     ips_e2e = world * B * K / (ms_e2e * 1e-3)
@@ -343,7 +375,7 @@ def run_b200(args):
             # (MMAs of the launch at that rate, one image per SM) / measured time.
             Nn, Hh, Ww, Cc = dom["shape"]
             nseg = (Hh * (Ww + 1) + 127) // 128
-            mmas = BLOCKS[0] * nseg * 9 * (Cc * 4 // 32)
+            mmas = BLOCKS[0] * nseg * 9 * (Cc * (2 if args.precision == "fast_f16" else 4) // 32)
             cyc = {16: 39.0, 32: 40.0, 64: 48.0}.get(Cc, Cc / 2.0)
             sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
             waves = -(-Nn // 148)
@@ -365,7 +397,8 @@ def run_b200(args):
         line = {
             "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "fast_tf32" else "f32(3xtf32)", "data": "synthetic",
+            "dtype": {"fast_f16": "f16 operands (11-bit significand = tf32 grade, rounded to nearest), f32 accumulate, f32 residual stream",
+                      "fast_tf32": "tf32", "strict": "f32(3xtf32)"}[args.precision], "data": "synthetic",
             "config": {"workload": "cfg3: antisymmetric ResNet 16/32/64, 108 Euler steps + 2 transitions, 32x32x3, "
                                    "fwd+loss+bwd%s+Adam" % ("+allreduce" if world > 1 else ""),
                        "global_batch": world * B, "batch_per_gpu": B, "h": H_STEP, "gamma": 0.0,
@@ -378,6 +411,8 @@ def run_b200(args):
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline, "kernels": recs, "final_loss": final_loss,
         }
+        if strict:
+            line["strict"] = strict
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -18,6 +18,7 @@
 #include "kernels_basic.cuh"
 #include "kernels_conv_tc.cuh"
 #include "kernels_chain_tc.cuh"
+#include "kernels_chain_f16.cuh"
 #include "kernels_glue.cuh"
 #include "kernels_wgrad_tc.cuh"
 
@@ -670,16 +671,21 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
 // One launch computes the weight gradients of L layers of equal shape (L = 1: a single layer).
 // Layer 0 reads its input from x0, layer l >= 1 from xrest + (l-1)*N*H*W*C (the saved outputs of
 // a chain); dz of layer l is dz + l*N*H*W*C; gradients go to grad_params + l*grad_layer_stride.
+// mode MODE_F16: 16-bit operands are fp16 (fp16 chains); `amax` != nullptr: the gradients carry the chain's backward
+// scale chain_grad_scale(h, *amax), undone by the fold kernels.
+enum { MODE_F16 = 3 };
 static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const void* xrest, const void* dz, int L, int N, int H,
                         int W, float* G, float* G_user, float* grad_params, long long grad_layer_stride, int accumulate,
-                        cudaStream_t st, int force_mgroups = 0) {
+                        cudaStream_t st, int force_mgroups = 0, const float* amax = nullptr, float amax_h = 1.0f) {
   const int C = lg.C;
+  const bool f16 = mode == MODE_F16;
+  if (f16) mode = MODE_BF16;
   const bool bf16 = mode == MODE_BF16, strict = mode == MODE_STRICT;
   const int eb = bf16 ? 2 : 4;
   int UKP = bf16 ? 16 : 8;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L; p.f16 = f16 ? 1 : 0;
   if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
   static const int pair_env = getenv("B200ODE_WGRAD_PAIR") ? atoi(getenv("B200ODE_WGRAD_PAIR")) : 1;   // debug switch
   p.pair = (!bf16 && !strict && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
@@ -787,7 +793,8 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     }
   }
   if (!KT && p.MB > 1 && !force_mgroups)   // all-channel strips do not fit (strict C = 256, tf32 C = 256 at W = 64): one M block per CTA
-    return run_wgrad_tc(mode, lg, x0, xrest, dz, L, N, H, W, G, G_user, grad_params, grad_layer_stride, accumulate, st, 1);
+    return run_wgrad_tc(f16 ? MODE_F16 : mode, lg, x0, xrest, dz, L, N, H, W, G, G_user, grad_params, grad_layer_stride, accumulate, st, 1,
+                        amax, amax_h);
   if (!KT) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad strips do not fit shared memory (C=%d W=%d)", C, W);
   if (KT > Q) KT = (int)((Q + UKP - 1) / UKP * UKP);
   p.tpi = (int)((Q + KT - 1) / KT);
@@ -876,16 +883,16 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && nparts <= 16 * PZ && tblocks * PZ >= 296;
   if (tiled) {
     const dim3 tgrid(T * (T + 1) / 2, lg.k * lg.k, L), tblock(32, 8, PZ);
-    if (PZ == 1) fold_reduce_tiled_kernel<1><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
-    else if (PZ == 2) fold_reduce_tiled_kernel<2><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
-    else fold_reduce_tiled_kernel<4><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride);
+    if (PZ == 1) fold_reduce_tiled_kernel<1><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride, amax, amax_h);
+    else if (PZ == 2) fold_reduce_tiled_kernel<2><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride, amax, amax_h);
+    else fold_reduce_tiled_kernel<4><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride, amax, amax_h);
     LAUNCH_CHECK("fold_reduce_tiled_kernel");
   }
   const long long nfold = tiled ? 4LL * C + (lg.use_bias ? C : 0) : nout;
   dim3 fgrid(blocks_for(nfold * fl, 256), L);
   fold_reduce_kernel<<<fgrid, 256, 0, st>>>(lg, ws, nparts, pstride, p.bias_partials, grad_params, accumulate,
                                             p.part_layer_stride, p.bias_layer_stride, grad_layer_stride, fl, p.pair ? p.P : 0,
-                                            tiled ? 1 : 0);
+                                            tiled ? 1 : 0, amax, amax_h);
   LAUNCH_CHECK("fold_reduce_kernel");
   return 0;
 }
@@ -1022,9 +1029,13 @@ extern "C" int b200ode_increment(int32_t* counter, void* stream) {
 struct b200ode_chain {
   LayerGeom g;
   int L;           // distinct weight layers
+  int mode;        // B200ODE_PREC_FAST_TF32 (kernels_chain_tc.cuh) or B200ODE_PREC_FAST_F16 (kernels_chain_f16.cuh)
   bool packed;
-  float* w_hi;     // [L][9][C][C] tf32-rounded, K-major B operand
+  float* w_hi;     // FAST_TF32: [L][9][C][C] tf32-rounded, K-major B operand
+  __half* w16;     // FAST_F16:  [L][9][C][C] fp16, K-major B operand
   float* bias;     // [L][C]
+  float* amax;     // FAST_F16: device scalar max|dy| of the last backward sweep (scale of dz_all)
+  float amax_h;    //           and the step size it was taken with
 };
 
 struct ChainPlan {
@@ -1075,7 +1086,45 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
   return true;
 }
 
+struct ChainF16Plan {
+  ChainF16Params p;
+  size_t smem;
+};
+
+// Shared-memory plan of chain_f16_kernel (both directions use the same layout); false when a whole image does not fit.
+static bool plan_chain_f16(int C, int H, int W, ChainF16Plan* plan) {
+  if (!chain_channels_ok(C)) return false;
+  const int rowb = C * 2;
+  const int P = W + 1;
+  if (P > 256 || H + 2 > 256) return false;
+  const int maxseg = C == 16 ? 9 : C == 32 ? 5 : 2;
+  const int nseg = (H * P + 127) / 128;
+  if (nseg > maxseg || nseg * C > 512) return false;
+  ChainF16Params p;
+  memset(&p, 0, sizeof(p));
+  p.H = H; p.W = W; p.P = P; p.nseg = nseg;
+  // rows a strip must hold: the halo image, and what the MMAs of the last segment reach (junk rows included)
+  const long long rows_img = (long long)(H + 2) * P + 1, rows_mma = 128LL * nseg + 2 * P + 3;
+  p.strip_stride = align_up((uint32_t)((rows_img > rows_mma ? rows_img : rows_mma) * rowb), 1024);
+  if (2 * P + 2 > 128 + P + 1) return false;          // wavefront hand-over: a segment's A rows reach into the NEXT segment only
+  p.w_off = 2 * p.strip_stride;                       // (the fp32 residual lives in registers)
+  p.w_box_bytes = (uint32_t)9 * C * rowb;
+  p.w_layer_bytes = align_up(p.w_box_bytes, 1024);
+  p.sw = 2;                                           // the next layer's weights are in flight while this one runs
+  p.bar_off = p.w_off + (uint32_t)p.sw * p.w_layer_bytes;
+  uint32_t cols = (uint32_t)nseg * C, pc = 32;
+  while (pc < cols) pc <<= 1;
+  p.tmem_cols = pc;
+  plan->p = p;
+  plan->smem = (size_t)p.bar_off + 512 + 1024;
+  return plan->smem <= (size_t)227 * 1024;
+}
+
 extern "C" int b200ode_chain_supported(int channels, int H, int W, int precision_mode) {
+  if (precision_mode == B200ODE_PREC_FAST_F16) {
+    ChainF16Plan pl;
+    return plan_chain_f16(channels, H, W, &pl) ? 1 : 0;
+  }
   if (precision_mode != B200ODE_PREC_FAST_TF32) return 0;
   ChainPlan pl;
   return plan_chain(channels, H, W, 0, &pl) && plan_chain(channels, H, W, 1, &pl) ? 1 : 0;
@@ -1086,7 +1135,8 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
   if (!out) return fail(B200ODE_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (n_layers < 1) return fail(B200ODE_ERR_INVALID, "n_layers must be >= 1");
-  if (precision_mode != B200ODE_PREC_FAST_TF32) return fail(B200ODE_ERR_UNSUPPORTED, "chains run in FAST_TF32 mode only");
+  if (precision_mode != B200ODE_PREC_FAST_TF32 && precision_mode != B200ODE_PREC_FAST_F16)
+    return fail(B200ODE_ERR_UNSUPPORTED, "chains run in FAST_TF32 or FAST_F16 mode");
   if (!chain_channels_ok(channels)) return fail(B200ODE_ERR_UNSUPPORTED, "chains need C in {16,32,64} (got %d)", channels);
   if (int rc = device_check()) return rc;
   b200ode_chain* ch = new b200ode_chain();
@@ -1096,9 +1146,12 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
   build_diag_tab(g);
   g.bias_off = (long long)g.tab.nd * channels + 9LL * channels * (channels - 1) / 2;
   g.nparams = g.bias_off + (use_bias ? channels : 0);
-  ch->L = n_layers;
-  cudaError_t e = cudaMalloc(&ch->w_hi, (size_t)n_layers * 9 * channels * channels * sizeof(float));
+  ch->L = n_layers; ch->mode = precision_mode; ch->amax_h = 1.0f;
+  const size_t wn = (size_t)n_layers * 9 * channels * channels;
+  cudaError_t e = precision_mode == B200ODE_PREC_FAST_F16 ? cudaMalloc(&ch->w16, wn * sizeof(__half)) : cudaMalloc(&ch->w_hi, wn * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ch->bias, (size_t)n_layers * channels * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ch->amax, sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(ch->amax, 0, sizeof(float));
   if (e != cudaSuccess) {
     b200ode_chain_destroy(ch);
     return fail(B200ODE_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
@@ -1109,7 +1162,7 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
 
 extern "C" int b200ode_chain_destroy(b200ode_chain_t* ch) {
   if (!ch) return 0;
-  cudaFree(ch->w_hi); cudaFree(ch->bias);
+  cudaFree(ch->w_hi); cudaFree(ch->w16); cudaFree(ch->bias); cudaFree(ch->amax);
   delete ch;
   return 0;
 }
@@ -1119,7 +1172,10 @@ extern "C" int b200ode_chain_pack(b200ode_chain_t* ch, const float* params, int6
   if (!ch || !params) return fail(B200ODE_ERR_INVALID, "chain/params is NULL");
   const long long total = 9LL * ch->g.C * ch->g.C;
   dim3 grid(blocks_for(total, 256), ch->L);
-  pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->bias);
+  if (ch->mode == B200ODE_PREC_FAST_F16)
+    pack_chain_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w16, ch->bias);
+  else
+    pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->bias);
   LAUNCH_CHECK("pack_chain_kernel");
   ch->packed = true;
   return 0;
@@ -1186,19 +1242,92 @@ static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CU
   return 0;
 }
 
-extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, float* acts, uint8_t* relu_masks, float* y_final, int N,
+static int make_chain_w16_map(CUtensorMap* m, const b200ode_chain* ch) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int C = ch->g.C, rowb = C * 2;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)9 * ch->L};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)C, 9};          // all nine taps of a layer in one box
+  cuuint32_t es[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ch->w16, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(fp16 chain weights) failed with %d", (int)r);
+  return 0;
+}
+
+static int chain_f16_grid(ChainF16Params& p, int C, int N) {
+  static const int cs_env = getenv("B200ODE_CHAIN_CLUSTER") ? atoi(getenv("B200ODE_CHAIN_CLUSTER")) : 0;   // debug override
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int cs = cs_env > 0 ? cs_env : (C >= 32 ? 4 : 1);
+  while (cs > 1 && cs > N) cs >>= 1;
+  int grid = N < sms ? N : sms;
+  grid = (grid + cs - 1) / cs * cs;
+  if (grid > sms) grid = sms / cs * cs;
+  p.cs = cs;
+  p.iters = (N + grid - 1) / grid;
+  return grid;
+}
+
+template <int DIR>
+static int launch_chain_f16(const b200ode_chain* ch, const ChainF16Plan& plan, const CUtensorMap& mw, int grid, cudaStream_t st) {
+  static const int ew_env = getenv("B200ODE_CHAIN_EW") ? atoi(getenv("B200ODE_CHAIN_EW")) : 0;   // debug: epilogue warps (8 | 16)
+  const int ew = ew_env == 8 || ew_env == 16 || (ew_env == 12 && ch->g.C == 16) ? ew_env : 8;
+#define CHF_LAUNCH(C_, EW_)                                                                                       \
+  do {                                                                                                            \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      CUDA_TRY(cudaFuncSetAttribute(chain_f16_kernel<C_, DIR, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    cudaLaunchConfig_t cfg;                                                                                       \
+    memset(&cfg, 0, sizeof(cfg));                                                                                 \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + EW_ * 32); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st; \
+    cudaLaunchAttribute attr[1];                                                                                  \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                             \
+    attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;             \
+    cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;                                                        \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_f16_kernel<C_, DIR, EW_>, mw, plan.p));                                \
+  } while (0)
+#define CHF_EW(C_) do { if (ew == 8) CHF_LAUNCH(C_, 8); else CHF_LAUNCH(C_, 16); } while (0)
+  switch (ch->g.C) {
+    case 16: if (ew == 12) CHF_LAUNCH(16, 12); else CHF_EW(16); break;
+    case 32: CHF_EW(32); break;
+    case 64: CHF_EW(64); break;
+    default: return fail(B200ODE_ERR_UNSUPPORTED, "chain: unsupported channel count %d", ch->g.C);
+  }
+#undef CHF_EW
+#undef CHF_LAUNCH
+  LAUNCH_CHECK("chain_f16_kernel");
+  return 0;
+}
+
+extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, void* acts, uint8_t* relu_masks, float* y_final, int N,
                                  int H, int W, float h, int n_steps, void* stream) {
   if (!ch || !x0) return fail(B200ODE_ERR_INVALID, "chain/x0 is NULL");
   if (!ch->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_chain_pack must run before compute calls");
   if (!acts && !y_final) return fail(B200ODE_ERR_INVALID, "need acts or y_final");
   if (n_steps < 1 || N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape");
   if (N == 0) return 0;
+  if (ch->mode == B200ODE_PREC_FAST_F16) {
+    if (!y_final) return fail(B200ODE_ERR_INVALID, "FAST_F16 chains: y_final (fp32 output of the last step) is required; acts holds the fp16 INPUTS of the steps");
+    ChainF16Plan plan;
+    if (!plan_chain_f16(ch->g.C, H, W, &plan))
+      return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
+    ChainF16Params& p = plan.p;
+    p.N = N; p.L = n_steps; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
+    p.x0 = x0; p.acts = (__half*)acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias; p.trace = g_trace;
+    CUtensorMap mw;
+    if (int rc = make_chain_w16_map(&mw, ch)) return rc;
+    return launch_chain_f16<0>(ch, plan, mw, chain_f16_grid(p, ch->g.C, N), (cudaStream_t)stream);
+  }
   ChainPlan plan;
   if (!plan_chain(ch->g.C, H, W, 0, &plan))
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = n_steps; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
-  p.acts = acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias; p.trace = g_trace;
+  p.acts = (float*)acts; p.masks = relu_masks; p.y_final = y_final; p.bias = ch->bias; p.trace = g_trace;
   const int C = ch->g.C, rowb = C * 4 >= 128 ? 128 : C * 4;
   CUtensorMap mx, mw;
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -1207,27 +1336,55 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, float* ac
   return launch_chain<0>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
 }
 
-extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, float* dz_all, float* dx,
+extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
                                    int N, int H, int W, float h, void* stream) {
   if (!ch || !dy || !relu_masks || !dz_all || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (!ch->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_chain_pack must run before compute calls");
   if (N == 0) return 0;
+  if (ch->mode == B200ODE_PREC_FAST_F16) {
+    ChainF16Plan plan;
+    if (!plan_chain_f16(ch->g.C, H, W, &plan))
+      return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
+    cudaStream_t st = (cudaStream_t)stream;
+    // scale of the fp16 backward strips: max|dy| -> device scalar (read by the chain kernel and by the gradient fold)
+    const long long n4 = (long long)N * H * W * ch->g.C / 4;
+    CUDA_TRY(cudaMemsetAsync(ch->amax, 0, sizeof(float), st));
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    const long long want = (n4 + 255) / 256;
+    amax_abs_kernel<<<(unsigned)(want < 2LL * sms ? want : 2LL * sms), 256, 0, st>>>((const float4*)dy, n4, (unsigned int*)ch->amax);
+    LAUNCH_CHECK("amax_abs_kernel");
+    ch->amax_h = h;
+    ChainF16Params& p = plan.p;
+    p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
+    p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (__half*)dz_all; p.dx = dx; p.amax = ch->amax; p.trace = g_trace;
+    CUtensorMap mw;
+    if (int rc = make_chain_w16_map(&mw, ch)) return rc;
+    return launch_chain_f16<1>(ch, plan, mw, chain_f16_grid(p, ch->g.C, N), st);
+  }
   ChainPlan plan;
   if (!plan_chain(ch->g.C, H, W, 1, &plan))
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
-  p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = dz_all; p.dx = dx; p.trace = g_trace;
+  p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (float*)dz_all; p.dx = dx; p.trace = g_trace;
   CUtensorMap mw;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
   return launch_chain<1>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream);
 }
 
-extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const float* acts, const float* dz_all,
+extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const void* acts, const void* dz_all,
                                    float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream) {
-  if (!ch || !x0 || !dz_all || !grad_params) return fail(B200ODE_ERR_INVALID, "NULL argument");
-  if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
+  if (!ch || !dz_all || !grad_params) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (N == 0) return 0;
+  if (ch->mode == B200ODE_PREC_FAST_F16) {
+    // acts[l] = fp16 input of layer l (written by b200ode_chain_fwd), dz_all[l] = fp16(S*dZ_l) (b200ode_chain_dgrad)
+    if (!acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
+    const __half* a16 = (const __half*)acts;
+    return run_wgrad_tc(MODE_F16, ch->g, a16, a16 + (size_t)N * H * W * ch->g.C, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params,
+                        grad_layer_stride, 0, (cudaStream_t)stream, 0, ch->amax, ch->amax_h);
+  }
+  if (!x0) return fail(B200ODE_ERR_INVALID, "x0 is NULL");
+  if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
   return run_wgrad_tc(MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params, grad_layer_stride, 0,
                       (cudaStream_t)stream);
 }

@@ -258,6 +258,24 @@ __device__ __forceinline__ void param_entries(const LayerGeom& g, long long i, l
   }
 }
 
+// Power-of-two scale S of the fp16 backward strips of the persistent chains (kernels_chain_f16.cuh):
+// 2^10 <= S*|h|*amax < 2^11, i.e. 32x headroom below the fp16 maximum for gradient growth along the chain and
+// 2^-35 of the maximum before an element underflows to zero.  Every consumer (chain kernel, gradient fold)
+// evaluates the same expression on the same device scalar `amax`, so the scale is undone exactly.
+__host__ __device__ inline float chain_grad_scale(float h, float amax) {
+  const float t = fabsf(h) * amax;
+  if (!(t > 0.0f) || !(t < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(t, &e);                       // t = m * 2^e, m in [0.5, 1)
+  int k = 11 - e;
+  k = k < -100 ? -100 : k > 100 ? 100 : k;
+  return ldexpf(1.0f, k);
+}
+// multiplier that undoes it in the gradient fold (1 when the gradients are unscaled: amax == nullptr)
+__device__ __forceinline__ float fold_out_scale(const float* amax, float h) {
+  return amax ? 1.0f / chain_grad_scale(h, *amax) : 1.0f;
+}
+
 // Fold a (reduced) dense gradient onto the free parameters.
 __global__ void fold_grad(LayerGeom g, const float* __restrict__ G, float* __restrict__ grad, int accumulate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,7 +319,7 @@ __global__ void reduce_parts_pair(const float* __restrict__ Gpart, int nparts, l
 __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts, long long part_stride,
                                    const float* __restrict__ bias_part, float* __restrict__ grad, int accumulate,
                                    long long part_layer_stride, long long bias_layer_stride, long long grad_layer_stride,
-                                   int lanes, int pair_P, int diag_only) {
+                                   int lanes, int pair_P, int diag_only, const float* __restrict__ amax = nullptr, float h = 1.0f) {
   Gpart += (long long)blockIdx.y * part_layer_stride;
   if (bias_part) bias_part += (long long)blockIdx.y * bias_layer_stride;
   grad += (long long)blockIdx.y * grad_layer_stride;
@@ -329,6 +347,7 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
     for (int p = l; p < nparts; p += lanes) val += bias_part[(long long)p * g.C + c];
   }
   for (int off = lanes >> 1; off > 0; off >>= 1) val += __shfl_xor_sync(mask, val, off, 32);
+  val *= fold_out_scale(amax, h);
   if (l == 0) grad[i] = accumulate ? grad[i] + val : val;
 }
 
@@ -341,7 +360,8 @@ __global__ void fold_reduce_kernel(LayerGeom g, const float* __restrict__ Gpart,
 template <int PZ>
 __global__ void __launch_bounds__(256 * PZ) fold_reduce_tiled_kernel(LayerGeom g, const float* __restrict__ Gpart, int nparts,
                                                                      long long part_stride, float* __restrict__ grad, int accumulate,
-                                                                     long long part_layer_stride, long long grad_layer_stride) {
+                                                                     long long part_layer_stride, long long grad_layer_stride,
+                                                                     const float* __restrict__ amax = nullptr, float h = 1.0f) {
   // blockDim = (32, 8, PZ): threadIdx.z deals the partials (part p goes to lane p % PZ); the PZ partial sums are
   // combined in a fixed order through shared memory.
   __shared__ float t1[PZ][32][33];
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(256 * PZ) fold_reduce_tiled_kernel(LayerGeom g
         float a = 0.0f, b = 0.0f;
 #pragma unroll
         for (int z = 0; z < PZ; ++z) { a += t1[z][tx][r]; b += t2[z][r][tx]; }
-        const float val = a - b;
+        const float val = (a - b) * fold_out_scale(amax, h);
         const long long i = w_block_off(g, o) + (long long)tap * (C - o - 1) + (ci - o - 1);
         grad[i] = accumulate ? grad[i] + val : val;
       }

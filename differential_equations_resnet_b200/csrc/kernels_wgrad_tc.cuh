@@ -21,6 +21,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -72,6 +73,7 @@ struct WgradParams {
   // zero-padded channels.  The row before each x strip is a zeroed 1 KB pad (x_off = 1024).
   // The accumulators are written raw ([3][128 lanes][32 cols] per part) and gathered by fold_reduce_kernel.
   int pair;
+  int f16;           // 16-bit operands are IEEE fp16 (saved activations / scaled dZ of the fp16 chains) instead of bf16
   int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
 };
@@ -167,7 +169,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
     const bool leader = elect_one();
     const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
-    const uint32_t idesc = make_instr_desc(BF16 ? FMT_BF16 : FMT_TF32, Mrows, p.NT, 1, 1);
+    const uint32_t idesc = make_instr_desc(BF16 ? (p.f16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.NT, 1, 1);
     const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
     const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
     const uint32_t hi32 = (sbo >> 4) | (1u << 14) | (lt << 29);
@@ -347,7 +349,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           uint32_t a = (uint32_t)(r0 + r) * p.RWB + (u << 4);
           a = BF16 ? swizzle_addr(a, p.RWB) : a ^ (((a >> 7) & 3u) << 5);
           const uint4 v = *reinterpret_cast<const uint4*>(cb + a);
-          if (BF16) {
+          if (BF16 && p.f16) {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+            acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+            acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+          } else if (BF16) {
             acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xFFFF0000u);
             acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xFFFF0000u);
             acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xFFFF0000u);

@@ -120,7 +120,10 @@ class ChainHandle:
         _abi.check(_abi.lib().b200ode_chain_create(int(channels), int(n_layers), float(gamma), int(bool(use_bias)),
                                                    int(precision), ctypes.byref(h)))
         self._h = h
-        self.channels, self.n_layers = int(channels), int(n_layers)
+        self.channels, self.n_layers, self.precision = int(channels), int(n_layers), int(precision)
+        self.f16 = self.precision == _abi.PREC_FAST_F16
+        # dtype of the saved weight-gradient operands (acts, dz_all): fp16 in FAST_F16 mode (acts[l] = INPUT of step l)
+        self.saved_dtype = torch.float16 if self.f16 else torch.float32
         self.num_params = int(_abi.lib().b200ode_chain_layer_params(h))
 
     def __del__(self):

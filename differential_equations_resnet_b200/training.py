@@ -84,7 +84,10 @@ class _Chain:
 
     def __init__(self, C, n_layers, gamma, precision, offset, persistent=True):
         self.C, self.n, self.gamma, self.precision = C, n_layers, gamma, precision
-        self.persistent = persistent and precision == "fast_tf32"
+        self.persistent = persistent and precision in _abi.CHAIN_PRECISIONS
+        self.chain_prec = _abi.CHAIN_PRECISIONS.get(precision, _abi.PREC_FAST_TF32)
+        # per-layer fallback of the fp16 chains (images too large for shared memory): the FAST_TF32 kernels
+        self.layer_prec = _abi.PRECISIONS["fast_tf32" if precision == "fast_f16" else precision]
         self._handles = None
         self.fused = None                         # ChainHandle once a shape that fits shared memory is seen
         self.np_layer = 4 * C + 9 * C * (C - 1) // 2 + C
@@ -100,16 +103,16 @@ class _Chain:
     def handles(self):
         """Per-layer handles (fallback path: strict mode, or images too large for shared memory)."""
         if self._handles is None:
-            self._handles = [LayerHandle(self.C, 3, self.gamma, (1, 1), True, True, _abi.PRECISIONS[self.precision],
+            self._handles = [LayerHandle(self.C, 3, self.gamma, (1, 1), True, True, self.layer_prec,
                                          _abi.LAYOUT_3BY3) for _ in range(self.n)]
             assert self._handles[0].num_params == self.np_layer
         return self._handles
 
     def use_fused(self, shape):
-        if not self.persistent or not ChainHandle.supported(self.C, shape[1], shape[2]):
+        if not self.persistent or not ChainHandle.supported(self.C, shape[1], shape[2], self.chain_prec):
             return False
         if self.fused is None:
-            self.fused = ChainHandle(self.C, self.n, self.gamma)
+            self.fused = ChainHandle(self.C, self.n, self.gamma, precision=self.chain_prec)
             assert self.fused.num_params == self.np_layer
         return True
 
@@ -120,11 +123,13 @@ class _Chain:
             return
         if shape not in self._fbufs:
             N, H, W, C = shape
+            sdt = self.fused.saved_dtype
             self._fbufs[shape] = dict(
-                f_acts=torch.empty((self.n,) + shape, dtype=torch.float32, device=device),
+                f_acts=torch.empty((self.n,) + shape, dtype=sdt, device=device),
                 f_masks=torch.empty((self.n, N, H, W, (C + 7) // 8), dtype=torch.uint8, device=device),
-                f_dz=torch.empty((self.n,) + shape, dtype=torch.float32, device=device),
-                f_dx=torch.empty(shape, dtype=torch.float32, device=device))
+                f_dz=torch.empty((self.n,) + shape, dtype=sdt, device=device),
+                f_dx=torch.empty(shape, dtype=torch.float32, device=device),
+                f_y=torch.empty(shape, dtype=torch.float32, device=device) if self.fused.f16 else None)
         for k, v in self._fbufs[shape].items():
             setattr(self, k, v)
         self._fshape = shape
@@ -132,6 +137,23 @@ class _Chain:
     def saved_mask(self, l):
         """relu bit mask [N,H,W,C/8] of Euler step l as saved by the last forward pass"""
         return self.f_masks[l] if self._last_fused else self.masks[l]
+
+    def fused_forward(self, x, h):
+        """All Euler steps of the chain in ONE launch (training form: saves the weight-gradient operands and relu
+        masks); returns the stage output."""
+        self.x0 = x
+        self._last_fused = True
+        if self.fused.f16:          # acts[l] = fp16 input of step l; the fp32 output of the last step goes to f_y
+            self.fused.forward(x, h, acts=self.f_acts, masks=self.f_masks, y_final=self.f_y)
+            return self.f_y
+        self.fused.forward(x, h, acts=self.f_acts, masks=self.f_masks)
+        return self.f_acts[self.n - 1]
+
+    def fused_backward(self, dy, h, grad_euler):
+        """Backward sweep (one launch) + weight gradients of all layers (one launch + fold); returns dL/dx0."""
+        self.fused.dgrad(dy, self.f_masks, self.f_dz, self.f_dx, h)
+        self.fused.wgrad(self.x0, self.f_acts, self.f_dz, grad_euler[self.offset:], self.np_layer)
+        return self.f_dx
 
     def ensure_buffers(self, shape, device):
         if self.acts is not None and self.acts[1].shape == shape:
@@ -160,10 +182,8 @@ class _ChainFn(torch.autograd.Function):
         if ctx.fused:
             # persistent path: pack all layers, then ONE launch runs every Euler step of the chain
             chain.ensure_fused_buffers(tuple(x.shape), x.device)
-            chain.x0 = x.detach()
             chain.fused.pack(net.theta_euler[chain.offset:], chain.np_layer)
-            chain.fused.forward(chain.x0, net.spec.h, acts=chain.f_acts, masks=chain.f_masks)
-            return chain.f_acts[chain.n - 1].view(N, H, W, C)
+            return chain.fused_forward(x.detach(), net.spec.h).view(N, H, W, C)
         chain.ensure_buffers(tuple(x.shape), x.device)
         dt = chain.handles[0].io_dtype
         ctx.in_dtype = x.dtype
@@ -185,10 +205,7 @@ class _ChainFn(torch.autograd.Function):
         lib, st = _abi.lib(), _stream_ptr()
         dy = dy.contiguous()
         if ctx.fused:
-            # backward sweep (one launch) + weight gradients of all layers (one launch + one fold)
-            chain.fused.dgrad(dy, chain.f_masks, chain.f_dz, chain.f_dx, net.spec.h)
-            chain.fused.wgrad(chain.x0, chain.f_acts, chain.f_dz, net.grad_euler[chain.offset:], chain.np_layer)
-            return chain.f_dx.view(N, H, W, C), None, None
+            return chain.fused_backward(dy, net.spec.h, net.grad_euler).view(N, H, W, C), None, None
         dt = chain.handles[0].io_dtype
         cur = dy.to(dt)
         is_bf16 = int(dt == torch.bfloat16)
@@ -214,8 +231,9 @@ class _ChainFn(torch.autograd.Function):
 class EulerNet:
     """Antisymmetric single-block ResNet with a fused train step.
 
-    precision: 'strict' (3xTF32, fp32-accurate), 'fast_tf32', 'fast_bf16' (bf16 operands and activations,
-    fp32 accumulate; per-layer kernels), or 'simt'."""
+    precision: 'strict' (3xTF32, fp32-accurate), 'fast_f16' (persistent chains with fp16 operands -- the tf32
+    significand -- around an fp32 residual stream), 'fast_tf32' (persistent chains with tf32 operands),
+    'fast_bf16' (bf16 operands and activations, fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
                  world_size=1, persistent=True, native_glue=True, comm=None):
@@ -429,13 +447,10 @@ class EulerNet:
                 cur = e["out"]
             else:
                 ch = e["chain"]
-                ch.x0 = cur
-                ch._last_fused = True
                 if not joined:
                     main.wait_event(packed)
                     joined = True
-                ch.fused.forward(cur, spec.h, acts=ch.f_acts, masks=ch.f_masks)
-                cur = ch.f_acts[ch.n - 1]
+                cur = ch.fused_forward(cur, spec.h)
         if not joined:
             main.wait_event(packed)
         fo = self._off("fc/kernel")
@@ -446,15 +461,14 @@ class EulerNet:
         for e in reversed(nb["plan"]):
             if e["kind"] == "chain":
                 ch = e["chain"]
-                ch.fused.dgrad(d, ch.f_masks, ch.f_dz, ch.f_dx, spec.h)
-                ch.fused.wgrad(ch.x0, ch.f_acts, ch.f_dz, self.grad_euler[ch.offset:], ch.np_layer)
+                dnext = ch.fused_backward(d, spec.h, self.grad_euler)
                 if self.world_size > 1 and not os.environ.get("B200ODE_NO_OVERLAP"):
                     # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
                     # overlaps the rest of the backward pass; joined in _optimizer before Adam
                     lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
                     self._pending.append(self._ar_async(self.grad_euler[lo:hi]))
                     self._reduced_upto = min(self._reduced_upto, lo)
-                d = ch.f_dx
+                d = dnext
             elif e["kind"] == "transition":
                 nm = e["name"]
                 _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),

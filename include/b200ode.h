@@ -45,6 +45,8 @@ typedef enum {
 #define B200ODE_PREC_FAST_TF32 1  /* tcgen05 1xTF32, fp32 accumulate, fp32 I/O                     */
 #define B200ODE_PREC_FAST_BF16 2  /* tcgen05 bf16 operands, fp32 accumulate, bf16 I/O              */
 #define B200ODE_PREC_SIMT_FP32 3  /* CUDA-core fp32 FMA kernels (any C, any k, any stride)         */
+#define B200ODE_PREC_FAST_F16  4  /* chains only: fp16 operands (11-bit significand = tf32 grade), rounded to nearest where they
+                                     are produced, fp32 accumulate, fp32 residual stream; saved activations / dZ in fp16 */
 
 /* param_layout: order of the free parameters in the flat packed vector = the
  * reference's variable creation order, each variable flattened C-order. */
@@ -153,8 +155,15 @@ int b200ode_gradient_mean_norms(const float* grads, const int64_t* offsets, cons
 /* ---- persistent Euler-step chains: the stage loop of models/tfkeras_resnets.py:575-593
  *      (n x single_layer_identity_block, :28-94, on a tensor of constant shape) forward and its
  *      TF-autodiff backward sweep (training/training.py:300) in ONE launch per direction.  One CTA
- *      keeps one image in shared memory across all steps.  FAST_TF32 only; shapes whose image does
- *      not fit shared memory are refused (b200ode_chain_supported == 0): use the per-layer calls. ---- */
+ *      keeps one image in shared memory across all steps.  Shapes whose image does not fit shared
+ *      memory are refused (b200ode_chain_supported == 0): use the per-layer calls.
+ *      Two formulations, chosen by precision_mode at create time:
+ *        FAST_TF32  tf32 operands straight from the fp32 residual stream (8 channels per MMA); saved
+ *                   activations and dZ are fp32; forward results equal the per-layer FAST_TF32 kernels bit for bit.
+ *        FAST_F16   fp16 operands (16 channels per MMA, same 11-bit significand) rounded to nearest where they are
+ *                   produced, fp32 residual stream kept in shared memory; saved operands (acts, dz_all) are fp16
+ *                   and the backward strips carry ONE power-of-two scale per launch derived from max|dy|
+ *                   (fp16 range); b200ode_chain_wgrad undoes it.  |activations| must stay below 65504. ---- */
 typedef struct b200ode_chain b200ode_chain_t;
 int b200ode_chain_supported(int channels, int H, int W, int precision_mode);
 /* n_layers distinct antisymmetric 3x3 layers (LAYOUT_3BY3 parameters, strides (1,1)) */
@@ -165,19 +174,23 @@ int64_t b200ode_chain_layer_params(const b200ode_chain_t* chain);
 /* K1 for all layers at once: params + l*param_layer_stride = packed parameters of layer l */
 int b200ode_chain_pack(b200ode_chain_t* chain, const float* params, int64_t param_layer_stride, void* stream);
 /* n_steps Euler steps x_{l+1} = x_l + h*relu(conv_{K_l}(x_l)+b_l); step l uses layer l % n_layers
- * (n_layers == 1: the long-horizon integration through one block).  acts: nullable fp32
- * [n_steps][N,H,W,C] receiving every x_{l+1}; relu_masks: nullable [n_steps][N,H,W,C/8];
- * y_final: nullable [N,H,W,C] (required when acts is NULL). */
-int b200ode_chain_fwd(b200ode_chain_t* chain, const float* x0, float* acts, uint8_t* relu_masks, float* y_final, int N,
+ * (n_layers == 1: the long-horizon integration through one block).  relu_masks: nullable
+ * [n_steps][N,H,W,C/8]; y_final: [N,H,W,C] fp32 output of the last step.
+ *   FAST_TF32: acts nullable fp32 [n_steps][N,H,W,C] receiving every x_{l+1}; y_final nullable (required when acts is NULL).
+ *   FAST_F16:  acts nullable fp16 [n_steps][N,H,W,C] receiving the INPUT of every step (acts[0] = fp16(x0)): the
+ *              weight-gradient operands; y_final required. */
+int b200ode_chain_fwd(b200ode_chain_t* chain, const float* x0, void* acts, uint8_t* relu_masks, float* y_final, int N,
                       int H, int W, float h, int n_steps, void* stream);
-/* backward sweep over the n_layers steps: dy = dL/dx_L -> dx = dL/dx_0; dz_all: fp32
- * [n_layers][N,H,W,C] receives dZ_l = h*dY_l*mask_l (input of the weight gradient). */
-int b200ode_chain_dgrad(b200ode_chain_t* chain, const float* dy, const uint8_t* relu_masks, float* dz_all, float* dx,
+/* backward sweep over the n_layers steps: dy = dL/dx_L -> dx = dL/dx_0 (both fp32); dz_all
+ * [n_layers][N,H,W,C] receives dZ_l = h*dY_l*mask_l, the input of the weight gradient: fp32 (FAST_TF32) or
+ * fp16 times the launch's power-of-two scale (FAST_F16; the scale lives in the chain handle). */
+int b200ode_chain_dgrad(b200ode_chain_t* chain, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
                         int N, int H, int W, float h, void* stream);
-/* weight + bias gradients of all layers in one launch (+ one fold/reduce launch):
- * layer l reads x_l (x0 for l = 0, acts[l-1] otherwise) and dz_all[l];
- * result at grad_params + l*grad_layer_stride. */
-int b200ode_chain_wgrad(b200ode_chain_t* chain, const float* x0, const float* acts, const float* dz_all,
+/* weight + bias gradients of all layers in one launch (+ fold/reduce launches); result at
+ * grad_params + l*grad_layer_stride.
+ *   FAST_TF32: layer l reads x_l (x0 for l = 0, acts[l-1] otherwise) and dz_all[l], all fp32.
+ *   FAST_F16:  layer l reads acts[l] and dz_all[l] (fp16, as written by the two calls above; x0 is ignored). */
+int b200ode_chain_wgrad(b200ode_chain_t* chain, const float* x0, const void* acts, const void* dz_all,
                         float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream);
 
 /* ---- stem / transition / head of the single-block ResNet, fp32 CUDA-core kernels.

@@ -348,11 +348,13 @@ def fold_grad_3by3(G, C, dbias=None):
     return flat
 
 
-def euler_step_bwd(dY, cache, K, h=1.0, bn_gamma=None):
+def euler_step_bwd(dY, cache, K, h=1.0, bn_gamma=None, mask=None):
     """Backward of euler_step_fwd.  Returns dX, G (dense dL/dK), dbias,
-    and (dgamma_bn, dbeta_bn) or None."""
+    and (dgamma_bn, dbeta_bn) or None.  `mask` (bool, parity tests only) overrides the relu branch decision
+    (u > 0): relu' is discontinuous, so an implementation whose pre-activation differs at rounding level may
+    legitimately take the other branch for a few elements; tests bound their number separately."""
     u = cache["u"]
-    dU = (np.asarray(h, dtype=dY.dtype) * dY) * (u > 0)
+    dU = (np.asarray(h, dtype=dY.dtype) * dY) * ((u > 0) if mask is None else mask)
     if cache["bn"] is not None:
         zhat, inv, _, _ = cache["bn"]
         dZ, dgam, dbet = bn_train_bwd(dU, zhat, inv, bn_gamma)

@@ -84,14 +84,24 @@ def test_train_step_fast_tf32_cuda_graph_matches_oracle():
     _run("fast_tf32", 2e-3, 3e-2, graph=True)
 
 
-def test_native_predict_matches_oracle():
+def test_train_step_fast_f16_matches_oracle():
+    """fast_f16: persistent chains with fp16 operands (the tf32 significand, rounded to nearest) around an fp32 residual stream."""
+    _run("fast_f16", 2e-3, 3e-2)
+
+
+def test_train_step_fast_f16_cuda_graph_matches_oracle():
+    _run("fast_f16", 2e-3, 3e-2, graph=True)
+
+
+@pytest.mark.parametrize("precision", ["fast_tf32", "fast_f16"])
+def test_native_predict_matches_oracle(precision):
     """Inference through stem + one chain launch per stage (activations never leave shared memory inside a
     stage) + transitions + head against the O1 forward pass; fast_tf32 tolerance on probabilities."""
     from differential_equations_resnet_b200.training import EulerNet, NetSpec
     kw = dict(blocks_per_stage=(4, 5, 3), filters_per_block=(16, 32, 64), h=0.125, gamma=-0.05)
     ospec = O1.NetSpec(**kw)
     P = O1.init_net_params(ospec, seed=9)
-    net = EulerNet(NetSpec(**kw), precision="fast_tf32", seed=0)
+    net = EulerNet(NetSpec(**kw), precision=precision, seed=0)
     net.import_params(P)
     gen = torch.Generator().manual_seed(4)
     for N in (1, 9):
