@@ -823,6 +823,15 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   int nparts = sms / (ngroups * L);
   if (nparts < 1) nparts = 1;
+  if (strict) {
+    // The tensor core accumulates with truncation (csrc/umma_probe.cu): the error of one TMEM accumulator grows
+    // linearly with the number of k-steps it absorbs (measured at N=256, 32x32: 1.9e-9 per position, 9e-5 at the
+    // 65k positions a C=256 part used to cover).  Strict mode therefore caps a part at ~2048 positions (<= 4e-6)
+    // and lets the fp32 round-to-nearest reduction of the partials (fold_reduce*) carry the rest: more CTAs than
+    // SMs, several waves.
+    const long long want = ((long long)p.total_tiles * p.tstride + 2047) / 2048;
+    if (want > nparts) nparts = (int)(want < 65535 ? want : 65535);
+  }
   if (nparts > p.total_tiles) nparts = p.total_tiles;
   p.nparts = nparts;
   const long long total = 9LL * C * C;
@@ -880,7 +889,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int T = (C + 31) / 32;
   const int PZ = nparts <= 4 ? 1 : nparts <= 16 ? 2 : 4;
   const long long tblocks = (long long)T * (T + 1) / 2 * lg.k * lg.k * L;
-  const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && nparts <= 16 * PZ && tblocks * PZ >= 296;
+  const bool tiled = !p.pair && lg.layout == 0 && lg.antisym && C >= 32 && (nparts <= 16 * PZ || (strict && C >= 64)) && tblocks * PZ >= 296;
   if (tiled) {
     const dim3 tgrid(T * (T + 1) / 2, lg.k * lg.k, L), tblock(32, 8, PZ);
     if (PZ == 1) fold_reduce_tiled_kernel<1><<<tgrid, tblock, 0, st>>>(lg, ws, nparts, pstride, grad_params, accumulate, p.part_layer_stride, grad_layer_stride, amax, amax_h);
