@@ -740,7 +740,12 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
   const long long Q = (long long)H * p.P;
-  const int max_smem = 227 * 1024 - 2048;
+  // Layer-batched launches (the chains' weight gradients) run on a side stream under the next stage's backward sweep
+  // (training.py): capped at ~half an SM's shared memory their CTAs co-reside with the chain CTAs (88-90 KB for the
+  // 16- and 32-channel stages) instead of waiting for them.
+  static const int wg_cap_env = getenv("B200ODE_WGRAD_SMEM_KB") ? atoi(getenv("B200ODE_WGRAD_SMEM_KB")) : 0;
+  const int cap_kb = wg_cap_env > 0 ? wg_cap_env : 227;
+  const int max_smem = (L > 1 && cap_kb < 227 ? cap_kb : 227) * 1024 - 2048;
   // Row-aligned tiles (bf16 / tf32, 128-channel operand blocks): a tile is R whole image rows, so the strips hold exactly
   // R+2 / R rows (x over-read (R+2)/R instead of the ~3x of position-granular tiles on row-granular strips) and
   // the k-steps run into a zeroed pad up to the next multiple of 16 positions.
@@ -1488,11 +1493,14 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
-  // bands of ~128 output pixels (4 per lane); each warp of a block owns one 8-channel slice
-  constexpr int COT = 8, PT = 4;
-  int orows = (128 + g.Wo - 1) / g.Wo;
+  // bands of 32*PT output pixels (PT per lane); each warp of a block owns one 8-channel slice.  Small bands = many
+  // blocks: the kernel is latency-bound (ncu: 11 % warps active, IPC 0.4 with 128-pixel bands on 256 blocks).
+  constexpr int COT = 8;
+  static const int pt_env = getenv("B200ODE_TR_FWD_PT") ? atoi(getenv("B200ODE_TR_FWD_PT")) : 1;
+  const int PT = pt_env == 4 ? 4 : pt_env == 2 ? 2 : 1;
+  int orows = (32 * PT + g.Wo - 1) / g.Wo;
   if (orows > g.Ho) orows = g.Ho;
-  int G = Cout / COT < 4 ? Cout / COT : 4;
+  int G = Cout / COT < 8 ? Cout / COT : 8;
   while ((Cout / COT) % G) --G;
   size_t smem = 0;
   for (; orows >= 1; orows >>= 1) {
@@ -1501,7 +1509,10 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   }
   if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_fwd: rows too wide (W=%d, Cin=%d)", W, Cin);
   const int bands = (g.Ho + orows - 1) / orows;
-  GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, PT>), dim3(N, bands, Cout / COT / G), 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
+  const dim3 grid(N, bands, Cout / COT / G);
+  if (PT == 4) GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 4>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
+  else if (PT == 2) GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 2>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
+  else GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 1>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
   LAUNCH_CHECK("transition_fwd_kernel");
   return 0;
 }
@@ -1515,9 +1526,12 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
   // band height: the staged output rows (dout + masked copy) and the weight slice must fit shared memory
-  constexpr int CIT = 8, PT = 4;
+  constexpr int CIT = 8;
   if (Cin % CIT) return fail(B200ODE_ERR_UNSUPPORTED, "transition_dgrad: Cin must be a multiple of %d (got %d)", CIT, Cin);
-  int rows = H < 16 ? H : 16;
+  static const int rows_env = getenv("B200ODE_TR_DGRAD_ROWS") ? atoi(getenv("B200ODE_TR_DGRAD_ROWS")) : 4;
+  static const int pt_env = getenv("B200ODE_TR_DGRAD_PT") ? atoi(getenv("B200ODE_TR_DGRAD_PT")) : 1;
+  const int PT = pt_env == 4 ? 4 : pt_env == 2 ? 2 : 1;
+  int rows = H < rows_env ? H : rows_env;
   size_t smem = 0;
   for (; rows >= 1; rows >>= 1) {
     const int nor = (rows - 1 + 2) / stride_h + 2;
@@ -1526,7 +1540,10 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   }
   if (rows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_dgrad: rows too wide (Wo=%d, Cout=%d)", g.Wo, Cout);
   const int bands = (H + rows - 1) / rows;
-  GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, PT>), dim3(N, bands, Cin / CIT), 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
+  const dim3 grid(N, bands, Cin / CIT);
+  if (PT == 4) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 4>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
+  else if (PT == 2) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 2>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
+  else GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 1>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   LAUNCH_CHECK("transition_dgrad_kernel");
   return 0;
 }
@@ -1544,7 +1561,8 @@ extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const
   const int ngroups = 256 / ntile > 10 ? 10 : 256 / ntile;
   const int tpg = (10 + ngroups - 1) / ngroups;
   // band of output rows per block: dout + masked copy + the input rows they touch
-  int orows = g.Ho < 4 ? g.Ho : 4;
+  static const int wrows_env = getenv("B200ODE_TR_WGRAD_ROWS") ? atoi(getenv("B200ODE_TR_WGRAD_ROWS")) : 4;
+  int orows = g.Ho < wrows_env ? g.Ho : wrows_env;
   size_t smem = 0;
   for (; orows >= 1; orows >>= 1) {
     const int nir = (orows - 1) * stride_h + 3;

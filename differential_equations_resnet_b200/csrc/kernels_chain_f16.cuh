@@ -236,7 +236,7 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
     for (uint32_t ic = 0; ic < (uint32_t)p.iters; ++ic) {
       for (int li = 0; li < p.L; ++li, ++sd) {
         // weights first (prefetched a layer ahead: this wait is hidden behind the previous step's epilogue)
-        mbar_wait(&w_full[ws], wph);
+        mbar_wait_lean(&w_full[ws], wph);
         if (ic == 0 && lane == 0) { if (li == TL) tr.mark(2); if (li == TL + 1) tr.mark(5); }
         const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
         const uint32_t b_base = (smem_base + p.w_off + ws * p.w_layer_bytes) >> 4;
@@ -245,10 +245,8 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
           // The A rows of segment sg span the strip rows the previous step's epilogue wrote for segments sg-1, sg and
           // sg+1 (sg-1 was awaited one iteration ago); its arrival also says the accumulator of sg has been read.
           // (one lane polls: 32 lanes spinning on shared memory next to running MMAs steal operand bandwidth)
-          const long long tw0 = tr.buf ? clock64() : 0;
-          if (sg == 0) mbar_wait(&seg_done[0], sd & 1);
-          if (sg + 1 < p.nseg) mbar_wait(&seg_done[sg + 1], sd & 1);
-          if (tr.buf && ic == 0 && li == TL && lane == 0) tr.buf[3] += (uint64_t)(clock64() - tw0);
+          if (sg == 0) mbar_wait_lean(&seg_done[0], sd & 1);
+          if (sg + 1 < p.nseg) mbar_wait_lean(&seg_done[sg + 1], sd & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
@@ -386,12 +384,9 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
           const bool valid = (vmask >> k) & 1u;
           const int pixl = pix_k[k];
           const uint32_t pos = (uint32_t)(sg * 128 + row + p.P + 1);
-          long long tb0 = 0;
           if ((k % IPS) == 0) {
-            const long long tw0 = tr.buf ? clock64() : 0;
-            mbar_wait_sleep(&acc_full[sg], lc & 1);
+            mbar_wait_sleep_lean(&acc_full[sg], lc & 1);
             tc_fence_after_sync();
-            if (tr.buf && lc == TL && lane == 0 && quarter == 2) { tb0 = clock64(); tr.buf[sub == 0 ? 7 : 14] += (uint64_t)(tb0 - tw0); }
             if (threadIdx.x == 64 && lc == TL && k == 0) tr.mark(6);
             if (threadIdx.x == 64 && lc == TL + 1 && k == 0) tr.mark(9);
           }
@@ -475,13 +470,12 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
             __syncwarp();
             if (lane == 0) mbar_arrive(&seg_done[sg]);
           }
-          if (tr.buf && lc == TL && threadIdx.x == 64 && IPS == 1) tr.buf[13] += (uint64_t)(clock64() - tb0);
         }
         if (threadIdx.x == 64 && lc == TL) tr.mark(8);
         if (last) {
           // Nobody leaves the image before ALL MMAs of its last step are complete: the next image's init rewrites
           // strip 0 (which they may read) and re-arms the segment barriers.
-          mbar_wait_sleep(&acc_full[p.nseg - 1], lc & 1);
+          mbar_wait_sleep_lean(&acc_full[p.nseg - 1], lc & 1);
           tc_fence_before_sync();
         }
       }

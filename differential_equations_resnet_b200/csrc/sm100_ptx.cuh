@@ -110,14 +110,30 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
   uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  while (!mbar_try_wait_hint(bar, parity, ns)) {
     if (++spins > (B200ODE_MBAR_SPIN_LIMIT >> 6)) {
       printf("b200ode: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
+  }
+}
+
+// Lean variants for hot loops: same bounded wait, but the failure path is a bare trap (the printf of the variants
+// above costs registers and instruction-cache footprint in every loop that contains a wait; the persistent chain
+// kernels lose ~20 % to such additions).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > B200ODE_MBAR_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_sleep_lean(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (B200ODE_MBAR_SPIN_LIMIT >> 6)) __trap();
   }
 }
 

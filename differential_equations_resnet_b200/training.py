@@ -149,11 +149,19 @@ class _Chain:
         self.fused.forward(x, h, acts=self.f_acts, masks=self.f_masks)
         return self.f_acts[self.n - 1]
 
-    def fused_backward(self, dy, h, grad_euler):
-        """Backward sweep (one launch) + weight gradients of all layers (one launch + fold); returns dL/dx0."""
+    def fused_dgrad(self, dy, h):
+        """Backward sweep over all steps of the chain (one launch); returns dL/dx0."""
         self.fused.dgrad(dy, self.f_masks, self.f_dz, self.f_dx, h)
-        self.fused.wgrad(self.x0, self.f_acts, self.f_dz, grad_euler[self.offset:], self.np_layer)
         return self.f_dx
+
+    def fused_wgrad(self, grad_euler):
+        """Weight + bias gradients of all layers (one launch + fold) into the flat bucket."""
+        self.fused.wgrad(self.x0, self.f_acts, self.f_dz, grad_euler[self.offset:], self.np_layer)
+
+    def fused_backward(self, dy, h, grad_euler):
+        dx = self.fused_dgrad(dy, h)
+        self.fused_wgrad(grad_euler)
+        return dx
 
     def ensure_buffers(self, shape, device):
         if self.acts is not None and self.acts[1].shape == shape:
@@ -420,6 +428,9 @@ class EulerNet:
         if getattr(self, "_pack_stream", None) is None:
             self._pack_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        overlap_wgrad = not os.environ.get("B200ODE_NO_WGRAD_OVERLAP")
         overlap_pack = not os.environ.get("B200ODE_NO_PACK_OVERLAP")
         if overlap_pack:
             self._pack_stream.wait_stream(main)
@@ -457,30 +468,45 @@ class EulerNet:
         _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
                                             _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
                                             spec.num_classes, st))
+        # Backward.  Critical path (main stream): head -> chain dgrad -> transition dgrad -> chain dgrad -> ...; every
+        # weight gradient (chain wgrad + fold, transition wgrad, stem wgrad: ~1/4 of the step) only feeds the optimiser,
+        # so it runs on a side stream, ordered by events after the data gradient that produces its dZ, and is joined
+        # before Adam.  The fork / join is captured in the CUDA graph like everything else.
         d = nb["head_dx"]
+        side = self._side_stream if overlap_wgrad else main
         for e in reversed(nb["plan"]):
             if e["kind"] == "chain":
                 ch = e["chain"]
-                dnext = ch.fused_backward(d, spec.h, self.grad_euler)
-                if self.world_size > 1 and not os.environ.get("B200ODE_NO_OVERLAP"):
-                    # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
-                    # overlaps the rest of the backward pass; joined in _optimizer before Adam
-                    lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
-                    self._pending.append(self._ar_async(self.grad_euler[lo:hi]))
-                    self._reduced_upto = min(self._reduced_upto, lo)
+                dnext = ch.fused_dgrad(d, spec.h)
+                if overlap_wgrad:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    ch.fused_wgrad(self.grad_euler)
+                    if self.world_size > 1 and not os.environ.get("B200ODE_NO_OVERLAP"):
+                        # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
+                        # overlaps the rest of the backward pass; joined in _optimizer before Adam
+                        lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
+                        self._pending.append(self._ar_async(self.grad_euler[lo:hi]))
+                        self._reduced_upto = min(self._reduced_upto, lo)
                 d = dnext
             elif e["kind"] == "transition":
                 nm = e["name"]
-                _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
-                                                        N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                with torch.cuda.stream(side):      # needs d (ready: the side stream already waits for the chain's dgrad)
+                    _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
+                                                            N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], side.cuda_stream))
                 _abi.check(lib.b200ode_transition_dgrad(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
                                                         _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
                                                         e["ci"], e["co"], e["st"][0], e["st"][1], st))
                 d = e["dx"]
             else:
-                _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
-                                                  _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
-                                                  e["co"], st))
+                with torch.cuda.stream(side):
+                    _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
+                                                      _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
+                                                      e["co"], side.cuda_stream))
+        if overlap_wgrad:
+            main.wait_stream(side)
         return nb["loss"].view(())
 
     def predict(self, images):

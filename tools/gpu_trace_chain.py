@@ -42,9 +42,8 @@ def main():
         if kind == "wgrad":
             nm = {1: "setup", 2: "mma:full0", 3: "mma:tile0 issued", 4: "mma:all issued", 5: "epi:bias done", 6: "epi:acc_full", 7: "epi:done", 9: "end", 10: "mma wait on stages"}
         elif ch.f16:
-            nm = {1: "setup", 2: "mma:L4 start", 3: "mma:L4 sum(wait seg_done)", 4: "mma:L4 issued", 5: "mma:L5 start", 6: "epi(w2):L4 first acc ready",
-                  7: "epi(w2):L4 sum(wait acc)", 13: "epi(w2):L4 sum(busy)", 14: "epi(w6):L4 sum(wait acc)", 8: "epi(w2):L4 done", 9: "epi(w2):L5 first acc ready",
-                  10: "mma:end", 11: "epi:end", 12: "end"}
+            nm = {1: "setup", 2: "mma:L4 start", 4: "mma:L4 issued", 5: "mma:L5 start", 6: "epi(w2):L4 first acc ready",
+                  8: "epi(w2):L4 done", 9: "epi(w2):L5 first acc ready", 10: "mma:end", 11: "epi:end", 12: "end"}
         else:
             nm = NAMES
         for cta in (0, t.shape[0] // 2, t.shape[0] - 1):
