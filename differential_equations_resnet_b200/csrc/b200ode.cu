@@ -685,7 +685,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   int UKP = bf16 ? 16 : 8;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L; p.f16 = f16 ? 1 : 0;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L;
   if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
   static const int pair_env = getenv("B200ODE_WGRAD_PAIR") ? atoi(getenv("B200ODE_WGRAD_PAIR")) : 1;   // debug switch
   p.pair = (!bf16 && !strict && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
@@ -865,18 +865,19 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
   }
   dim3 grid(nparts, ngroups, L);
-#define WG_LAUNCH(M_)                                                                                          \
+#define WG_LAUNCH(M_, F_)                                                                                      \
   do {                                                                                                         \
     static bool attr_set = false;                                                                              \
     if (!attr_set) {                                                                                           \
-      CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<M_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    wgrad_tc_kernel<M_><<<grid, (M_ == MODE_STRICT ? 10 : 6) * 32, smem, st>>>(mx0, mx, md, p);                \
+    wgrad_tc_kernel<M_, F_><<<grid, (M_ == MODE_STRICT ? 10 : 6) * 32, smem, st>>>(mx0, mx, md, p);            \
   } while (0)
-  if (mode == MODE_STRICT) WG_LAUNCH(MODE_STRICT);
-  else if (mode == MODE_TF32) WG_LAUNCH(MODE_TF32);
-  else WG_LAUNCH(MODE_BF16);
+  if (mode == MODE_STRICT) WG_LAUNCH(MODE_STRICT, false);
+  else if (mode == MODE_TF32) WG_LAUNCH(MODE_TF32, false);
+  else if (f16) WG_LAUNCH(MODE_BF16, true);
+  else WG_LAUNCH(MODE_BF16, false);
 #undef WG_LAUNCH
   LAUNCH_CHECK("wgrad_tc_kernel");
   if (G_user && L == 1) {   // dense gradient requested (tests / diagnostics)

@@ -161,13 +161,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row0 = q0 / p.P;  // first halo row of the strip (halo row r <-> image row r-1)
         for (int kb = 0; kb < NKB; ++kb) {
           const uint32_t s = as_, ph = aph;
-          mbar_wait_sleep(&a_empty[s], ph ^ 1);
+          mbar_wait_sleep_lean(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], p.a_bytes);
           tma_load_4d(smem + p.a_off + s * p.a_stride, &map_a, &a_full[s], kb * KB, -1, row0 - 1, n0);
           if (++as_ == (uint32_t)p.sa) { as_ = 0; aph ^= 1; }
           for (int tg = 0; tg < 9; tg += p.tw) {
             const uint32_t sw_ = ws, phw = wph;
-            mbar_wait_sleep(&w_empty[sw_], phw ^ 1);     // this CTA's MMAs are done with the stage's previous contents
+            mbar_wait_sleep_lean(&w_empty[sw_], phw ^ 1);     // this CTA's MMAs are done with the stage's previous contents
             uint8_t* wdst = smem + p.w_off + sw_ * p.w_stride;
             if (p.cs == 1) {
               mbar_expect_tx(&w_full[sw_], STRICT ? 2 * p.w_bytes : p.w_bytes);
@@ -205,18 +205,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
     auto toff_of = [&](int t) -> uint32_t { return (uint32_t)((t / 3) * p.P + (t % 3)) * RU; };
     uint32_t as_ = 0, aph_ = 0, ws = 0, wph = 0, it = 0;
-    long long st_a = 0, st_w = 0, st_acc = 0;   // cycles this warp spent waiting for strips / weights / free accumulators (trace)
     for (int itile = 0; itile < p.iters; ++itile, ++it) {
       const int tile = blockIdx.x + itile * gridDim.x;
       const int q0 = (tile % p.tpi) * T;
       const uint32_t off0_units = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
-      { const long long t0 = clock64(); mbar_wait(&acc_empty[as], aph ^ 1); st_acc += clock64() - t0; }
+      mbar_wait_lean(&acc_empty[as], aph ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tile = tmem_base + as * mt * ACCW;
       for (int kb = 0; kb < NKB; ++kb) {
         const uint32_t s = as_, ph = aph_;
-        { const long long t0 = clock64(); mbar_wait(STRICT ? &a_conv[s] : &a_full[s], ph); st_a += clock64() - t0; }
+        mbar_wait_lean(STRICT ? &a_conv[s] : &a_full[s], ph);
         if (it == 0 && kb == 0 && lane == 0) tr.mark(2);
         const uint32_t a_units = ((smem_base + p.a_off + s * p.a_stride) >> 4) + off0_units;
         // Taps-per-stage and k-steps are compile-time: per segment the stage's MMAs form one straight-line
@@ -226,7 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
         for (int tg = 0; tg < 9; tg += TW) {
           const uint32_t sw_ = ws, phw = wph;
-          { const long long t0 = clock64(); mbar_wait(&w_full[sw_], phw); st_w += clock64() - t0; }
+          mbar_wait_lean(&w_full[sw_], phw);
           if (it == 0 && kb == 0 && tg == 0 && lane == 0) tr.mark(3);
           tc_fence_after_sync();
           const uint32_t b_base = (smem_base + p.w_off + sw_ * p.w_stride) >> 4;
@@ -268,7 +267,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
     }
     if (lane == 0) tr.mark(5);
-    if (lane == 0 && tr.buf) { tr.buf[10] = (uint64_t)st_a; tr.buf[11] = (uint64_t)st_w; tr.buf[12] = (uint64_t)st_acc; }
   } else if (warp < 2 + 4 * Cfg::EPQ) {
     // ===================== epilogue warps 2..9: two warps per TMEM lane quarter =====================
     // Work item = (segment, G-channel group); the items of a tile alternate between the two warps of a
@@ -335,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         bool valid, nvalid = false; long long pix, npix = 0; int c0, nc0 = 0, sg, nsg = 0;
         geom(0, valid, pix, c0, sg);
         request(valid, pix, c0, cin, csk);
-        mbar_wait_sleep(&acc_full[as], aph);
+        mbar_wait_sleep_lean(&acc_full[as], aph);
         if (it == 0 && threadIdx.x == 64) tr.mark(6);
         tc_fence_after_sync();
 #pragma unroll 1
@@ -431,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < UV; ++j) { cin[j] = nin[j]; csk[j] = nsk[j]; }
         }
       } else {
-      mbar_wait_sleep(&acc_full[as], aph);
+      mbar_wait_sleep_lean(&acc_full[as], aph);
       if (it == 0 && threadIdx.x == 64) tr.mark(6);
       tc_fence_after_sync();
       for (int sg = 0; sg < mt; ++sg) {
@@ -623,7 +621,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int itile = 0; itile < p.iters; ++itile) {
         for (int kb = 0; kb < NKB; ++kb) {
           const uint32_t s = ia % p.sa, ph = (ia / p.sa) & 1;
-          mbar_wait_sleep(&a_full[s], ph);
+          mbar_wait_sleep_lean(&a_full[s], ph);
           const uint4* src = reinterpret_cast<const uint4*>(smem + p.a_off + s * p.a_stride);
           uint4* dst = reinterpret_cast<uint4*>(smem + p.a_off + s * p.a_stride + p.a_lo_off);
           const int n16 = p.a_bytes / 16;

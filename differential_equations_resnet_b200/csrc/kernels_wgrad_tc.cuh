@@ -73,12 +73,11 @@ struct WgradParams {
   // zero-padded channels.  The row before each x strip is a zeroed 1 KB pad (x_off = 1024).
   // The accumulators are written raw ([3][128 lanes][32 cols] per part) and gathered by fold_reduce_kernel.
   int pair;
-  int f16;           // 16-bit operands are IEEE fp16 (saved activations / scaled dZ of the fp16 chains) instead of bf16
   int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
 };
 
-template <int MODE>
+template <int MODE, bool F16 = false>
 __global__ void __launch_bounds__((MODE == MODE_STRICT ? 10 : 6) * 32, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
@@ -156,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         const int xc0 = p.pair ? 0 : -1;    // pair mode: the zero slots sit at the END of every row
         const uint32_t s = rs, ph = rph;
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
-        mbar_wait_sleep(&empty[s], ph ^ 1);
+        mbar_wait_sleep_lean(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
         for (int c = 0; c < p.xchunks; ++c)
@@ -169,7 +168,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
     const bool leader = elect_one();
     const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
-    const uint32_t idesc = make_instr_desc(BF16 ? (p.f16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.NT, 1, 1);
+    const uint32_t idesc = make_instr_desc(BF16 ? (F16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.NT, 1, 1);
     const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
     const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
     const uint32_t hi32 = (sbo >> 4) | (1u << 14) | (lt << 29);
@@ -198,16 +197,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
     const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
-    long long mma_wait = 0;   // trace: cycles spent waiting for operand stages
     uint32_t it = 0, rs = 0, rph = 0;
     for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
       const int q0 = (tile % p.tpi) * p.tstride;
       const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t s = rs, ph = rph;
       if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
-      const long long tw0 = tr.buf ? clock64() : 0;
-      mbar_wait(STRICT ? &conv[s] : &full[s], ph);
-      if (tr.buf) mma_wait += clock64() - tw0;
+      mbar_wait_lean(STRICT ? &conv[s] : &full[s], ph);
       if (it == 0 && lane == 0) tr.mark(2);
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
@@ -314,7 +310,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     }
     if (leader) umma_commit(acc_full);
     if (lane == 0) tr.mark(4);
-    if (lane == 0 && tr.buf) tr.buf[10] = (uint64_t)mma_wait;
   } else if (warp < 6) {
     // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
     // to accumulate the bias gradient sum_q dz[q, o] from the dz strips already in shared memory
@@ -342,14 +337,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         const int r0 = (q0 - (q0 / p.P) * p.P) / ppr;
         const uint32_t s = rs, ph = rph;
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
-        mbar_wait_sleep(&full[s], ph);
+        mbar_wait_sleep_lean(&full[s], ph);
         const uint8_t* cb = smem + s * p.stage_stride + p.d_off + ck * p.d_chunk_stride;
 #pragma unroll 4
         for (int r = k0 < tpu ? k0 : nr; r < nr; r += tpu) {
           uint32_t a = (uint32_t)(r0 + r) * p.RWB + (u << 4);
           a = BF16 ? swizzle_addr(a, p.RWB) : a ^ (((a >> 7) & 3u) << 5);
           const uint4 v = *reinterpret_cast<const uint4*>(cb + a);
-          if (BF16 && p.f16) {
+          if (BF16 && F16) {
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
             acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
