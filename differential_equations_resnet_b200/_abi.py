@@ -23,7 +23,8 @@ COLSUM_PARTS = 256
 
 _lib = None
 
-c_void_p, c_int, c_float, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64
+c_void_p, c_int, c_float, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64, ctypes.c_size_t
+GLUE_STEM_WGRAD, GLUE_TRANSITION_WGRAD, GLUE_HEAD = 0, 1, 2
 
 _SIGNATURES = {
     "b200ode_version": (c_int, []),
@@ -63,12 +64,17 @@ _SIGNATURES = {
     "b200ode_stem_fwd": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "b200ode_stem_wgrad": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                   c_int, c_int, c_void_p]),
+                                   c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200ode_transition_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
     "b200ode_transition_dgrad": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
-    "b200ode_transition_wgrad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    "b200ode_transition_wgrad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
     "b200ode_head_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_int, c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200ode_layer_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "b200ode_layer_set_workspace": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "b200ode_chain_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "b200ode_chain_set_workspace": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "b200ode_glue_workspace_bytes": (c_int, [c_int] * 8 + [ctypes.POINTER(c_size_t)]),
     "b200ode_chain_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "b200ode_chain_create": (c_int, [c_int, c_int, c_float, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "b200ode_chain_destroy": (c_int, [c_void_p]),

@@ -90,33 +90,42 @@ static int device_check() {
   return 0;
 }
 
-// process-wide scratch (split-K partials, SIMT pre-activations); stream-ordered single-stream use
-struct Scratch {
+// Device scratch of ONE compute call (split-K partials of the weight gradients, SIMT pre-activations, glue partials).
+// The caller owns it: a block bound to the handle (b200ode_*_set_workspace) or passed with the call (glue entry points),
+// sized by the *_workspace_bytes queries.  When the caller gives none the block comes from the device's stream-ordered
+// memory pool (cudaMallocAsync / cudaFreeAsync on the call's stream): no device synchronisation, every call gets its own
+// block (calls on different streams do not share scratch), capturable in a CUDA graph.  Nothing is retained past the call.
+struct WsLease {
   void* ptr = nullptr;
-  size_t bytes = 0;
+  bool pooled = false;
+  cudaStream_t st = nullptr;
+  ~WsLease() { if (pooled && ptr) cudaFreeAsync(ptr, st); }
 };
-static Scratch g_scratch[3];
-static std::mutex g_scratch_mu;
-static int get_scratch(int slot, size_t bytes, void** out) {
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  Scratch& s = g_scratch[slot];
-  if (s.bytes < bytes) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    void* np = nullptr;
-    cudaError_t e = cudaMalloc(&np, bytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail(B200ODE_ERR_CUDA, "scratch allocation of %zu bytes failed (%s); run one eager warm-up call before CUDA-graph capture",
-                  bytes, cudaGetErrorString(e));
-    }
-    (void)st;
-    // the old block may still be in use by queued work: leak-free deferred free is not needed for
-    // correctness of stream order because cudaFree synchronises the device.
-    if (s.ptr) cudaFree(s.ptr);
-    s.ptr = np;
-    s.bytes = bytes;
+static int lease_ws(void* bound, size_t bound_bytes, size_t need, cudaStream_t st, WsLease* out) {
+  if (need == 0) need = 16;
+  if (bound) {
+    if (bound_bytes < need)
+      return fail(B200ODE_ERR_INVALID, "workspace too small: %zu bytes bound, this call needs %zu (see b200ode_*_workspace_bytes)", bound_bytes, need);
+    out->ptr = bound;
+    return 0;
   }
-  *out = s.ptr;
+  static std::once_flag once;
+  std::call_once(once, [] {   // keep freed blocks in the pool instead of returning them to the OS at every synchronisation
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  });
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, need, st);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200ODE_ERR_CUDA, "stream-ordered workspace allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
+  }
+  out->ptr = p; out->pooled = true; out->st = st;
   return 0;
 }
 
@@ -134,6 +143,8 @@ struct b200ode_layer {
   __nv_bfloat16* w_bf;
   float* bias;     // [C]
   float* colsum_ws;
+  void* ws;        // caller-owned workspace (b200ode_layer_set_workspace), may be NULL
+  size_t ws_bytes;
   CUtensorMap map_w_hi, map_w_lo, map_w_bf;
 };
 
@@ -588,9 +599,13 @@ extern "C" int b200ode_euler_fwd(b200ode_layer_t* L, const void* x, void* y, uin
   const long long total = (long long)N * g.Ho * g.Wo * g.C;
   const bool plain = !(fuse_flags & (B200ODE_F_RELU | B200ODE_F_RESIDUAL)) && !scale_h && !relu_mask;
   float* zbuf = z_out;
+  WsLease lease;
   if (!zbuf) {
     if (plain) zbuf = (float*)y;
-    else if (int rc = get_scratch(0, (size_t)total * sizeof(float), (void**)&zbuf)) return rc;
+    else {
+      if (int rc = lease_ws(L->ws, L->ws_bytes, (size_t)total * sizeof(float), st, &lease)) return rc;
+      zbuf = (float*)lease.ptr;
+    }
   }
   simt_conv_fwd<<<blocks_for(total, 256), 256, 0, st>>>(g, (const float*)x, L->Kdense,
                                                        (fuse_flags & B200ODE_F_BIAS) && L->g.use_bias ? L->bias : nullptr, zbuf);
@@ -674,9 +689,14 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
 // mode MODE_F16: 16-bit operands are fp16 (fp16 chains); `amax` != nullptr: the gradients carry the chain's backward
 // scale chain_grad_scale(h, *amax), undone by the fold kernels.
 enum { MODE_F16 = 3 };
+struct WsArg {          // the caller's workspace (ptr may be NULL: stream-ordered pool); query != NULL: plan only, report the bytes
+  void* ptr;
+  size_t bytes;
+  size_t* query;
+};
 static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const void* xrest, const void* dz, int L, int N, int H,
                         int W, float* G, float* G_user, float* grad_params, long long grad_layer_stride, int accumulate,
-                        cudaStream_t st, int force_mgroups = 0, const float* amax = nullptr, float amax_h = 1.0f) {
+                        cudaStream_t st, const WsArg& wsa, int force_mgroups = 0, const float* amax = nullptr, float amax_h = 1.0f) {
   const int C = lg.C;
   const bool f16 = mode == MODE_F16;
   if (f16) mode = MODE_BF16;
@@ -798,7 +818,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     }
   }
   if (!KT && p.MB > 1 && !force_mgroups)   // all-channel strips do not fit (strict C = 256, tf32 C = 256 at W = 64): one M block per CTA
-    return run_wgrad_tc(f16 ? MODE_F16 : mode, lg, x0, xrest, dz, L, N, H, W, G, G_user, grad_params, grad_layer_stride, accumulate, st, 1,
+    return run_wgrad_tc(f16 ? MODE_F16 : mode, lg, x0, xrest, dz, L, N, H, W, G, G_user, grad_params, grad_layer_stride, accumulate, st, wsa, 1,
                         amax, amax_h);
   if (!KT) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad strips do not fit shared memory (C=%d W=%d)", C, W);
   if (KT > Q) KT = (int)((Q + UKP - 1) / UKP * UKP);
@@ -842,8 +862,11 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const long long total = 9LL * C * C;
   const long long pstride = p.pair ? 3LL * 128 * 32 : total;   // floats per partial
   p.part_stride = pstride;
-  float* ws = nullptr;
-  if (int rc = get_scratch(1, (size_t)L * nparts * (pstride + C) * sizeof(float), (void**)&ws)) return rc;
+  const size_t ws_need = (size_t)L * nparts * (pstride + C) * sizeof(float);
+  if (wsa.query) { *wsa.query = ws_need; return 0; }
+  WsLease lease;
+  if (int rc = lease_ws(wsa.ptr, wsa.bytes, ws_need, st, &lease)) return rc;
+  float* ws = (float*)lease.ptr;
   p.partials = ws;
   p.trace = g_trace;
   p.bias_partials = ws + (size_t)L * nparts * pstride;
@@ -920,13 +943,15 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long npix = (long long)N * g.Ho * g.Wo;
   if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
-    return run_wgrad_tc(L->mode_eff, L->g, x, x, dz, 1, N, H, W, L->Gdense, G_dense, grad_params, 0, accumulate, st);
+    return run_wgrad_tc(L->mode_eff, L->g, x, x, dz, 1, N, H, W, L->Gdense, G_dense, grad_params, 0, accumulate, st,
+                        WsArg{L->ws, L->ws_bytes, nullptr});
   } else {
     int parts = (int)(npix / 64);
     if (parts < 1) parts = 1;
     if (parts > 128) parts = 128;
-    float* ws = nullptr;
-    if (int rc = get_scratch(1, (size_t)parts * total * sizeof(float), (void**)&ws)) return rc;
+    WsLease lease;
+    if (int rc = lease_ws(L->ws, L->ws_bytes, (size_t)parts * total * sizeof(float), st, &lease)) return rc;
+    float* ws = (float*)lease.ptr;
     dim3 grid(blocks_for(total, 128), parts);
     simt_conv_wgrad<<<grid, 128, 0, st>>>(g, (const float*)x, (const float*)dz, ws, parts);
     LAUNCH_CHECK("simt_conv_wgrad");
@@ -1051,6 +1076,8 @@ struct b200ode_chain {
   float* bias;     // [L][C]
   float* amax;     // FAST_F16: device scalar max|dy| of the last backward sweep (scale of dz_all)
   float amax_h;    //           and the step size it was taken with
+  void* ws;        // caller-owned workspace (b200ode_chain_set_workspace), may be NULL
+  size_t ws_bytes;
 };
 
 struct ChainPlan {
@@ -1396,12 +1423,12 @@ extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const v
     if (!acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
     const __half* a16 = (const __half*)acts;
     return run_wgrad_tc(MODE_F16, ch->g, a16, a16 + (size_t)N * H * W * ch->g.C, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params,
-                        grad_layer_stride, 0, (cudaStream_t)stream, 0, ch->amax, ch->amax_h);
+                        grad_layer_stride, 0, (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr}, 0, ch->amax, ch->amax_h);
   }
   if (!x0) return fail(B200ODE_ERR_INVALID, "x0 is NULL");
   if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
   return run_wgrad_tc(MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params, grad_layer_stride, 0,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr});
 }
 
 
@@ -1409,6 +1436,13 @@ extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const v
 // stem / transition / head layers (kernels_glue.cuh)
 // ------------------------------------------------------------------------------------------------
 static int reduce_rows(const float* ws, int R, long long stride, long long n, float* out, cudaStream_t st);
+
+enum { STEM_WGRAD_ROWS = 8 };
+static size_t stem_wgrad_ws_bytes(int N, int H, int Cin, int Cout) {
+  const int bands = (H + STEM_WGRAD_ROWS - 1) / STEM_WGRAD_ROWS;
+  return (size_t)N * bands * (9 * (size_t)Cin * Cout + Cout) * sizeof(float);
+}
+static size_t head_ws_bytes(int N, int C, int K) { return (size_t)N * ((size_t)C * K + K + 1) * sizeof(float); }
 
 static GlueConv glue_geom(int N, int H, int W, int Cin, int Cout, int sh, int sw) {
   GlueConv g;
@@ -1436,14 +1470,15 @@ extern "C" int b200ode_stem_fwd(const void* images, int images_are_u8, float sub
 
 extern "C" int b200ode_stem_wgrad(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
                                   const float* out, const float* dout, float* dparams, int N, int H, int W, int Cin, int Cout,
-                                  void* stream) {
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!images || !out || !dout || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (N == 0) return 0;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, 1, 1);
-  const int rows = 8, bands = (H + rows - 1) / rows;
+  const int rows = STEM_WGRAD_ROWS, bands = (H + rows - 1) / rows;
   const long long nout = 9LL * Cin * Cout + Cout;
-  float* ws = nullptr;
-  if (int rc = get_scratch(2, (size_t)N * bands * nout * sizeof(float), (void**)&ws)) return rc;
+  WsLease lease;
+  if (int rc = lease_ws(workspace, workspace_bytes, stem_wgrad_ws_bytes(N, H, Cin, Cout), (cudaStream_t)stream, &lease)) return rc;
+  float* ws = (float*)lease.ptr;
   const size_t smem = ((size_t)rows * W * Cout + (size_t)(rows + 2) * (W + 2) * Cin) * sizeof(float);
   if (smem > 48 * 1024) return fail(B200ODE_ERR_UNSUPPORTED, "stem_wgrad: image too wide (W=%d, filters=%d)", W, Cout);
   stem_wgrad_partial<<<dim3(N, bands), 256, smem, (cudaStream_t)stream>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev,
@@ -1549,31 +1584,46 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   return 0;
 }
 
-extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
-                                        int W, int Cin, int Cout, int stride_h, int stride_w, void* stream) {
-  if (!x || !dout || !relu_mask || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
-  if (int rc = transition_check(Cin, Cout)) return rc;
-  if (N == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
-  const long long nout = 9LL * Cin * Cout + Cout + (long long)Cin * Cout + Cout;
+struct TransWgradPlan { int tpg, orows, bands; size_t smem, ws_bytes; long long nout; };
+static int plan_transition_wgrad(const GlueConv& g, TransWgradPlan* pl) {
+  const int Cin = g.Cin, Cout = g.Cout;
+  pl->nout = 9LL * Cin * Cout + Cout + (long long)Cin * Cout + Cout;
   const int ntile = (Cin / 4) * (Cout / 4);
   if (ntile > 256 || 256 % ntile) return fail(B200ODE_ERR_UNSUPPORTED, "transition_wgrad: unsupported channel pair %d -> %d", Cin, Cout);
   const int ngroups = 256 / ntile > 10 ? 10 : 256 / ntile;
-  const int tpg = (10 + ngroups - 1) / ngroups;
+  pl->tpg = (10 + ngroups - 1) / ngroups;
   // band of output rows per block: dout + masked copy + the input rows they touch
   static const int wrows_env = getenv("B200ODE_TR_WGRAD_ROWS") ? atoi(getenv("B200ODE_TR_WGRAD_ROWS")) : 4;
   int orows = g.Ho < wrows_env ? g.Ho : wrows_env;
   size_t smem = 0;
   for (; orows >= 1; orows >>= 1) {
-    const int nir = (orows - 1) * stride_h + 3;
-    smem = ((size_t)2 * orows * g.Wo * Cout + (size_t)nir * W * Cin) * sizeof(float);
+    const int nir = (orows - 1) * g.sh + 3;
+    smem = ((size_t)2 * orows * g.Wo * Cout + (size_t)nir * g.W * Cin) * sizeof(float);
     if (smem <= 100 * 1024) break;
   }
-  if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_wgrad: rows too wide (W=%d)", W);
-  const int bands = (g.Ho + orows - 1) / orows;
-  float* ws = nullptr;
-  if (int rc = get_scratch(2, (size_t)N * bands * nout * sizeof(float), (void**)&ws)) return rc;
+  if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_wgrad: rows too wide (W=%d)", g.W);
+  pl->orows = orows; pl->smem = smem;
+  pl->bands = (g.Ho + orows - 1) / orows;
+  pl->ws_bytes = (size_t)g.N * pl->bands * pl->nout * sizeof(float);
+  return 0;
+}
+
+extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
+                                        int W, int Cin, int Cout, int stride_h, int stride_w, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (!x || !dout || !relu_mask || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (int rc = transition_check(Cin, Cout)) return rc;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  TransWgradPlan pl;
+  if (int rc = plan_transition_wgrad(g, &pl)) return rc;
+  const int tpg = pl.tpg, orows = pl.orows, bands = pl.bands;
+  const size_t smem = pl.smem;
+  const long long nout = pl.nout;
+  WsLease lease;
+  if (int rc = lease_ws(workspace, workspace_bytes, pl.ws_bytes, st, &lease)) return rc;
+  float* ws = (float*)lease.ptr;
   switch (tpg) {
     case 1: GLUE_SMEM_LAUNCH(transition_wgrad_partial<1>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
     case 2: GLUE_SMEM_LAUNCH(transition_wgrad_partial<2>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
@@ -1585,17 +1635,80 @@ extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const
 }
 
 extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
-                                    float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* stream) {
+                                    float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
   if (!x || !fc_kernel || !fc_bias || !onehot || !loss) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (K > 32 || K > C || C > 1024 || (C % 32)) return fail(B200ODE_ERR_UNSUPPORTED, "head: need classes <= 32 <= channels (multiple of 32, <= 1024)");
   if (int rc = device_check()) return rc;
   if (N == 0) return 0;
   const long long nout = (long long)C * K + K + 1;
-  float* ws = nullptr;
-  if (int rc = get_scratch(2, (size_t)N * nout * sizeof(float), (void**)&ws)) return rc;
+  WsLease lease;
+  if (int rc = lease_ws(workspace, workspace_bytes, head_ws_bytes(N, C, K), (cudaStream_t)stream, &lease)) return rc;
+  float* ws = (float*)lease.ptr;
   head_kernel<<<N, C, (C + 33) * sizeof(float), (cudaStream_t)stream>>>(x, HW, C, K, fc_kernel, fc_bias, onehot, eps, N, probs, dx, ws);
   LAUNCH_CHECK("head_kernel");
   if (dparams)
     if (int rc = reduce_rows(ws, N, nout, nout - 1, dparams, (cudaStream_t)stream)) return rc;
   return reduce_rows(ws + (nout - 1), N, nout, 1, loss, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace queries / binding (the caller owns the workspace)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200ode_layer_workspace_bytes(const b200ode_layer_t* L, int N, int H, int W, size_t* bytes_out) {
+  if (!L || !bytes_out) return fail(B200ODE_ERR_INVALID, "layer/bytes_out is NULL");
+  if (N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
+  *bytes_out = 0;
+  if (N == 0) return 0;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {   // tensor path: only the weight gradient needs scratch (split-K partials)
+    return run_wgrad_tc(L->mode_eff, L->g, nullptr, nullptr, nullptr, 1, N, H, W, nullptr, nullptr, nullptr, 0, 0, nullptr,
+                        WsArg{nullptr, 0, bytes_out});
+  }
+  const ConvGeom g = conv_geom(L, N, H, W);
+  const long long npix = (long long)N * g.Ho * g.Wo;
+  long long parts = npix / 64;
+  parts = parts < 1 ? 1 : parts > 128 ? 128 : parts;
+  const size_t fwd = (size_t)npix * g.C * sizeof(float);                              // pre-activations of a fused forward
+  const size_t wg = (size_t)parts * g.k * g.k * g.C * g.C * sizeof(float);            // weight-gradient partials
+  *bytes_out = fwd > wg ? fwd : wg;
+  return 0;
+}
+extern "C" int b200ode_layer_set_workspace(b200ode_layer_t* L, void* workspace, size_t bytes) {
+  if (!L) return fail(B200ODE_ERR_INVALID, "layer is NULL");
+  if (workspace && ((uintptr_t)workspace & 255)) return fail(B200ODE_ERR_INVALID, "workspace must be 256-byte aligned");
+  L->ws = workspace; L->ws_bytes = workspace ? bytes : 0;
+  return 0;
+}
+extern "C" int b200ode_chain_workspace_bytes(const b200ode_chain_t* ch, int N, int H, int W, size_t* bytes_out) {
+  if (!ch || !bytes_out) return fail(B200ODE_ERR_INVALID, "chain/bytes_out is NULL");
+  if (N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
+  *bytes_out = 0;
+  if (N == 0) return 0;
+  return run_wgrad_tc(ch->mode == B200ODE_PREC_FAST_F16 ? MODE_F16 : MODE_TF32, ch->g, nullptr, nullptr, nullptr, ch->L, N, H, W,
+                      nullptr, nullptr, nullptr, 0, 0, nullptr, WsArg{nullptr, 0, bytes_out});
+}
+extern "C" int b200ode_chain_set_workspace(b200ode_chain_t* ch, void* workspace, size_t bytes) {
+  if (!ch) return fail(B200ODE_ERR_INVALID, "chain is NULL");
+  if (workspace && ((uintptr_t)workspace & 255)) return fail(B200ODE_ERR_INVALID, "workspace must be 256-byte aligned");
+  ch->ws = workspace; ch->ws_bytes = workspace ? bytes : 0;
+  return 0;
+}
+extern "C" int b200ode_glue_workspace_bytes(int op, int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w,
+                                            size_t* bytes_out) {
+  if (!bytes_out) return fail(B200ODE_ERR_INVALID, "bytes_out is NULL");
+  if (N < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return fail(B200ODE_ERR_INVALID, "bad shape");
+  *bytes_out = 0;
+  if (N == 0) return 0;
+  switch (op) {
+    case B200ODE_GLUE_STEM_WGRAD: *bytes_out = stem_wgrad_ws_bytes(N, H, Cin, Cout); return 0;
+    case B200ODE_GLUE_TRANSITION_WGRAD: {
+      if (int rc = transition_check(Cin, Cout)) return rc;
+      TransWgradPlan pl;
+      if (int rc = plan_transition_wgrad(glue_geom(N, H, W, Cin, Cout, stride_h, stride_w), &pl)) return rc;
+      *bytes_out = pl.ws_bytes;
+      return 0;
+    }
+    case B200ODE_GLUE_HEAD: *bytes_out = head_ws_bytes(N, Cin, Cout); return 0;
+    default: return fail(B200ODE_ERR_INVALID, "unknown glue op %d", op);
+  }
 }

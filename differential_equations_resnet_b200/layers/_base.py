@@ -35,6 +35,11 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _alloc_workspace(nbytes, device):
+    """Caller-owned workspace block for the *_set_workspace / glue entry points (torch allocations are 512-byte aligned)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
 def truncated_normal_(t: torch.Tensor, stddev: float, generator=None):
     """tf.initializers.truncated_normal: resample outside +-2 sigma, no variance rescale
     (layers/tfkeras_layer_Conv2DAntisymmetric3By3.py:95-98)."""
@@ -67,6 +72,17 @@ class LayerHandle:
                 self._h = None
         except Exception:
             pass
+
+    # -- workspace (include/b200ode.h: the caller owns it; unbound handles draw from the stream-ordered pool) ----------
+    def workspace_bytes(self, N, H, W):
+        n = ctypes.c_size_t()
+        _abi.check(_abi.lib().b200ode_layer_workspace_bytes(self._h, int(N), int(H), int(W), ctypes.byref(n)))
+        return int(n.value)
+
+    def bind_workspace(self, ws):
+        """ws: uint8 CUDA tensor (kept alive by the handle) or None to unbind."""
+        _abi.check(_abi.lib().b200ode_layer_set_workspace(self._h, _ptr(ws), 0 if ws is None else ws.numel()))
+        self._ws = ws
 
     # -- K1 ------------------------------------------------------------------------------------
     def pack(self, params: torch.Tensor, dense_out: torch.Tensor = None, force=False):
@@ -137,6 +153,15 @@ class ChainHandle:
     @staticmethod
     def supported(channels, H, W, precision=_abi.PREC_FAST_TF32):
         return bool(_abi.lib().b200ode_chain_supported(int(channels), int(H), int(W), int(precision)))
+
+    def workspace_bytes(self, N, H, W):
+        n = ctypes.c_size_t()
+        _abi.check(_abi.lib().b200ode_chain_workspace_bytes(self._h, int(N), int(H), int(W), ctypes.byref(n)))
+        return int(n.value)
+
+    def bind_workspace(self, ws):
+        _abi.check(_abi.lib().b200ode_chain_set_workspace(self._h, _ptr(ws), 0 if ws is None else ws.numel()))
+        self._ws = ws
 
     def pack(self, params, layer_stride=None):
         _abi.check(_abi.lib().b200ode_chain_pack(self._h, _ptr(params), int(layer_stride or self.num_params),

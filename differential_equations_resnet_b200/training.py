@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _abi
-from .layers._base import ChainHandle, LayerHandle, truncated_normal_, _ptr, _stream_ptr
+from .layers._base import ChainHandle, LayerHandle, truncated_normal_, _alloc_workspace, _ptr, _stream_ptr
 from .parallel import allreduce_async, allreduce_bucket
 
 
@@ -129,7 +129,8 @@ class _Chain:
                 f_masks=torch.empty((self.n, N, H, W, (C + 7) // 8), dtype=torch.uint8, device=device),
                 f_dz=torch.empty((self.n,) + shape, dtype=sdt, device=device),
                 f_dx=torch.empty(shape, dtype=torch.float32, device=device),
-                f_y=torch.empty(shape, dtype=torch.float32, device=device) if self.fused.f16 else None)
+                f_y=torch.empty(shape, dtype=torch.float32, device=device) if self.fused.f16 else None,
+                f_ws=_alloc_workspace(self.fused.workspace_bytes(N, H, W), device))   # split-K partials of the chain wgrad
         for k, v in self._fbufs[shape].items():
             setattr(self, k, v)
         self._fshape = shape
@@ -156,6 +157,8 @@ class _Chain:
 
     def fused_wgrad(self, grad_euler):
         """Weight + bias gradients of all layers (one launch + fold) into the flat bucket."""
+        if getattr(self.fused, "_ws", None) is not self.f_ws:
+            self.fused.bind_workspace(self.f_ws)
         self.fused.wgrad(self.x0, self.f_acts, self.f_dz, grad_euler[self.offset:], self.np_layer)
 
     def fused_backward(self, dy, h, grad_euler):
@@ -172,6 +175,10 @@ class _Chain:
         self.masks = [torch.empty((N, H, W, (C + 7) // 8), dtype=torch.uint8, device=device) for _ in range(self.n)]
         self.dz = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]   # dZ_l lives in dz[l & 1]
         self.dx = [torch.empty(shape, dtype=dt, device=device) for _ in range(2)]
+        # one workspace for all per-layer handles of the chain (their calls are serialised on one stream)
+        self.ws = _alloc_workspace(self.handles[0].workspace_bytes(N, H, W), device)
+        for hd in self.handles:
+            hd.bind_workspace(self.ws)
 
 
 class _ChainFn(torch.autograd.Function):
@@ -381,7 +388,8 @@ class EulerNet:
                 _, ci, co, st, name = seg
                 ok = ok and tuple(st) == (1, 1) and co % 4 == 0 and ci == c
                 plan.append(dict(kind="stem", name=name, ci=ci, co=co, h=h, w=w,
-                                 out=torch.empty((N, h, w, co), dtype=torch.float32, device=device)))
+                                 out=torch.empty((N, h, w, co), dtype=torch.float32, device=device),
+                                 ws=self._glue_ws(ok, _abi.GLUE_STEM_WGRAD, N, h, w, ci, co, 1, 1, device)))
                 c = co
             elif seg[0] == "transition":
                 _, ci, co, st, name = seg
@@ -391,7 +399,8 @@ class EulerNet:
                 plan.append(dict(kind="transition", name=name, ci=ci, co=co, h=h, w=w, st=tuple(st),
                                  out=torch.empty((N, ho, wo, co), dtype=torch.float32, device=device),
                                  mask=torch.empty((N, ho, wo, co // 8), dtype=torch.uint8, device=device),
-                                 dx=torch.empty((N, h, w, ci), dtype=torch.float32, device=device)))
+                                 dx=torch.empty((N, h, w, ci), dtype=torch.float32, device=device),
+                                 ws=self._glue_ws(ok, _abi.GLUE_TRANSITION_WGRAD, N, h, w, ci, co, st[0], st[1], device)))
                 h, w, c = ho, wo, co
             else:
                 ch = seg[1]
@@ -405,12 +414,22 @@ class EulerNet:
         else:
             self._nb = dict(shape=tuple(shape), plan=plan, hw=h * w, c=c,
                             head_dx=torch.empty((N, h, w, c), dtype=torch.float32, device=device),
+                            head_ws=self._glue_ws(True, _abi.GLUE_HEAD, N, 1, 1, c, spec.num_classes, 1, 1, device),
                             loss=torch.zeros(1, dtype=torch.float32, device=device))
         self._nb_cache[tuple(shape)] = self._nb
         return self._nb
 
     def _off(self, name):
         return self.torch_params[name][0]
+
+    @staticmethod
+    def _glue_ws(ok, op, N, H, W, ci, co, sh, sw, device):
+        """Caller-owned workspace of a stem / transition / head gradient call (b200ode_glue_workspace_bytes)."""
+        if not ok:
+            return None
+        n = ctypes.c_size_t()
+        _abi.check(_abi.lib().b200ode_glue_workspace_bytes(op, N, H, W, ci, co, sh, sw, ctypes.byref(n)))
+        return _alloc_workspace(n.value, device)
 
     def _fwd_bwd_native(self, images, onehot, nb):
         lib, st, spec = _abi.lib(), _stream_ptr(), self.spec
@@ -467,7 +486,7 @@ class EulerNet:
         fo = self._off("fc/kernel")
         _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
                                             _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
-                                            spec.num_classes, st))
+                                            spec.num_classes, _ptr(nb["head_ws"]), nb["head_ws"].numel(), st))
         # Backward.  Critical path (main stream): head -> chain dgrad -> transition dgrad -> chain dgrad -> ...; every
         # weight gradient (chain wgrad + fold, transition wgrad, stem wgrad: ~1/4 of the step) only feeds the optimiser,
         # so it runs on a side stream, ordered by events after the data gradient that produces its dZ, and is joined
@@ -495,7 +514,8 @@ class EulerNet:
                 nm = e["name"]
                 with torch.cuda.stream(side):      # needs d (ready: the side stream already waits for the chain's dgrad)
                     _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
-                                                            N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], side.cuda_stream))
+                                                            N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1],
+                                                            _ptr(e["ws"]), e["ws"].numel(), side.cuda_stream))
                 _abi.check(lib.b200ode_transition_dgrad(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
                                                         _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
                                                         e["ci"], e["co"], e["st"][0], e["st"][1], st))
@@ -504,7 +524,7 @@ class EulerNet:
                 with torch.cuda.stream(side):
                     _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
                                                       _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
-                                                      e["co"], side.cuda_stream))
+                                                      e["co"], _ptr(e["ws"]), e["ws"].numel(), side.cuda_stream))
         if overlap_wgrad:
             main.wait_stream(side)
         return nb["loss"].view(())
@@ -550,7 +570,7 @@ class EulerNet:
         fo = self._off("fc/kernel")
         _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(zeros), 1e-7,
                                             _ptr(probs), _ptr(nb["loss"]), None, None, N, nb["hw"], nb["c"],
-                                            spec.num_classes, st))
+                                            spec.num_classes, _ptr(nb["head_ws"]), nb["head_ws"].numel(), st))
         return probs
 
     def _fwd_bwd(self, images, onehot):

@@ -15,9 +15,19 @@
  *     contiguous; shapes are explicit ints; `stream` is a cudaStream_t passed as void*.
  *   - every function returns 0 on success or a negative b200ode_status; the message is
  *     available through b200ode_last_error() (thread local).  Nothing aborts or throws.
- *   - stream-ordered and asynchronous: no hidden device synchronisation.
- *   - the caller owns every tensor; the library owns only the opaque handles (staged
- *     weights, TMA descriptors, split-K workspace).
+ *   - stream-ordered and asynchronous: no hidden device synchronisation, no cudaMalloc / cudaFree
+ *     inside a compute call.
+ *   - the caller owns every tensor, the WORKSPACE included; the library owns only the opaque
+ *     handles (staged weights, TMA descriptors).  Calls that need device scratch (the split-K
+ *     partials of a weight gradient, the CUDA-core pre-activation buffer, the partials of the
+ *     stem / transition / head gradients) take it from the block the caller bound to the handle
+ *     (b200ode_layer_set_workspace / b200ode_chain_set_workspace) or passed with the call (glue
+ *     entry points), sized by the *_workspace_bytes queries; a bound block that is too small is
+ *     an error.  A handle with a bound block serves ONE call at a time.  With no block (NULL)
+ *     the scratch comes from the device's stream-ordered memory pool (cudaMallocAsync /
+ *     cudaFreeAsync on the call's stream: no synchronisation, graph capturable) and every call
+ *     gets its own block, so calls on different streams -- also on one handle, after pack --
+ *     never share scratch.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  */
 #ifndef B200ODE_H_
@@ -30,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B200ODE_VERSION 100
+#define B200ODE_VERSION 200
 
 typedef enum {
   B200ODE_OK = 0,
@@ -76,6 +86,11 @@ int b200ode_layer_destroy(b200ode_layer_t* layer);
 int64_t b200ode_layer_num_params(const b200ode_layer_t* layer);
 /* precision mode actually in effect (SIMT is selected for shapes the tensor path cannot take) */
 int b200ode_layer_effective_mode(const b200ode_layer_t* layer);
+
+/* Workspace of the layer's compute calls for inputs of shape [N,H,W,C] (max over forward, data and weight gradient;
+ * 0 when none is needed) and binding of a caller-owned, 256-byte aligned device block (NULL unbinds).  SURVEY.md 8b. */
+int b200ode_layer_workspace_bytes(const b200ode_layer_t* layer, int N, int H, int W, size_t* bytes_out);
+int b200ode_layer_set_workspace(b200ode_layer_t* layer, void* workspace, size_t bytes);
 
 /* ---- K1 antisym_pack: replaces the assembly graph 3By3.py:113-141,268-293 (re-executed every
  *      sess.run by the reference).  params: device fp32 [num_params].  Writes the handle's
@@ -171,6 +186,9 @@ int b200ode_chain_create(int channels, int n_layers, float gamma, int use_bias, 
                          b200ode_chain_t** out);
 int b200ode_chain_destroy(b200ode_chain_t* chain);
 int64_t b200ode_chain_layer_params(const b200ode_chain_t* chain);
+/* workspace of b200ode_chain_wgrad (split-K partials of all layers) for [N,H,W,C] images; binding as for layers */
+int b200ode_chain_workspace_bytes(const b200ode_chain_t* chain, int N, int H, int W, size_t* bytes_out);
+int b200ode_chain_set_workspace(b200ode_chain_t* chain, void* workspace, size_t bytes);
 /* K1 for all layers at once: params + l*param_layer_stride = packed parameters of layer l */
 int b200ode_chain_pack(b200ode_chain_t* chain, const float* params, int64_t param_layer_stride, void* stream);
 /* n_steps Euler steps x_{l+1} = x_l + h*relu(conv_{K_l}(x_l)+b_l); step l uses layer l % n_layers
@@ -194,7 +212,14 @@ int b200ode_chain_wgrad(b200ode_chain_t* chain, const float* x0, const void* act
                         float* grad_params, int64_t grad_layer_stride, int N, int H, int W, void* stream);
 
 /* ---- stem / transition / head of the single-block ResNet, fp32 CUDA-core kernels.
- *      All tensors NHWC fp32 (images: uint8 or fp32); kernels in the Keras HWIO layout. ---- */
+ *      All tensors NHWC fp32 (images: uint8 or fp32); kernels in the Keras HWIO layout.
+ *      The three gradient entry points take their scratch as (workspace, workspace_bytes): a device block of at least
+ *      b200ode_glue_workspace_bytes(op, ...) bytes, or NULL for the stream-ordered pool. ---- */
+#define B200ODE_GLUE_STEM_WGRAD 0        /* (N,H,W,Cin,Cout) of b200ode_stem_wgrad; strides ignored            */
+#define B200ODE_GLUE_TRANSITION_WGRAD 1  /* (N,H,W,Cin,Cout,stride_h,stride_w) of b200ode_transition_wgrad      */
+#define B200ODE_GLUE_HEAD 2              /* N, Cin = channels, Cout = classes of b200ode_head_fwd_bwd; H,W >= 1 */
+int b200ode_glue_workspace_bytes(int op, int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w,
+                                 size_t* bytes_out);
 /* input Lambda layers + conv1 + relu (models/tfkeras_resnets.py:555-572), 3x3, strides (1,1):
  * out = relu(conv_SAME((images - subtract_mean) / divide_by_stddev) + bias)   [normalize == 0: raw images] */
 int b200ode_stem_fwd(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
@@ -203,7 +228,7 @@ int b200ode_stem_fwd(const void* images, int images_are_u8, float subtract_mean,
 /* dparams = [dkernel (3,3,Cin,Cout) | dbias (Cout)] from dout = dL/dout and the saved stem output */
 int b200ode_stem_wgrad(const void* images, int images_are_u8, float subtract_mean, float divide_by_stddev, int normalize,
                        const float* out, const float* dout, float* dparams, int N, int H, int W, int Cin, int Cout,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* single_layer_conv_block (models/tfkeras_resnets.py:204-269): out = relu(conv3x3_s(x)+bm) + conv1x1_s(x)+bs,
  * TF SAME padding (pad_before = total/2); relu_mask: 1 bit per output element ((main > 0), as euler_fwd). */
 int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
@@ -214,13 +239,15 @@ int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const 
                              int stride_w, void* stream);
 /* dparams = [dmain_kernel (3,3,Cin,Cout) | dmain_bias | dshort_kernel (Cin,Cout) | dshort_bias] */
 int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H, int W,
-                             int Cin, int Cout, int stride_h, int stride_w, void* stream);
+                             int Cin, int Cout, int stride_h, int stride_w, void* workspace, size_t workspace_bytes,
+                             void* stream);
 /* GlobalAveragePooling2D -> Dense(softmax) (models/tfkeras_resnets.py:595-597) -> mean
  * K.categorical_crossentropy(onehot, probs) with clipping eps (training/training.py:295), forward and
  * backward in one call: loss (1 float), dx = dL/dx [N,HW,C] (nullable), dparams = [dfc_kernel (C,K) | dfc_bias]
  * (nullable), probs [N,K] (nullable). */
 int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
-                         float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* stream);
+                         float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- gradient exchange ------------------------------------------------------------
  * The reference has no collective (single tf.Session, training/training.py:132); data parallel training sums

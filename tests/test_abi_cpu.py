@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_abi.EXPORTED_SYMBOLS) == syms
-    assert lib.b200ode_version() == 100
+    assert lib.b200ode_version() == 200
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine without a GPU")

@@ -45,7 +45,7 @@ def test_stem_matches_oracle(u8):
     imgd, Kd, bd, dd = img.cuda(), K.detach().cuda(), b.detach().cuda(), dout.cuda()   # keep the device copies alive
     _abi.check(lib.b200ode_stem_fwd(P(imgd), int(u8), 127.5, 127.5, 1, P(Kd), P(bd), P(out), N, H, W, Ci, Co, None))
     dp = torch.empty(27 * Co + Co, device="cuda")
-    _abi.check(lib.b200ode_stem_wgrad(P(imgd), int(u8), 127.5, 127.5, 1, P(out), P(dd), P(dp), N, H, W, Ci, Co, None))
+    _abi.check(lib.b200ode_stem_wgrad(P(imgd), int(u8), 127.5, 127.5, 1, P(out), P(dd), P(dp), N, H, W, Ci, Co, None, 0, None))
     torch.cuda.synchronize()
     assert rel(out, ref) <= 1e-5
     assert rel(dp[:27 * Co].view(3, 3, Ci, Co), K.grad) <= 1e-5
@@ -78,7 +78,7 @@ def test_transition_matches_oracle(Ci, Co, H, W, st):
     _abi.check(lib.b200ode_transition_dgrad(P(dd), P(mask), P(Wmd), P(Wsd), P(dx), N, H, W, Ci, Co, st[0], st[1], None))
     nm = 9 * Ci * Co
     dp = torch.empty(nm + Co + Ci * Co + Co, device="cuda")
-    _abi.check(lib.b200ode_transition_wgrad(P(xd), P(dd), P(mask), P(dp), N, H, W, Ci, Co, st[0], st[1], None))
+    _abi.check(lib.b200ode_transition_wgrad(P(xd), P(dd), P(mask), P(dp), N, H, W, Ci, Co, st[0], st[1], None, 0, None))
     torch.cuda.synchronize()
     assert rel(out, ref) <= 1e-5
     bits = np.unpackbits(mask.cpu().numpy(), axis=-1, bitorder="little").astype(bool)
@@ -104,7 +104,7 @@ def test_head_matches_oracle():
     probs = torch.empty((N, K), device="cuda"); loss = torch.zeros(1, device="cuda")
     dx = torch.empty((N, H, W, C), device="cuda"); dp = torch.empty(C * K + K, device="cuda")
     xd, Wd, bd, od = x.detach().cuda(), Wfc.detach().cuda(), bfc.detach().cuda(), onehot.cuda()   # keep alive
-    _abi.check(lib.b200ode_head_fwd_bwd(P(xd), P(Wd), P(bd), P(od), 1e-7, P(probs), P(loss), P(dx), P(dp), N, H * W, C, K, None))
+    _abi.check(lib.b200ode_head_fwd_bwd(P(xd), P(Wd), P(bd), P(od), 1e-7, P(probs), P(loss), P(dx), P(dp), N, H * W, C, K, None, 0, None))
     torch.cuda.synchronize()
     assert rel(probs, probs_ref) <= 1e-5
     assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))

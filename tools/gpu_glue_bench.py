@@ -35,7 +35,7 @@ out1 = torch.empty((N, 32, 32, 16), device=dev); d1 = torch.randn((N, 32, 32, 16
 dp1 = torch.empty(27 * 16 + 16, device=dev)
 timeit("stem_fwd 3->16 @32x32", lambda: _abi.check(lib.b200ode_stem_fwd(P(img), 1, 127.5, 127.5, 1, P(K1), P(b1), P(out1), N, 32, 32, 3, 16, None)),
        img.numel() + out1.numel() * 4, 2.0 * N * 1024 * 27 * 16)
-timeit("stem_wgrad", lambda: _abi.check(lib.b200ode_stem_wgrad(P(img), 1, 127.5, 127.5, 1, P(out1), P(d1), P(dp1), N, 32, 32, 3, 16, None)),
+timeit("stem_wgrad", lambda: _abi.check(lib.b200ode_stem_wgrad(P(img), 1, 127.5, 127.5, 1, P(out1), P(d1), P(dp1), N, 32, 32, 3, 16, None, 0, None)),
        img.numel() + 2 * out1.numel() * 4, 2.0 * N * 1024 * 27 * 16)
 for (Ci, Co, H) in ((16, 32, 32), (32, 64, 16)):
     x = torch.randn((N, H, H, Ci), device=dev, generator=g)
@@ -51,12 +51,12 @@ for (Ci, Co, H) in ((16, 32, 32), (32, 64, 16)):
            (x.numel() + out.numel()) * 4, fl)
     timeit("transition_dgrad " + tag, lambda: _abi.check(lib.b200ode_transition_dgrad(P(dout), P(mask), P(Km), P(Ks), P(dx), N, H, H, Ci, Co, 2, 2, None)),
            (x.numel() + out.numel()) * 4, fl)
-    timeit("transition_wgrad " + tag, lambda: _abi.check(lib.b200ode_transition_wgrad(P(x), P(dout), P(mask), P(dp), N, H, H, Ci, Co, 2, 2, None)),
+    timeit("transition_wgrad " + tag, lambda: _abi.check(lib.b200ode_transition_wgrad(P(x), P(dout), P(mask), P(dp), N, H, H, Ci, Co, 2, 2, None, 0, None)),
            (x.numel() + out.numel()) * 4, fl)
 xh = torch.randn((N, 8, 8, 64), device=dev, generator=g); Wf = torch.randn((64, 10), device=dev, generator=g) * 0.1; bf = torch.zeros(10, device=dev)
 oh = torch.nn.functional.one_hot(torch.randint(0, 10, (N,), device=dev), 10).float()
 loss = torch.zeros(1, device=dev); dxh = torch.empty_like(xh); dph = torch.empty(64 * 10 + 10, device=dev)
-timeit("head fwd+bwd (GAP, FC, CE)", lambda: _abi.check(lib.b200ode_head_fwd_bwd(P(xh), P(Wf), P(bf), P(oh), 1e-7, None, P(loss), P(dxh), P(dph), N, 64, 64, 10, None)),
+timeit("head fwd+bwd (GAP, FC, CE)", lambda: _abi.check(lib.b200ode_head_fwd_bwd(P(xh), P(Wf), P(bf), P(oh), 1e-7, None, P(loss), P(dxh), P(dph), N, 64, 64, 10, None, 0, None)),
        2 * xh.numel() * 4, 0)
 n = 899_866
 th, gr, m, v = (torch.randn(n, device=dev) for _ in range(4)); v.abs_()
