@@ -19,7 +19,7 @@ CHAIN_PRECISIONS = {"fast_tf32": PREC_FAST_TF32, "fast": PREC_FAST_TF32, "fast_f
 LAYOUT_3BY3, LAYOUT_GENERAL = 0, 1
 F_BIAS, F_RELU, F_SCALE, F_RESIDUAL = 1, 2, 4, 8
 F_EULER = 15
-COLSUM_PARTS = 256
+COLSUM_PARTS = 2048
 
 _lib = None
 
@@ -54,6 +54,8 @@ _SIGNATURES = {
     "b200ode_euler_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                    c_float, c_int, c_void_p]),
     "b200ode_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b200ode_euler_fwd_bn_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int), c_int, c_int, c_int, c_void_p]),
+    "b200ode_bn_stats_finalize": (c_int, [c_void_p, c_int] + [c_void_p] * 10 + [c_int64, c_int, c_float, c_float, c_void_p]),
     "b200ode_bn_finalize": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_float, c_float, c_void_p]),
     "b200ode_bn_bwd_reduce": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_void_p]),
     "b200ode_bn_bwd_apply": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_float, c_void_p]),

@@ -21,6 +21,7 @@
 #include "kernels_chain_f16.cuh"
 #include "kernels_glue.cuh"
 #include "kernels_wgrad_tc.cuh"
+#include "kernels_bn.cuh"
 
 using namespace b200ode;
 
@@ -55,6 +56,12 @@ static uint64_t* g_trace = nullptr;   // debug timeline buffer (device), see b20
 extern "C" int b200ode_debug_set_trace(void* device_buffer) { g_trace = (uint64_t*)device_buffer; return 0; }
 
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+template <typename... Ts>
+static inline bool aligned16(Ts... ptrs) {   // every non-NULL pointer is 16-byte aligned (vector kernels)
+  uintptr_t acc = 0;
+  ((acc |= reinterpret_cast<uintptr_t>(ptrs)), ...);
+  return (acc & 15) == 0;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -142,7 +149,6 @@ struct b200ode_layer {
   float* w_lo;     // strict only
   __nv_bfloat16* w_bf;
   float* bias;     // [C]
-  float* colsum_ws;
   void* ws;        // caller-owned workspace (b200ode_layer_set_workspace), may be NULL
   size_t ws_bytes;
   CUtensorMap map_w_hi, map_w_lo, map_w_bf;
@@ -312,7 +318,6 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
   cudaError_t e = cudaMalloc(&L->Kdense, kbytes);
   if (e == cudaSuccess) e = cudaMalloc(&L->Gdense, kbytes);
   if (e == cudaSuccess) e = cudaMalloc(&L->bias, (size_t)C * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&L->colsum_ws, (size_t)2 * B200ODE_COLSUM_PARTS * C * sizeof(float));
   if (e == cudaSuccess && L->mode_eff != B200ODE_PREC_SIMT_FP32) {
     if (L->mode_eff == B200ODE_PREC_FAST_BF16) e = cudaMalloc(&L->w_bf, (size_t)9 * C * C * 2);
     else {
@@ -341,7 +346,7 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
 extern "C" int b200ode_layer_destroy(b200ode_layer_t* L) {
   if (!L) return 0;
   cudaFree(L->Kdense); cudaFree(L->Gdense); cudaFree(L->w_hi); cudaFree(L->w_lo); cudaFree(L->w_bf);
-  cudaFree(L->bias); cudaFree(L->colsum_ws);
+  cudaFree(L->bias);
   delete L;
   return 0;
 }
@@ -497,9 +502,12 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, in
   return 0;
 }
 
-template <int MODE, int C>
+template <int MODE, int C, bool BN = false>
 static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
-  auto kern = conv_tc_kernel<MODE, C>;
+  if constexpr (!BN && MODE != MODE_BF16) {
+    if (plan.p.bn_part) return launch_conv_tc_t<MODE, C, true>(L, plan, map_a, st);
+  }
+  auto kern = conv_tc_kernel<MODE, C, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -540,6 +548,8 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   p.in = epi.in; p.skip = epi.skip; p.out = epi.out; p.z_out = epi.z_out; p.mask = epi.mask; p.bias = epi.bias;
   p.acc_scale = epi.acc_scale; p.c_in = epi.c_in; p.h = epi.h; p.relu = epi.relu; p.scale_h = epi.scale_h;
   p.mask2 = epi.mask2; p.out2 = epi.out2; p.h2 = epi.h2;
+  p.bn_part = epi.bn_part;
+  if (epi.bn_rows_out) *epi.bn_rows_out = plan.grid * 8;   // one row of partial sums per epilogue warp
   p.trace = g_trace;
   const int eb = mode == MODE_BF16 ? 2 : 4;
   const int rowb = C * eb >= 128 ? 128 : C * eb;
@@ -553,6 +563,8 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   }
   return fail(B200ODE_ERR_INVALID, "bad mode");
 }
+
+static size_t colsum_ws_bytes(int C) { return (size_t)2 * B200ODE_COLSUM_PARTS * C * sizeof(float); }
 
 static ConvGeom conv_geom(const b200ode_layer* L, int N, int H, int W) {
   ConvGeom g;
@@ -569,6 +581,13 @@ extern "C" int b200ode_euler_tail(const float* z, const float* scale, const floa
   if ((fuse_flags & B200ODE_F_RESIDUAL) && !x) return fail(B200ODE_ERR_INVALID, "RESIDUAL needs x");
   const long long n = pixels * ((channels + 7) / 8);
   if (n == 0) return 0;
+  if ((channels % 8) == 0 && aligned16(z, scale, shift, x, y)) {
+    euler_tail_vec_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)z, (const float4*)scale, (const float4*)shift,
+                                                                                (const float4*)x, (float4*)y, relu_mask, n, channels / 8, h,
+                                                                                fuse_flags);
+    LAUNCH_CHECK("euler_tail_vec_kernel");
+    return 0;
+  }
   euler_tail_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, x, y, relu_mask, pixels, channels, h,
                                                                           fuse_flags);
   LAUNCH_CHECK("euler_tail_kernel");
@@ -661,12 +680,35 @@ extern "C" int b200ode_euler_dgrad_fused(b200ode_layer_t* L, const void* dz, con
   return b200ode_relu_scale_bwd(dx, prev_relu_mask, dz_prev, (int64_t)N * H * W, L->g.C, h, 0, stream);
 }
 
-static int colsum_impl(ColsumArgs A, float* out0, float* out1, float* ws, long long pixels, int C, cudaStream_t st) {
-  const int parts = (int)(pixels < B200ODE_COLSUM_PARTS ? (pixels > 0 ? pixels : 1) : B200ODE_COLSUM_PARTS);
+// stage 1 of the per-channel sums: partial rows into ws ([2][parts][C]); returns the number of rows
+static int colsum_stage1_launch(ColsumArgs A, float* ws, long long pixels, int C, cudaStream_t st, int* rows_out) {
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const int C4 = C / 4;
+  if ((C % 4) == 0 && C4 <= 256 && aligned16(A.a, A.b, A.scale, A.shift, A.mean, A.inv)) {
+    // 16-byte loads, four per operand in flight; at least 16 pixel rows per thread (few partial rows for small
+    // tensors: the second stage is pure latency), up to 4 blocks per SM for large ones
+    const int rows = 256 / C4;
+    long long parts = (pixels + 16LL * rows - 1) / (16LL * rows);
+    parts = parts < 1 ? 1 : parts > 4LL * sms ? 4LL * sms : parts;
+    if (parts > B200ODE_COLSUM_PARTS) parts = B200ODE_COLSUM_PARTS;
+    if (A.mode == 0) colsum_vec_stage1<0><<<(unsigned)parts, 256, 0, st>>>(A, ws, pixels, C, (int)parts);
+    else colsum_vec_stage1<1><<<(unsigned)parts, 256, 0, st>>>(A, ws, pixels, C, (int)parts);
+    LAUNCH_CHECK("colsum_vec_stage1");
+    *rows_out = (int)parts;
+    return 0;
+  }
+  const int parts = (int)(pixels < 256 ? (pixels > 0 ? pixels : 1) : 256);
   colsum_stage1<<<parts, 256, 2 * 256 * sizeof(float), st>>>(A, ws, pixels, C, parts);
   LAUNCH_CHECK("colsum_stage1");
-  colsum_stage2<<<blocks_for(C, 128), 128, 0, st>>>(ws, out0, out1, C, parts);
-  LAUNCH_CHECK("colsum_stage2");
+  *rows_out = parts;
+  return 0;
+}
+static int colsum_impl(ColsumArgs A, float* out0, float* out1, float* ws, long long pixels, int C, cudaStream_t st) {
+  int rows = 0;
+  if (int rc = colsum_stage1_launch(A, ws, pixels, C, st, &rows)) return rc;
+  bn_stats_finalize_kernel<<<blocks_for(C, 8), 256, 0, st>>>(ws, rows, C, out0, out1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr, nullptr, pixels, 0.0f, 0.0f);
+  LAUNCH_CHECK("bn_stats_finalize_kernel");
   return 0;
 }
 
@@ -679,6 +721,46 @@ extern "C" int b200ode_colsum(const float* a, const float* b, float* out_sum, fl
   return colsum_impl(A, out_sum, out_sumprod, workspace, pixels, channels, (cudaStream_t)stream);
 }
 
+// BatchNorm Euler step, forward part 1: z = conv_K(x) + b (fp32) and the partial sums of z, z*z per channel.
+// Tensor path: the sums come from the epilogue registers of the convolution kernel (one row per epilogue warp);
+// CUDA-core path: a vectorised pass over z.
+extern "C" int b200ode_euler_fwd_bn_stats(b200ode_layer_t* L, const void* x, float* z_out, float* stats_ws, int* rows_out, int N,
+                                          int H, int W, void* stream) {
+  if (!L || !x || !z_out || !stats_ws || !rows_out) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (!L->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_pack_kernel must run before compute calls");
+  if (N < 1 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
+  if (L->mode_eff == B200ODE_PREC_FAST_BF16) return fail(B200ODE_ERR_UNSUPPORTED, "BatchNorm needs fp32 activations (STRICT / FAST_TF32 / SIMT)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+    ConvTcParams e;
+    memset(&e, 0, sizeof(e));
+    e.z_out = z_out; e.bias = L->g.use_bias ? L->bias : nullptr; e.acc_scale = 1.0f; e.c_in = 1.0f; e.h = 1.0f;
+    e.bn_part = stats_ws; e.bn_rows_out = rows_out;
+    if (int rc = run_conv_tc(L, x, N, H, W, e, st)) return rc;
+    if (*rows_out > B200ODE_COLSUM_PARTS) return fail(B200ODE_ERR_INVALID, "internal: %d statistic rows", *rows_out);
+    return 0;
+  }
+  if (int rc = b200ode_euler_fwd(L, x, nullptr, nullptr, z_out, N, H, W, 1.0f, B200ODE_F_BIAS, stream)) return rc;
+  const ConvGeom g = conv_geom(L, N, H, W);
+  ColsumArgs A;
+  memset(&A, 0, sizeof(A));
+  A.a = z_out; A.mode = 0;
+  return colsum_stage1_launch(A, stats_ws, (long long)N * g.Ho * g.Wo, g.C, st, rows_out);
+}
+
+extern "C" int b200ode_bn_stats_finalize(const float* stats_ws, int rows, float* out_sum, float* out_sumsq, const float* bn_gamma,
+                                         const float* bn_beta, float* mean, float* inv_std, float* scale, float* shift,
+                                         float* moving_mean, float* moving_var, int64_t pixels, int channels, float eps,
+                                         float momentum, void* stream) {
+  if (!stats_ws || rows < 1 || channels < 1) return fail(B200ODE_ERR_INVALID, "bad statistics workspace");
+  if (bn_gamma && (!bn_beta || !mean || !inv_std || !scale || !shift)) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (!bn_gamma && !out_sum && !out_sumsq) return fail(B200ODE_ERR_INVALID, "nothing to compute");
+  bn_stats_finalize_kernel<<<blocks_for(channels, 8), 256, 0, (cudaStream_t)stream>>>(stats_ws, rows, channels, out_sum, out_sumsq, bn_gamma,
+                                                                                      bn_beta, mean, inv_std, scale, shift, moving_mean,
+                                                                                      moving_var, pixels, eps, momentum);
+  LAUNCH_CHECK("bn_stats_finalize_kernel");
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // tensor-core weight gradient planning + launch
@@ -942,6 +1024,8 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
   const ConvGeom g = conv_geom(L, N, H, W);
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long npix = (long long)N * g.Ho * g.Wo;
+  WsLease lease;
+  float* colsum_ws = nullptr;
   if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
     return run_wgrad_tc(L->mode_eff, L->g, x, x, dz, 1, N, H, W, L->Gdense, G_dense, grad_params, 0, accumulate, st,
                         WsArg{L->ws, L->ws_bytes, nullptr});
@@ -949,9 +1033,9 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
     int parts = (int)(npix / 64);
     if (parts < 1) parts = 1;
     if (parts > 128) parts = 128;
-    WsLease lease;
-    if (int rc = lease_ws(L->ws, L->ws_bytes, (size_t)parts * total * sizeof(float), st, &lease)) return rc;
+    if (int rc = lease_ws(L->ws, L->ws_bytes, (size_t)parts * total * sizeof(float) + colsum_ws_bytes(g.C), st, &lease)) return rc;
     float* ws = (float*)lease.ptr;
+    colsum_ws = ws + (size_t)parts * total;
     dim3 grid(blocks_for(total, 128), parts);
     simt_conv_wgrad<<<grid, 128, 0, st>>>(g, (const float*)x, (const float*)dz, ws, parts);
     LAUNCH_CHECK("simt_conv_wgrad");
@@ -969,7 +1053,7 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
     ColsumArgs A;
     memset(&A, 0, sizeof(A));
     A.a = (const float*)dz; A.mode = 0;
-    return colsum_impl(A, grad_params + L->g.bias_off, nullptr, L->colsum_ws, npix, g.C, st);
+    return colsum_impl(A, grad_params + L->g.bias_off, nullptr, colsum_ws, npix, g.C, st);
   }
   return 0;
 }
@@ -979,6 +1063,14 @@ extern "C" int b200ode_relu_scale_bwd(const void* dy, const uint8_t* relu_mask, 
   if (!dy || !relu_mask || !dz) return fail(B200ODE_ERR_INVALID, "NULL argument");
   const long long n = pixels * ((channels + 7) / 8);
   if (n == 0) return 0;
+  if (!is_bf16 && (channels % 8) == 0 && aligned16(dy, dz)) {
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    const long long want = (n + 255) / 256;
+    relu_scale_bwd_vec_kernel<<<(unsigned)(want < 16LL * sms ? want : 16LL * sms), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, relu_mask, (float4*)dz, n, h);
+    LAUNCH_CHECK("relu_scale_bwd_vec_kernel");
+    return 0;
+  }
   if (is_bf16)
     relu_scale_bwd_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, relu_mask, (__nv_bfloat16*)dz, pixels, channels, h);
@@ -1015,6 +1107,16 @@ extern "C" int b200ode_bn_bwd_apply(const float* dy, const float* z, const float
   if (!dy || !z || !dz) return fail(B200ODE_ERR_INVALID, "NULL argument");
   const long long n = pixels * channels;
   if (n == 0) return 0;
+  const int C4 = channels / 4;
+  if ((channels % 4) == 0 && C4 <= 256 && (256 % C4) == 0 &&
+      aligned16(dy, z, scale, shift, mean, inv_std, bn_gamma, dgamma, dbeta, dz)) {   // a thread keeps its 4-channel group: per-channel terms in registers
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    const long long n4 = n / 4, want = (n4 + 1023) / 1024;
+    bn_bwd_apply_vec_kernel<<<(unsigned)(want < 8LL * sms ? want : 8LL * sms), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, (const float4*)z, scale, shift, mean, inv_std, bn_gamma, dgamma, dbeta, (float4*)dz, n4, C4, pixels, h);
+    LAUNCH_CHECK("bn_bwd_apply_vec_kernel");
+    return 0;
+  }
   bn_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, z, scale, shift, mean, inv_std, bn_gamma, dgamma,
                                                                             dbeta, dz, pixels, channels, h);
   LAUNCH_CHECK("bn_bwd_apply_kernel");
@@ -1025,9 +1127,21 @@ extern "C" int b200ode_adam_step(float* params, const float* grads, float* m, fl
                                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   if (!params || !grads || !m || !v || !step_counter) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (n == 0) return 0;
-  adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, step_counter, lr, beta1, beta2, eps,
-                                                                    grad_scale);
-  LAUNCH_CHECK("adam_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long done = 0;
+  if (n >= 1024 && !(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15)) {   // 16-byte vectors + scalar tail
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    const long long n4 = n / 4, want = (n4 + 255) / 256;
+    adam_vec_kernel<<<(unsigned)(want < 8LL * sms ? want : 8LL * sms), 256, 0, st>>>((float4*)params, (const float4*)grads, (float4*)m,
+                                                                                   (float4*)v, n4, step_counter, lr, beta1, beta2, eps, grad_scale);
+    LAUNCH_CHECK("adam_vec_kernel");
+    done = n4 * 4;
+  }
+  if (done < n) {
+    adam_kernel<<<blocks_for(n - done, 256), 256, 0, st>>>(params + done, grads + done, m + done, v + done, n - done, step_counter, lr,
+                                                          beta1, beta2, eps, grad_scale);
+    LAUNCH_CHECK("adam_kernel");
+  }
   return 0;
 }
 
@@ -1669,7 +1783,7 @@ extern "C" int b200ode_layer_workspace_bytes(const b200ode_layer_t* L, int N, in
   long long parts = npix / 64;
   parts = parts < 1 ? 1 : parts > 128 ? 128 : parts;
   const size_t fwd = (size_t)npix * g.C * sizeof(float);                              // pre-activations of a fused forward
-  const size_t wg = (size_t)parts * g.k * g.k * g.C * g.C * sizeof(float);            // weight-gradient partials
+  const size_t wg = (size_t)parts * g.k * g.k * g.C * g.C * sizeof(float) + colsum_ws_bytes(g.C);   // weight-gradient partials + bias sums
   *bytes_out = fwd > wg ? fwd : wg;
   return 0;
 }

@@ -58,6 +58,11 @@ struct ConvTcParams {
   const uint8_t* mask2;  // nullable [pixels][C/8]
   void* out2;            // nullable
   float h2;
+  // BatchNorm statistics of the pre-activation from the epilogue registers (fp32 modes): every epilogue warp of
+  // every CTA owns one row of per-channel partial sums, [2][gridDim.x * 8][C] floats (sum rows first, then the
+  // sum-of-squares rows: the layout colsum_stage2 / bn_stats_finalize_kernel reduce in a fixed order -> deterministic)
+  float* bn_part;        // nullable
+  int* bn_rows_out;      // host-side only (run_conv_tc reports the number of partial rows = 8 * grid)
   uint64_t* trace;     // nullable timeline buffer (debug)
   // Thread-block cluster: the CTAs of a cluster walk their tiles in lockstep on the weight ring, so each
   // weight stage is fetched from L2 ONCE per cluster (TMA multicast by rank 0).  At C >= 128 every 256-position
@@ -90,7 +95,29 @@ struct ConvTcCfg {
 
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
 
-template <int MODE, int C>
+// Column sums over the 32 lanes of a warp for G per-lane values (one pixel row per lane, G channels): recursive halving,
+// G - 1 shuffles instead of 5 * G.  On return v[0] holds the sum over all lanes of channel `lane` (G == 32) or
+// `lane >> 1` (G == 16, both lanes of a pair hold it).
+template <int G>
+__device__ __forceinline__ void warp_column_sums(float (&v)[G], int lane) {
+  static_assert(G == 32 || G == 16, "32 or 16 channels per item");
+  constexpr int OFF0 = 16;
+#pragma unroll
+  for (int n = G / 2, off = OFF0; n >= 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float send = upper ? v[j] : v[j + n];
+      const float keep = upper ? v[j + n] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+    }
+  }
+  if (G == 16) v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], 1);
+}
+
+// BN = true: the variant that also emits the BatchNorm partial sums (ConvTcParams::bn_part); a separate instantiation so
+// that the extra live registers do not touch the plain kernels (inline, they pushed the tf32 kernels into spills).
+template <int MODE, int C, bool BN = false>
 __global__ void __launch_bounds__(ConvTcCfg<MODE, C>::NWARPS * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
@@ -281,6 +308,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const IoT* in = reinterpret_cast<const IoT*>(p.in);
     const IoT* skip = reinterpret_cast<const IoT*>(p.skip);
     IoT* out = reinterpret_cast<IoT*>(p.out);
+    float bn_s[BN ? NGR : 1], bn_q[BN ? NGR : 1];   // BatchNorm partial sums of this warp (p.bn_part), channel = f(lane)
+#pragma unroll
+    for (int j = 0; j < (BN ? NGR : 1); ++j) bn_s[j] = bn_q[j] = 0.0f;
     for (int itile = 0; itile < p.iters; ++itile, ++it) {
       const int tile = blockIdx.x + itile * gridDim.x;   // ghost tiles: n0 >= N, nothing is stored
       const int n0 = (tile / p.tpi) * p.nimg;
@@ -528,6 +558,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           tmem_ld_wait();
+          if constexpr (BN && MODE != MODE_BF16) {
+            float s1[G], s2[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+              float a = __uint_as_float(r[j]);
+              if (STRICT) a += __uint_as_float(r2[j]);
+              a = p.acc_scale * a;
+              if (has_bias) a += bs[j];
+              a = valid ? a : 0.0f;                           // junk rows of the strip (halo / padding positions)
+              s1[j] = a; s2[j] = a * a;
+            }
+            warp_column_sums<G>(s1, lane);
+            warp_column_sums<G>(s2, lane);
+            bn_s[gi] += s1[0]; bn_q[gi] += s2[0];
+          }
           if (valid) {
             float v[G];
 #pragma unroll
@@ -611,6 +656,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (it == 0 && threadIdx.x == 64) tr.mark(7);
+    }
+    if constexpr (BN && MODE != MODE_BF16) {
+      const size_t rows = (size_t)gridDim.x * (4 * Cfg::EPQ), rowi = (size_t)blockIdx.x * (4 * Cfg::EPQ) + (warp - 2);
+      if (G == 32 || (lane & 1) == 0) {
+        const int ch = G == 32 ? lane : lane >> 1;
+#pragma unroll
+        for (int gi = 0; gi < NGR; ++gi) {
+          p.bn_part[rowi * C + gi * G + ch] = bn_s[gi];
+          p.bn_part[(rows + rowi) * C + gi * G + ch] = bn_q[gi];
+        }
+      }
     }
     if (threadIdx.x == 64) tr.mark(8);
   } else {

@@ -107,6 +107,16 @@ class LayerHandle:
                                                 int(flags), _stream_ptr()))
         return y, mask, z
 
+    # -- K2 + BatchNorm statistics from the epilogue ----------------------------------------------
+    def forward_bn_stats(self, x, z, stats_ws):
+        """z = conv_K(x) + b (fp32, into `z`) and the per-channel partial sums of z, z*z (rows of `stats_ws`) in one
+        kernel; returns the number of rows written (b200ode_euler_fwd_bn_stats)."""
+        N, H, W, C = x.shape
+        rows = ctypes.c_int()
+        _abi.check(_abi.lib().b200ode_euler_fwd_bn_stats(self._h, _ptr(x), _ptr(z), _ptr(stats_ws), ctypes.byref(rows), N, H, W,
+                                                         _stream_ptr()))
+        return rows.value
+
     # -- K3 ------------------------------------------------------------------------------------
     def dgrad(self, dz, skip, in_hw):
         N, _, _, C = dz.shape
@@ -182,6 +192,76 @@ class ChainHandle:
         N, H, W, C = x0.shape
         _abi.check(_abi.lib().b200ode_chain_wgrad(self._h, _ptr(x0), _ptr(acts), _ptr(dz_all), _ptr(grad),
                                                   int(layer_stride or self.num_params), N, H, W, _stream_ptr()))
+
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99        # tf.keras.layers.BatchNormalization defaults (models/tfkeras_resnets.py:85-87)
+
+
+class BNEulerStep:
+    """x + h*relu(BN(conv_K(x)+b)) in training mode on the CUDA kernels (single_layer_identity_block with
+    use_batch_norm=True, models/tfkeras_resnets.py:70-92), shared by the Keras-shaped model mirror and the EulerNet trainer.
+
+    forward : conv kernel (z + partial sums from its epilogue) -> bn_stats_finalize (mean, inv_std, scale, shift, moving
+              statistics) -> euler_tail (y = x + h*relu(z*scale+shift))                                   3 launches
+    backward: bn_bwd_reduce (2) -> bn_bwd_apply -> dgrad with the skip add fused -> wgrad + fold
+    `allreduce`: optional callable summing a small fp32 tensor over the data-parallel ranks in place (SyncBN: the
+    statistics and the two backward sums are taken over the GLOBAL batch, `world` ranks of equal local size)."""
+
+    @staticmethod
+    def stats_workspace(C, device):
+        return torch.empty(2 * _abi.COLSUM_PARTS * C, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def forward(hd, x, bn_gamma, bn_beta, moving_mean, moving_var, h, z, y, stat, stats_ws, allreduce=None, world=1):
+        """stat: fp32 [6, C] = (mean, inv_std, scale, shift, sum, sumsq) written here; z, y: [N,H,W,C] fp32 outputs."""
+        lib, st = _abi.lib(), _stream_ptr()
+        N, H, W, C = x.shape
+        M = N * H * W
+        rows = hd.forward_bn_stats(x, z, stats_ws)
+        if allreduce is None or world == 1:
+            _abi.check(lib.b200ode_bn_stats_finalize(_ptr(stats_ws), rows, None, None, _ptr(bn_gamma), _ptr(bn_beta), _ptr(stat[0]),
+                                                     _ptr(stat[1]), _ptr(stat[2]), _ptr(stat[3]), _ptr(moving_mean), _ptr(moving_var),
+                                                     M, C, BN_EPS, BN_MOMENTUM, st))
+        else:
+            _abi.check(lib.b200ode_bn_stats_finalize(_ptr(stats_ws), rows, _ptr(stat[4]), _ptr(stat[5]), None, None, None, None, None,
+                                                     None, None, None, M, C, BN_EPS, BN_MOMENTUM, st))
+            allreduce(stat[4:6])
+            _abi.check(lib.b200ode_bn_finalize(_ptr(stat[4]), _ptr(stat[5]), _ptr(bn_gamma), _ptr(bn_beta), _ptr(stat[0]), _ptr(stat[1]),
+                                               _ptr(stat[2]), _ptr(stat[3]), _ptr(moving_mean), _ptr(moving_var), M * world, C,
+                                               BN_EPS, BN_MOMENTUM, st))
+        flags = _abi.F_RELU | _abi.F_RESIDUAL | (_abi.F_SCALE if h != 1.0 else 0)
+        _abi.check(lib.b200ode_euler_tail(_ptr(z), _ptr(stat[2]), _ptr(stat[3]), _ptr(x), _ptr(y), None, M, C, float(h), flags, st))
+
+    @staticmethod
+    def backward(hd, x, dy, z, stat, bn_gamma, h, dz, dx, grad_params, dbn, stats_ws, allreduce=None, world=1, want_dx=True):
+        """dbn: fp32 [2, C] receives (dgamma, dbeta) of THIS rank's batch; dz / dx: [N,H,W,C] fp32 outputs;
+        grad_params: packed conv gradient (fold + bias) written by the wgrad kernels."""
+        lib, st = _abi.lib(), _stream_ptr()
+        N, H, W, C = x.shape
+        M = N * H * W
+        _abi.check(lib.b200ode_bn_bwd_reduce(_ptr(dy), _ptr(z), _ptr(stat[2]), _ptr(stat[3]), _ptr(stat[0]), _ptr(stat[1]),
+                                             _ptr(dbn[0]), _ptr(dbn[1]), _ptr(stats_ws), M, C, float(h), st))
+        red = dbn
+        if allreduce is not None and world > 1:
+            red = stat[4:6]                      # global sums for the data gradient; the bucket keeps the local ones
+            red.copy_(dbn)
+            allreduce(red)
+        _abi.check(lib.b200ode_bn_bwd_apply(_ptr(dy), _ptr(z), _ptr(stat[2]), _ptr(stat[3]), _ptr(stat[0]), _ptr(stat[1]),
+                                            _ptr(bn_gamma), _ptr(red[0]), _ptr(red[1]), _ptr(dz), M * world, C, float(h), st))
+        if want_dx:
+            _abi.check(lib.b200ode_euler_dgrad(hd._h, _ptr(dz), _ptr(dy), _ptr(dx), N, H, W, st))
+        _abi.check(lib.b200ode_euler_wgrad(hd._h, _ptr(x), _ptr(dz), _ptr(grad_params), None, N, H, W, 0, st))
+
+    @staticmethod
+    def inference(hd, x, bn_gamma, bn_beta, moving_mean, moving_var, h, z, y):
+        """Inference mode: BN with the moving statistics (an affine per channel) fused into the tail."""
+        lib, st = _abi.lib(), _stream_ptr()
+        N, H, W, C = x.shape
+        scale = bn_gamma / torch.sqrt(moving_var + BN_EPS)
+        shift = bn_beta - moving_mean * scale
+        _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(x), None, None, _ptr(z), N, H, W, 1.0, _abi.F_BIAS, st))
+        flags = _abi.F_RELU | _abi.F_RESIDUAL | (_abi.F_SCALE if h != 1.0 else 0)
+        _abi.check(lib.b200ode_euler_tail(_ptr(z), _ptr(scale), _ptr(shift), _ptr(x), _ptr(y), None, N * H * W, C, float(h), flags, st))
 
 
 def relu_scale_bwd(dy, mask, h):

@@ -6,7 +6,7 @@
 The reference builds a static tf.keras graph; here the same calls build an eager `Model` whose
 layers are created on first use and reused afterwards.  The Euler step
 x_{n+1} = x_n + h*relu(BN?(conv_K(x_n)+b)) runs on the hand-written CUDA kernels
-(fused single kernel without BN; conv + column-sum + BN finalize + fused tail with BN).
+(fused single kernel without BN; conv with the batch statistics from its epilogue + BN finalize + fused tail with BN).
 Stem / transition / head layers are regular Keras layers in the reference and run as torch ops here
 (SURVEY.md section 8f-1).  The bottleneck ResNet-50/101/152 builders are out of scope (SURVEY.md
 section 2, row 6).
@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from .. import _abi
-from ..layers._base import _ptr, _stream_ptr, as_torch, relu_scale_bwd, truncated_normal_
+from ..layers._base import BNEulerStep, _ptr, _stream_ptr, as_torch, relu_scale_bwd, truncated_normal_
 from ..layers.tfkeras_layer_Conv2DAntisymmetric3By3 import Conv2DAntisymmetric3By3
 from ..training import conv2d_same_nhwc
 
@@ -110,49 +110,35 @@ class _BatchNorm:
 
 
 class _EulerBNFn(torch.autograd.Function):
-    """x + h*relu(BN(conv_K(x)+b)) in training mode on the CUDA kernels: conv (z) -> column sums ->
-    bn_finalize -> fused tail; backward: BN reductions, BN apply (dz), dgrad with skip, wgrad + fold."""
+    """x + h*relu(BN(conv_K(x)+b)) in training mode on the CUDA kernels (layers._base.BNEulerStep): conv with the batch
+    statistics taken from its epilogue -> finalize -> fused tail; backward: BN reductions, BN apply (dz), dgrad with the
+    skip add, wgrad + fold."""
 
     @staticmethod
     def forward(ctx, x, params, bn_gamma, bn_beta, layer, bn, h):
-        lib, st = _abi.lib(), _stream_ptr()
         hd = layer._handle
         hd.pack(params)
-        N, H, W, C = x.shape
-        M = N * H * W
-        _, _, z = hd.forward(x, 1.0, _abi.F_BIAS, want_z=True, want_y=False)
-        dev = x.device
-        ws = torch.empty(2 * _abi.COLSUM_PARTS * C, device=dev)
-        s1, s2 = torch.empty(C, device=dev), torch.empty(C, device=dev)
-        _abi.check(lib.b200ode_colsum(_ptr(z), None, _ptr(s1), _ptr(s2), _ptr(ws), M, C, st))
-        mean, inv, scale, shift = (torch.empty(C, device=dev) for _ in range(4))
-        _abi.check(lib.b200ode_bn_finalize(_ptr(s1), _ptr(s2), _ptr(bn_gamma), _ptr(bn_beta), _ptr(mean), _ptr(inv),
-                                           _ptr(scale), _ptr(shift), _ptr(bn.moving_mean), _ptr(bn.moving_var), M, C,
-                                           BN_EPS, BN_MOMENTUM, st))
-        y = torch.empty_like(x)
-        flags = _abi.F_RELU | _abi.F_RESIDUAL | (_abi.F_SCALE if h != 1.0 else 0)
-        _abi.check(lib.b200ode_euler_tail(_ptr(z), _ptr(scale), _ptr(shift), _ptr(x), _ptr(y), None, M, C, float(h), flags, st))
-        ctx.save_for_backward(x, params, bn_gamma, z, mean, inv, scale, shift)
+        C = x.shape[-1]
+        z, y = torch.empty_like(x), torch.empty_like(x)
+        stat = torch.empty((6, C), dtype=torch.float32, device=x.device)
+        ws = BNEulerStep.stats_workspace(C, x.device)
+        BNEulerStep.forward(hd, x, bn_gamma.detach(), bn_beta.detach(), bn.moving_mean, bn.moving_var, h, z, y, stat, ws)
+        ctx.save_for_backward(x, params, bn_gamma, z, stat)
         ctx.hd, ctx.h, ctx.ws = hd, h, ws
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, params, bn_gamma, z, mean, inv, scale, shift = ctx.saved_tensors
-        lib, st, hd, h = _abi.lib(), _stream_ptr(), ctx.hd, ctx.h
+        x, params, bn_gamma, z, stat = ctx.saved_tensors
+        hd, h = ctx.hd, ctx.h
         dy = dy.contiguous()
-        N, H, W, C = x.shape
-        M = N * H * W
-        dgamma, dbeta = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
-        _abi.check(lib.b200ode_bn_bwd_reduce(_ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(inv),
-                                             _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), M, C, float(h), st))
-        dz = torch.empty_like(x)
-        _abi.check(lib.b200ode_bn_bwd_apply(_ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(inv),
-                                            _ptr(bn_gamma), _ptr(dgamma), _ptr(dbeta), _ptr(dz), M, C, float(h), st))
+        C = x.shape[-1]
+        dbn = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        dz, dx = torch.empty_like(x), torch.empty_like(x)
+        gp = torch.empty(hd.num_params, dtype=torch.float32, device=x.device)
         hd.pack(params)
-        dx = hd.dgrad(dz, dy, (H, W))
-        gp = hd.wgrad(x, dz)
-        return dx, gp, dgamma, dbeta, None, None, None
+        BNEulerStep.backward(hd, x, dy, z, stat, bn_gamma.detach(), h, dz, dx, gp, dbn, ctx.ws)
+        return dx, gp, dbn[0], dbn[1], None, None, None
 
 
 def single_layer_identity_block(input_tensor,

@@ -22,7 +22,8 @@ import torch
 import torch.nn.functional as F
 
 from . import _abi
-from .layers._base import ChainHandle, LayerHandle, truncated_normal_, _alloc_workspace, _ptr, _stream_ptr
+from .layers._base import (BN_EPS, BN_MOMENTUM, BNEulerStep, ChainHandle, LayerHandle, truncated_normal_, _alloc_workspace, _ptr,
+                           _stream_ptr)
 from .parallel import allreduce_async, allreduce_bucket
 
 
@@ -32,9 +33,7 @@ class NetSpec:
     def __init__(self, num_stages=4, blocks_per_stage=(3, 3, 3), filters_per_block=(16, 32, 64),
                  strides=((1, 1), (2, 2), (2, 2)), h=1.0, gamma=0.0, num_classes=10, use_batch_norm=False,
                  subtract_mean=127.5, divide_by_stddev=127.5, kernel_size=3, in_channels=3):
-        if use_batch_norm:
-            raise NotImplementedError("the fused trainer covers the reference's no-BN configuration "
-                                      "(experiments v6/v7); BN Euler blocks are available in models.tfkeras_resnets")
+        self.use_batch_norm = bool(use_batch_norm)
         if kernel_size != 3:
             raise ValueError("antisymmetric Euler blocks are 3x3")
         self.num_stages, self.blocks_per_stage = num_stages, list(blocks_per_stage)
@@ -82,9 +81,16 @@ def conv2d_same_nhwc(x, w_hwio, bias, strides):
 class _Chain:
     """One run of consecutive Euler steps with equal shape: handles + saved activations."""
 
-    def __init__(self, C, n_layers, gamma, precision, offset, persistent=True):
+    def __init__(self, C, n_layers, gamma, precision, offset, persistent=True, bn=False):
         self.C, self.n, self.gamma, self.precision = C, n_layers, gamma, precision
-        self.persistent = persistent and precision in _abi.CHAIN_PRECISIONS
+        # BatchNorm needs the batch statistics of every step before its activation: per-layer kernels (the conv kernel
+        # emits the partial sums from its epilogue), not the one-image-per-CTA persistent chains
+        self.bn = bn
+        self.bn_offset = None                     # offset of [gamma_0, beta_0, gamma_1, ...] (C floats each) in the flat bucket
+        self.bn_moving = None                     # [n, 2, C] moving mean / variance (not trained)
+        if bn and precision == "fast_bf16":
+            raise ValueError("use_batch_norm=True needs fp32 activations (precision strict / fast_tf32 / fast_f16 / simt)")
+        self.persistent = persistent and precision in _abi.CHAIN_PRECISIONS and not bn
         self.chain_prec = _abi.CHAIN_PRECISIONS.get(precision, _abi.PREC_FAST_TF32)
         # per-layer fallback of the fp16 chains (images too large for shared memory): the FAST_TF32 kernels
         self.layer_prec = _abi.PRECISIONS["fast_tf32" if precision == "fast_f16" else precision]
@@ -179,6 +185,10 @@ class _Chain:
         self.ws = _alloc_workspace(self.handles[0].workspace_bytes(N, H, W), device)
         for hd in self.handles:
             hd.bind_workspace(self.ws)
+        if self.bn:   # pre-activations and batch statistics of every step (saved for the backward pass)
+            self.z = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(self.n)]
+            self.stat = torch.empty((self.n, 6, C), dtype=torch.float32, device=device)
+            self.stats_ws = BNEulerStep.stats_workspace(C, device)
 
 
 class _ChainFn(torch.autograd.Function):
@@ -206,6 +216,12 @@ class _ChainFn(torch.autograd.Function):
         for l, hd in enumerate(chain.handles):
             off = chain.offset + l * chain.np_layer
             _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(net.theta_euler[off:]), None, st))
+            if chain.bn:
+                bo = chain.bn_offset + 2 * C * l
+                BNEulerStep.forward(hd, chain.acts[l], net.theta[bo:bo + C], net.theta[bo + C:bo + 2 * C], chain.bn_moving[l, 0],
+                                    chain.bn_moving[l, 1], net.spec.h, chain.z[l], chain.acts[l + 1], chain.stat[l], chain.stats_ws,
+                                    net._bn_allreduce, net.world_size)
+                continue
             _abi.check(lib.b200ode_euler_fwd(hd._h, _ptr(chain.acts[l]), _ptr(chain.acts[l + 1]), _ptr(chain.masks[l]),
                                              None, N, H, W, net.spec.h, _abi.F_EULER, st))
         return chain.acts[chain.n].view(N, H, W, C).to(ctx.in_dtype)
@@ -225,6 +241,16 @@ class _ChainFn(torch.autograd.Function):
         cur = dy.to(dt)
         is_bf16 = int(dt == torch.bfloat16)
         top = chain.n - 1
+        if chain.bn:
+            for l in range(top, -1, -1):
+                off = chain.offset + l * chain.np_layer
+                bo = chain.bn_offset + 2 * C * l
+                nxt = chain.dx[l & 1]
+                BNEulerStep.backward(chain.handles[l], chain.acts[l], cur, chain.z[l], chain.stat[l], net.theta[bo:bo + C], net.spec.h,
+                                     chain.dz[0], nxt, net.grad_euler[off:], net.grad[bo:bo + 2 * C].view(2, C), chain.stats_ws,
+                                     net._bn_allreduce, net.world_size)
+                cur = nxt
+            return cur.view(N, H, W, C).to(ctx.in_dtype), None, None
         _abi.check(lib.b200ode_relu_scale_bwd(_ptr(cur), _ptr(chain.masks[top]), _ptr(chain.dz[top & 1]), N * H * W, C,
                                               net.spec.h, is_bf16, st))
         for l in range(top, -1, -1):
@@ -243,6 +269,30 @@ class _ChainFn(torch.autograd.Function):
         return cur.view(N, H, W, C).to(ctx.in_dtype), None, None
 
 
+class _SyncStats(torch.autograd.Function):
+    """Per-channel (mean, biased variance) of an NHWC tensor over the GLOBAL batch: local sums -> all-reduce of 2C
+    floats -> statistics; backward all-reduces (d mean, d var) the same way (every rank's loss sees the shared statistics)."""
+
+    @staticmethod
+    def forward(ctx, z, net):
+        C = z.shape[-1]
+        Mg = (z.numel() // C) * net.world_size
+        s = torch.stack([z.sum(dim=(0, 1, 2)), (z * z).sum(dim=(0, 1, 2))])
+        net._ar(s)
+        mu = s[0] / Mg
+        var = (s[1] / Mg - mu * mu).clamp_min(0.0)
+        ctx.save_for_backward(z, mu)
+        ctx.net, ctx.Mg = net, Mg
+        return torch.stack([mu, var])
+
+    @staticmethod
+    def backward(ctx, g):
+        z, mu = ctx.saved_tensors
+        g = g.contiguous().clone()
+        ctx.net._ar(g)
+        return (g[0] + 2.0 * g[1] * (z - mu)) / ctx.Mg, None
+
+
 class EulerNet:
     """Antisymmetric single-block ResNet with a fused train step.
 
@@ -251,7 +301,7 @@ class EulerNet:
     'fast_bf16' (bf16 operands and activations, fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1, persistent=True, native_glue=True, comm=None):
+                 world_size=1, persistent=True, native_glue=True, comm=None, sync_bn=True):
         _abi.require_device()
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
         self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
@@ -269,7 +319,7 @@ class EulerNet:
                 j = i
                 while j < len(plan) and plan[j][0] == "euler" and plan[j][2] == co:
                     j += 1
-                ch = _Chain(co, j - i, spec.gamma, precision, off, persistent)
+                ch = _Chain(co, j - i, spec.gamma, precision, off, persistent, bn=spec.use_batch_norm)
                 off += ch.np_layer * ch.n
                 self.segments.append(("chain", ch))
                 i = j
@@ -284,15 +334,34 @@ class EulerNet:
             if seg[0] == "stem":
                 _, ci, co, st, name = seg
                 self.torch_shapes += [(name + "/kernel", (k, k, ci, co), k * k * ci), (name + "/bias", (co,), 0)]
+                if spec.use_batch_norm:      # bn_conv1 (models/tfkeras_resnets.py:570-571); fan_in -1 = ones
+                    self.torch_shapes += [("bn_" + name + "/gamma", (co,), -1), ("bn_" + name + "/beta", (co,), 0)]
             elif seg[0] == "transition":
                 _, ci, co, st, name = seg
                 self.torch_shapes += [(name + "2/kernel", (k, k, ci, co), k * k * ci), (name + "2/bias", (co,), 0),
                                       (name + "1/kernel", (1, 1, ci, co), ci), (name + "1/bias", (co,), 0)]
+                if spec.use_batch_norm:      # bn{s}_0_branch2 / branch1 (models/tfkeras_resnets.py:258-263)
+                    bn = name.replace("res", "bn")
+                    for br in ("2", "1"):
+                        self.torch_shapes += [(bn + br + "/gamma", (co,), -1), (bn + br + "/beta", (co,), 0)]
         c_last = spec.filters_per_block[spec.num_stages - 2]
         self.torch_shapes += [("fc/kernel", (c_last, spec.num_classes), c_last), ("fc/bias", (spec.num_classes,), 0)]
         n_torch = sum(math.prod(s) for _, s, _ in self.torch_shapes)
-        self.n_params = off + n_torch
+        # BatchNorm scale / offset of the Euler steps (bn{s}_{b}_branch2): per chain [layer][gamma (C) | beta (C)] behind the
+        # regular parameters, in the same flat bucket (same Adam launch, same all-reduce)
+        n_bn = 0
+        for seg in self.segments:
+            if seg[0] == "chain" and seg[1].bn:
+                if (off + n_torch + n_bn) % 4:     # 16-byte aligned slices: the BN kernels read gamma / beta as float4
+                    n_bn += 4 - (off + n_torch + n_bn) % 4
+                seg[1].bn_offset = off + n_torch + n_bn
+                n_bn += seg[1].n * 2 * seg[1].C
+        self.n_params = off + n_torch + n_bn
         theta = torch.zeros(self.n_params, dtype=torch.float32)
+        for seg in self.segments:
+            if seg[0] == "chain" and seg[1].bn:
+                ch = seg[1]
+                theta[ch.bn_offset:ch.bn_offset + ch.n * 2 * ch.C].view(ch.n, 2, ch.C)[:, 0, :] = 1.0
         # Euler layers: truncated normal sigma = sqrt(2/(9C)), zero bias (reference 3By3.py:95-98,148-153)
         for seg in self.segments:
             if seg[0] != "chain":
@@ -305,9 +374,11 @@ class EulerNet:
         self.torch_params = {}
         for name, shape, fan_in in self.torch_shapes:
             n = math.prod(shape)
-            if fan_in:  # Keras he_normal (VarianceScaling(2, fan_in, truncated normal))
+            if fan_in > 0:  # Keras he_normal (VarianceScaling(2, fan_in, truncated normal))
                 std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
                 truncated_normal_(theta[cur:cur + n], std, gen)
+            elif fan_in < 0:
+                theta[cur:cur + n] = 1.0
             self.torch_params[name] = (cur, shape)
             cur += n
         self.theta = theta.to(self.device)
@@ -330,6 +401,19 @@ class EulerNet:
         self._nb = None
         self._nb_cache = {}
         self._pending, self._reduced_upto = [], self.n_euler_params     # overlapped all-reduces of this step
+        # BatchNorm state: moving statistics (not trained) and the SyncBN hook (statistics over the GLOBAL batch)
+        self.training = True
+        self.bn_moving = {}
+        for seg in self.segments:
+            if seg[0] == "chain" and seg[1].bn:
+                ch = seg[1]
+                ch.bn_moving = torch.zeros((ch.n, 2, ch.C), dtype=torch.float32, device=self.device)
+                ch.bn_moving[:, 1, :] = 1.0
+        for name, shape, _ in self.torch_shapes:
+            if name.endswith("/gamma"):
+                self.bn_moving[name[:-6]] = [torch.zeros(shape, device=self.device), torch.ones(shape, device=self.device)]
+        self.sync_bn = bool(sync_bn) and world_size > 1 and spec.use_batch_norm
+        self._bn_allreduce = (lambda t: self._ar(t)) if self.sync_bn else None
 
     # ----------------------------------------------------------------------------------------------
     def forward(self, images):
@@ -341,20 +425,64 @@ class EulerNet:
         if spec.divide_by_stddev is not None:
             x = x / spec.divide_by_stddev
         L = self.leaves
+        bn = self._glue_bn if spec.use_batch_norm else (lambda t, name: t)
         for seg in self.segments:
             if seg[0] == "stem":
                 _, ci, co, st, name = seg
-                x = torch.relu(conv2d_same_nhwc(x, L[name + "/kernel"], L[name + "/bias"], st))
+                x = torch.relu(bn(conv2d_same_nhwc(x, L[name + "/kernel"], L[name + "/bias"], st), "bn_" + name))
             elif seg[0] == "transition":
                 _, ci, co, st, name = seg
-                main = conv2d_same_nhwc(x, L[name + "2/kernel"], L[name + "2/bias"], st)
-                short = conv2d_same_nhwc(x, L[name + "1/kernel"], L[name + "1/bias"], st)
+                bname = name.replace("res", "bn")
+                main = bn(conv2d_same_nhwc(x, L[name + "2/kernel"], L[name + "2/bias"], st), bname + "2")
+                short = bn(conv2d_same_nhwc(x, L[name + "1/kernel"], L[name + "1/bias"], st), bname + "1")
                 x = torch.relu(main) + short          # models/tfkeras_resnets.py:266-267
+            elif seg[1].bn and not self.training:
+                x = self._chain_bn_inference(seg[1], x)
             else:
                 x = _ChainFn.apply(x, seg[1], self)
         x = x.mean(dim=(1, 2))
         logits = x @ L["fc/kernel"] + L["fc/bias"]
         return torch.softmax(logits, dim=-1)
+
+    def _chain_bn_inference(self, chain, x):
+        """Euler steps with BatchNorm in inference mode (moving statistics): conv kernel + fused affine/relu/h/residual tail."""
+        x = x.detach().contiguous().float()
+        chain.ensure_buffers(tuple(x.shape), x.device)
+        C, lib, st = chain.C, _abi.lib(), _stream_ptr()
+        cur = x
+        for l, hd in enumerate(chain.handles):
+            off, bo = chain.offset + l * chain.np_layer, chain.bn_offset + 2 * C * l
+            _abi.check(lib.b200ode_pack_kernel(hd._h, _ptr(self.theta_euler[off:]), None, st))
+            BNEulerStep.inference(hd, cur, self.theta[bo:bo + C], self.theta[bo + C:bo + 2 * C], chain.bn_moving[l, 0],
+                                  chain.bn_moving[l, 1], self.spec.h, chain.z[l], chain.acts[l + 1])
+            cur = chain.acts[l + 1]
+        return cur.clone()
+
+    def _glue_bn(self, z, name):
+        """BatchNormalization(axis=3) of a stem / transition branch as torch ops (SURVEY 8f-1 glue): batch statistics
+        (over the global batch under SyncBN) in training mode, moving statistics otherwise."""
+        g, b = self.leaves[name + "/gamma"], self.leaves[name + "/beta"]
+        mm, mv = self.bn_moving[name]
+        if not self.training:
+            return g * (z - mm) / torch.sqrt(mv + BN_EPS) + b
+        M = z.numel() // z.shape[-1]
+        if self.sync_bn:
+            stats = _SyncStats.apply(z, self)
+            mu, var = stats[0], stats[1]
+            M = M * self.world_size
+        else:
+            mu, var = z.mean(dim=(0, 1, 2)), z.var(dim=(0, 1, 2), unbiased=False)
+        with torch.no_grad():
+            mm.mul_(BN_MOMENTUM).add_(mu.detach(), alpha=1 - BN_MOMENTUM)
+            mv.mul_(BN_MOMENTUM).add_(var.detach() * (M / max(M - 1, 1)), alpha=1 - BN_MOMENTUM)
+        return g * (z - mu) / torch.sqrt(var + BN_EPS) + b
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
 
     @staticmethod
     def loss_fn(probs, onehot, eps=1e-7):
@@ -379,7 +507,7 @@ class EulerNet:
             return self._nb
         spec = self.spec
         N, H, W, Cin = shape
-        ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32
+        ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32 and not spec.use_batch_norm
         plan, h, w, c = [], H, W, Cin
         for seg in self.segments:
             if not ok:
@@ -536,8 +664,13 @@ class EulerNet:
         path does not take."""
         nb = self._native_plan(images.shape, images.device)
         if nb["plan"] is None:
-            with torch.no_grad():
-                return self.forward(images)
+            was = self.training
+            self.training = False                  # BatchNorm: moving statistics
+            try:
+                with torch.no_grad():
+                    return self.forward(images)
+            finally:
+                self.training = was
         lib, st, spec = _abi.lib(), _stream_ptr(), self.spec
         N = images.shape[0]
         is_u8 = images.dtype == torch.uint8
@@ -648,15 +781,36 @@ class EulerNet:
         return self._static_loss
 
     # ----------------------------------------------------------------------------------------------
+    def bn_param_slices(self):
+        """(bn layer name, offset of gamma, C, chain, index) of every Euler-step BatchNorm (`bn{s}_{b}_branch2`,
+        models/tfkeras_resnets.py:66, 85-87); beta follows gamma."""
+        out, idx = [], 0
+        plan = [p for p in self.spec.plan() if p[0] == "euler"]
+        for seg in self.segments:
+            if seg[0] != "chain":
+                continue
+            ch = seg[1]
+            for l in range(ch.n):
+                if ch.bn:
+                    out.append((plan[idx][4].replace("res", "bn"), ch.bn_offset + 2 * ch.C * l, ch.C, ch, l))
+                idx += 1
+        return out
+
     def export_params(self):
         """dict name -> CPU tensor: '<layer>/packed' for Euler layers (reference variable order,
-        flattened), '<layer>/kernel' (HWIO) and '<layer>/bias' for regular layers."""
+        flattened), '<layer>/kernel' (HWIO) and '<layer>/bias' for regular layers, '<bn>/gamma|beta|moving_mean|
+        moving_variance' for BatchNorm layers (the Keras variable names)."""
         out = {}
         th = self.theta.detach().cpu()
         for name, off, n, C in self.layer_param_slices():
             out[name + "/packed"] = th[off:off + n].clone()
         for name, (a, shape) in self.torch_params.items():
             out[name] = th[a:a + math.prod(shape)].view(shape).clone()
+        for name, off, C, ch, l in self.bn_param_slices():
+            out[name + "/gamma"], out[name + "/beta"] = th[off:off + C].clone(), th[off + C:off + 2 * C].clone()
+            out[name + "/moving_mean"], out[name + "/moving_variance"] = ch.bn_moving[l, 0].cpu().clone(), ch.bn_moving[l, 1].cpu().clone()
+        for name, (mm, mv) in self.bn_moving.items():
+            out[name + "/moving_mean"], out[name + "/moving_variance"] = mm.cpu().clone(), mv.cpu().clone()
         return out
 
     def import_params(self, params):
@@ -665,6 +819,16 @@ class EulerNet:
                 self.theta[off:off + n].copy_(params[name + "/packed"].reshape(-1))
             for name, (a, shape) in self.torch_params.items():
                 self.theta[a:a + math.prod(shape)].copy_(params[name].reshape(-1))
+            for name, off, C, ch, l in self.bn_param_slices():
+                self.theta[off:off + C].copy_(params[name + "/gamma"])
+                self.theta[off + C:off + 2 * C].copy_(params[name + "/beta"])
+                if name + "/moving_mean" in params:
+                    ch.bn_moving[l, 0].copy_(params[name + "/moving_mean"])
+                    ch.bn_moving[l, 1].copy_(params[name + "/moving_variance"])
+            for name, (mm, mv) in self.bn_moving.items():
+                if name + "/moving_mean" in params:
+                    mm.copy_(params[name + "/moving_mean"])
+                    mv.copy_(params[name + "/moving_variance"])
 
     def export_grads(self):
         out = {}
@@ -673,6 +837,8 @@ class EulerNet:
             out[name + "/packed"] = g[off:off + n].clone()
         for name, (a, shape) in self.torch_params.items():
             out[name] = g[a:a + math.prod(shape)].view(shape).clone()
+        for name, off, C, ch, l in self.bn_param_slices():
+            out[name + "/gamma"], out[name + "/beta"] = g[off:off + C].clone(), g[off + C:off + 2 * C].clone()
         return out
 
     def layer_param_slices(self):

@@ -137,9 +137,21 @@ int b200ode_euler_tail(const float* z, const float* scale, const float* shift, c
                        uint8_t* relu_mask, int64_t pixels, int channels, float h, int fuse_flags, void* stream);
 /* per-channel sums over pixels: out_sum[c] = sum a[p,c], out_sumsq[c] = sum a[p,c]*b[p,c] (b nullable -> a*a).
  * workspace: device fp32 [2 * B200ODE_COLSUM_PARTS * channels]. Deterministic. */
-#define B200ODE_COLSUM_PARTS 256
+#define B200ODE_COLSUM_PARTS 2048
 int b200ode_colsum(const float* a, const float* b, float* out_sum, float* out_sumprod, float* workspace, int64_t pixels,
                    int channels, void* stream);
+/* BatchNorm Euler step (models/tfkeras_resnets.py:70-87), forward part 1: z_out = conv_K(x) + b as fp32 [N,H,W,C] and, from
+ * the epilogue registers of the SAME kernel (no second pass over z), per-channel partial sums of z and z*z:
+ * stats_ws = device fp32 [2 * B200ODE_COLSUM_PARTS * C] receives *rows_out (host int) rows of sums, then as many rows of
+ * sums of squares.  fp32 modes only (STRICT / FAST_TF32 / SIMT). */
+int b200ode_euler_fwd_bn_stats(b200ode_layer_t* layer, const void* x, float* z_out, float* stats_ws, int* rows_out, int N, int H,
+                               int W, void* stream);
+/* part 2: fixed-order reduction of the rows (deterministic) into out_sum / out_sumsq (nullable, [C] each) and, when
+ * bn_gamma != NULL, b200ode_bn_finalize over `pixels` in the same launch.  Data parallel SyncBN: call with bn_gamma = NULL,
+ * all-reduce the 2C sums, then b200ode_bn_finalize with the global pixel count. */
+int b200ode_bn_stats_finalize(const float* stats_ws, int rows, float* out_sum, float* out_sumsq, const float* bn_gamma,
+                              const float* bn_beta, float* mean, float* inv_std, float* scale, float* shift, float* moving_mean,
+                              float* moving_var, int64_t pixels, int channels, float eps, float momentum, void* stream);
 /* training-mode BatchNormalization(axis=3) (models/tfkeras_resnets.py:85-87; Keras eps 1e-3):
  * from sums -> mean, inv_std, and the affine (scale, shift) that b200ode_euler_tail consumes;
  * updates moving statistics (momentum) when moving_mean != NULL. */
