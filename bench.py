@@ -45,8 +45,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode (fp32-grade) measurement of the same step")
-    ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "torch"), choices=["torch", "abi"],
-                    help="gradient exchange: torch.distributed NCCL, or NCCL bound by libb200ode (b200ode_comm_*)")
+    ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "abi"), choices=["torch", "abi"],
+                    help="gradient exchange: NCCL bound by libb200ode through the C ABI (b200ode_comm_*; default), or "
+                         "torch.distributed NCCL; the other one is measured too and reported under comm_alt")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short cfg1 / cfg2 / cfg4 / cfg5 measurements (other_configs)")
     return ap.parse_args()
 
 
@@ -234,6 +236,104 @@ def kernel_microbench(torch, precision, batch):
     return recs
 
 
+def other_configs(torch, peaks):
+    """Short, bounded measurements of the other BASELINE.json configurations on this GPU (N = 1 only), so that the
+    driver's bench record carries them next to the cfg3 headline: cfg2 rows against the roof that binds each
+    (tools/gpu_sweep.py is the full sweep), one cfg4 train step at full size, the cfg1 net with and without BatchNorm,
+    the cfg5 long-horizon integration.  CUDA events, inputs rotated / larger than L2 where the kernel is memory-bound."""
+    from differential_equations_resnet_b200 import _abi
+    from differential_equations_resnet_b200.layers._base import ChainHandle
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_sweep
+    out = {}
+    bf16_peak, hbm_peak = float(peaks.get("bf16_tflops", 1648.7)), float(peaks.get("hbm_gbs", 6456.5))
+
+    def ev_time(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters      # ms
+
+    # ---- cfg2: single Euler layer, N = 256, 32x32 --------------------------------------------------------------
+    rows = []
+    for C, prec in ((16, "fast_tf32"), (32, "fast_tf32"), (64, "fast_bf16"), (128, "fast_bf16"), (256, "fast_bf16"), (64, "strict"),
+                    (256, "strict")):
+        try:
+            for r in gpu_sweep.bench_layer(256, 32, 32, C, prec, reps=2, quiet=True):
+                # roof: bf16 peak (fast_bf16), bf16/2 (tf32, estimated), bf16/6 (strict 3xTF32, estimated); HBM where it binds
+                tpk = bf16_peak / {"fast_bf16": 1.0, "fast_tf32": 2.0, "strict": 6.0}[prec]
+                t_hbm, t_tc = r["alg_bytes"] / (hbm_peak * 1e9), r["alg_TFLOPs"] * r["us"] * 1e-6 / tpk
+                bound = "hbm" if t_hbm > t_tc else "tensor"
+                rows.append({"kernel": r["kernel"], "C": C, "mode": prec, "us": r["us"], "TFLOPs": r["alg_TFLOPs"], "GBps": r["GBps"],
+                             "bound": bound, "frac": max(t_hbm, t_tc) / (r["us"] * 1e-6)})
+        except Exception as e:      # a configuration this build refuses: say so, keep the line
+            rows.append({"C": C, "mode": prec, "error": str(e)[:120]})
+        torch.cuda.empty_cache()
+    out["cfg2"] = {"workload": "single Euler-step layer, N=256, 32x32 (fwd / dgrad / wgrad)", "rows": rows,
+                   "roofs": "tensor: measured bf16 peak %.1f TFLOP/s (tf32: /2, strict 3xTF32: /6, both estimated); hbm: %.1f GB/s" % (bf16_peak, hbm_peak)}
+    # ---- cfg4: wide net, 256 channels at 64x64, batch 512, bf16 ------------------------------------------------
+    try:
+        B4, C4, L4, HW4 = 512, 256, 8, 64
+        net = EulerNet(NetSpec(num_stages=2, blocks_per_stage=(L4,), filters_per_block=(C4,), strides=((1, 1),), h=1.0 / L4),
+                       precision="fast_bf16", seed=0)
+        g = torch.Generator().manual_seed(0)
+        img = torch.randint(0, 256, (B4, HW4, HW4, 3), generator=g, dtype=torch.uint8).cuda()
+        lab = torch.nn.functional.one_hot(torch.randint(0, 10, (B4,), generator=g), 10).float().cuda()
+        ms = ev_time(lambda: net.train_step(img, lab), 3, warm=2)
+        flops = 3 * L4 * 2.0 * B4 * HW4 * HW4 * 9 * C4 * C4
+        out["cfg4"] = {"workload": "stem 3->256 @64x64, 8 Euler steps x 256 ch, GAP+FC, batch 512, fast_bf16, full train step",
+                       "ms_per_step": ms, "images_per_s": B4 / (ms * 1e-3), "euler_block_TFLOPs_over_whole_step": flops / (ms * 1e-3) * 1e-12,
+                       "frac_of_bf16_peak": flops / (ms * 1e-3) * 1e-12 / bf16_peak, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del net, img, lab
+    except Exception as e:
+        out["cfg4"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+    # ---- cfg1: CIFAR net 16/32/64, batch 128, 18 blocks per stage (54 Euler steps), without and with BatchNorm ------
+    try:
+        g = torch.Generator().manual_seed(1)
+        img = torch.randint(0, 256, (128, 32, 32, 3), generator=g, dtype=torch.uint8).cuda()
+        lab = torch.nn.functional.one_hot(torch.randint(0, 10, (128,), generator=g), 10).float().cuda()
+        c1 = {}
+        for tag, bn, prec in (("no_bn_fast_f16", False, "fast_f16"), ("bn_fast_tf32", True, "fast_tf32"), ("bn_strict", True, "strict")):
+            net = EulerNet(NetSpec(blocks_per_stage=(18, 18, 18), h=4.0 / 54, use_batch_norm=bn), precision=prec, seed=0)
+            net.train_step(img, lab)
+            l0 = _abi.launch_count()
+            net.train_step(img, lab)
+            nl = _abi.launch_count() - l0
+            net.capture(img, lab)
+            ms = ev_time(lambda: net.train_step_graph(), 5, warm=2)
+            c1[tag] = {"ms_per_step": ms, "images_per_s": 128 / (ms * 1e-3), "libb200ode_launches_per_step": int(nl), "cuda_graph": True}
+            net.release()
+            del net
+        out["cfg1"] = {"workload": "antisymmetric ResNet 16/32/64, 3 x 18 Euler steps, batch 128, fwd+loss+bwd+Adam", **c1}
+    except Exception as e:
+        out["cfg1"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+    # ---- cfg5: 1000 Euler steps through one antisymmetric block (shared weights), one launch ----------------------
+    try:
+        c5 = {}
+        for C in (16, 64):
+            ch = ChainHandle(C, 1, -0.1, precision=_abi.PREC_FAST_F16)
+            th = (torch.randn(ch.num_params, generator=torch.Generator().manual_seed(C)) * (2.0 / (9 * C)) ** 0.5).cuda()
+            ch.pack(th)
+            HW = 32 if C == 16 else 8
+            x = torch.relu(torch.randn((8, HW, HW, C), generator=torch.Generator().manual_seed(2))).cuda()
+            y = torch.empty_like(x)
+            ms = ev_time(lambda: ch.forward(x, 0.01, n_steps=1000, y_final=y), 3, warm=1)
+            c5["C%d" % C] = {"ms_per_1000_steps": ms, "norm_ratio": float(y.norm() / x.norm())}
+        out["cfg5"] = {"workload": "1000 Euler steps, one antisymmetric block, N=8, h=0.01, gamma=-0.1, one launch (fast_f16 chain)", **c5}
+    except Exception as e:
+        out["cfg5"] = {"error": str(e)[:200]}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -247,10 +347,11 @@ def run_b200(args):
     from differential_equations_resnet_b200.training import EulerNet, NetSpec
 
     spec = NetSpec(blocks_per_stage=BLOCKS, filters_per_block=FILTERS, h=H_STEP, gamma=0.0)
-    comm = None
-    if world > 1 and args.comm == "abi":
+    comm = abi_comm = None
+    if world > 1:
         from differential_equations_resnet_b200.parallel import AbiComm
-        comm = AbiComm(rank, world)
+        abi_comm = AbiComm(rank, world)          # NCCL bound by libb200ode itself (b200ode_comm_*)
+        comm = abi_comm if args.comm == "abi" else None
     net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
     B = args.batch
     g = torch.Generator().manual_seed(1236 + rank)
@@ -336,6 +437,38 @@ def run_b200(args):
                   "e2e": {"value": world * B * Ks / (ms_se * 1e-3), "unit": "images/s", "ms_per_step": ms_se / Ks},
                   "gpu_launches_per_step": int(strict_launches), "final_loss": float(loss_h.item())}
         del net_s
+    # Data parallel extras: the same weak-scaling step through the OTHER gradient-exchange path, and the strong-scaling
+    # form of cfg3 (128 images GLOBAL, 128 / N per GPU; SURVEY.md 8d "stated separately").
+    comm_alt = strong = None
+    if world > 1:
+        alt = None if args.comm == "abi" else abi_comm
+        net_a = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=alt)
+        net_a.train_step(img_d, lab_d)
+        if use_graph:
+            net_a.capture(img_d, lab_d)
+            a_step = lambda: net_a.train_step_graph()
+        else:
+            a_step = lambda: net_a.train_step(img_d, lab_d)
+        ms_a = timed(a_step, K, 3)
+        comm_alt = {"comm": "torch.distributed" if args.comm == "abi" else "abi (b200ode_comm_*)", "value": world * B * K / (ms_a * 1e-3),
+                    "unit": "images/s", "ms_per_step": ms_a / K}
+        net_a.release()
+        del net_a, a_step
+        if BATCH_PER_GPU % world == 0:
+            Bs = BATCH_PER_GPU // world
+            net_g = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
+            net_g.train_step(img_d[:Bs].contiguous(), lab_d[:Bs].contiguous())
+            if use_graph:
+                net_g.capture(img_d[:Bs].contiguous(), lab_d[:Bs].contiguous())
+                g_step = lambda: net_g.train_step_graph()
+            else:
+                xi, xl = img_d[:Bs].contiguous(), lab_d[:Bs].contiguous()
+                g_step = lambda: net_g.train_step(xi, xl)
+            ms_g = timed(g_step, K, 3)
+            strong = {"global_batch": BATCH_PER_GPU, "batch_per_gpu": Bs, "value": BATCH_PER_GPU * K / (ms_g * 1e-3), "unit": "images/s",
+                      "ms_per_step": ms_g / K, "scaling": "strong"}
+            net_g.release()
+            del net_g, g_step
     clocks = sampler.stop() if rank == 0 else None
 
     ips = world * B * K / (ms_dev * 1e-3)
@@ -382,6 +515,12 @@ def run_b200(args):
             roofline["issue_bound_frac"] = waves * mmas * cyc / sm_hz / (dom["us"] * 1e-6)
             roofline["note"] = ("chain kernels are bound by the tcgen05 issue rate at N=C columns, not by HBM: "
                                 "issue_bound_frac = MMA count x measured cycles per MMA / time")
+        others = None
+        if world == 1 and not args.no_configs:
+            s2 = ClockSampler(local)
+            s2.start()
+            others = other_configs(torch, peaks)
+            others["clocks"] = s2.stop()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -403,6 +542,7 @@ def run_b200(args):
                                    "fwd+loss+bwd%s+Adam" % ("+allreduce" if world > 1 else ""),
                        "global_batch": world * B, "batch_per_gpu": B, "h": H_STEP, "gamma": 0.0,
                        "precision": args.precision, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
+                       "comm": ("abi (NCCL bound by libb200ode, b200ode_comm_*)" if comm is not None else "torch.distributed NCCL") if world > 1 else None,
                        "l2": "per-step working set (saved activations + dZ of 108 layers, >1 GB) exceeds the 126 MB L2; "
                              "each microbenchmarked chain launch streams 75-300 MB"},
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(img_h.numel() + lab_h.numel() * 4),
@@ -413,19 +553,28 @@ def run_b200(args):
         }
         if strict:
             line["strict"] = strict
+        if comm_alt:
+            line["comm_alt"] = comm_alt
+        if strong:
+            line["strong_scaling"] = strong
+        if others:
+            line["other_configs"] = others
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:
-        # All ranks meet once more, then leave without tearing the communicator down: destroying NCCL
-        # communicators whose collectives were captured into a (still alive) CUDA graph blocked the
-        # process on this stack (torch 2.11 / NCCL 2.28.9); the processes are finished anyway.
-        dist.barrier()
+        # Orderly teardown: a communicator must not be destroyed while a CUDA graph that captured its collectives is
+        # alive (that blocked the process in round 1), so the graphs go first, then the communicators.
+        import gc
+        net.release()
+        del net
+        gc.collect()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        dist.barrier()
+        if abi_comm is not None:
+            abi_comm.close()
+        dist.destroy_process_group()
 
 
 def main():

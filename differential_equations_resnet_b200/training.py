@@ -621,6 +621,8 @@ class EulerNet:
         # before Adam.  The fork / join is captured in the CUDA graph like everything else.
         d = nb["head_dx"]
         side = self._side_stream if overlap_wgrad else main
+        # data parallel only: on one GPU the extra Adam launches cost more than the ~10 us they take off the critical path
+        early = self._early_slices(nb) if overlap_wgrad and self.world_size > 1 and not os.environ.get("B200ODE_NO_EARLY_ADAM") else None
         for e in reversed(nb["plan"]):
             if e["kind"] == "chain":
                 ch = e["chain"]
@@ -648,6 +650,23 @@ class EulerNet:
                                                         _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
                                                         e["ci"], e["co"], e["st"][0], e["st"][1], st))
                 d = e["dx"]
+                if early is not None and e is early["after"]:
+                    # Everything behind the first stage is final now (gradients written, parameters no longer read by
+                    # this step): exchange and update those slices on the side stream while the first stage's backward
+                    # sweep and weight gradient run; only the first chain + stem slices are left for _optimizer.
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        if self.world_size > 1:
+                            lo, hi = early["slices"][-1]
+                            self._pending.append(self._ar_async(self.grad[lo:hi]))
+                            for w in self._pending:
+                                w.wait()
+                            self._pending, self._reduced_upto = [], self.n_euler_params
+                        for lo, hi in early["slices"]:
+                            self._adam(lo, hi, side.cuda_stream)
+                    self._adam_done = early["slices"]
             else:
                 with torch.cuda.stream(side):
                     _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
@@ -728,23 +747,59 @@ class EulerNet:
     def _ar(self, t):
         return self.comm.allreduce_bucket(t) if self.comm is not None else allreduce_bucket(t, self.world_size)
 
+    def _early_slices(self, nb):
+        """Slices of the flat bucket that are final once the FIRST transition's data gradient is queued: the chains behind
+        the first one and the glue parameters behind the stem ([first transition .. fc]).  None for nets without that shape."""
+        plan = nb["plan"]
+        if len(plan) < 3 or plan[0]["kind"] != "stem" or plan[1]["kind"] != "chain" or plan[2]["kind"] != "transition":
+            return None
+        first = plan[1]["chain"]
+        lo_e = first.offset + first.n * first.np_layer
+        name = plan[0]["name"]
+        a, shape = self.torch_params[name + "/bias"]
+        lo_g = a + math.prod(shape)
+        if self.torch_params[name + "/kernel"][0] != self.n_euler_params or lo_e >= self.n_euler_params:
+            return None
+        return dict(after=plan[2], slices=[(lo_e, self.n_euler_params), (lo_g, self.n_params)])
+
+    def _adam(self, lo, hi, stream):
+        _abi.check(_abi.lib().b200ode_adam_step(_ptr(self.theta[lo:]), _ptr(self.grad[lo:]), _ptr(self.adam_m[lo:]), _ptr(self.adam_v[lo:]),
+                                                hi - lo, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,
+                                                1.0 / self.world_size, stream))
+
     def _optimizer(self):
-        if self._pending:
-            # chains were reduced stage by stage (they sit at the front of the flat bucket in forward order,
-            # i.e. [reduced_upto, n_euler) is done); reduce what is left, then join the overlapped collectives
-            if self._reduced_upto > 0:
-                self._ar(self.grad[:self._reduced_upto])
-            self._ar(self.grad[self.n_euler_params:])
-            for w in self._pending:
-                w.wait()
-            self._pending, self._reduced_upto = [], self.n_euler_params
-        else:
-            self._ar(self.grad)
-        lib, st = _abi.lib(), _stream_ptr()
-        _abi.check(lib.b200ode_adam_step(_ptr(self.theta), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
-                                         self.n_params, _ptr(self.step_counter), self.lr, 0.9, 0.999, self.adam_eps,
-                                         1.0 / self.world_size, st))
-        _abi.check(lib.b200ode_increment(_ptr(self.step_counter), st))
+        """All-reduce (data parallel) and Adam for every slice of the flat bucket the step has not updated yet
+        (`_adam_done`: slices exchanged and updated early, under the tail of the backward pass)."""
+        done = sorted(getattr(self, "_adam_done", None) or [])
+        self._adam_done = []
+        rest, cur = [], 0
+        for lo, hi in done:
+            if lo > cur:
+                rest.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < self.n_params:
+            rest.append((cur, self.n_params))
+        if self.world_size > 1:
+            if self._pending or done:
+                # chains were reduced stage by stage as their weight gradients were queued: [reduced_upto, n_euler) is in
+                # flight or done; reduce what is left of the remaining slices, then join the overlapped collectives
+                for lo, hi in rest:
+                    if lo < self.n_euler_params:
+                        hi_e = min(hi, self._reduced_upto)
+                        if hi_e > lo:
+                            self._pending.append(self._ar_async(self.grad[lo:hi_e]))
+                        lo = max(lo, self.n_euler_params)
+                    if hi > lo and hi > self.n_euler_params:
+                        self._pending.append(self._ar_async(self.grad[lo:hi]))
+                for w in self._pending:
+                    w.wait()
+                self._pending, self._reduced_upto = [], self.n_euler_params
+            else:
+                self._ar(self.grad)
+        st = _stream_ptr()
+        for lo, hi in rest:
+            self._adam(lo, hi, st)
+        _abi.check(_abi.lib().b200ode_increment(_ptr(self.step_counter), st))
 
     def train_step(self, images, onehot):
         """Eager step; returns the loss tensor (device)."""
@@ -772,6 +827,13 @@ class EulerNet:
         with torch.cuda.graph(self._graph):
             self._static_loss = self.train_step(*self._static_in)
         return self
+
+    def release(self):
+        """Drop the captured CUDA graph and its static inputs (before a communicator whose collectives it captured is
+        destroyed: NCCL teardown blocks while such a graph is alive)."""
+        self._graph = None
+        self._static_in = None
+        self._static_loss = None
 
     def train_step_graph(self, images=None, onehot=None):
         if images is not None:

@@ -18,7 +18,7 @@ from differential_equations_resnet_b200 import _abi  # noqa: E402
 from differential_equations_resnet_b200.layers._base import LayerHandle, _ptr  # noqa: E402
 
 
-def bench_layer(N, H, W, C, prec, min_bytes=400e6, reps=3):
+def bench_layer(N, H, W, C, prec, min_bytes=400e6, reps=3, quiet=False):
     lib = _abi.lib()
     st = torch.cuda.current_stream().cuda_stream
     hd = LayerHandle(C, 3, -0.1, (1, 1), True, True, _abi.PRECISIONS[prec], _abi.LAYOUT_3BY3)
@@ -54,7 +54,8 @@ def bench_layer(N, H, W, C, prec, min_bytes=400e6, reps=3):
             for i in range(min(nbuf, 4)):
                 fn(i)
         except Exception as e:  # unsupported combination: report, keep going
-            print("%-6s %s %-9s unsupported: %s" % (name, (N, H, W, C), prec, e), flush=True)
+            if not quiet:
+                print("%-6s %s %-9s unsupported: %s" % (name, (N, H, W, C), prec, e), flush=True)
             continue
         torch.cuda.synchronize()
         best = 1e30
@@ -70,8 +71,9 @@ def bench_layer(N, H, W, C, prec, min_bytes=400e6, reps=3):
         rec = {"kernel": name, "shape": [N, H, W, C], "mode": prec, "us": best, "alg_bytes": nbytes,
                "GBps": nbytes / best * 1e-3, "alg_TFLOPs": fl / best * 1e-6}
         out.append(rec)
-        print("%-6s %s %-9s %9.1f us  %7.1f GB/s (alg)  %7.1f TFLOP/s (alg)" %
-              (name, (N, H, W, C), prec, best, rec["GBps"], rec["alg_TFLOPs"]), flush=True)
+        if not quiet:
+            print("%-6s %s %-9s %9.1f us  %7.1f GB/s (alg)  %7.1f TFLOP/s (alg)" %
+                  (name, (N, H, W, C), prec, best, rec["GBps"], rec["alg_TFLOPs"]), flush=True)
     del xs, ys, ms
     torch.cuda.empty_cache()
     return out
