@@ -45,14 +45,29 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode (fp32-grade) measurement of the same step")
-    ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "abi"), choices=["torch", "abi"],
-                    help="gradient exchange: NCCL bound by libb200ode through the C ABI (b200ode_comm_*; default), or "
-                         "torch.distributed NCCL; the other one is measured too and reported under comm_alt")
+    ap.add_argument("--comm", default=os.environ.get("B200ODE_BENCH_COMM", "p2p"), choices=["p2p", "abi", "torch"],
+                    help="gradient exchange: p2p = summed from NVLink peer memory inside the Adam kernel (b200ode_comm_adam_step; "
+                         "default), abi = NCCL all-reduce bound by libb200ode (b200ode_comm_allreduce_bucket), torch = "
+                         "torch.distributed NCCL; a second path is measured too and reported under comm_alt")
     ap.add_argument("--no-configs", action="store_true", help="skip the short cfg1 / cfg2 / cfg4 / cfg5 measurements (other_configs)")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------
+class StdoutToStderr:
+    """Redirect the process' stdout file descriptor to stderr for a block (native libraries printing banners)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -342,17 +357,29 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from differential_equations_resnet_b200 import _abi
     from differential_equations_resnet_b200.training import EulerNet, NetSpec
 
     spec = NetSpec(blocks_per_stage=BLOCKS, filters_per_block=FILTERS, h=H_STEP, gamma=0.0)
-    comm = abi_comm = None
+    comm = abi_comm = p2p_comm = None
     if world > 1:
         from differential_equations_resnet_b200.parallel import AbiComm
-        abi_comm = AbiComm(rank, world)          # NCCL bound by libb200ode itself (b200ode_comm_*)
-        comm = abi_comm if args.comm == "abi" else None
-    net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
+        with StdoutToStderr():                   # NCCL prints its version banner on stdout: keep stdout = ONE JSON line
+            abi_comm = AbiComm(rank, world)      # NCCL bound by libb200ode itself (b200ode_comm_*)
+            if args.comm == "p2p":
+                try:
+                    p2p_comm = AbiComm(rank, world, p2p=True)
+                    net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=p2p_comm)
+                    comm = p2p_comm
+                except Exception as e:           # no peer access between these GPUs: NCCL all-reduce through the C ABI
+                    sys.stderr.write("p2p exchange unavailable (%s); using the NCCL path\n" % e)
+                    args.comm, p2p_comm = "abi", None
+        if args.comm != "p2p":
+            comm = abi_comm if args.comm == "abi" else None
+    if comm is None or not getattr(comm, "p2p", False):
+        net = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
     B = args.batch
     g = torch.Generator().manual_seed(1236 + rank)
     img_h = torch.randint(0, 256, (B, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory()
@@ -441,7 +468,7 @@ def run_b200(args):
     # form of cfg3 (128 images GLOBAL, 128 / N per GPU; SURVEY.md 8d "stated separately").
     comm_alt = strong = None
     if world > 1:
-        alt = None if args.comm == "abi" else abi_comm
+        alt = None if args.comm == "abi" else abi_comm      # p2p / torch -> NCCL through the C ABI; abi -> torch.distributed
         net_a = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=alt)
         net_a.train_step(img_d, lab_d)
         if use_graph:
@@ -450,13 +477,14 @@ def run_b200(args):
         else:
             a_step = lambda: net_a.train_step(img_d, lab_d)
         ms_a = timed(a_step, K, 3)
-        comm_alt = {"comm": "torch.distributed" if args.comm == "abi" else "abi (b200ode_comm_*)", "value": world * B * K / (ms_a * 1e-3),
+        comm_alt = {"comm": "torch.distributed NCCL all-reduce" if args.comm == "abi" else "NCCL all-reduce through the C ABI (b200ode_comm_allreduce_bucket)",
+                    "value": world * B * K / (ms_a * 1e-3),
                     "unit": "images/s", "ms_per_step": ms_a / K}
         net_a.release()
         del net_a, a_step
         if BATCH_PER_GPU % world == 0:
             Bs = BATCH_PER_GPU // world
-            net_g = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=comm)
+            net_g = EulerNet(spec, precision=args.precision, seed=1236, world_size=world, comm=abi_comm)
             net_g.train_step(img_d[:Bs].contiguous(), lab_d[:Bs].contiguous())
             if use_graph:
                 net_g.capture(img_d[:Bs].contiguous(), lab_d[:Bs].contiguous())
@@ -542,7 +570,9 @@ def run_b200(args):
                                    "fwd+loss+bwd%s+Adam" % ("+allreduce" if world > 1 else ""),
                        "global_batch": world * B, "batch_per_gpu": B, "h": H_STEP, "gamma": 0.0,
                        "precision": args.precision, "parallelism": "dp%d" % world, "cuda_graph": use_graph,
-                       "comm": ("abi (NCCL bound by libb200ode, b200ode_comm_*)" if comm is not None else "torch.distributed NCCL") if world > 1 else None,
+                       "comm": {"p2p": "p2p: gradients summed from NVLink peer memory inside the Adam kernel (b200ode_comm_adam_step)",
+                                "abi": "abi: NCCL all-reduce bound by libb200ode (b200ode_comm_allreduce_bucket)",
+                                "torch": "torch.distributed NCCL all-reduce"}[args.comm] if world > 1 else None,
                        "l2": "per-step working set (saved activations + dZ of 108 layers, >1 GB) exceeds the 126 MB L2; "
                              "each microbenchmarked chain launch streams 75-300 MB"},
             "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": int(img_h.numel() + lab_h.numel() * 4),
@@ -572,8 +602,9 @@ def run_b200(args):
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
-        if abi_comm is not None:
-            abi_comm.close()
+        for c in (p2p_comm, abi_comm):
+            if c is not None:
+                c.close()
         dist.destroy_process_group()
 
 

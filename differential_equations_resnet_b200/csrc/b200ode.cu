@@ -226,6 +226,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -240,15 +241,24 @@ int load_nccl() {
   a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
   a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
   a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
   a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.AllGather || !a.CommDestroy || !a.GetErrorString)
     return fail(B200ODE_ERR_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
   g_nccl = a;
   return 0;
 }
 }  // namespace
-struct b200ode_comm { void* nccl; int nranks, rank; };
+struct b200ode_comm {
+  void* nccl;
+  int nranks, rank;
+  // peer-memory gradient bucket (b200ode_comm_shared_alloc): [flags 4 KB | n floats], mapped into every rank (CUDA IPC)
+  void* region;                       // this rank's allocation
+  size_t region_floats;
+  void* peer[B200ODE_MAX_RANKS];      // peer[r] = rank r's region in this process' address space (peer[rank] = region)
+  unsigned* ctl;                      // local control words: [0] epoch, [1] block counter
+};
 #define NCCL_TRY(x)                                                                                          \
   do {                                                                                                       \
     int e__ = (x);                                                                                           \
@@ -270,7 +280,10 @@ extern "C" int b200ode_comm_init(int nranks, int rank, const void* nccl_unique_i
   memcpy(&id, nccl_unique_id, sizeof(id));
   void* c = nullptr;
   NCCL_TRY(g_nccl.CommInitRank(&c, nranks, id, rank));
-  *out = new b200ode_comm{c, nranks, rank};
+  b200ode_comm* cm = new b200ode_comm();
+  memset(cm, 0, sizeof(*cm));
+  cm->nccl = c; cm->nranks = nranks; cm->rank = rank;
+  *out = cm;
   return 0;
 }
 extern "C" int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, size_t n, void* stream) {
@@ -279,8 +292,87 @@ extern "C" int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, s
   NCCL_TRY(g_nccl.AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->nccl, (cudaStream_t)stream));
   return 0;
 }
+// ---- peer-memory gradient bucket + all-reduce fused into the optimiser step (kernels_bn.cuh: adam_p2p_kernel) ----
+enum { P2P_FLAG_BYTES = 4096 };   // arrive[MAX_RANKS] at +0, done[MAX_RANKS] at +1024 (uint32 each), then the floats
+
+extern "C" int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out) {
+  if (!comm || !local_out || n_floats == 0) return fail(B200ODE_ERR_INVALID, "comm/local_out is NULL or n_floats == 0");
+  if (comm->region) return fail(B200ODE_ERR_INVALID, "this communicator already owns a shared bucket");
+  if (comm->nranks > B200ODE_MAX_RANKS) return fail(B200ODE_ERR_UNSUPPORTED, "peer-memory exchange supports up to %d ranks", B200ODE_MAX_RANKS);
+  const size_t bytes = P2P_FLAG_BYTES + ((n_floats + 3) / 4 * 4) * sizeof(float);
+  void* reg = nullptr;
+  CUDA_TRY(cudaMalloc(&reg, bytes));
+  CUDA_TRY(cudaMemset(reg, 0, bytes));
+  cudaIpcMemHandle_t mine;
+  CUDA_TRY(cudaIpcGetMemHandle(&mine, reg));
+  // exchange the 64-byte handles with the one out-of-band channel the library has: an all-gather of bytes
+  char* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, (size_t)(comm->nranks + 1) * sizeof(mine)));
+  CUDA_TRY(cudaMemcpy(dev, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  NCCL_TRY(g_nccl.AllGather(dev, dev + sizeof(mine), sizeof(mine), /*ncclInt8*/ 0, comm->nccl, nullptr));
+  CUDA_TRY(cudaStreamSynchronize(nullptr));
+  cudaIpcMemHandle_t all[B200ODE_MAX_RANKS];
+  CUDA_TRY(cudaMemcpy(all, dev + sizeof(mine), (size_t)comm->nranks * sizeof(mine), cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  for (int r = 0; r < comm->nranks; ++r) {
+    if (r == comm->rank) { comm->peer[r] = reg; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&comm->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B200ODE_ERR_UNSUPPORTED, "cannot map rank %d's gradient bucket (cudaIpcOpenMemHandle: %s): no peer access between these GPUs",
+                  r, cudaGetErrorString(e));
+    }
+  }
+  CUDA_TRY(cudaMalloc((void**)&comm->ctl, 64));
+  CUDA_TRY(cudaMemset(comm->ctl, 0, 64));
+  comm->region = reg; comm->region_floats = n_floats;
+  *local_out = reinterpret_cast<float*>(static_cast<char*>(reg) + P2P_FLAG_BYTES);
+  // nobody touches a peer's flags before every rank has zeroed its region
+  float* tmp = *local_out;
+  NCCL_TRY(g_nccl.AllReduce(tmp, tmp, 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->nccl, nullptr));
+  CUDA_TRY(cudaStreamSynchronize(nullptr));
+  CUDA_TRY(cudaMemset(tmp, 0, 16));
+  return 0;
+}
+
+extern "C" int b200ode_comm_adam_step(b200ode_comm_t* comm, float* params, const float* grads_local, float* m, float* v, int64_t n,
+                                      float lr, float beta1, float beta2, float eps, const int32_t* step_counter, void* stream) {
+  if (!comm || !params || !grads_local || !m || !v || !step_counter) return fail(B200ODE_ERR_INVALID, "NULL argument");
+  if (!comm->region) return fail(B200ODE_ERR_INVALID, "b200ode_comm_shared_alloc must run first");
+  if (n == 0) return 0;
+  const float* base = reinterpret_cast<const float*>(static_cast<char*>(comm->region) + P2P_FLAG_BYTES);
+  const long long off = grads_local - base;
+  if (off < 0 || (size_t)(off + n) > comm->region_floats) return fail(B200ODE_ERR_INVALID, "grads_local is not inside the shared bucket");
+  if ((off & 3) || (n & 3) || !aligned16(params, m, v)) return fail(B200ODE_ERR_INVALID, "slice offset / length must be multiples of 4 floats, pointers 16-byte aligned");
+  P2PAdamArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nranks = comm->nranks; A.rank = comm->rank;
+  for (int r = 0; r < comm->nranks; ++r) {
+    char* reg = static_cast<char*>(comm->peer[r]);
+    A.arrive[r] = reinterpret_cast<unsigned*>(reg);
+    A.done[r] = reinterpret_cast<unsigned*>(reg + 1024);
+    A.g[r] = reinterpret_cast<const float4*>(reg + P2P_FLAG_BYTES) + off / 4;
+  }
+  A.ctl = comm->ctl;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const long long n4 = n / 4, want = (n4 + 255) / 256;
+  adam_p2p_kernel<<<(unsigned)(want < sms ? want : sms), 256, 0, (cudaStream_t)stream>>>(A, (float4*)params, (float4*)m, (float4*)v, n4,
+                                                                                       step_counter, lr, beta1, beta2, eps,
+                                                                                       1.0f / (float)comm->nranks);
+  LAUNCH_CHECK("adam_p2p_kernel");
+  return 0;
+}
+
 extern "C" int b200ode_comm_destroy(b200ode_comm_t* comm) {
   if (!comm) return 0;
+  if (comm->region) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < comm->nranks; ++r)
+      if (r != comm->rank && comm->peer[r]) cudaIpcCloseMemHandle(comm->peer[r]);
+    cudaFree(comm->region);
+    cudaFree(comm->ctl);
+    comm->region = nullptr;
+  }
   int e = g_nccl.CommDestroy ? g_nccl.CommDestroy(comm->nccl) : 0;
   delete comm;
   return e ? fail(B200ODE_ERR_CUDA, "ncclCommDestroy failed: %s", g_nccl.GetErrorString(e)) : 0;

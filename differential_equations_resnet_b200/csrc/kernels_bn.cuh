@@ -227,4 +227,88 @@ __global__ void __launch_bounds__(256) adam_vec_kernel(float4* __restrict__ p, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient all-reduce FUSED into the optimiser step over NVLink / NVSwitch peer memory: every rank's
+// gradient bucket is mapped into all ranks (CUDA IPC); the Adam kernel of rank r reads the N replicas of each gradient
+// vector straight from peer memory, sums them in rank order (the same order on every rank -> parameters stay
+// bit-identical across ranks) and updates its own parameter replica.  No all-reduce launch, no NCCL kernel competing
+// with the persistent chain kernels for SMs; 3.5 MB x (N-1) of NVLink reads per step for the cfg3 net.
+// Synchronisation = two flag barriers in peer memory with a monotonically increasing epoch kept on the device:
+//   arrive: rank r stores the epoch into slot r of every rank's arrive[] (its gradients are complete: stream order),
+//           every block waits until all slots of the LOCAL arrive[] carry the epoch, then reads the peers' gradients;
+//   done:   the last block to finish stores the epoch into slot r of every rank's done[] and waits for all local slots:
+//           the kernel does not complete before every peer has finished reading this rank's gradients, so the next
+//           step's weight-gradient kernels may overwrite them.
+// Every rank must issue the same sequence of calls (same slices, same order).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef B200ODE_MAX_RANKS
+#define B200ODE_MAX_RANKS 8
+#endif
+struct P2PAdamArgs {
+  const float4* g[B200ODE_MAX_RANKS];
+  unsigned* arrive[B200ODE_MAX_RANKS];
+  unsigned* done[B200ODE_MAX_RANKS];
+  unsigned* ctl;       // local: [0] epoch of the last completed call, [1] finished-block counter
+  int nranks, rank;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) adam_p2p_kernel(P2PAdamArgs A, float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                                       long long n4, const int* __restrict__ step, float lr, float b1, float b2, float eps,
+                                                       float gscale) {
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(A.ctl) + 1u;   // stable until the last block of THIS call bumps it
+  if (blockIdx.x == 0 && threadIdx.x < A.nranks) st_release_sys(A.arrive[threadIdx.x] + A.rank, epoch);
+  if (threadIdx.x < A.nranks) {
+    const unsigned* slot = A.arrive[A.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(slot) - epoch) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  const float t = (float)(*step);
+  const float lr_t = lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+  auto one = [&](float& pp, float gg, float& mm, float& vv) {
+    const float gi = gg * gscale;
+    mm = b1 * mm + (1.0f - b1) * gi;
+    vv = b2 * vv + (1.0f - b2) * gi * gi;
+    pp -= lr_t * mm / (sqrtf(vv) + eps);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gr[B200ODE_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < B200ODE_MAX_RANKS; ++r)
+      if (r < A.nranks) gr[r] = ld_relaxed_sys_v4(A.g[r] + i);          // all replicas in flight together
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    float4 gs = gr[0];
+#pragma unroll
+    for (int r = 1; r < B200ODE_MAX_RANKS; ++r)
+      if (r < A.nranks) { gs.x += gr[r].x; gs.y += gr[r].y; gs.z += gr[r].z; gs.w += gr[r].w; }   // rank order: identical on every rank
+    one(pp.x, gs.x, mm.x, vv.x); one(pp.y, gs.y, mm.y, vv.y); one(pp.z, gs.z, mm.z, vv.z); one(pp.w, gs.w, mm.w, vv.w);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+  __syncthreads();
+  __shared__ unsigned last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(A.ctl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x < A.nranks) {
+    st_release_sys(A.done[threadIdx.x] + A.rank, epoch);
+    const unsigned* slot = A.done[A.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(slot) - epoch) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { A.ctl[1] = 0u; __threadfence(); A.ctl[0] = epoch; }
+}
+
 }  // namespace b200ode

@@ -50,7 +50,10 @@ class AbiComm:
     graph).  The 128-byte unique id travels from rank 0 through the already initialised `torch.distributed` group
     (any backend; only a broadcast of 128 bytes) or, without one, through `id_bytes` supplied by the launcher."""
 
-    def __init__(self, rank: int, world_size: int, id_bytes: bytes = None):
+    def __init__(self, rank: int, world_size: int, id_bytes: bytes = None, p2p: bool = False):
+        """p2p=True: the trainer keeps its gradient bucket in peer-mapped memory (`shared_bucket`) and the all-reduce
+        happens INSIDE the Adam kernel (`adam_step`: b200ode_comm_adam_step reads the N gradient replicas over NVLink in
+        rank order); p2p=False: NCCL all-reduce of bucket slices on a side stream (`allreduce_async`)."""
         import ctypes
         from . import _abi
         lib = _abi.lib()
@@ -69,6 +72,30 @@ class AbiComm:
         _abi.check(lib.b200ode_comm_init(world_size, rank, self._id, ctypes.byref(h)))
         self._h = h
         self.stream = torch.cuda.Stream()
+        self.p2p = bool(p2p) and world_size > 1
+        self._bucket = None
+
+    def shared_bucket(self, n_floats: int) -> torch.Tensor:
+        """This rank's gradient bucket inside the library's peer-mapped region (collective call: every rank, same size),
+        as a zero-copy torch tensor."""
+        import ctypes
+        ptr = ctypes.c_void_p()
+        self._abi.check(self._lib.b200ode_comm_shared_alloc(self._h, int(n_floats), ctypes.byref(ptr)))
+
+        class _Dev:   # __cuda_array_interface__ view of the library-owned allocation (kept alive by the communicator)
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr.value), False), "version": 3,
+                                      "strides": None}
+        self._bucket = torch.as_tensor(d, device="cuda")
+        return self._bucket
+
+    def adam_step(self, theta, grad_slice, m, v, step_counter, lr, eps, stream=None):
+        """Adam over one slice with the gradient summed over ranks from peer memory inside the kernel (1/world folded in)."""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._abi.check(self._lib.b200ode_comm_adam_step(self._h, theta.data_ptr(), grad_slice.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                         grad_slice.numel(), float(lr), 0.9, 0.999, float(eps),
+                                                         step_counter.data_ptr(), st))
 
     def allreduce_async(self, flat_slice: torch.Tensor):
         ready = torch.cuda.Event()

@@ -356,7 +356,7 @@ class EulerNet:
                     n_bn += 4 - (off + n_torch + n_bn) % 4
                 seg[1].bn_offset = off + n_torch + n_bn
                 n_bn += seg[1].n * 2 * seg[1].C
-        self.n_params = off + n_torch + n_bn
+        self.n_params = (off + n_torch + n_bn + 3) // 4 * 4      # whole 16-byte vectors (the pad is never read by a layer)
         theta = torch.zeros(self.n_params, dtype=torch.float32)
         for seg in self.segments:
             if seg[0] == "chain" and seg[1].bn:
@@ -382,7 +382,10 @@ class EulerNet:
             self.torch_params[name] = (cur, shape)
             cur += n
         self.theta = theta.to(self.device)
-        self.grad = torch.zeros_like(self.theta)
+        self.p2p = bool(getattr(comm, "p2p", False)) and world_size > 1
+        # peer-memory exchange: the gradient bucket lives in the communicator's peer-mapped region, the all-reduce happens
+        # inside the Adam kernel (parallel.AbiComm.adam_step)
+        self.grad = comm.shared_bucket(self.n_params) if self.p2p else torch.zeros_like(self.theta)
         self.adam_m = torch.zeros_like(self.theta)
         self.adam_v = torch.zeros_like(self.theta)
         self.theta_euler = self.theta[:off]
@@ -621,8 +624,11 @@ class EulerNet:
         # before Adam.  The fork / join is captured in the CUDA graph like everything else.
         d = nb["head_dx"]
         side = self._side_stream if overlap_wgrad else main
-        # data parallel only: on one GPU the extra Adam launches cost more than the ~10 us they take off the critical path
-        early = self._early_slices(nb) if overlap_wgrad and self.world_size > 1 and not os.environ.get("B200ODE_NO_EARLY_ADAM") else None
+        # Opt-in (B200ODE_EARLY_ADAM / B200ODE_AR_OVERLAP): exchanging slices under the backward pass was measured SLOWER than
+        # one exchange at the end (N=2: 1.239 vs 1.198 ms/step) -- NCCL's CTAs cannot co-reside with the one-CTA-per-SM chain
+        # kernels (registers), so a chain launch that meets them runs a second wave.  Default: peer-memory exchange inside the
+        # Adam kernel (p2p), else ONE all-reduce of the whole bucket before Adam.
+        early = self._early_slices(nb) if overlap_wgrad and self.world_size > 1 and not self.p2p and os.environ.get("B200ODE_EARLY_ADAM") else None
         for e in reversed(nb["plan"]):
             if e["kind"] == "chain":
                 ch = e["chain"]
@@ -633,9 +639,9 @@ class EulerNet:
                     side.wait_event(ev)
                 with torch.cuda.stream(side):
                     ch.fused_wgrad(self.grad_euler)
-                    if self.world_size > 1 and not os.environ.get("B200ODE_NO_OVERLAP"):
-                        # the stage's packed gradients are final: start their all-reduce now (NCCL stream), it
-                        # overlaps the rest of the backward pass; joined in _optimizer before Adam
+                    if self.world_size > 1 and not self.p2p and os.environ.get("B200ODE_AR_OVERLAP"):
+                        # the stage's packed gradients are final: start their all-reduce now (NCCL stream); joined in
+                        # _optimizer before Adam (opt-in, see above)
                         lo, hi = ch.offset, ch.offset + ch.n * ch.np_layer
                         self._pending.append(self._ar_async(self.grad_euler[lo:hi]))
                         self._reduced_upto = min(self._reduced_upto, lo)
@@ -770,6 +776,10 @@ class EulerNet:
     def _optimizer(self):
         """All-reduce (data parallel) and Adam for every slice of the flat bucket the step has not updated yet
         (`_adam_done`: slices exchanged and updated early, under the tail of the backward pass)."""
+        if self.p2p:
+            self.comm.adam_step(self.theta, self.grad, self.adam_m, self.adam_v, self.step_counter, self.lr, self.adam_eps)
+            _abi.check(_abi.lib().b200ode_increment(_ptr(self.step_counter), _stream_ptr()))
+            return
         done = sorted(getattr(self, "_adam_done", None) or [])
         self._adam_done = []
         rest, cur = [], 0

@@ -272,6 +272,19 @@ int b200ode_comm_unique_id(void* id_out /* B200ODE_UNIQUE_ID_BYTES bytes */);
 int b200ode_comm_init(int nranks, int rank, const void* nccl_unique_id, b200ode_comm_t** out);
 /* in-place sum of buf[0..n) (device pointer, fp32) over all ranks, stream ordered, graph capturable */
 int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, size_t n, void* stream);
+/* Peer-memory exchange fused into the optimiser (one box, NVLink / NVSwitch, up to B200ODE_MAX_RANKS ranks):
+ * b200ode_comm_shared_alloc (collective, once per communicator) allocates this rank's gradient bucket of n_floats inside
+ * the library, maps it into every other rank (CUDA IPC; the handles travel through the communicator) and returns the
+ * LOCAL pointer: the caller's weight-gradient kernels write their gradients there.  b200ode_comm_adam_step is
+ * b200ode_adam_step over a slice of that bucket (grads_local points into it; offset and n multiples of 4) whose
+ * gradient is the SUM over ranks, read straight from peer memory inside the Adam kernel in rank order (bit-identical
+ * parameters on every rank) and scaled by 1/nranks: no separate all-reduce launch.  Stream ordered, graph capturable;
+ * every rank must issue the same sequence of calls.  The kernel returns only after all ranks have read this rank's
+ * slice, so the next step may overwrite it. */
+#define B200ODE_MAX_RANKS 8
+int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out);
+int b200ode_comm_adam_step(b200ode_comm_t* comm, float* params, const float* grads_local, float* m, float* v, int64_t n,
+                           float lr, float beta1, float beta2, float eps, const int32_t* step_counter, void* stream);
 int b200ode_comm_destroy(b200ode_comm_t* comm);
 
 /* test hook: number of kernel launches issued by this library in this process */
