@@ -34,7 +34,7 @@ _SIGNATURES = {
     "b200ode_comm_unique_id": (c_int, [c_void_p]),
     "b200ode_comm_init": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(c_void_p)]),
     "b200ode_comm_allreduce_bucket": (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
-    "b200ode_comm_shared_alloc": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "b200ode_comm_shared_alloc": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "b200ode_comm_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                        c_void_p, c_void_p]),
     "b200ode_comm_destroy": (c_int, [c_void_p]),

@@ -295,11 +295,12 @@ extern "C" int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, s
 // ---- peer-memory gradient bucket + all-reduce fused into the optimiser step (kernels_bn.cuh: adam_p2p_kernel) ----
 enum { P2P_FLAG_BYTES = 4096 };   // arrive[MAX_RANKS] at +0, done[MAX_RANKS] at +1024 (uint32 each), then the floats
 
-extern "C" int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out) {
+extern "C" int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out, float** params_out) {
   if (!comm || !local_out || n_floats == 0) return fail(B200ODE_ERR_INVALID, "comm/local_out is NULL or n_floats == 0");
   if (comm->region) return fail(B200ODE_ERR_INVALID, "this communicator already owns a shared bucket");
   if (comm->nranks > B200ODE_MAX_RANKS) return fail(B200ODE_ERR_UNSUPPORTED, "peer-memory exchange supports up to %d ranks", B200ODE_MAX_RANKS);
-  const size_t bytes = P2P_FLAG_BYTES + ((n_floats + 3) / 4 * 4) * sizeof(float);
+  const size_t n_pad = (n_floats + 3) / 4 * 4;
+  const size_t bytes = P2P_FLAG_BYTES + 2 * n_pad * sizeof(float);      // [flags | gradient bucket | parameter replica]
   void* reg = nullptr;
   CUDA_TRY(cudaMalloc(&reg, bytes));
   CUDA_TRY(cudaMemset(reg, 0, bytes));
@@ -327,6 +328,7 @@ extern "C" int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, 
   CUDA_TRY(cudaMemset(comm->ctl, 0, 64));
   comm->region = reg; comm->region_floats = n_floats;
   *local_out = reinterpret_cast<float*>(static_cast<char*>(reg) + P2P_FLAG_BYTES);
+  if (params_out) *params_out = *local_out + n_pad;
   // nobody touches a peer's flags before every rank has zeroed its region
   float* tmp = *local_out;
   NCCL_TRY(g_nccl.AllReduce(tmp, tmp, 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->nccl, nullptr));
@@ -344,6 +346,10 @@ extern "C" int b200ode_comm_adam_step(b200ode_comm_t* comm, float* params, const
   const long long off = grads_local - base;
   if (off < 0 || (size_t)(off + n) > comm->region_floats) return fail(B200ODE_ERR_INVALID, "grads_local is not inside the shared bucket");
   if ((off & 3) || (n & 3) || !aligned16(params, m, v)) return fail(B200ODE_ERR_INVALID, "slice offset / length must be multiples of 4 floats, pointers 16-byte aligned");
+  const size_t n_pad = (comm->region_floats + 3) / 4 * 4;
+  // parameters inside the shared region at the gradient's offset -> two-shot exchange (each rank reduces and updates
+  // 1/nranks of the slice and writes the new parameters into every replica); private parameters -> one-shot
+  const bool two_shot = params == base + n_pad + off;
   P2PAdamArgs A;
   memset(&A, 0, sizeof(A));
   A.nranks = comm->nranks; A.rank = comm->rank;
@@ -352,10 +358,19 @@ extern "C" int b200ode_comm_adam_step(b200ode_comm_t* comm, float* params, const
     A.arrive[r] = reinterpret_cast<unsigned*>(reg);
     A.done[r] = reinterpret_cast<unsigned*>(reg + 1024);
     A.g[r] = reinterpret_cast<const float4*>(reg + P2P_FLAG_BYTES) + off / 4;
+    A.pw[r] = reinterpret_cast<float4*>(reg + P2P_FLAG_BYTES) + (n_pad + off) / 4;
   }
   A.ctl = comm->ctl;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  const long long n4 = n / 4, want = (n4 + 255) / 256;
+  const long long n4 = n / 4;
+  if (two_shot) {
+    const long long per = (n4 + comm->nranks - 1) / comm->nranks, want = (per + 255) / 256;
+    adam_p2p_shard_kernel<<<(unsigned)(want < sms ? want : sms), 256, 0, (cudaStream_t)stream>>>(A, (float4*)m, (float4*)v, n4, step_counter, lr,
+                                                                                               beta1, beta2, eps, 1.0f / (float)comm->nranks);
+    LAUNCH_CHECK("adam_p2p_shard_kernel");
+    return 0;
+  }
+  const long long want = (n4 + 255) / 256;
   adam_p2p_kernel<<<(unsigned)(want < sms ? want : sms), 256, 0, (cudaStream_t)stream>>>(A, (float4*)params, (float4*)m, (float4*)v, n4,
                                                                                        step_counter, lr, beta1, beta2, eps,
                                                                                        1.0f / (float)comm->nranks);
@@ -1667,6 +1682,17 @@ extern "C" int b200ode_stem_fwd(const void* images, int images_are_u8, float sub
   if (int rc = device_check()) return rc;
   if (N == 0) return 0;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, 1, 1);
+  const size_t psm = ((size_t)9 * Cin * Cout + Cout + 256) * sizeof(float);
+  if ((Cout == 8 || Cout == 16 || Cout == 32) && psm <= 48 * 1024 && aligned16(kernel_hwio, out)) {
+    // one thread per pixel, all filters: weights + the uint8 normalisation table in shared memory
+    const long long npix = (long long)N * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 8) stem_fwd_pixel_kernel<8><<<blocks_for(npix, 256), 256, psm, st>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev, normalize, kernel_hwio, bias, out);
+    else if (Cout == 16) stem_fwd_pixel_kernel<16><<<blocks_for(npix, 256), 256, psm, st>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev, normalize, kernel_hwio, bias, out);
+    else stem_fwd_pixel_kernel<32><<<blocks_for(npix, 256), 256, psm, st>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev, normalize, kernel_hwio, bias, out);
+    LAUNCH_CHECK("stem_fwd_pixel_kernel");
+    return 0;
+  }
   const long long total = (long long)N * H * W * (Cout / 4);
   stem_fwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g, images, images_are_u8, subtract_mean, divide_by_stddev,
                                                                            normalize, kernel_hwio, bias, out);

@@ -248,6 +248,7 @@ struct P2PAdamArgs {
   const float4* g[B200ODE_MAX_RANKS];
   unsigned* arrive[B200ODE_MAX_RANKS];
   unsigned* done[B200ODE_MAX_RANKS];
+  float4* pw[B200ODE_MAX_RANKS];   // two-shot: every rank's parameter replica at the slice offset
   unsigned* ctl;       // local: [0] epoch of the last completed call, [1] finished-block counter
   int nranks, rank;
 };
@@ -300,6 +301,64 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(P2PAdamArgs A, float4* __
     __threadfence();
     last = atomicAdd(A.ctl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
   }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x < A.nranks) {
+    st_release_sys(A.done[threadIdx.x] + A.rank, epoch);
+    const unsigned* slot = A.done[A.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(slot) - epoch) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { A.ctl[1] = 0u; __threadfence(); A.ctl[0] = epoch; }
+}
+
+// Two-shot form (parameters live in the peer-mapped region too): rank r sums the N gradient replicas of ITS 1/N shard of
+// the slice (reduce-scatter over NVLink reads), applies Adam to that shard (its moments m, v are the only ones it ever
+// touches: optimiser state is sharded for free) and stores the new parameters into every rank's replica (all-gather
+// over NVLink writes).  (N-1)/N of the slice crosses NVLink in each direction instead of (N-1) x the slice.  The `done`
+// barrier now also means: every rank's shard has landed in this rank's parameter replica.
+__global__ void __launch_bounds__(256) adam_p2p_shard_kernel(P2PAdamArgs A, float4* __restrict__ m, float4* __restrict__ v, long long n4,
+                                                             const int* __restrict__ step, float lr, float b1, float b2, float eps,
+                                                             float gscale) {
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(A.ctl) + 1u;
+  if (blockIdx.x == 0 && threadIdx.x < A.nranks) st_release_sys(A.arrive[threadIdx.x] + A.rank, epoch);
+  if (threadIdx.x < A.nranks) {
+    const unsigned* slot = A.arrive[A.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(slot) - epoch) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  const float t = (float)(*step);
+  const float lr_t = lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+  auto one = [&](float& pp, float gg, float& mm, float& vv) {
+    const float gi = gg * gscale;
+    mm = b1 * mm + (1.0f - b1) * gi;
+    vv = b2 * vv + (1.0f - b2) * gi * gi;
+    pp -= lr_t * mm / (sqrtf(vv) + eps);
+  };
+  const long long per = (n4 + A.nranks - 1) / A.nranks;
+  const long long lo = per * A.rank, hi = lo + per < n4 ? lo + per : n4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float4* p = A.pw[A.rank];
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    float4 gr[B200ODE_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < B200ODE_MAX_RANKS; ++r)
+      if (r < A.nranks) gr[r] = ld_relaxed_sys_v4(A.g[r] + i);
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    float4 gs = gr[0];
+#pragma unroll
+    for (int r = 1; r < B200ODE_MAX_RANKS; ++r)
+      if (r < A.nranks) { gs.x += gr[r].x; gs.y += gr[r].y; gs.z += gr[r].z; gs.w += gr[r].w; }
+    one(pp.x, gs.x, mm.x, vv.x); one(pp.y, gs.y, mm.y, vv.y); one(pp.z, gs.z, mm.z, vv.z); one(pp.w, gs.w, mm.w, vv.w);
+    m[i] = mm; v[i] = vv;
+#pragma unroll
+    for (int r = 0; r < B200ODE_MAX_RANKS; ++r)
+      if (r < A.nranks) A.pw[r][i] = pp;                 // own replica and all peers'
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned last;
+  if (threadIdx.x == 0) last = atomicAdd(A.ctl + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
   if (!last) return;
   if (threadIdx.x < A.nranks) {

@@ -58,6 +58,60 @@ __global__ void stem_fwd_kernel(GlueConv g, const void* __restrict__ img, int is
   *reinterpret_cast<float4*>(out + (((long long)n * g.H + y) * g.W + x) * g.Cout + c0) = acc;
 }
 
+// Stem forward, one thread per output pixel computing all COUT channels (COUT = 8, 16 or 32): the 27 * COUT weights and,
+// for uint8 images, the 256-entry table of normalised input values ((v - sub) / div: two IEEE operations per input
+// element in the generic kernel, 27 divisions per thread) live in shared memory; weight reads are warp-uniform broadcasts.
+// Same accumulation order as stem_fwd_kernel (bias, then taps row-major, then input channels): bit-identical results.
+template <int COUT>
+__global__ void __launch_bounds__(256) stem_fwd_pixel_kernel(GlueConv g, const void* __restrict__ img, int is_u8, float sub, float div,
+                                                             int norm, const float* __restrict__ Wk, const float* __restrict__ bias,
+                                                             float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* wsm = sm;                      // [9 * Cin][COUT]
+  float* bsm = wsm + 9 * g.Cin * COUT;  // [COUT]
+  float* lut = bsm + COUT;              // [256] (uint8 input)
+  for (int i = threadIdx.x; i < 9 * g.Cin * COUT; i += blockDim.x) wsm[i] = Wk[i];
+  if (threadIdx.x < COUT) bsm[threadIdx.x] = bias[threadIdx.x];
+  if (is_u8) {
+    const float v = (float)threadIdx.x;
+    if (threadIdx.x < 256) lut[threadIdx.x] = norm ? __fdiv_rn(__fsub_rn(v, sub), div) : v;
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)g.N * g.H * g.W) return;
+  const int x = (int)(pix % g.W), y = (int)((pix / g.W) % g.H);
+  const long long n = pix / ((long long)g.W * g.H);
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = bsm[j];
+  const uint8_t* i8 = reinterpret_cast<const uint8_t*>(img);
+  const float* i32 = reinterpret_cast<const float*>(img);
+  for (int a = 0; a < 3; ++a) {
+    const int iy = y + a - 1;
+    if (iy < 0 || iy >= g.H) continue;
+    for (int b = 0; b < 3; ++b) {
+      const int ix = x + b - 1;
+      if (ix < 0 || ix >= g.W) continue;
+      const long long ib = ((n * g.H + iy) * g.W + ix) * g.Cin;
+      const float* wt = wsm + (a * 3 + b) * g.Cin * COUT;
+      for (int ci = 0; ci < g.Cin; ++ci) {
+        const float v = is_u8 ? lut[i8[ib + ci]] : (norm ? __fdiv_rn(__fsub_rn(i32[ib + ci], sub), div) : i32[ib + ci]);
+        const float4* w4 = reinterpret_cast<const float4*>(wt + ci * COUT);
+#pragma unroll
+        for (int j = 0; j < COUT / 4; ++j) {
+          const float4 w = w4[j];
+          acc[4 * j] = fmaf(v, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  float4* op = reinterpret_cast<float4*>(out + pix * COUT);
+#pragma unroll
+  for (int j = 0; j < COUT / 4; ++j)
+    op[j] = make_float4(fmaxf(acc[4 * j], 0.0f), fmaxf(acc[4 * j + 1], 0.0f), fmaxf(acc[4 * j + 2], 0.0f), fmaxf(acc[4 * j + 3], 0.0f));
+}
+
 // stem weight gradient partials: block = (image, band of `rows` output rows).  The band's masked dz
 // (dout * [out > 0]) and the normalised input patch (zero halo) are staged in shared memory; thread t
 // owns kernel entries o = t, t + blockDim, ... (and the Cout bias entries) and walks the band's pixels.

@@ -79,15 +79,16 @@ class AbiComm:
         """This rank's gradient bucket inside the library's peer-mapped region (collective call: every rank, same size),
         as a zero-copy torch tensor."""
         import ctypes
-        ptr = ctypes.c_void_p()
-        self._abi.check(self._lib.b200ode_comm_shared_alloc(self._h, int(n_floats), ctypes.byref(ptr)))
+        ptr, pptr = ctypes.c_void_p(), ctypes.c_void_p()
+        self._abi.check(self._lib.b200ode_comm_shared_alloc(self._h, int(n_floats), ctypes.byref(ptr), ctypes.byref(pptr)))
 
         class _Dev:   # __cuda_array_interface__ view of the library-owned allocation (kept alive by the communicator)
-            pass
-        d = _Dev()
-        d.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr.value), False), "version": 3,
-                                      "strides": None}
-        self._bucket = torch.as_tensor(d, device="cuda")
+            def __init__(self, p):
+                self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(p), False), "version": 3,
+                                                 "strides": None}
+        self._bucket = torch.as_tensor(_Dev(ptr.value), device="cuda")
+        # parameter replica in the same peer-mapped region: adam_step on it takes the two-shot form (sharded update)
+        self.shared_params = torch.as_tensor(_Dev(pptr.value), device="cuda")
         return self._bucket
 
     def adam_step(self, theta, grad_slice, m, v, step_counter, lr, eps, stream=None):

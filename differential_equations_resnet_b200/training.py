@@ -386,6 +386,11 @@ class EulerNet:
         # peer-memory exchange: the gradient bucket lives in the communicator's peer-mapped region, the all-reduce happens
         # inside the Adam kernel (parallel.AbiComm.adam_step)
         self.grad = comm.shared_bucket(self.n_params) if self.p2p else torch.zeros_like(self.theta)
+        if self.p2p and not os.environ.get("B200ODE_P2P_ONESHOT"):
+            # parameters in the peer-mapped region too: two-shot exchange (this rank reduces and updates 1/world of the bucket
+            # and writes the new parameters into every replica; its Adam moments are the only ones it touches)
+            comm.shared_params.copy_(self.theta)
+            self.theta = comm.shared_params
         self.adam_m = torch.zeros_like(self.theta)
         self.adam_v = torch.zeros_like(self.theta)
         self.theta_euler = self.theta[:off]

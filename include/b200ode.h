@@ -280,9 +280,13 @@ int b200ode_comm_allreduce_bucket(b200ode_comm_t* comm, float* buf, size_t n, vo
  * gradient is the SUM over ranks, read straight from peer memory inside the Adam kernel in rank order (bit-identical
  * parameters on every rank) and scaled by 1/nranks: no separate all-reduce launch.  Stream ordered, graph capturable;
  * every rank must issue the same sequence of calls.  The kernel returns only after all ranks have read this rank's
- * slice, so the next step may overwrite it. */
+ * slice, so the next step may overwrite it.
+ * Two-shot form: the region also holds a parameter replica (*params_out, nullable).  When `params` of
+ * b200ode_comm_adam_step points into it at the gradient's offset, every rank sums and updates only its 1/nranks shard
+ * of the slice (its m, v entries are the only ones touched: sharded optimiser state) and stores the new parameters
+ * into every rank's replica: (nranks-1)/nranks of the slice crosses NVLink each way instead of (nranks-1) x. */
 #define B200ODE_MAX_RANKS 8
-int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out);
+int b200ode_comm_shared_alloc(b200ode_comm_t* comm, size_t n_floats, float** local_out, float** params_out);
 int b200ode_comm_adam_step(b200ode_comm_t* comm, float* params, const float* grads_local, float* m, float* v, int64_t n,
                            float lr, float beta1, float beta2, float eps, const int32_t* step_counter, void* stream);
 int b200ode_comm_destroy(b200ode_comm_t* comm);
