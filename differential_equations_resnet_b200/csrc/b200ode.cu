@@ -907,7 +907,20 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.xchunks = Cpad / p.CH;
   p.trick = (p.pair || (p.xchunks == 1 && 4 * p.CH <= 128)) ? 1 : 0;
   p.mgroups = 1;
-  if (p.pair) {
+  // double-shift mode (kernels_wgrad_tc.cuh): 16-bit operands, one chunk holds all channels
+  static const int s2_env = getenv("B200ODE_WGRAD_SHIFT2") ? atoi(getenv("B200ODE_WGRAD_SHIFT2")) : 1;   // debug switch
+  // On for C = 64 (measured, 36 layers of 128x8x8x64: 100 -> 67 us; nine M = 64 MMAs per 16 positions become two M = 128 ones).
+  // C = 16 / 32 (B200ODE_WGRAD_SHIFT2=2 forces it): SLOWER than the beta trick (213 vs 180 us, 85 vs 78 us) -- with 32 / 64-byte
+  // operand rows an MMA costs one shared-memory wavefront per (position, chunk) unless the chunks share a 128-byte line, and
+  // chunks one kernel row apart never do; the beta trick's chunks (one position apart) do.
+  p.shift2 = (bf16 && !strict && !p.pair && C == p.CH && (C == 64 || (s2_env == 2 && (C == 16 || C == 32))) && s2_env) ? 1 : 0;
+  if (p.shift2) {
+    p.P = W + 2;
+    if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 254");
+    p.trick = 0;
+    p.s2_M = C == 64 ? 128 : 4 * C; p.s2_N = C == 64 ? 192 : 4 * C; p.s2_nmma = C == 64 ? 2 : 1;
+    p.TG = 9; p.NT = C; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = p.s2_M; p.dchunks = 1;
+  } else if (p.pair) {
     p.TG = 9; p.NT = 32; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 128; p.dchunks = 1;
   } else if (p.trick) {
     p.TG = 9; p.NT = p.CH; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 4 * p.CH; p.dchunks = 1;
@@ -945,7 +958,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int ngroups = p.ntapgroups * p.nngroups * p.mgroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;
   if (p.trick && strict && 3 * p.NT * 2 > 512) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad TMEM");
-  uint32_t cols = (uint32_t)nent * p.NT * (strict ? 2 : 1), pc = 32;
+  uint32_t cols = p.shift2 ? (uint32_t)(p.s2_nmma * p.s2_N) : (uint32_t)nent * p.NT * (strict ? 2 : 1), pc = 32;
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
   const long long Q = (long long)H * p.P;
@@ -960,7 +973,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // the k-steps run into a zeroed pad up to the next multiple of 16 positions.
   static const int rows_env = getenv("B200ODE_WGRAD_ROWS") ? atoi(getenv("B200ODE_WGRAD_ROWS")) : -1;   // debug override (0 = off)
   int rows = 0;
-  if (!strict && !p.trick && !p.pair && p.Mblk == 128 && rows_env != 0) {
+  if (!strict && !p.trick && !p.pair && !p.shift2 && p.Mblk == 128 && rows_env != 0) {
     auto stage_bytes = [&](int R) -> long long {
       const int kt = (R * p.P + UKP - 1) / UKP * UKP;
       const uint32_t xs = align_up((uint32_t)(kt + 2 * p.P + 3) * p.PB, 1024), ds = align_up((uint32_t)kt * p.PB, 1024);
@@ -996,10 +1009,13 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   } else {
   // positions per tile: as large as fits two stages (one as a fallback)
   const int off_max = p.P - 1;   // largest offset of a tile start inside its strip
+  // positions a tile's MMAs reach beyond its last position: x two kernel rows (+ the junk row of the double-shift
+  // mode's fourth chunk), dz nothing (double shift: the three shifted chunks)
+  const int xreach = (p.shift2 ? 3 : 2) * p.P + 8, dreach = p.shift2 ? 3 : 0;
   int KT = 0, stages = 0;
   for (int st_try = 2; st_try >= 1 && !KT; --st_try) {
     for (int kt = p.pair ? 1024 : 512; kt >= UKP; kt -= UKP) {
-      const int RBx = (off_max + kt + 2 * p.P + 8 + p.P - 1) / p.P, RBd = (off_max + kt + p.P - 1) / p.P;
+      const int RBx = (off_max + kt + xreach + p.P - 1) / p.P, RBd = (off_max + kt + dreach + p.P - 1) / p.P;
       if (RBx > 256) continue;
       const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
       const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
@@ -1014,14 +1030,14 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.tpi = (int)((Q + KT - 1) / KT);
   KT = (int)(((Q + p.tpi - 1) / p.tpi + UKP - 1) / UKP * UKP);
   {  // small tiles (small images): deepen the TMA pipeline with the shared memory that is left
-    const int RBx = (off_max + KT + 2 * p.P + 8 + p.P - 1) / p.P, RBd = (off_max + KT + p.P - 1) / p.P;
+    const int RBx = (off_max + KT + xreach + p.P - 1) / p.P, RBd = (off_max + KT + dreach + p.P - 1) / p.P;
     const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
     const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
     while (stages < 6 && stage * (stages + 1) + 1024 + 4608 <= max_smem) ++stages;
   }
   p.KT = KT; p.tstride = KT; p.stages = stages;
-  p.RBx = (off_max + KT + 2 * p.P + 8 + p.P - 1) / p.P;
-  p.RBd = (off_max + KT + p.P - 1) / p.P;
+  p.RBx = (off_max + KT + xreach + p.P - 1) / p.P;
+  p.RBd = (off_max + KT + dreach + p.P - 1) / p.P;
   p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.PB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.PB;
   p.x_chunk_stride = align_up(p.x_chunk_bytes, 1024); p.d_chunk_stride = align_up(p.d_chunk_bytes, 1024);
   }
@@ -1058,6 +1074,8 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   float* ws = (float*)lease.ptr;
   p.partials = ws;
   p.trace = g_trace;
+  static const int wdbg_env = getenv("B200ODE_WGRAD_DBG") ? atoi(getenv("B200ODE_WGRAD_DBG")) : 0;
+  p.dbg = wdbg_env;
   p.bias_partials = ws + (size_t)L * nparts * pstride;
   p.part_layer_stride = (long long)nparts * pstride;
   p.bias_layer_stride = (long long)nparts * C;

@@ -73,6 +73,16 @@ struct WgradParams {
   // zero-padded channels.  The row before each x strip is a zeroed 1 KB pad (x_off = 1024).
   // The accumulators are written raw ([3][128 lanes][32 cols] per part) and gathered by fold_reduce_kernel.
   int pair;
+  // Double-shift mode (16-bit operands, all channels in one chunk: C = 16 / 32 / 64).  BOTH operands carry tap shifts
+  // through their MN-major chunk stride: A (x strip) = s2_M / C chunks one KERNEL ROW apart (chunk a <-> alpha = a),
+  // B (dz strip) = s2_N / C chunks one POSITION apart (chunk j <-> beta = 2 - j, A starting one position after B), so
+  // ONE M = 4C x N = 4C MMA per 16 positions yields all nine taps (7 of its 16 blocks are junk) instead of three
+  // M = 4C x N = C MMAs -- the MMAs of these small layers are bound by a fixed issue cost (~50 cycles measured at
+  // M = 64, N = 16), not by their size.  C = 64: two M = 128 (alpha 0,1 | 2,-) x N = 192 MMAs instead of nine 64 x 64.
+  // Both strips use pitch P = W + 2 with the two zero columns on the LEFT (TMA box from column -2), so the positions a
+  // shifted B chunk reads before / after a row are zeros and nothing outside a strip's rows is ever needed.
+  int shift2, s2_M, s2_N, s2_nmma;
+  int dbg;           // debug (B200ODE_WGRAD_DBG): bit 0 = issue no MMAs, bit 1 = no bias column sums (timing experiments only)
   int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
 };
@@ -106,7 +116,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   const int b_units = p.dchunks * b_upr;           // column units of this CTA's dz strip (power of two, <= 64)
   const int b_roles = p.trick ? 1 : p.ntapgroups * p.mgroups, b_rid = p.trick ? 0 : tapgroup * p.mgroups + mgroup;
   const int b_lo = b_rid * b_units / b_roles, b_n = (b_rid + 1) * b_units / b_roles - b_lo;
-  const bool do_bias = b_n > 0;
+  const bool do_bias = b_n > 0 && !(p.dbg & 2);
   const int part = blockIdx.x;
   const int layer = blockIdx.z;
   const int ukp = p.pair ? 16 : UKP;    // positions per k-step
@@ -152,7 +162,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
         const int n = tile / p.tpi, q0 = (tile % p.tpi) * p.tstride;
         const int row0 = q0 / p.P;
-        const int xc0 = p.pair ? 0 : -1;    // pair mode: the zero slots sit at the END of every row
+        const int xc0 = p.pair ? 0 : p.shift2 ? -2 : -1;    // pair mode: the zero slots sit at the END of every row
+        const int dc0 = p.shift2 ? -2 : 0;
         const uint32_t s = rs, ph = rph;
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
         mbar_wait_sleep_lean(&empty[s], ph ^ 1);
@@ -161,14 +172,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         for (int c = 0; c < p.xchunks; ++c)
           tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk * (p.mgroups > 1) + c * p.CH, xc0, row0 - 1, img_x0 + n);
         for (int c = 0; c < p.dchunks; ++c)
-          tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, 0, row0, img_d0 + n);
+          tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + c * p.CH, dc0, row0, img_d0 + n);
       }
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
-    const bool leader = elect_one();
-    const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
-    const uint32_t idesc = make_instr_desc(BF16 ? (F16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.NT, 1, 1);
+    const bool committer = elect_one();
+    const bool leader = committer && !(p.dbg & 1);
+    const int Mrows = p.pair ? 128 : p.shift2 ? p.s2_M : p.trick ? 4 * p.CH : p.Mblk;
+    const uint32_t idesc = make_instr_desc(BF16 ? (F16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.shift2 ? p.s2_N : p.NT, 1, 1);
     const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
     const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
     const uint32_t hi32 = (sbo >> 4) | (1u << 14) | (lt << 29);
@@ -208,7 +220,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
       uint32_t du = ((smem_base + s * p.stage_stride + p.d_off) >> 4) + off0;
-      if (p.trick && !STRICT) {
+      if (BF16 && p.shift2) {
+        // double shift: chunk stride of A = one kernel row, of B = one position; A starts one position after B
+        const uint32_t lbo_a2 = ((((uint32_t)p.P * (uint32_t)p.RWB) >> 4) & 0x3FFF) << 16;
+        const uint32_t lbo_b2 = (((uint32_t)p.RWB >> 4) & 0x3FFF) << 16;
+        const uint32_t e1 = 2u * (uint32_t)p.P * RU;          // second MMA (C = 64): kernel rows 2 (and a junk row 3)
+        const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)p.s2_N;
+        const bool two = p.s2_nmma == 2;
+        xu += RU;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
+          const uint64_t dsc_b = mk(du, lbo_b2);
+          const uint32_t accum = (it | ks) != 0;
+          const uint64_t a0 = mk(xu, lbo_a2), a1 = mk(xu + e1, lbo_a2);
+          if (leader) {
+            umma_f16(d0, a0, dsc_b, idesc, accum);
+            if (two) umma_f16(d1, a1, dsc_b, idesc, accum);
+          }
+        }
+      } else if (p.trick && !STRICT) {
         // beta trick: three M = 4*CH MMAs per k-step (one per kernel row), offsets held in registers
         // start row of kernel row alpha: alpha*P positions; pair mode: alpha*P/2 - 1 operand rows (8 units each)
         const uint32_t e0 = p.pair ? 0u - 8u : 0u;
@@ -304,11 +334,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           }
         }
       }
-      if (leader) umma_commit(&empty[s]);
+      if (committer) umma_commit(&empty[s]);
       if (it == 0 && lane == 0) tr.mark(3);
       __syncwarp();
     }
-    if (leader) umma_commit(acc_full);
+    if (committer) umma_commit(acc_full);
     if (lane == 0) tr.mark(4);
   } else if (warp < 6) {
     // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
@@ -393,7 +423,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     mbar_wait_sleep(acc_full, 0);
     if (threadIdx.x == 64) tr.mark(6);
     tc_fence_after_sync();
-    const int Mrows = p.pair ? 128 : p.trick ? 4 * p.CH : p.Mblk;
+    const int Mrows = p.pair ? 128 : p.shift2 ? p.s2_M : p.trick ? 4 * p.CH : p.Mblk;
     const int nent = p.trick ? 3 : p.TG * p.MB;
     int m;  // accumulator row held by this thread's TMEM lane
     bool row_ok;
@@ -412,6 +442,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    } else if (p.shift2) {
+      // accumulator e: rows (a, ci) <-> alpha = e * MA + a, columns (j, o) <-> beta = 2 - j
+      const int MA = p.s2_M / p.CH, NB = p.s2_N / p.CH;
+      const int a = m / p.CH, ci = m % p.CH;
+      for (int e = 0; e < p.s2_nmma; ++e) {
+        const int alpha = e * MA + a;
+        const bool ok = row_ok && alpha < 3;
+        for (int j = 0; j < (NB < 3 ? NB : 3); ++j) {
+          float* dst = part_base + ((size_t)(alpha * 3 + (2 - j)) * p.C + ci) * p.C;
+          for (int c0 = 0; c0 < p.CH; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * p.s2_N + j * p.CH + c0, r);
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4)
+                *reinterpret_cast<float4*>(dst + c0 + jj) = make_float4(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1]),
+                                                                         __uint_as_float(r[jj + 2]), __uint_as_float(r[jj + 3]));
+            }
+          }
         }
       }
     } else
