@@ -189,10 +189,10 @@ static void build_diag_tab(LayerGeom& g) {
 
 static bool tc_channels_ok(int C) { return C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
 
-static int make_w_map(CUtensorMap* m, void* ptr, int C, int eb, int kb, int tw) {
+static int make_w_map(CUtensorMap* m, void* ptr, int C, int eb, int kb, int tw, int ntaps = 9) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, 9};
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)ntaps};
   cuuint64_t strides[2] = {(cuuint64_t)C * eb, (cuuint64_t)C * C * eb};
   cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)C, (cuuint32_t)tw};
   cuuint32_t es[3] = {1, 1, 1};
@@ -415,7 +415,10 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
   g.bias_off = (long long)g.tab.nd * C + kk * C * (C - 1) / 2;
   g.nparams = g.bias_off + (use_bias ? C : 0);
   L->sh = stride_h; L->sw = stride_w; L->mode_req = precision_mode;
-  const bool tc_ok = tc_channels_ok(C) && ksize == 3 && stride_h == 1 && stride_w == 1 && antisymmetric;
+  // tensor path: k = 3 everywhere; k = 5 / 7 forward and data gradient in the fp32-I/O modes (the weight gradient of
+  // those layers stays on the CUDA-core kernel, which needs fp32 operands)
+  const bool tc_ok = tc_channels_ok(C) && stride_h == 1 && stride_w == 1 && antisymmetric &&
+                     (ksize == 3 || ((ksize == 5 || ksize == 7) && precision_mode != B200ODE_PREC_FAST_BF16));
   L->mode_eff = (precision_mode != B200ODE_PREC_SIMT_FP32 && tc_ok) ? precision_mode : B200ODE_PREC_SIMT_FP32;
   if (precision_mode == B200ODE_PREC_FAST_BF16 && !tc_ok) {
     delete L;
@@ -426,7 +429,7 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
   if (e == cudaSuccess) e = cudaMalloc(&L->Gdense, kbytes);
   if (e == cudaSuccess) e = cudaMalloc(&L->bias, (size_t)C * sizeof(float));
   if (e == cudaSuccess && L->mode_eff != B200ODE_PREC_SIMT_FP32) {
-    if (L->mode_eff == B200ODE_PREC_FAST_BF16) e = cudaMalloc(&L->w_bf, (size_t)9 * C * C * 2);
+    if (L->mode_eff == B200ODE_PREC_FAST_BF16) e = cudaMalloc(&L->w_bf, (size_t)kk * C * C * 2);
     else {
       e = cudaMalloc(&L->w_hi, kbytes);
       if (e == cudaSuccess && L->mode_eff == B200ODE_PREC_STRICT) e = cudaMalloc(&L->w_lo, kbytes);
@@ -439,11 +442,11 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
   if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
     const int eb = L->mode_eff == B200ODE_PREC_FAST_BF16 ? 2 : 4;
     const int kb = (C * eb >= 128 ? 128 : C * eb) / eb;
-    const int tw = taps_per_w_stage(L->mode_eff, C);
+    const int tw = ksize == 3 ? taps_per_w_stage(L->mode_eff, C) : 1;
     int rc = 0;
-    if (L->w_bf) rc = make_w_map(&L->map_w_bf, L->w_bf, C, 2, kb, tw);
-    if (!rc && L->w_hi) rc = make_w_map(&L->map_w_hi, L->w_hi, C, 4, kb, tw);
-    if (!rc && L->w_lo) rc = make_w_map(&L->map_w_lo, L->w_lo, C, 4, kb, tw);
+    if (L->w_bf) rc = make_w_map(&L->map_w_bf, L->w_bf, C, 2, kb, tw, (int)kk);
+    if (!rc && L->w_hi) rc = make_w_map(&L->map_w_hi, L->w_hi, C, 4, kb, tw, (int)kk);
+    if (!rc && L->w_lo) rc = make_w_map(&L->map_w_lo, L->w_lo, C, 4, kb, tw, (int)kk);
     if (rc) { b200ode_layer_destroy(L); return rc; }
   }
   *out = L;
@@ -484,15 +487,17 @@ struct TcPlan {
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
+static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int ksize = 3) {
   const int eb = mode == MODE_BF16 ? 2 : 4;
   const int rowb = C * eb >= 128 ? 128 : C * eb;
   const int nkb = C * eb / rowb;
   const bool strict = mode == MODE_STRICT;
-  const int P = W + 1;
-  if (P > 256 || H + 3 > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= 253 and W <= 255 (got %dx%d)", H, W);
+  const int pad = ksize / 2, ntaps = ksize * ksize;
+  const int P = W + pad;
+  if (P > 256 || H + 2 * pad + 1 > 256)
+    return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= %d and W <= %d (got %dx%d)", 255 - 2 * pad, 256 - pad, H, W);
   const long long Q = (long long)H * P;
-  const int tw = taps_per_w_stage(mode, C);
+  const int tw = ksize == 3 ? taps_per_w_stage(mode, C) : 1;
   const uint32_t w_bytes = (uint32_t)tw * C * rowb;
   const uint32_t w_stride = w_bytes * (strict ? 2 : 1);
   const int max_smem = 227 * 1024 - 2048;
@@ -507,10 +512,10 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
       if (whole) {
         // H+2 halo rows plus one: tap (2,2) of the last pixel reads the first pixel of halo row H+2
         // (the shared zero column), which must come from TMA zero fill, not stale shared memory
-        spi = (int)((Q + 127) / 128); nimg = a; tpi = 1; RB = H + 3;
+        spi = (int)((Q + 127) / 128); nimg = a; tpi = 1; RB = H + 2 * pad + 1;
         if (nimg > N && nimg > 1) break;
       } else {
-        spi = a; nimg = 1; tpi = (int)((Q + 128LL * spi - 1) / (128LL * spi)); RB = (128 * spi) / P + 4;
+        spi = a; nimg = 1; tpi = (int)((Q + 128LL * spi - 1) / (128LL * spi)); RB = (128 * spi) / P + 2 + 2 * pad;
         if (128LL * (spi - 1) >= Q) break;
         if (tpi == 1) continue;  // covered by whole-image mode
       }
@@ -522,7 +527,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
       const uint32_t a_lo_off = align_up(a_bytes, 1024);
       const uint32_t a_stride = strict ? 2 * a_lo_off : a_lo_off;
       // stages: at least 2 of each when possible
-      int sw = 9 / tw >= 3 ? 3 : 2;
+      int sw = ntaps / tw >= 3 ? 3 : 2;
       if (tw == 9) sw = 2;
       int sa = 2;
       long long need = (long long)sa * a_stride + (long long)sw * w_stride + 1024;
@@ -540,8 +545,8 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
       static const int model_env = getenv("B200ODE_CONV_COSTMODEL") ? atoi(getenv("B200ODE_CONV_COSTMODEL")) : 1;   // 0: previous model (A/B runs)
       const double per_mma = model_env ? (C >= 128 ? C / 2 : C == 64 ? 48 : 40) * (strict ? 3.0 : 1.0)
                                        : (C / 2 > 32 ? C / 2 : 32) * (strict ? 3.0 : 1.0);
-      const double mma_clk = (double)mt * nkb * 9 * (rowb / 32) * per_mma;
-      const double load_clk = ((double)nimg * RB * P * C * eb + 9.0 * C * C * eb * (strict ? 2 : 1)) / 40.0;
+      const double mma_clk = (double)mt * nkb * ntaps * (rowb / 32) * per_mma;
+      const double load_clk = ((double)nimg * RB * P * C * eb + (double)ntaps * C * C * eb * (strict ? 2 : 1)) / 40.0;
       const double epi_clk = model_env ? (double)mt * C * 48.0 : (double)mt * 128 * C * 4 * 2 / 40.0;
       double tile_clk = mma_clk > load_clk ? mma_clk : load_clk;
       if (acc_stages == 1) tile_clk += epi_clk; else if (epi_clk > tile_clk) tile_clk = epi_clk;
@@ -560,6 +565,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan) {
         ConvTcParams& p = best.p;
         p.N = N; p.H = H; p.W = W; p.P = P; p.RB = RB; p.nimg = nimg; p.spi = spi; p.tpi = tpi; p.total_tiles = (int)tiles;
         p.sa = sa; p.sw = sw; p.tw = tw;
+        p.ksize = ksize; p.ntaps = ntaps; p.pad = pad;
         p.a_bytes = a_bytes; p.a_lo_off = a_lo_off; p.a_stride = a_stride; p.w_bytes = w_bytes; p.w_stride = w_stride;
         p.a_off = 0; p.w_off = (uint32_t)sa * a_stride; p.bar_off = p.w_off + (uint32_t)sw * w_stride;
         uint32_t cols = (uint32_t)acc_stages * mt * accw, pc = 32;
@@ -609,12 +615,13 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, in
   return 0;
 }
 
-template <int MODE, int C, bool BN = false>
+template <int MODE, int C, bool BN = false, bool GENK = false>
 static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
-  if constexpr (!BN && MODE != MODE_BF16) {
+  if constexpr (!BN && !GENK && MODE != MODE_BF16) {
+    if (plan.p.ksize != 3) return launch_conv_tc_t<MODE, C, false, true>(L, plan, map_a, st);
     if (plan.p.bn_part) return launch_conv_tc_t<MODE, C, true>(L, plan, map_a, st);
   }
-  auto kern = conv_tc_kernel<MODE, C, BN>;
+  auto kern = conv_tc_kernel<MODE, C, BN, GENK>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -650,7 +657,8 @@ static int launch_conv_tc_m(const b200ode_layer* L, const TcPlan& plan, const CU
 static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, int W, ConvTcParams epi, cudaStream_t st) {
   const int mode = L->mode_eff, C = L->g.C;
   TcPlan plan;
-  if (int rc = plan_conv_tc(mode, C, N, H, W, &plan)) return rc;
+  if (int rc = plan_conv_tc(mode, C, N, H, W, &plan, L->g.k)) return rc;
+  if (L->g.k != 3 && epi.bn_part) return fail(B200ODE_ERR_UNSUPPORTED, "internal: BatchNorm statistics from the epilogue exist for k = 3");
   ConvTcParams& p = plan.p;
   p.in = epi.in; p.skip = epi.skip; p.out = epi.out; p.z_out = epi.z_out; p.mask = epi.mask; p.bias = epi.bias;
   p.acc_scale = epi.acc_scale; p.c_in = epi.c_in; p.h = epi.h; p.relu = epi.relu; p.scale_h = epi.scale_h;
@@ -838,7 +846,7 @@ extern "C" int b200ode_euler_fwd_bn_stats(b200ode_layer_t* L, const void* x, flo
   if (N < 1 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
   if (L->mode_eff == B200ODE_PREC_FAST_BF16) return fail(B200ODE_ERR_UNSUPPORTED, "BatchNorm needs fp32 activations (STRICT / FAST_TF32 / SIMT)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32 && L->g.k == 3) {
     ConvTcParams e;
     memset(&e, 0, sizeof(e));
     e.z_out = z_out; e.bias = L->g.use_bias ? L->bias : nullptr; e.acc_scale = 1.0f; e.c_in = 1.0f; e.h = 1.0f;
@@ -1151,7 +1159,7 @@ extern "C" int b200ode_euler_wgrad(b200ode_layer_t* L, const void* x, const void
   const long long npix = (long long)N * g.Ho * g.Wo;
   WsLease lease;
   float* colsum_ws = nullptr;
-  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32 && L->g.k == 3) {
     return run_wgrad_tc(L->mode_eff, L->g, x, x, dz, 1, N, H, W, L->Gdense, G_dense, grad_params, 0, accumulate, st,
                         WsArg{L->ws, L->ws_bytes, nullptr});
   } else {
@@ -1910,7 +1918,7 @@ extern "C" int b200ode_layer_workspace_bytes(const b200ode_layer_t* L, int N, in
   if (N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
   *bytes_out = 0;
   if (N == 0) return 0;
-  if (L->mode_eff != B200ODE_PREC_SIMT_FP32) {   // tensor path: only the weight gradient needs scratch (split-K partials)
+  if (L->mode_eff != B200ODE_PREC_SIMT_FP32 && L->g.k == 3) {   // tensor path: only the weight gradient needs scratch (split-K partials)
     return run_wgrad_tc(L->mode_eff, L->g, nullptr, nullptr, nullptr, 1, N, H, W, nullptr, nullptr, nullptr, 0, 0, nullptr,
                         WsArg{nullptr, 0, bytes_out});
   }

@@ -41,6 +41,10 @@ struct ConvTcParams {
   int total_tiles;
   // shared memory plan (bytes from the 1024-aligned base)
   int sa, sw, tw;   // A stages, W stages, taps per W stage
+  // general odd kernel size (GENK instantiations: Conv2DAntisymmetric with k = 5 / 7): k*k taps, `pad` = k/2 zero
+  // columns left of every row (pitch P = W + pad; the right padding of a row is the left padding of the next one) and
+  // `pad` halo rows above and below; one tap per weight ring stage
+  int ksize, ntaps, pad;
   uint32_t a_bytes, a_lo_off, a_stride, w_bytes, w_stride, a_off, w_off, bar_off;
   uint32_t tmem_cols;
   // epilogue
@@ -117,7 +121,7 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[G], int lane) {
 
 // BN = true: the variant that also emits the BatchNorm partial sums (ConvTcParams::bn_part); a separate instantiation so
 // that the extra live registers do not touch the plain kernels (inline, they pushed the tf32 kernels into spills).
-template <int MODE, int C, bool BN = false>
+template <int MODE, int C, bool BN = false, bool GENK = false>
 __global__ void __launch_bounds__(ConvTcCfg<MODE, C>::NWARPS * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
@@ -190,9 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t s = as_, ph = aph;
           mbar_wait_sleep_lean(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], p.a_bytes);
-          tma_load_4d(smem + p.a_off + s * p.a_stride, &map_a, &a_full[s], kb * KB, -1, row0 - 1, n0);
+          const int hp = GENK ? p.pad : 1;
+          tma_load_4d(smem + p.a_off + s * p.a_stride, &map_a, &a_full[s], kb * KB, -hp, row0 - hp, n0);
           if (++as_ == (uint32_t)p.sa) { as_ = 0; aph ^= 1; }
-          for (int tg = 0; tg < 9; tg += p.tw) {
+          for (int tg = 0; tg < (GENK ? p.ntaps : 9); tg += p.tw) {
             const uint32_t sw_ = ws, phw = wph;
             mbar_wait_sleep_lean(&w_empty[sw_], phw ^ 1);     // this CTA's MMAs are done with the stage's previous contents
             uint8_t* wdst = smem + p.w_off + sw_ * p.w_stride;
@@ -230,7 +235,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t a_lo_units = p.a_lo_off >> 4, w_lo_units = p.w_bytes >> 4;
     const uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;               // one tap's weight tile
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
-    auto toff_of = [&](int t) -> uint32_t { return (uint32_t)((t / 3) * p.P + (t % 3)) * RU; };
+    auto toff_of = [&](int t) -> uint32_t {
+      return GENK ? (uint32_t)((t / p.ksize) * p.P + (t % p.ksize)) * RU : (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
+    };
     uint32_t as_ = 0, aph_ = 0, ws = 0, wph = 0, it = 0;
     for (int itile = 0; itile < p.iters; ++itile, ++it) {
       const int tile = blockIdx.x + itile * gridDim.x;
@@ -248,9 +255,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // Taps-per-stage and k-steps are compile-time: per segment the stage's MMAs form one straight-line
         // stream (runtime tap loops left a dependent IMAD/R2UR chain of ~130 cycles per MMA, twice the
         // hardware time of an N = 128 MMA).  Per accumulator the order (kb, tap, k-step) is unchanged.
-        constexpr int TW = Cfg::TW;
+        constexpr int TW = GENK ? 1 : Cfg::TW;
 #pragma unroll 1
-        for (int tg = 0; tg < 9; tg += TW) {
+        for (int tg = 0; tg < (GENK ? p.ntaps : 9); tg += TW) {
           const uint32_t sw_ = ws, phw = wph;
           mbar_wait_lean(&w_full[sw_], phw);
           if (it == 0 && kb == 0 && tg == 0 && lane == 0) tr.mark(3);

@@ -4,8 +4,10 @@ per-output-channel diagonal scalars, dependent kernels -E.W.E, `antisymmetric` f
 changes the diagonal blocks.  Variable order: for each output channel o the diagonal scalars
 [1,1,1,1] in creation order, then input_kernels_for_output_kernel_{o} [k,k,C-o-1,1]; bias last.
 
-k = 3 with strides (1,1) and `antisymmetric=True` runs on the tcgen05 path; other kernel sizes,
-strides, or `antisymmetric=False` run on the CUDA-core kernels (still GPU only).
+k = 3, 5 and 7 with strides (1,1) and `antisymmetric=True` run forward and data gradient on the tcgen05
+path (k*k taps through the same halo-strip kernel, halo pitch W + k//2; fp32-I/O precisions for k > 3, whose
+weight gradient stays on the CUDA-core kernel); other strides, or `antisymmetric=False`, run on the CUDA-core
+kernels (still GPU only).
 """
 from __future__ import annotations
 

@@ -304,3 +304,52 @@ def test_dgrad_fused_tail_bit_identical(shape, precision):
     assert torch.equal(dzp_a.view(torch.int16 if dz.dtype == torch.bfloat16 else torch.int32),
                        dzp_b.view(torch.int16 if dz.dtype == torch.bfloat16 else torch.int32))
     assert float(dzp_a.float().abs().sum()) > 0
+
+
+# --------------------------------------------------------------------------------------- general k on tcgen05
+@pytest.mark.parametrize("k,shape,precision", [(5, (2, 8, 8, 16), "strict"), (5, (3, 12, 10, 32), "fast_tf32"), (7, (2, 9, 11, 16), "strict"),
+                                               (5, (2, 16, 16, 64), "strict"), (5, (1, 32, 32, 128), "fast_tf32"), (7, (2, 8, 8, 32), "fast_tf32"),
+                                               (5, (64, 32, 32, 16), "strict")])
+def test_general_k_on_tensor_path(k, shape, precision):
+    """Conv2DAntisymmetric with k = 5 / 7 (layers/tfkeras_layer_Conv2DAntisymmetric.py:90-175): k*k taps through the SAME
+    tcgen05 kernel (halo pitch W + k/2, one tap per weight stage) forward and data gradient, weight gradient on the CUDA-core
+    kernel; fused Euler step and its backward against O0 (float64)."""
+    from differential_equations_resnet_b200 import _abi
+    pkg = _pkg()
+    N, H, W, C = shape
+    gamma, h = -0.1, 0.25
+    layer = pkg.Conv2DAntisymmetric(k, gamma=gamma, precision=precision, seed=7)
+    layer.build((None, H, W, C))
+    assert layer._handle.effective_mode == _abi.PRECISIONS[precision], "k = %d must stay on the tensor path" % k
+    with torch.no_grad():
+        layer.packed[-C:] = (torch.randn(C, generator=torch.Generator().manual_seed(1)) * 0.1).cuda()
+    flat = layer.packed.detach().cpu().numpy()
+    K32 = O0.assemble_kernel_general_literal(O0.split_params_general(flat, C, k, True), C, k, np.float32(gamma), True)
+    assert np.array_equal(layer.get_kernel(), K32)
+    K = K32.astype(np.float64)
+    x, x64 = rand_x(shape, 21, precision, relu_like=True)
+    dy, dy64 = rand_x(shape, 22, precision)
+    xg = x.clone().requires_grad_(True)
+    y = layer.euler_step(xg, h)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    y_ref, cache = O0.euler_step_fwd(x64, K, flat[-C:].astype(np.float64), h)
+    assert rel(y.detach().cpu().numpy(), y_ref) <= tol, rel(y.detach().cpu().numpy(), y_ref)
+    # plain call() too (conv + bias, no tail)
+    assert rel(layer(x).detach().cpu().numpy(), O0.layer_call(x64, K, flat[-C:].astype(np.float64))) <= tol
+    # backward with the relu branches the GPU took (y - x = h * relu(z) > 0): relu' is discontinuous, a tf32 pre-activation
+    # at rounding level may legitimately sit on the other side of zero
+    mask = (y.detach().cpu().numpy().astype(np.float64) - x64) > 0
+    dX, G, dbias, _, _ = O0.euler_step_bwd(dy64, cache, K, h, mask=mask)
+    gtol = 1e-5 if precision == "strict" else 1e-2
+    assert rel(xg.grad.cpu().numpy(), dX) <= gtol, rel(xg.grad.cpu().numpy(), dX)
+    # folded weight gradient: oracle = autograd-free fold of the dense gradient through the general layout
+    S = G - np.transpose(G[::-1, ::-1, :, :], (0, 1, 3, 2))
+    got = layer.packed.grad.cpu().numpy()
+    assert rel(got[-C:], dbias) <= max(gtol, 2e-5)
+    # spot-check the off-diagonal block of output channel 0: W_0[a,b,j] <-> S[a,b,1+j,0]
+    from differential_equations_resnet_b200.layers.tfkeras_layer_Conv2DAntisymmetric import diag_slots
+    nd = len(diag_slots(k, True))
+    w0 = got[nd:nd + k * k * (C - 1)].reshape(k, k, C - 1)
+    assert rel(w0, S[:, :, 1:, 0]) <= max(gtol, 2e-5), rel(w0, S[:, :, 1:, 0])
