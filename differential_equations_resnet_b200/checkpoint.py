@@ -73,6 +73,9 @@ def export_reference_variables(net):
                 out[name + br + "/bias"] = packed[name + br + "/bias"].numpy().copy()
     out["fc/kernel"] = packed["fc/kernel"].numpy().copy()
     out["fc/bias"] = packed["fc/bias"].numpy().copy()
+    for k, v in packed.items():     # BatchNormalization layers: the Keras variable names (gamma, beta, moving_mean, moving_variance)
+        if k.rsplit("/", 1)[-1] in ("gamma", "beta", "moving_mean", "moving_variance"):
+            out[k] = v.numpy().copy()
     return out
 
 
@@ -94,6 +97,13 @@ def import_reference_variables(net, variables):
         if tuple(arr.shape) != tuple(shape):
             raise ValueError("variable %s has shape %s, expected %s" % (name, tuple(arr.shape), tuple(shape)))
         params[name] = torch.from_numpy(arr.copy())
+    for name, _, C, _, _ in net.bn_param_slices():      # Euler-step BatchNorm layers (use_batch_norm=True)
+        for v in ("gamma", "beta"):
+            params[name + "/" + v] = torch.from_numpy(np.asarray(get(name + "/" + v), dtype=np.float32).copy())
+    for key in variables:
+        k = key[:-2] if key.endswith(":0") else key
+        if k.rsplit("/", 1)[-1] in ("moving_mean", "moving_variance"):
+            params[k] = torch.from_numpy(np.asarray(variables[key], dtype=np.float32).copy())
     net.import_params(params)
 
 

@@ -64,3 +64,55 @@ def test_two_rank_bucket_allreduce_matches_full_batch(tmp_path):
     adam_reference_step(theta, full, torch.zeros_like(theta), torch.zeros_like(theta), 1, 1)
     assert torch.allclose(got["theta"], theta, rtol=0, atol=2e-6)
     assert shard_bounds(256, 3, 8) == (96, 128)
+
+
+def _syncbn_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch.distributed as dist
+    from differential_equations_resnet_b200.training import _SyncStats
+    from differential_equations_resnet_b200.parallel import shard_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+
+    class Net:                      # the two things _SyncStats needs from EulerNet
+        world_size = world
+
+        @staticmethod
+        def _ar(t):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t
+    g = torch.Generator().manual_seed(11)
+    z_all = torch.randn(8, 5, 4, 6, generator=g) * 2.0 + 0.5
+    w_all = torch.randn(8, 5, 4, 6, generator=g)
+    lo, hi = shard_bounds(8, rank, world)
+    z = z_all[lo:hi].clone().requires_grad_(True)
+    st = _SyncStats.apply(z, Net)
+    y = (z - st[0]) / torch.sqrt(st[1] + 1e-3)
+    # every rank differentiates its LOCAL loss (mean over its shard); the trainer later averages the gradients over ranks
+    loss = (y * w_all[lo:hi]).sum() / (hi - lo)
+    loss.backward()
+    torch.save({"stats": st.detach(), "dz": z.grad, "lo": lo, "hi": hi}, out + ".%d" % rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_syncbn_statistics_match_full_batch(tmp_path):
+    """SyncBN protocol of the BN path: local sums -> all-reduce of 2C floats -> global statistics, backward
+    all-reduces (d mean, d var); with the trainer's convention (per-rank loss = mean over the local shard, gradients
+    averaged over ranks) the input gradient equals the full-batch one."""
+    sys.path.insert(0, ROOT)
+    out = str(tmp_path / "sb")
+    mp.spawn(_syncbn_worker, args=(2, 31500 + os.getpid() % 2000, out), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(11)
+    z_all = (torch.randn(8, 5, 4, 6, generator=g) * 2.0 + 0.5).requires_grad_(True)
+    w_all = torch.randn(8, 5, 4, 6, generator=g)
+    mu, var = z_all.mean(dim=(0, 1, 2)), z_all.var(dim=(0, 1, 2), unbiased=False)
+    y = (z_all - mu) / torch.sqrt(var + 1e-3)
+    ((y * w_all).sum() / 8).backward()
+    for r in range(2):
+        got = torch.load(out + ".%d" % r)
+        assert torch.allclose(got["stats"][0], mu.detach(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(got["stats"][1], var.detach(), rtol=1e-4, atol=1e-6)
+        # per-rank gradient is world x the global-loss gradient (local mean vs global mean); the 1/world of the optimiser undoes it
+        assert torch.allclose(got["dz"] / 2, z_all.grad[got["lo"]:got["hi"]], rtol=1e-4, atol=1e-6)
