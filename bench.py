@@ -515,12 +515,13 @@ def run_b200(args):
         # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
         traffic, ncu_extra = None, {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            src = "profiles/r02_ncu_chain_f16.json" if args.precision == "fast_f16" else "profiles/r01_ncu_traffic.json"
+            tj = json.load(open(os.path.join(ROOT, src)))
             rec = tj["kernels"].get("%s|%d" % (dom["kernel"], dom["shape"][3]))
             if rec and B == BATCH_PER_GPU:
                 traffic = rec["dram_bytes_per_launch"]
                 ncu_extra = {"ncu_tensor_pipe_active_pct": rec["tensor_pipe_active_pct"],
-                             "ncu_dram_throughput_pct": rec["dram_throughput_pct"], "ncu_source": "profiles/r01_ncu_traffic.json"}
+                             "ncu_dram_throughput_pct": rec["dram_throughput_pct"], "ncu_source": src}
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
@@ -529,6 +530,11 @@ def run_b200(args):
                     "peak_source": peak_src,
                     "share_of_step": dom["us"] * dom["launches_per_step"] / (1e3 * ms_dev / K)}
         roofline.update(ncu_extra)
+        if dom["kernel"].startswith("chain_wgrad"):
+            roofline["note"] = ("layer-batched weight gradient: DRAM traffic equals the algorithmic bytes (no re-reads); what binds it is the "
+                                "operand-read cost of its small MN-major MMAs (32-byte operand rows at C = 16: one shared-memory wavefront per "
+                                "position and chunk), not HBM -- with the MMAs switched off (B200ODE_WGRAD_DBG=1) the same launch streams its "
+                                "302 MB at 3.1 TB/s (profiles/r02_wgrad_split_experiments.log)")
         if dom["kernel"].startswith(("chain_fwd", "chain_dgrad")):
             # Context for the HBM fraction: the persistent chains are not HBM-bound by design (one image stays in shared
             # memory for all steps); what binds them is the tcgen05 issue / operand-read rate at N = C <= 64 columns
