@@ -152,6 +152,7 @@ struct b200ode_layer {
   void* ws;        // caller-owned workspace (b200ode_layer_set_workspace), may be NULL
   size_t ws_bytes;
   CUtensorMap map_w_hi, map_w_lo, map_w_bf;
+  CUtensorMap map_w_bf_half;   // CTA-pair kernels (bf16, C >= 128): boxes of C/2 output channels
 };
 
 static void build_diag_tab(LayerGeom& g) {
@@ -189,12 +190,12 @@ static void build_diag_tab(LayerGeom& g) {
 
 static bool tc_channels_ok(int C) { return C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
 
-static int make_w_map(CUtensorMap* m, void* ptr, int C, int eb, int kb, int tw, int ntaps = 9) {
+static int make_w_map(CUtensorMap* m, void* ptr, int C, int eb, int kb, int tw, int ntaps = 9, int box_rows = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)ntaps};
   cuuint64_t strides[2] = {(cuuint64_t)C * eb, (cuuint64_t)C * C * eb};
-  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)C, (cuuint32_t)tw};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)(box_rows > 0 ? box_rows : C), (cuuint32_t)tw};
   cuuint32_t es[3] = {1, 1, 1};
   const int rowb = kb * eb;
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -445,6 +446,7 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
     const int tw = ksize == 3 ? taps_per_w_stage(L->mode_eff, C) : 1;
     int rc = 0;
     if (L->w_bf) rc = make_w_map(&L->map_w_bf, L->w_bf, C, 2, kb, tw, (int)kk);
+    if (!rc && L->w_bf && C >= 128 && ksize == 3) rc = make_w_map(&L->map_w_bf_half, L->w_bf, C, 2, kb, tw, 9, C / 2);
     if (!rc && L->w_hi) rc = make_w_map(&L->map_w_hi, L->w_hi, C, 4, kb, tw, (int)kk);
     if (!rc && L->w_lo) rc = make_w_map(&L->map_w_lo, L->w_lo, C, 4, kb, tw, (int)kk);
     if (rc) { b200ode_layer_destroy(L); return rc; }
@@ -487,7 +489,9 @@ struct TcPlan {
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int ksize = 3) {
+// two != 0: plan for CTA pairs (kernels_conv_tc.cuh, TWO): one image per tile, each CTA stages half of every weight tile,
+// tiles are counted in pairs (the same tile-in-image of two consecutive images), the grid is even
+static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int ksize = 3, int two = 0) {
   const int eb = mode == MODE_BF16 ? 2 : 4;
   const int rowb = C * eb >= 128 ? 128 : C * eb;
   const int nkb = C * eb / rowb;
@@ -498,7 +502,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int 
     return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports H <= %d and W <= %d (got %dx%d)", 255 - 2 * pad, 256 - pad, H, W);
   const long long Q = (long long)H * P;
   const int tw = ksize == 3 ? taps_per_w_stage(mode, C) : 1;
-  const uint32_t w_bytes = (uint32_t)tw * C * rowb;
+  const uint32_t w_bytes = (uint32_t)tw * (two ? C / 2 : C) * rowb;
   const uint32_t w_stride = w_bytes * (strict ? 2 : 1);
   const int max_smem = 227 * 1024 - 2048;
   double best_cost = 1e30;
@@ -522,6 +526,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int 
       const int mt = nimg * spi;
       const int accw = strict ? 2 * C : C;
       if (mt * accw > 512 || RB > 256 || nimg > 256) continue;
+      if (two && nimg != 1) continue;
       const int acc_stages = 2 * mt * accw <= 512 ? 2 : 1;
       const uint32_t a_bytes = (uint32_t)nimg * RB * P * rowb;
       const uint32_t a_lo_off = align_up(a_bytes, 1024);
@@ -536,7 +541,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int 
       if (need > max_smem) continue;
       while (sw < 6 && tw == 1 && need + w_stride <= max_smem) { ++sw; need += w_stride; }
       if (nkb > 1 || true) while (sa < 3 && need + a_stride <= max_smem) { ++sa; need += a_stride; }
-      const long long tiles = whole ? (N + nimg - 1) / nimg : (long long)N * tpi;
+      const long long tiles = two ? (long long)((N + 1) / 2) * tpi : whole ? (N + nimg - 1) / nimg : (long long)N * tpi;
       // Per-tile cycle model, calibrated on per-CTA timelines (tools/gpu_trace.py): MMA issue (M = 128: 40 cycles up
       // to N = 32, 48 at N = 64, N/2 above), L2 -> smem fill at ~40 B/clk, and the drain of the accumulators at ~48
       // cycles per (segment, channel) (C = 16: 7.8k cycles for 9 segments, C = 256 bf16: 22k for 2).  With double-
@@ -556,7 +561,7 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int 
       if (sa == 1) tile_clk = mma_clk + load_clk + (acc_stages == 1 ? epi_clk : 0);
       tile_clk += 600;
       const int sms = g_num_sms > 0 ? g_num_sms : 148;
-      const double waves = std::ceil((double)tiles / sms);
+      const double waves = std::ceil((double)tiles / (two ? sms / 2 : sms));
       double cost = waves * tile_clk;
       if (model_env && acc_stages == 2) cost += mma_clk < epi_clk ? mma_clk : epi_clk;
       if (cost < best_cost) {
@@ -584,6 +589,12 @@ static int plan_conv_tc(int mode, int C, int N, int H, int W, TcPlan* plan, int 
         if (grid > sms) grid = sms / cs * cs;
         p.cs = cs;
         p.iters = (int)((tiles + grid - 1) / grid);
+        if (two) {   // one cluster of 2 per pair-tile
+          const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
+          grid = (int)(2 * pairs);
+          p.cs = 2;
+          p.iters = (int)((tiles + pairs - 1) / pairs);
+        }
         best.grid = grid;
         best.box_rows = RB; best.box_imgs = nimg;
       }
@@ -615,19 +626,22 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, in
   return 0;
 }
 
-template <int MODE, int C, bool BN = false, bool GENK = false>
-static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
+template <int MODE, int C, bool BN = false, bool GENK = false, bool TWO = false>
+static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st, bool two = false) {
   if constexpr (!BN && !GENK && MODE != MODE_BF16) {
     if (plan.p.ksize != 3) return launch_conv_tc_t<MODE, C, false, true>(L, plan, map_a, st);
     if (plan.p.bn_part) return launch_conv_tc_t<MODE, C, true>(L, plan, map_a, st);
   }
-  auto kern = conv_tc_kernel<MODE, C, BN, GENK>;
+  if constexpr (!TWO && MODE == MODE_BF16 && C >= 128) {
+    if (two) return launch_conv_tc_t<MODE, C, false, false, true>(L, plan, map_a, st);
+  }
+  auto kern = conv_tc_kernel<MODE, C, BN, GENK, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const CUtensorMap& mw = MODE == MODE_BF16 ? L->map_w_bf : L->map_w_hi;
+  const CUtensorMap& mw = MODE == MODE_BF16 ? (TWO ? L->map_w_bf_half : L->map_w_bf) : L->map_w_hi;
   const CUtensorMap& mwl = MODE == MODE_STRICT ? L->map_w_lo : mw;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -642,13 +656,13 @@ static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CU
 }
 
 template <int MODE>
-static int launch_conv_tc_m(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st) {
+static int launch_conv_tc_m(const b200ode_layer* L, const TcPlan& plan, const CUtensorMap& map_a, cudaStream_t st, bool two = false) {
   switch (L->g.C) {
     case 16: return launch_conv_tc_t<MODE, 16>(L, plan, map_a, st);
     case 32: return launch_conv_tc_t<MODE, 32>(L, plan, map_a, st);
     case 64: return launch_conv_tc_t<MODE, 64>(L, plan, map_a, st);
-    case 128: return launch_conv_tc_t<MODE, 128>(L, plan, map_a, st);
-    case 256: return launch_conv_tc_t<MODE, 256>(L, plan, map_a, st);
+    case 128: return launch_conv_tc_t<MODE, 128>(L, plan, map_a, st, two);
+    case 256: return launch_conv_tc_t<MODE, 256>(L, plan, map_a, st, two);
   }
   return fail(B200ODE_ERR_UNSUPPORTED, "tensor path: unsupported channel count %d", L->g.C);
 }
@@ -657,6 +671,11 @@ static int launch_conv_tc_m(const b200ode_layer* L, const TcPlan& plan, const CU
 static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, int W, ConvTcParams epi, cudaStream_t st) {
   const int mode = L->mode_eff, C = L->g.C;
   TcPlan plan;
+  // CTA pairs (cta_group::2) for the wide bf16 layers; B200ODE_CONV_2CTA=0 keeps the single-CTA kernel (A/B runs)
+  static const int two_env = getenv("B200ODE_CONV_2CTA") ? atoi(getenv("B200ODE_CONV_2CTA")) : 1;
+  bool two = two_env && mode == MODE_BF16 && C >= 128 && L->g.k == 3 && !epi.bn_part && N >= 2;
+  if (two && plan_conv_tc(mode, C, N, H, W, &plan, 3, 1) != 0) two = false;     // no pair plan fits: single-CTA kernel
+  if (!two)
   if (int rc = plan_conv_tc(mode, C, N, H, W, &plan, L->g.k)) return rc;
   if (L->g.k != 3 && epi.bn_part) return fail(B200ODE_ERR_UNSUPPORTED, "internal: BatchNorm statistics from the epilogue exist for k = 3");
   ConvTcParams& p = plan.p;
@@ -674,7 +693,7 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   switch (mode) {
     case MODE_STRICT: return launch_conv_tc_m<MODE_STRICT>(L, plan, map_a, st);
     case MODE_TF32: return launch_conv_tc_m<MODE_TF32>(L, plan, map_a, st);
-    case MODE_BF16: return launch_conv_tc_m<MODE_BF16>(L, plan, map_a, st);
+    case MODE_BF16: return launch_conv_tc_m<MODE_BF16>(L, plan, map_a, st, two);
   }
   return fail(B200ODE_ERR_INVALID, "bad mode");
 }

@@ -121,10 +121,19 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[G], int lane) {
 
 // BN = true: the variant that also emits the BatchNorm partial sums (ConvTcParams::bn_part); a separate instantiation so
 // that the extra live registers do not touch the plain kernels (inline, they pushed the tf32 kernels into spills).
-template <int MODE, int C, bool BN = false, bool GENK = false>
+// TWO = true (bf16, C >= 128): CTA PAIRS (cta_group::2).  A single-CTA M = 128 MMA reads its A tile (128 x 32 B) and the
+// whole B tile (C x 32 B) from ONE SM's shared memory at 128 B/clk: 64 cycles at N = 128 and 96 at N = 256 against 32 / 64
+// cycles of tensor math -- the 50 % / 67 % at which the single-CTA kernels sit.  A pair issues ONE M = 256 MMA over the
+// two CTAs' A tiles with B split between their shared memories (C/2 rows each): 48 / 64 cycles of operand reads per SM.
+// The two CTAs of a pair (cluster of 2) work on the same tile-in-image of two consecutive images, so one descriptor
+// (same shared-memory offsets) addresses both A strips; each loads its own strip and its half of every weight stage with
+// the complete_tx routed to the LEADER's barriers; the leader's MMA warp issues for both and its commits are multicast;
+// each CTA drains its own TMEM half and releases the accumulator on the leader's barrier.
+template <int MODE, int C, bool BN = false, bool GENK = false, bool TWO = false>
 __global__ void __launch_bounds__(ConvTcCfg<MODE, C>::NWARPS * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
+  static_assert(!TWO || (MODE == MODE_BF16 && !BN && !GENK && C >= 128), "CTA pairs: bf16, C >= 128, k = 3");
   using Cfg = ConvTcCfg<MODE, C>;
   constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS;
   constexpr bool STRICT = Cfg::STRICT;
@@ -158,12 +167,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (STRICT) tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_conv[i], 4); }
     for (int i = 0; i < p.sw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&w_empty_cl[i], p.cs > 1 ? p.cs - 1 : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * Cfg::EPQ); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (TWO ? 2 : 1) * 4 * Cfg::EPQ); }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (TWO) { tmem_alloc2(tmem_slot, p.tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -185,6 +194,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t iw = 0;
       const uint32_t crank = p.cs > 1 ? cluster_ctarank() : 0u;
       const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+      if constexpr (TWO) {
+        // CTA pair: own A strip + own half (C/2 output channels) of every weight stage, complete_tx on the leader's barriers
+        for (int itile = 0; itile < p.iters; ++itile) {
+          const int pt = (int)(blockIdx.x >> 1) + itile * (int)(gridDim.x >> 1);   // >= total_tiles: ghost pair
+          const int n0 = 2 * (pt / p.tpi) + (int)crank;
+          const int row0 = ((pt % p.tpi) * T) / p.P;
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t s = as_, ph = aph;
+            mbar_wait_sleep_lean(&a_empty[s], ph ^ 1);
+            if (crank == 0) mbar_expect_tx(&a_full[s], 2 * p.a_bytes);
+            tma_load_4d_pair(smem + p.a_off + s * p.a_stride, &map_a, mapa_u32(smem_u32(&a_full[s]), 0), kb * KB, -1, row0 - 1, n0);
+            if (++as_ == (uint32_t)p.sa) { as_ = 0; aph ^= 1; }
+            for (int tg = 0; tg < 9; tg += p.tw) {
+              const uint32_t sw_ = ws, phw = wph;
+              mbar_wait_sleep_lean(&w_empty[sw_], phw ^ 1);
+              if (crank == 0) mbar_expect_tx(&w_full[sw_], 2 * p.w_bytes);
+              tma_load_3d_pair(smem + p.w_off + sw_ * p.w_stride, &map_w, mapa_u32(smem_u32(&w_full[sw_]), 0), kb * KB,
+                               (int)crank * (C / 2), tg);
+              if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+      } else
       for (int itile = 0; itile < p.iters; ++itile) {
         const int tile = blockIdx.x + itile * gridDim.x;   // >= total_tiles: ghost (TMA zero-fills the out-of-bounds strip)
         const int n0 = (tile / p.tpi) * p.nimg;
@@ -225,22 +257,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // The whole warp runs the (uniform) control flow so descriptors live in uniform registers; one
     // elected lane issues the tcgen05 instructions.  Descriptor low words are advanced by adds of
     // precomputed 16-byte-unit offsets: a handful of integer instructions per MMA.
-    const bool leader = elect_one();
-    const uint32_t idesc = make_instr_desc(MODE == MODE_BF16 ? FMT_BF16 : FMT_TF32, 128, C, 0, 0);
+    const bool leader = elect_one() && (!TWO || cluster_ctarank() == 0);   // CTA pair: the leader CTA issues for both
+    const uint32_t idesc = make_instr_desc(MODE == MODE_BF16 ? FMT_BF16 : FMT_TF32, TWO ? 256 : 128, C, 0, 0);
     const uint32_t desc_hi32 = (SBO >> 4) | (1u << 14) | (LT << 29);   // bits 32..63 of the smem descriptor
     constexpr uint32_t LBO_FIELD = 1u << 16;
     constexpr uint32_t RU = ROWB >> 4;                                  // 16-byte units per pixel row
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t seg_img_step = (uint32_t)(p.RB * p.P) * RU;          // next image inside the strip
     const uint32_t a_lo_units = p.a_lo_off >> 4, w_lo_units = p.w_bytes >> 4;
-    const uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;               // one tap's weight tile
+    const uint32_t tap_units = (uint32_t)((TWO ? C / 2 : C) * ROWB) >> 4;   // one tap's weight tile (CTA pair: this CTA's half)
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
     auto toff_of = [&](int t) -> uint32_t {
       return GENK ? (uint32_t)((t / p.ksize) * p.P + (t % p.ksize)) * RU : (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
     };
     uint32_t as_ = 0, aph_ = 0, ws = 0, wph = 0, it = 0;
+    if (TWO && cluster_ctarank() != 0) {
+      // peer CTA of a pair: its operands are consumed by the leader's MMAs; nothing to issue
+    } else
     for (int itile = 0; itile < p.iters; ++itile, ++it) {
-      const int tile = blockIdx.x + itile * gridDim.x;
+      const int tile = TWO ? (int)(blockIdx.x >> 1) + itile * (int)(gridDim.x >> 1) : (int)(blockIdx.x + itile * gridDim.x);
       const int q0 = (tile % p.tpi) * T;
       const uint32_t off0_units = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
@@ -277,7 +312,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   const uint32_t acc = (tg | tt | ks) ? 1u : (kb ? 1u : 0u);
                   if (leader) {
                     if (MODE == MODE_BF16) {
-                      umma_f16(d_seg, da, db, idesc, acc);
+                      if constexpr (TWO) umma_f16_2cta(d_seg, da, db, idesc, acc);
+                      else umma_f16(d_seg, da, db, idesc, acc);
                     } else {
                       umma_tf32(d_seg, da, db, idesc, acc);
                       if (STRICT) {
@@ -290,13 +326,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-          if (leader) umma_commit(&w_empty[sw_]);
+          if (leader) { if constexpr (TWO) umma_commit_2cta(&w_empty[sw_], 3); else umma_commit(&w_empty[sw_]); }
           if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
         }
-        if (leader) umma_commit(&a_empty[s]);
+        if (leader) { if constexpr (TWO) umma_commit_2cta(&a_empty[s], 3); else umma_commit(&a_empty[s]); }
         if (++as_ == (uint32_t)p.sa) { as_ = 0; aph_ ^= 1; }
       }
-      if (leader) umma_commit(&acc_full[as]);
+      if (leader) { if constexpr (TWO) umma_commit_2cta(&acc_full[as], 3); else umma_commit(&acc_full[as]); }
       if (it == 0 && lane == 0) tr.mark(4);
       __syncwarp();
     }
@@ -318,9 +354,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float bn_s[BN ? NGR : 1], bn_q[BN ? NGR : 1];   // BatchNorm partial sums of this warp (p.bn_part), channel = f(lane)
 #pragma unroll
     for (int j = 0; j < (BN ? NGR : 1); ++j) bn_s[j] = bn_q[j] = 0.0f;
+    const int pair_rank = TWO ? (int)cluster_ctarank() : 0;
     for (int itile = 0; itile < p.iters; ++itile, ++it) {
-      const int tile = blockIdx.x + itile * gridDim.x;   // ghost tiles: n0 >= N, nothing is stored
-      const int n0 = (tile / p.tpi) * p.nimg;
+      // ghost tiles: n0 >= N, nothing is stored.  CTA pair: the same tile-in-image of images 2m (leader) and 2m + 1 (peer)
+      const int tile = TWO ? (int)(blockIdx.x >> 1) + itile * (int)(gridDim.x >> 1) : (int)(blockIdx.x + itile * gridDim.x);
+      const int n0 = TWO ? 2 * (tile / p.tpi) + pair_rank : (tile / p.tpi) * p.nimg;
       const int q0 = (tile % p.tpi) * T;
       const uint32_t as = acc_stages == 2 ? (it & 1) : 0u, aph = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
       if constexpr (MODE == MODE_BF16 && NGR >= 2) {
@@ -661,7 +699,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }   // per-item path (fp32 modes, C < 64)
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) { if constexpr (TWO) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]); }
       if (it == 0 && threadIdx.x == 64) tr.mark(7);
     }
     if constexpr (BN && MODE != MODE_BF16) {
@@ -709,7 +747,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 1) { if constexpr (TWO) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
   if (threadIdx.x == 0) { tr.mark(9); tr.wall(15); }
 }
 
