@@ -152,7 +152,7 @@ struct b200ode_layer {
   void* ws;        // caller-owned workspace (b200ode_layer_set_workspace), may be NULL
   size_t ws_bytes;
   CUtensorMap map_w_hi, map_w_lo, map_w_bf;
-  CUtensorMap map_w_bf_half;   // CTA-pair kernels (bf16, C >= 128): boxes of C/2 output channels
+  CUtensorMap map_w_bf_half, map_w_hi_half;   // CTA-pair kernels (bf16 / tf32, C >= 128): boxes of C/2 output channels
 };
 
 static void build_diag_tab(LayerGeom& g) {
@@ -448,6 +448,7 @@ extern "C" int b200ode_layer_create(int C, int ksize, float gamma, int stride_h,
     if (L->w_bf) rc = make_w_map(&L->map_w_bf, L->w_bf, C, 2, kb, tw, (int)kk);
     if (!rc && L->w_bf && C >= 128 && ksize == 3) rc = make_w_map(&L->map_w_bf_half, L->w_bf, C, 2, kb, tw, 9, C / 2);
     if (!rc && L->w_hi) rc = make_w_map(&L->map_w_hi, L->w_hi, C, 4, kb, tw, (int)kk);
+    if (!rc && L->w_hi && C >= 128 && ksize == 3) rc = make_w_map(&L->map_w_hi_half, L->w_hi, C, 4, kb, tw, 9, C / 2);
     if (!rc && L->w_lo) rc = make_w_map(&L->map_w_lo, L->w_lo, C, 4, kb, tw, (int)kk);
     if (rc) { b200ode_layer_destroy(L); return rc; }
   }
@@ -632,7 +633,7 @@ static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CU
     if (plan.p.ksize != 3) return launch_conv_tc_t<MODE, C, false, true>(L, plan, map_a, st);
     if (plan.p.bn_part) return launch_conv_tc_t<MODE, C, true>(L, plan, map_a, st);
   }
-  if constexpr (!TWO && MODE == MODE_BF16 && C >= 128) {
+  if constexpr (!TWO && !BN && !GENK && MODE != MODE_STRICT && C >= 128) {
     if (two) return launch_conv_tc_t<MODE, C, false, false, true>(L, plan, map_a, st);
   }
   auto kern = conv_tc_kernel<MODE, C, BN, GENK, TWO>;
@@ -641,7 +642,7 @@ static int launch_conv_tc_t(const b200ode_layer* L, const TcPlan& plan, const CU
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const CUtensorMap& mw = MODE == MODE_BF16 ? (TWO ? L->map_w_bf_half : L->map_w_bf) : L->map_w_hi;
+  const CUtensorMap& mw = MODE == MODE_BF16 ? (TWO ? L->map_w_bf_half : L->map_w_bf) : (TWO ? L->map_w_hi_half : L->map_w_hi);
   const CUtensorMap& mwl = MODE == MODE_STRICT ? L->map_w_lo : mw;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -673,7 +674,7 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   TcPlan plan;
   // CTA pairs (cta_group::2) for the wide bf16 layers; B200ODE_CONV_2CTA=0 keeps the single-CTA kernel (A/B runs)
   static const int two_env = getenv("B200ODE_CONV_2CTA") ? atoi(getenv("B200ODE_CONV_2CTA")) : 1;
-  bool two = two_env && mode == MODE_BF16 && C >= 128 && L->g.k == 3 && !epi.bn_part && N >= 2;
+  bool two = two_env && mode != MODE_STRICT && C >= 128 && L->g.k == 3 && !epi.bn_part && N >= 2;
   if (two && plan_conv_tc(mode, C, N, H, W, &plan, 3, 1) != 0) two = false;     // no pair plan fits: single-CTA kernel
   if (!two)
   if (int rc = plan_conv_tc(mode, C, N, H, W, &plan, L->g.k)) return rc;
@@ -692,7 +693,7 @@ static int run_conv_tc(const b200ode_layer* L, const void* input, int N, int H, 
   if (int rc = make_act_map(&map_a, input, N, H, W, C, eb, rowb / eb, p.P, plan.box_rows, plan.box_imgs, sw)) return rc;
   switch (mode) {
     case MODE_STRICT: return launch_conv_tc_m<MODE_STRICT>(L, plan, map_a, st);
-    case MODE_TF32: return launch_conv_tc_m<MODE_TF32>(L, plan, map_a, st);
+    case MODE_TF32: return launch_conv_tc_m<MODE_TF32>(L, plan, map_a, st, two);
     case MODE_BF16: return launch_conv_tc_m<MODE_BF16>(L, plan, map_a, st, two);
   }
   return fail(B200ODE_ERR_INVALID, "bad mode");

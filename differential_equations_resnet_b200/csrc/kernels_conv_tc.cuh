@@ -121,7 +121,7 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[G], int lane) {
 
 // BN = true: the variant that also emits the BatchNorm partial sums (ConvTcParams::bn_part); a separate instantiation so
 // that the extra live registers do not touch the plain kernels (inline, they pushed the tf32 kernels into spills).
-// TWO = true (bf16, C >= 128): CTA PAIRS (cta_group::2).  A single-CTA M = 128 MMA reads its A tile (128 x 32 B) and the
+// TWO = true (bf16 / tf32, C >= 128): CTA PAIRS (cta_group::2).  A single-CTA M = 128 MMA reads its A tile (128 x 32 B) and the
 // whole B tile (C x 32 B) from ONE SM's shared memory at 128 B/clk: 64 cycles at N = 128 and 96 at N = 256 against 32 / 64
 // cycles of tensor math -- the 50 % / 67 % at which the single-CTA kernels sit.  A pair issues ONE M = 256 MMA over the
 // two CTAs' A tiles with B split between their shared memories (C/2 rows each): 48 / 64 cycles of operand reads per SM.
@@ -133,7 +133,7 @@ template <int MODE, int C, bool BN = false, bool GENK = false, bool TWO = false>
 __global__ void __launch_bounds__(ConvTcCfg<MODE, C>::NWARPS * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_w_lo, const ConvTcParams p) {
-  static_assert(!TWO || (MODE == MODE_BF16 && !BN && !GENK && C >= 128), "CTA pairs: bf16, C >= 128, k = 3");
+  static_assert(!TWO || (MODE != MODE_STRICT && !BN && !GENK && C >= 128), "CTA pairs: bf16 / tf32, C >= 128, k = 3");
   using Cfg = ConvTcCfg<MODE, C>;
   constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS;
   constexpr bool STRICT = Cfg::STRICT;
@@ -315,7 +315,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                       if constexpr (TWO) umma_f16_2cta(d_seg, da, db, idesc, acc);
                       else umma_f16(d_seg, da, db, idesc, acc);
                     } else {
-                      umma_tf32(d_seg, da, db, idesc, acc);
+                      if constexpr (TWO) umma_tf32_2cta(d_seg, da, db, idesc, acc);
+                      else umma_tf32(d_seg, da, db, idesc, acc);
                       if (STRICT) {
                         umma_tf32(d_seg + C, da, mk(b_units + w_lo_units + 2 * ks), idesc, acc);
                         umma_tf32(d_seg + C, mk(a_tap + a_lo_units + 2 * ks), db, idesc, 1);
