@@ -1824,8 +1824,10 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   if (orows < 1) return fail(B200ODE_ERR_UNSUPPORTED, "transition_fwd: rows too wide (W=%d, Cin=%d)", W, Cin);
   const int bands = (g.Ho + orows - 1) / orows;
   const dim3 grid(N, bands, Cout / COT / G);
+  const bool s2 = stride_h == 2 && stride_w == 2;     // the reference's transitions (compile-time strides)
   if (PT == 4) GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 4>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
   else if (PT == 2) GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 2>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
+  else if (s2) GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 1, 2>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
   else GLUE_SMEM_LAUNCH((transition_fwd_kernel<COT, 1>), grid, 32 * G, smem, st, g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, orows);
   LAUNCH_CHECK("transition_fwd_kernel");
   return 0;
@@ -1857,6 +1859,9 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   const dim3 grid(N, bands, Cin / CIT);
   if (PT == 4) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 4>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   else if (PT == 2) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 2>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
+  // compile-time strides: measured 39 -> 34 us for 16 -> 32 channels at 32x32, but 53 -> 59 us for 32 -> 64 at 16x16 (the fully
+  // unrolled tap loop is larger than what the second shape amortises): on for narrow inputs only
+  else if (stride_h == 2 && stride_w == 2 && Cin <= 16) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 1, 2>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   else GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 1>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   LAUNCH_CHECK("transition_dgrad_kernel");
   return 0;

@@ -181,7 +181,9 @@ __global__ void reduce_rows_kernel(const float* __restrict__ part, int R, long l
 // forward: block = (image, band of output rows, group of G channel slices); warp w of the block owns the
 // COT-channel slice (blockIdx.z * G + w) whose weights W[10 taps][Cin][COT] sit in shared memory; lane l
 // computes the PT pixels l, l+32, .. of the band (PT*COT register accumulators, ~10 FMAs per shared load).
-template <int COT, int PT>
+// S > 0: both strides equal S at compile time (the address arithmetic of every tap loses its integer divisions; the
+// round-1 kernels issued ~4 instructions per useful FMA, ncu: issue slots 57 % busy at 25 % FMA share); S = 0: run-time strides.
+template <int COT, int PT, int S = 0>
 __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, const float* __restrict__ Wm,
                                       const float* __restrict__ bm, const float* __restrict__ Ws,
                                       const float* __restrict__ bs, float* __restrict__ out, uint8_t* __restrict__ mask,
@@ -191,11 +193,12 @@ __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, c
   const int o0 = blockIdx.y * orows, o1 = min(g.Ho, o0 + orows);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, G = blockDim.x >> 5;
   const int c0 = (blockIdx.z * G + warp) * COT;
-  int i0 = o0 * g.sh - g.pt; if (i0 < 0) i0 = 0;
-  int i1 = (o1 - 1) * g.sh + 2 - g.pt + 1; if (i1 > g.H) i1 = g.H;
+  const int gsh = S ? S : g.sh, gsw = S ? S : g.sw;
+  int i0 = o0 * gsh - g.pt; if (i0 < 0) i0 = 0;
+  int i1 = (o1 - 1) * gsh + 2 - g.pt + 1; if (i1 > g.H) i1 = g.H;
   const int PS = g.Cin + 4;                          // padded pixel stride (floats)
   float* xs = sm;
-  float* wsm = sm + ((orows - 1) * g.sh + 3) * g.W * PS + warp * 10 * g.Cin * COT;    // this warp's weight slice
+  float* wsm = sm + ((orows - 1) * gsh + 3) * g.W * PS + warp * 10 * g.Cin * COT;    // this warp's weight slice
 #pragma unroll 4
   for (int i = threadIdx.x; i < (i1 - i0) * g.W * (g.Cin / 4); i += blockDim.x) {
     const int c4 = i % (g.Cin / 4), pix = i / (g.Cin / 4);
@@ -222,18 +225,17 @@ __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, c
 #pragma unroll
       for (int j = 0; j < COT; ++j) { acc[k][j] = __ldg(bm + c0 + j); sc[k][j] = __ldg(bs + c0 + j); }
     }
-    for (int t = 0; t < 10; ++t) {                     // 9 main taps + the 1x1 shortcut
-      const bool sh_ = t == 9;
-      const int a = sh_ ? g.pt : t / 3, b = sh_ ? g.pl : t % 3;
+    // one tap (a, b) of weight slice wp into the register tile d (taps 0..8 -> acc, the 1x1 shortcut -> sc: two call sites,
+    // so the tile is never reached through a run-time pointer)
+    auto tap = [&](const int a, const int b, const float* wp, float (&d)[PT][COT]) {
       const float* xp[PT];
       bool in[PT];
 #pragma unroll
       for (int k = 0; k < PT; ++k) {
-        const int iy = oy[k] * g.sh + a - g.pt, ix = ox[k] * g.sw + b - g.pl;
+        const int iy = oy[k] * gsh + a - g.pt, ix = ox[k] * gsw + b - g.pl;
         in[k] = ok[k] && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
         xp[k] = xs + ((in[k] ? iy - i0 : 0) * g.W + (in[k] ? ix : 0)) * PS;
       }
-      const float* wp = wsm + t * g.Cin * COT;
       for (int ci = 0; ci < g.Cin; ci += 4) {
         float xv[PT][4];
 #pragma unroll
@@ -248,14 +250,16 @@ __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, c
             const float4 w = *reinterpret_cast<const float4*>(wp + (ci + e) * COT + 4 * j);
 #pragma unroll
             for (int k = 0; k < PT; ++k) {
-              float* d = sh_ ? sc[k] : acc[k];
-              d[4 * j] = fmaf(xv[k][e], w.x, d[4 * j]); d[4 * j + 1] = fmaf(xv[k][e], w.y, d[4 * j + 1]);
-              d[4 * j + 2] = fmaf(xv[k][e], w.z, d[4 * j + 2]); d[4 * j + 3] = fmaf(xv[k][e], w.w, d[4 * j + 3]);
+              d[k][4 * j] = fmaf(xv[k][e], w.x, d[k][4 * j]); d[k][4 * j + 1] = fmaf(xv[k][e], w.y, d[k][4 * j + 1]);
+              d[k][4 * j + 2] = fmaf(xv[k][e], w.z, d[k][4 * j + 2]); d[k][4 * j + 3] = fmaf(xv[k][e], w.w, d[k][4 * j + 3]);
             }
           }
         }
       }
-    }
+    };
+#pragma unroll
+    for (int t = 0; t < 9; ++t) tap(t / 3, t % 3, wsm + t * g.Cin * COT, acc);   // same order as before: bit-identical sums
+    tap(g.pt, g.pl, wsm + 9 * g.Cin * COT, sc);
 #pragma unroll
     for (int k = 0; k < PT; ++k) {
       if (!ok[k]) continue;
@@ -282,11 +286,13 @@ __global__ void transition_fwd_kernel(GlueConv g, const float* __restrict__ x, c
 // rows reaching the band (dout and masked dmain) and the slice's weights W[10][CIT][Cout] are staged in
 // shared memory.  Work items = (stride-parity class, chunk of 32*PT pixels of the class): within an item the
 // set of contributing taps is warp-uniform; lane l computes the pixels l, l+32, .. of the chunk.
-template <int CIT, int PT>
-__global__ void transition_dgrad_kernel(GlueConv g, const float* __restrict__ dout, const uint8_t* __restrict__ mask,
+template <int CIT, int PT, int S = 0>
+__global__ void transition_dgrad_kernel(GlueConv g_, const float* __restrict__ dout, const uint8_t* __restrict__ mask,
                                         const float* __restrict__ Wm, const float* __restrict__ Ws, float* __restrict__ dx,
                                         int rows) {
   extern __shared__ float sm[];
+  GlueConv g = g_;
+  if (S) { g.sh = S; g.sw = S; }        // compile-time strides: every "/ g.sh", "% g.sw" below folds into shifts / masks
   const int n = blockIdx.x;
   const int y0 = blockIdx.y * rows, y1 = min(g.H, y0 + rows);
   const int ci0 = blockIdx.z * CIT;
@@ -342,6 +348,7 @@ __global__ void transition_dgrad_kernel(GlueConv g, const float* __restrict__ do
       for (int c = 0; c < CIT; ++c) acc[k][c] = 0.0f;
     }
     // taps of this class: a = cy, cy + sh, ... (< 3), b likewise; tap index 9 = the 1x1 shortcut (class (pt%sh, pl%sw))
+#pragma unroll
     for (int t = 0; t < 10; ++t) {
       const bool sh_ = t == 9;
       const int a = sh_ ? g.pt : t / 3, b = sh_ ? g.pl : t % 3;

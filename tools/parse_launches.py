@@ -13,11 +13,11 @@ a, b = ends[-2] + 2, ends[-1] + 2
 step = L[a:b]
 tot = sum(t for _, t, _ in step) / 1e3
 print('launches', len(step), 'total us %.1f' % tot)
-big = [(n, t, g) for n, t, g in step if 'chain_' in n or 'wgrad_tc' in n]
+big = [(n, t, g) for n, t, g in step if 'chain_f16_kernel' in n or 'chain_tc_kernel' in n or 'wgrad_tc' in n]
 print('chain + wgrad kernels: %.1f us' % (sum(t for _, t, _ in big) / 1e3))
 for n, t, g in big:
     print(f"{t/1e3:8.1f}us {g:>14} {n[:70]}")
-rest = [(n, t, g) for n, t, g in step if not ('chain_' in n or 'wgrad_tc' in n)]
+rest = [(n, t, g) for n, t, g in step if not ('chain_f16_kernel' in n or 'chain_tc_kernel' in n or 'wgrad_tc' in n)]
 print('everything else (stem, transitions, head, packs, folds, reductions, amax, Adam): %.1f us in %d launches' % (sum(t for _, t, _ in rest) / 1e3, len(rest)))
 for n, t, g in rest:
     print(f"{t/1e3:8.1f}us {g:>14} {n[:70]}")
