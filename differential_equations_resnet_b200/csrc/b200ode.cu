@@ -983,6 +983,14 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     if (p.TG == 3 && 5 * p.MB * p.NT * (strict ? 2 : 1) <= 512) p.TG = 5;
     p.ntapgroups = (9 + p.TG - 1) / p.TG; p.nngroups = C / p.NT; p.dchunks = p.NT / p.CH;
   }
+  // CTA pairs (kernels_wgrad_tc.cuh, TWO): the two 128-channel M blocks of C = 256 as a cluster of 2 issuing M = 256 MMAs, the
+  // dz strip split between them.  B200ODE_WGRAD_2CTA=0 keeps two independent CTAs (A/B runs).
+  static const int w2_env = getenv("B200ODE_WGRAD_2CTA") ? atoi(getenv("B200ODE_WGRAD_2CTA")) : 1;
+  // Measured (N=256, C=256 bf16): 32x32 images 286 -> 257 us (1201 TFLOP/s = 73 % of the measured bf16 peak); 64x64 images 578 -> 664 us
+  // (the row-aligned tiles of wide images are already load-balanced around whole dz strips; =2 forces pairs there for A/B runs)
+  const bool two = w2_env && bf16 && !f16 && !strict && !p.trick && !p.pair && !p.shift2 && p.mgroups == 2 && p.Mblk == 128 && p.MB == 1 &&
+                   (p.dchunks % 2) == 0 && (W <= 32 || w2_env == 2);
+  if (two) p.dchunks /= 2;      // chunks of the dz strip THIS CTA stages
   const int ngroups = p.ntapgroups * p.nngroups * p.mgroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;
   if (p.trick && strict && 3 * p.NT * 2 > 512) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad TMEM");
@@ -1123,6 +1131,21 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
   }
   dim3 grid(nparts, ngroups, L);
+  if (two) {
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+      CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<MODE_BF16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set2 = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * nparts, ngroups / 2, L); cfg.blockDim = dim3(6 * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // x = 2 * part + M group
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<MODE_BF16, false, true>, mx0, mx, md, p));
+  } else {
 #define WG_LAUNCH(M_, F_)                                                                                      \
   do {                                                                                                         \
     static bool attr_set = false;                                                                              \
@@ -1137,6 +1160,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   else if (f16) WG_LAUNCH(MODE_BF16, true);
   else WG_LAUNCH(MODE_BF16, false);
 #undef WG_LAUNCH
+  }
   LAUNCH_CHECK("wgrad_tc_kernel");
   if (G_user && L == 1) {   // dense gradient requested (tests / diagnostics)
     if (p.pair) reduce_parts_pair<<<blocks_for(total, 256), 256, 0, st>>>(ws, nparts, pstride, total, G, G_user, p.P);

@@ -87,13 +87,20 @@ struct WgradParams {
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
 };
 
-template <int MODE, bool F16 = false>
+// TWO = true (bf16, C = 256 with one 128-channel M block per CTA): CTA PAIRS (cta_group::2, see kernels_conv_tc.cuh).  The
+// two M blocks of an (N range, tap group, position slice) used to be two independent CTAs that each staged the whole dz
+// strip; as a cluster of 2 they issue ONE M = 256 MMA per tap and k-step -- rows 0..127 = input channels 0..127 from the
+// leader's x strip, rows 128..255 = channels 128..255 from the peer's -- with the dz strip split between them (NT/2 output
+// channels each): per SM 4 KB + NT*16 B of operand reads per MMA instead of 4 KB + NT*32 B, and half the dz staging.
+template <int MODE, bool F16 = false, bool TWO = false>
 __global__ void __launch_bounds__((MODE == MODE_STRICT ? 10 : 6) * 32, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_d, const WgradParams p) {
   constexpr bool STRICT = MODE == MODE_STRICT;
   constexpr bool BF16 = MODE == MODE_BF16;
   constexpr int UKP = BF16 ? 16 : 8;  // positions per MMA
+  static_assert(!TWO || (BF16 && !F16), "CTA pairs: bf16 weight gradient");
+  const uint32_t prank = TWO ? cluster_ctarank() : 0u;   // = M group of this CTA (the pair's cluster spans the M groups)
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,17 +114,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   Trace tr;
   tr.begin(p.trace);
   if (threadIdx.x == 0) tr.wall(0);
-  const int group = blockIdx.y;
+  // CTA pair: the cluster spans blockIdx.x (x = 2 * part + M group), blockIdx.y = (tap group, N range)
+  const int group = TWO ? (int)blockIdx.y * p.mgroups + (int)(blockIdx.x & 1) : (int)blockIdx.y;
   const int mgroup = group % p.mgroups;
   const int tapgroup = (group / p.mgroups) / p.nngroups, ngroup = (group / p.mgroups) % p.nngroups;
   // The dz column sums (bias gradient) of an N range are dealt over the CTAs that stage the same dz strip (all tap
   // groups and M blocks): each sums its share of the strip's 16-byte column units, so no role is slower than the others.
   const int b_upr = p.RWB >> 4;                    // 16-byte units per operand row
   const int b_units = p.dchunks * b_upr;           // column units of this CTA's dz strip (power of two, <= 64)
-  const int b_roles = p.trick ? 1 : p.ntapgroups * p.mgroups, b_rid = p.trick ? 0 : tapgroup * p.mgroups + mgroup;
+  // (CTA pair: each CTA stages only ITS half of the strip, shared with the other tap groups of the same pair position)
+  const int b_roles = p.trick ? 1 : TWO ? p.ntapgroups : p.ntapgroups * p.mgroups, b_rid = p.trick ? 0 : TWO ? tapgroup : tapgroup * p.mgroups + mgroup;
   const int b_lo = b_rid * b_units / b_roles, b_n = (b_rid + 1) * b_units / b_roles - b_lo;
   const bool do_bias = b_n > 0 && !(p.dbg & 2);
-  const int part = blockIdx.x;
+  const int part = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int layer = blockIdx.z;
   const int ukp = p.pair ? 16 : UKP;    // positions per k-step
   const CUtensorMap* mx = layer == 0 ? &map_x0 : &map_x;
@@ -127,11 +136,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(mx);
     tma_prefetch_desc(&map_d);
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], do_bias ? 5 : 1); mbar_init(&conv[i], 4); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], do_bias ? 5 : 1); mbar_init(&conv[i], TWO ? 1 : 4); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (TWO) { tmem_alloc2(tmem_slot, p.tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+  }
   if (p.pair) {   // zero the 1 KB pad in front of every stage's x strip (row -1 of the first kernel row)
     for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x)
       reinterpret_cast<uint4*>(smem + (i >> 6) * p.stage_stride)[i & 63] = make_uint4(0u, 0u, 0u, 0u);
@@ -151,6 +163,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();     // both CTAs' barriers exist before any remote complete_tx / multicast commit
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tr.mark(1);
@@ -167,8 +180,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         const uint32_t s = rs, ph = rph;
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
         mbar_wait_sleep_lean(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sb = smem + s * p.stage_stride;
+        if constexpr (TWO) {
+          // p.dchunks = the chunks THIS CTA stages (its half of the N range).  The loads complete on this CTA's OWN barrier
+          // (its bias warps read the dz strip too); the peer's MMA warp forwards "stage full" to the leader (conv[s]).
+          mbar_expect_tx(&full[s], stage_bytes);
+          for (int c = 0; c < p.xchunks; ++c)
+            tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk + c * p.CH, xc0, row0 - 1, img_x0 + n);
+          for (int c = 0; c < p.dchunks; ++c)
+            tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + ((int)prank * p.dchunks + c) * p.CH, dc0, row0,
+                        img_d0 + n);
+          continue;
+        }
+        mbar_expect_tx(&full[s], stage_bytes);
         for (int c = 0; c < p.xchunks; ++c)
           tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk * (p.mgroups > 1) + c * p.CH, xc0, row0 - 1, img_x0 + n);
         for (int c = 0; c < p.dchunks; ++c)
@@ -177,9 +201,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform control flow, one elected lane issues (see kernels_conv_tc.cuh)
-    const bool committer = elect_one();
+    const bool committer = elect_one() && prank == 0;       // CTA pair: the leader CTA issues and commits for both
     const bool leader = committer && !(p.dbg & 1);
-    const int Mrows = p.pair ? 128 : p.shift2 ? p.s2_M : p.trick ? 4 * p.CH : p.Mblk;
+    const int Mrows = TWO ? 256 : p.pair ? 128 : p.shift2 ? p.s2_M : p.trick ? 4 * p.CH : p.Mblk;
     const uint32_t idesc = make_instr_desc(BF16 ? (F16 ? FMT_F16 : FMT_BF16) : FMT_TF32, Mrows, p.shift2 ? p.s2_N : p.NT, 1, 1);
     const uint32_t lt = BF16 ? swz_layout_type(p.RWB) : 1u;   // 1 = SWIZZLE_128B_BASE32B
     const uint32_t sbo = BF16 ? 8u * p.RWB : 512u;
@@ -210,12 +234,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
     uint32_t it = 0, rs = 0, rph = 0;
+    if (TWO && prank != 0) {
+      // peer CTA of a pair: its strips are consumed by the leader's MMAs; this warp tells the leader when a stage has landed
+      for (int tile = part; tile < p.total_tiles; tile += p.nparts) {
+        const uint32_t s = rs, ph = rph;
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
+        mbar_wait_lean(&full[s], ph);
+        if (lane == 0) mbar_arrive_cluster(&conv[s], 0);
+        __syncwarp();
+      }
+    } else
     for (int tile = part; tile < p.total_tiles; tile += p.nparts, ++it) {
       const int q0 = (tile % p.tpi) * p.tstride;
       const uint32_t off0 = (uint32_t)(q0 - (q0 / p.P) * p.P) * RU;
       const uint32_t s = rs, ph = rph;
       if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
       mbar_wait_lean(STRICT ? &conv[s] : &full[s], ph);
+      if constexpr (TWO) mbar_wait_lean(&conv[s], ph);     // the peer's half of the stage
       if (it == 0 && lane == 0) tr.mark(2);
       tc_fence_after_sync();
       uint32_t xu = ((smem_base + s * p.stage_stride + p.x_off) >> 4) + off0;
@@ -272,7 +307,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
               const uint32_t d_tmem = tmem_base + e * ACCW;
               const uint64_t dsc_a = mk(au, lbo_a);
               if (leader) {
-                if (BF16) umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum);
+                if (BF16) { if constexpr (TWO) umma_f16_2cta(d_tmem, dsc_a, dsc_b, idesc, accum); else umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum); }
                 else {
                   umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
                   if (STRICT) {
@@ -334,11 +369,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           }
         }
       }
-      if (committer) umma_commit(&empty[s]);
+      if (committer) { if constexpr (TWO) umma_commit_2cta(&empty[s], 3); else umma_commit(&empty[s]); }
       if (it == 0 && lane == 0) tr.mark(3);
       __syncwarp();
     }
-    if (committer) umma_commit(acc_full);
+    if (committer) { if constexpr (TWO) umma_commit_2cta(acc_full, 3); else umma_commit(acc_full); }
     if (lane == 0) tr.mark(4);
   } else if (warp < 6) {
     // epilogue warps.  While the main loop runs they are otherwise idle, so tap group 0 uses them
@@ -410,7 +445,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         for (int idx = t; idx < units * epu; idx += 128) {
           const int ul = idx / epu, jj = idx % epu, un = b_lo + ul;
           const int c = (un % upr) * epu + jj;
-          const int ch = ngroup * p.NT + (un / upr) * p.CH + c;
+          const int ch = ngroup * p.NT + ((TWO ? (int)prank * p.dchunks : 0) + un / upr) * p.CH + c;
           if (c < p.CH && ch < p.C) {
             float sum = 0.0f;
             for (int k = 0; k < tpu; ++k) sum += bs[(k * units + ul) * 8 + jj];
@@ -524,7 +559,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   if (threadIdx.x == 64) tr.mark(7);
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (TWO) cluster_sync_all();     // the leader's last multicast commit has landed in the peer before either leaves
+  if (warp == 1) { if constexpr (TWO) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
   if (threadIdx.x == 0) { tr.mark(9); tr.wall(15); }
 }
 
