@@ -990,7 +990,14 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // (the row-aligned tiles of wide images are already load-balanced around whole dz strips; =2 forces pairs there for A/B runs)
   const bool two = w2_env && bf16 && !f16 && !strict && !p.trick && !p.pair && !p.shift2 && p.mgroups == 2 && p.Mblk == 128 && p.MB == 1 &&
                    (p.dchunks % 2) == 0 && (W <= 32 || w2_env == 2);
-  if (two) p.dchunks /= 2;      // chunks of the dz strip THIS CTA stages
+  // ... and, for ONE 128-channel M block (C = 128), pairs by TAPS: kernel rows (0 | 1) and (2 | -) per tap group
+  // OFF by default (B200ODE_WGRAD_TAPPAIR=1|2 to try): measured SLOWER than three independent tap groups (N=256, C=128: 32x32 104.6 ->
+  // 111.3 us, 64x64 167 -> 241 us) -- a quarter of the pair's MMA rows is junk (kernel row 3) and two tap groups balance worse than three
+  static const int w2t_env = getenv("B200ODE_WGRAD_TAPPAIR") ? atoi(getenv("B200ODE_WGRAD_TAPPAIR")) : 0;
+  const bool two_tap = w2t_env && w2_env && bf16 && !f16 && !strict && !p.trick && !p.pair && !p.shift2 && C == 128 && p.mgroups == 1 &&
+                       p.Mblk == 128 && p.MB == 1 && (W <= 32 || w2t_env == 2);
+  if (two_tap) { p.TG = 3; p.NT = 128; p.ntapgroups = 2; p.nngroups = 1; p.dchunks = p.NT / p.CH; p.tappair = 1; }
+  if (two || two_tap) p.dchunks /= 2;      // chunks of the dz strip THIS CTA stages
   const int ngroups = p.ntapgroups * p.nngroups * p.mgroups;
   const int nent = p.trick ? 3 : p.TG * p.MB;
   if (p.trick && strict && 3 * p.NT * 2 > 512) return fail(B200ODE_ERR_UNSUPPORTED, "wgrad TMEM");
@@ -1087,7 +1094,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const size_t smem = (size_t)p.bar_off + 256 + 1024;
   p.total_tiles = N * p.tpi;
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  int nparts = sms / (ngroups * L);
+  int nparts = sms / (ngroups * L * (two_tap ? 2 : 1));
   if (nparts < 1) nparts = 1;
   if (strict) {
     // The tensor core accumulates with truncation (csrc/umma_probe.cu): the error of one TMEM accumulator grows
@@ -1131,7 +1138,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     if (int rc = make_act_map(&md, dz, L * N, H, W, C, eb, p.CH, p.P, p.RBd, 1, sw)) return rc;
   }
   dim3 grid(nparts, ngroups, L);
-  if (two) {
+  if (two || two_tap) {
     static bool attr_set2 = false;
     if (!attr_set2) {
       CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<MODE_BF16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1139,7 +1146,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * nparts, ngroups / 2, L); cfg.blockDim = dim3(6 * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(2 * nparts, two_tap ? ngroups : ngroups / 2, L); cfg.blockDim = dim3(6 * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   // x = 2 * part + M group

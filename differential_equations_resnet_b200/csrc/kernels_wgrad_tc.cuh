@@ -82,6 +82,10 @@ struct WgradParams {
   // Both strips use pitch P = W + 2 with the two zero columns on the LEFT (TMA box from column -2), so the positions a
   // shifted B chunk reads before / after a row are zeros and nothing outside a strip's rows is ever needed.
   int shift2, s2_M, s2_N, s2_nmma;
+  // CTA pairs by TAPS (TWO with one M block, C = 128): both CTAs of the pair stage the SAME input channels, the peer one image
+  // row lower, so the rows 128..255 of the pair's M = 256 MMA are kernel row alpha + 1 of the leader's alpha: six M = 256 MMAs
+  // per k-step (three of them half junk: kernel row 3) replace nine M = 128 ones, and each CTA stages half of the dz strip.
+  int tappair;
   int dbg;           // debug (B200ODE_WGRAD_DBG): bit 0 = issue no MMAs, bit 1 = no bias column sums (timing experiments only)
   int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
@@ -115,7 +119,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   tr.begin(p.trace);
   if (threadIdx.x == 0) tr.wall(0);
   // CTA pair: the cluster spans blockIdx.x (x = 2 * part + M group), blockIdx.y = (tap group, N range)
-  const int group = TWO ? (int)blockIdx.y * p.mgroups + (int)(blockIdx.x & 1) : (int)blockIdx.y;
+  const int group = (TWO && !p.tappair) ? (int)blockIdx.y * p.mgroups + (int)(blockIdx.x & 1) : (int)blockIdx.y;
   const int mgroup = group % p.mgroups;
   const int tapgroup = (group / p.mgroups) / p.nngroups, ngroup = (group / p.mgroups) % p.nngroups;
   // The dz column sums (bias gradient) of an N range are dealt over the CTAs that stage the same dz strip (all tap
@@ -186,7 +190,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           // (its bias warps read the dz strip too); the peer's MMA warp forwards "stage full" to the leader (conv[s]).
           mbar_expect_tx(&full[s], stage_bytes);
           for (int c = 0; c < p.xchunks; ++c)
-            tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk + c * p.CH, xc0, row0 - 1, img_x0 + n);
+            tma_load_4d(sb + p.x_off + c * p.x_chunk_stride, mx, &full[s], mgroup * p.Mblk + c * p.CH, xc0,
+                        row0 - 1 + (p.tappair ? (int)prank : 0), img_x0 + n);
           for (int c = 0; c < p.dchunks; ++c)
             tma_load_4d(sb + p.d_off + c * p.d_chunk_stride, &map_d, &full[s], ngroup * p.NT + ((int)prank * p.dchunks + c) * p.CH, dc0, row0,
                         img_d0 + n);
@@ -221,7 +226,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       int shift; uint32_t a_off;
       if (p.trick) { shift = lane * p.P; a_off = 0; }
       else {
-        const int tap = tapgroup * p.TG + lane / p.MB;
+        const int tap = tapgroup * p.TG * (TWO && p.tappair ? 2 : 1) + lane / p.MB;    // tap pairs: the LEADER's kernel row 2 * tapgroup
         shift = (tap / 3) * p.P + (tap % 3);
         a_off = (lane % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
       }
@@ -506,6 +511,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       int tap, ci;
       bool ok = row_ok;
       if (p.trick) { const int beta = m / p.CH; tap = e * 3 + beta; ci = m % p.CH; ok = ok && beta < 3; }
+      else if (TWO && p.tappair) { tap = (2 * tapgroup + (int)prank) * p.TG + e; ci = m; }
       else { tap = tapgroup * p.TG + e / p.MB; ci = (e % p.MB) * p.Mblk + m + (p.mgroups > 1 ? mgroup * p.Mblk : 0); }
       ok = ok && ci < p.C && tap < 9;
       float* dst = part_base + ((size_t)tap * p.C + ci) * p.C + ngroup * p.NT;
