@@ -849,6 +849,35 @@ class EulerNet:
         self._graph = None
         self._static_in = None
         self._static_loss = None
+        self._stage = None
+
+    # ---- input pipeline of the captured step: the next batch travels host -> device while the current step runs ----------
+    def prefetch(self, images_host, onehot_host):
+        """Start the host -> device copy of the NEXT step's batch (pinned host tensors) on a copy stream, into staging
+        buffers; `train_step_graph_prefetched` moves them into the graph's static inputs (device -> device, ~2 us) right
+        before its replay.  The copy overlaps the step that is running; the static inputs are never written while a replay
+        may still read them (the stem's weight gradient reads the images at the END of the step)."""
+        if getattr(self, "_stage", None) is None:
+            self._stage = (torch.empty_like(self._static_in[0]), torch.empty_like(self._static_in[1]))
+            self._copy_stream = torch.cuda.Stream()
+            self._copied, self._stage_free = torch.cuda.Event(), None
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free is not None:
+                self._copy_stream.wait_event(self._stage_free)      # the previous batch has left the staging buffers
+            self._stage[0].copy_(images_host, non_blocking=True)
+            self._stage[1].copy_(onehot_host, non_blocking=True)
+            self._copied.record(self._copy_stream)
+
+    def train_step_graph_prefetched(self):
+        """Replay the captured step on the batch delivered by the last `prefetch` call."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copied)
+        self._static_in[0].copy_(self._stage[0], non_blocking=True)
+        self._static_in[1].copy_(self._stage[1], non_blocking=True)
+        self._stage_free = torch.cuda.Event()
+        self._stage_free.record(cur)
+        self._graph.replay()
+        return self._static_loss
 
     def train_step_graph(self, images=None, onehot=None):
         if images is not None:
