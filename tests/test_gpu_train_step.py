@@ -135,3 +135,26 @@ def test_gradient_history_metrics():
         assert abs(norms[key] - ref) <= 1e-5 * ref, key
     row = net.history_row(loss, net.predict(img), lab).split(" ")
     assert len(row) == 3 + len(names) and int(row[0]) == 1 and abs(float(row[1]) - float(loss)) < 1e-6
+
+
+def test_prefetched_graph_step_equals_direct_step():
+    """EulerNet.prefetch + train_step_graph_prefetched (copy stream, staging buffers, device-to-device hand-over) runs the
+    same captured step on the same batches as train_step_graph(images, onehot): identical losses and parameters."""
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    kw = dict(blocks_per_stage=(2, 2, 2), filters_per_block=(16, 32, 64), h=0.25, gamma=-0.05)
+    gen = torch.Generator().manual_seed(11)
+    batches = [(torch.randint(0, 256, (8, 32, 32, 3), generator=gen, dtype=torch.uint8).pin_memory(),
+                torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=gen), 10).float().pin_memory()) for _ in range(4)]
+    nets = [EulerNet(NetSpec(**kw), precision="fast_f16", seed=4) for _ in range(2)]
+    for n in nets:
+        n.capture(batches[0][0].cuda(), batches[0][1].cuda(), warmup=1)
+    la = [float(nets[0].train_step_graph(*b)) for b in batches]
+    lb = []
+    nets[1].prefetch(*batches[0])
+    for i in range(len(batches)):
+        out = nets[1].train_step_graph_prefetched()
+        if i + 1 < len(batches):
+            nets[1].prefetch(*batches[i + 1])          # overlaps the replay that was just queued
+        lb.append(float(out))
+    torch.cuda.synchronize()
+    assert la == lb and torch.equal(nets[0].theta, nets[1].theta)
