@@ -67,6 +67,8 @@ def export_reference_variables(net):
         elif kind == "stem":
             out[name + "/kernel"] = packed[name + "/kernel"].numpy().copy()
             out[name + "/bias"] = packed[name + "/bias"].numpy().copy()
+        elif kind == "maxpool":
+            continue
         else:   # transition block: main 3x3 branch '...branch2', 1x1 shortcut '...branch1'
             for br in ("2", "1"):
                 out[name + br + "/kernel"] = packed[name + br + "/kernel"].numpy().copy()
@@ -151,6 +153,8 @@ def dense_layer_weights(net):
             out.append({"kernel": K.cpu().numpy(), "bias": flat[-C:].cpu().numpy()})
         elif kind == "stem":
             out.append({"kernel": packed[name + "/kernel"].numpy().copy(), "bias": packed[name + "/bias"].numpy().copy()})
+        elif kind == "maxpool":
+            continue
         else:
             for br in ("2", "1"):
                 out.append({"kernel": packed[name + br + "/kernel"].numpy().copy(),

@@ -32,8 +32,10 @@ class NetSpec:
 
     def __init__(self, num_stages=4, blocks_per_stage=(3, 3, 3), filters_per_block=(16, 32, 64),
                  strides=((1, 1), (2, 2), (2, 2)), h=1.0, gamma=0.0, num_classes=10, use_batch_norm=False,
-                 subtract_mean=127.5, divide_by_stddev=127.5, kernel_size=3, in_channels=3):
+                 subtract_mean=127.5, divide_by_stddev=127.5, kernel_size=3, in_channels=3, use_max_pooling=None):
         self.use_batch_norm = bool(use_batch_norm)
+        # MaxPooling2D(2,2) in front of stage s+2 (models/tfkeras_resnets.py:577-578); such a stage starts with a conv block
+        self.use_max_pooling = list(use_max_pooling) if use_max_pooling is not None else [False] * (num_stages - 1)
         if kernel_size != 3:
             raise ValueError("antisymmetric Euler blocks are 3x3")
         self.num_stages, self.blocks_per_stage = num_stages, list(blocks_per_stage)
@@ -47,11 +49,15 @@ class NetSpec:
         fp, st = self.filters_per_block, self.strides
         ops = [("stem", self.in_channels, fp[0], st[0], "conv1")]
         for s in range(self.num_stages - 1):
-            if s == 0 or (fp[s] == fp[s - 1] and st[s] == (1, 1)):
+            pool = self.use_max_pooling[s]
+            if pool:
+                c = fp[s - 1] if s > 0 else fp[0]
+                ops.append(("maxpool", c, c, (2, 2), "stage%d_pooling" % (s + 2)))
+            if not pool and (s == 0 or (fp[s] == fp[s - 1] and st[s] == (1, 1))):
                 for b in range(self.blocks_per_stage[s]):
                     ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
             else:
-                ops.append(("transition", fp[s - 1], fp[s], st[s], "res%d_0_branch" % (s + 2)))
+                ops.append(("transition", fp[s - 1] if s > 0 else fp[0], fp[s], st[s], "res%d_0_branch" % (s + 2)))
                 for b in range(1, self.blocks_per_stage[s]):
                     ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
         return ops
@@ -336,6 +342,8 @@ class EulerNet:
                 self.torch_shapes += [(name + "/kernel", (k, k, ci, co), k * k * ci), (name + "/bias", (co,), 0)]
                 if spec.use_batch_norm:      # bn_conv1 (models/tfkeras_resnets.py:570-571); fan_in -1 = ones
                     self.torch_shapes += [("bn_" + name + "/gamma", (co,), -1), ("bn_" + name + "/beta", (co,), 0)]
+            elif seg[0] == "maxpool":
+                continue
             elif seg[0] == "transition":
                 _, ci, co, st, name = seg
                 self.torch_shapes += [(name + "2/kernel", (k, k, ci, co), k * k * ci), (name + "2/bias", (co,), 0),
@@ -438,6 +446,8 @@ class EulerNet:
             if seg[0] == "stem":
                 _, ci, co, st, name = seg
                 x = torch.relu(bn(conv2d_same_nhwc(x, L[name + "/kernel"], L[name + "/bias"], st), "bn_" + name))
+            elif seg[0] == "maxpool":       # Keras MaxPooling2D((2,2)): torch op (the native step has no pooling kernel)
+                x = F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
             elif seg[0] == "transition":
                 _, ci, co, st, name = seg
                 bname = name.replace("res", "bn")
@@ -515,7 +525,7 @@ class EulerNet:
             return self._nb
         spec = self.spec
         N, H, W, Cin = shape
-        ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32 and not spec.use_batch_norm
+        ok = self.native_glue and spec.kernel_size == 3 and spec.num_classes <= 32 and not spec.use_batch_norm and not any(spec.use_max_pooling)
         plan, h, w, c = [], H, W, Cin
         for seg in self.segments:
             if not ok:
@@ -696,8 +706,8 @@ class EulerNet:
         if nb["plan"] is None:
             was = self.training
             self.training = False                  # BatchNorm: moving statistics
-            try:
-                with torch.no_grad():
+            try:   # strict mode: the torch-op layers (stem / transitions / head) must not use TF32 either
+                with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "strict"):
                     return self.forward(images)
             finally:
                 self.training = was

@@ -156,7 +156,8 @@ class NetSpec:
     def __init__(self, num_stages=4, blocks_per_stage=(3, 3, 3), filters_per_block=(16, 32, 64),
                  strides=((1, 1), (2, 2), (2, 2)), h=1.0, gamma=0.0, num_classes=10,
                  use_batch_norm=False, subtract_mean=127.5, divide_by_stddev=127.5, kernel_size=3,
-                 in_channels=3):
+                 in_channels=3, use_max_pooling=None):
+        self.use_max_pooling = list(use_max_pooling) if use_max_pooling is not None else [False] * (num_stages - 1)
         self.num_stages = num_stages
         self.blocks_per_stage = list(blocks_per_stage)
         self.filters_per_block = list(filters_per_block)
@@ -169,16 +170,21 @@ class NetSpec:
         self.in_channels = in_channels
 
     def plan(self):
-        """List of ('stem'|'euler'|'transition', C_in, C_out, stride, name) in graph order
-        (stage loop models/tfkeras_resnets.py:575-593; use_max_pooling=False)."""
+        """List of ('stem'|'euler'|'transition'|'maxpool', C_in, C_out, stride, name) in graph order
+        (stage loop models/tfkeras_resnets.py:575-593; MaxPooling2D(2,2) in front of a stage when use_max_pooling[s], :577-578,
+        after which the stage starts with a conv block, :589-593)."""
         fp, st = self.filters_per_block, self.strides
         ops = [("stem", self.in_channels, fp[0], st[0], "conv1")]
         for s in range(self.num_stages - 1):
-            if s == 0 or (fp[s] == fp[s - 1] and st[s] == (1, 1)):
+            pool = self.use_max_pooling[s]
+            if pool:
+                c = fp[s - 1] if s > 0 else fp[0]
+                ops.append(("maxpool", c, c, (2, 2), "stage%d_pooling" % (s + 2)))
+            if not pool and (s == 0 or (fp[s] == fp[s - 1] and st[s] == (1, 1))):
                 for b in range(self.blocks_per_stage[s]):
                     ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
             else:
-                ops.append(("transition", fp[s - 1], fp[s], st[s], "res%d_0_branch" % (s + 2)))
+                ops.append(("transition", fp[s - 1] if s > 0 else fp[0], fp[s], st[s], "res%d_0_branch" % (s + 2)))
                 for b in range(1, self.blocks_per_stage[s]):
                     ops.append(("euler", fp[s], fp[s], (1, 1), "res%d_%d_branch2" % (s + 2, b)))
         return ops
@@ -211,6 +217,8 @@ def init_net_params(spec: NetSpec, seed=0):
             if spec.use_batch_norm:
                 bn = name.replace("res", "bn")
                 P[bn + "/gamma"], P[bn + "/beta"] = torch.ones(co), torch.zeros(co)
+        elif kind == "maxpool":
+            pass
         else:
             P[name + "2/kernel"] = he_normal_keras(gen, (k, k, ci, co), k * k * ci)
             P[name + "2/bias"] = torch.zeros(co)
@@ -241,6 +249,8 @@ def net_forward(spec: NetSpec, P, images_u8_or_f32, assembly="closed", forced_ma
             if spec.use_batch_norm:
                 x = batch_norm_train(x, P["bn_conv1/gamma"], P["bn_conv1/beta"])
             x = torch.relu(x)
+        elif kind == "maxpool":
+            x = F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)     # Keras MaxPooling2D((2,2)): 'valid', floor
         elif kind == "euler":
             flat = P[name + "/packed"]
             if assembly == "closed":

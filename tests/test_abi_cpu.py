@@ -75,6 +75,12 @@ def test_netspec_plan_matches_oracle_plan():
     assert NetSpec(**kw).plan() == O1.NetSpec(**kw).plan()
     kinds = [p[0] for p in NetSpec(**kw).plan()]
     assert kinds.count("euler") == 108 and kinds.count("transition") == 2
+    # MaxPooling2D in front of a stage (models/tfkeras_resnets.py:577-578): that stage starts with a conv block (:589-593)
+    kp = dict(blocks_per_stage=(2, 3, 2), filters_per_block=(16, 16, 32), strides=((1, 1), (1, 1), (2, 2)), use_max_pooling=[False, True, False])
+    plan = NetSpec(**kp).plan()
+    assert plan == O1.NetSpec(**kp).plan()
+    assert [p[0] for p in plan] == ["stem", "euler", "euler", "maxpool", "transition", "euler", "euler", "transition", "euler"]
+    assert plan[3][4] == "stage3_pooling" and plan[4][1:4] == (16, 16, (1, 1))
 
 
 def test_conv_tile_planner_decisions():

@@ -158,3 +158,29 @@ def test_prefetched_graph_step_equals_direct_step():
         lb.append(float(out))
     torch.cuda.synchronize()
     assert la == lb and torch.equal(nets[0].theta, nets[1].theta)
+
+
+def test_train_step_with_max_pooling_stage_matches_oracle():
+    """`use_max_pooling` (models/tfkeras_resnets.py:577-578): MaxPooling2D(2,2) in front of a stage, which then starts with a conv
+    block; the Euler chains keep their CUDA kernels, the pooling itself is a torch op.  Loss and gradients vs O1."""
+    from differential_equations_resnet_b200.training import EulerNet, NetSpec
+    kw = dict(blocks_per_stage=(2, 3, 2), filters_per_block=(16, 16, 32), strides=((1, 1), (1, 1), (2, 2)), h=0.25, gamma=-0.05,
+              use_max_pooling=[False, True, False])
+    ospec = O1.NetSpec(**kw)
+    P = O1.init_net_params(ospec, seed=5)
+    net = EulerNet(NetSpec(**kw), precision="strict", seed=0)
+    net.import_params(P)
+    gen = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (8, 32, 32, 3), generator=gen, dtype=torch.uint8)
+    lab = torch.nn.functional.one_hot(torch.randint(0, 10, (8,), generator=gen), 10).float()
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    lr, gr = O1.train_step(ospec, P, M, V, 1, img, lab)
+    l = float(net.train_step(img.cuda(), lab.cuda()))
+    assert abs(l - lr) <= 1e-5 * max(1.0, abs(lr))
+    g = net.export_grads()
+    for k in gr:
+        err = float((g[k].double() - gr[k].double()).norm() / max(float(gr[k].double().norm()), 1e-30))
+        assert err <= 1e-3, (k, err)     # max-pool argmax near-ties and relu branches at rounding level: measured 4e-4 at conv1
+    p = net.predict(img.cuda()).cpu()
+    assert float((p - O1.net_forward(ospec, {k: v for k, v in net.export_params().items()}, img)).abs().max()) <= 1e-4
