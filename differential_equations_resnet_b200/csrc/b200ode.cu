@@ -954,6 +954,11 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     p.TG = 9; p.NT = p.CH; p.ntapgroups = 1; p.nngroups = 1; p.MB = 1; p.Mblk = 4 * p.CH; p.dchunks = 1;
   } else {
     p.Mblk = Cpad < 128 ? Cpad : 128;
+    // strict, C >= 128: 64-channel M blocks dealt to different CTAs -- hi + lo strips of 128 input channels leave no room
+    // for a second stage of even ONE image row; M = 64 MMAs run at half rate, but this kernel is bound by its staging
+    static const int sm64_env = getenv("B200ODE_WGRAD_STRICT_M64") ? atoi(getenv("B200ODE_WGRAD_STRICT_M64")) : 1;
+    const bool strict_m64 = strict && sm64_env && Cpad >= 128;
+    if (strict_m64) p.Mblk = 64;
     p.MB = Cpad / p.Mblk;
     // More than one M block (C = 256): deal the blocks to different CTAs.  Staging all C input channels leaves
     // room for only ~64 positions per stage (3x halo over-read, L2-bound); one 128-channel block per CTA fits
@@ -962,7 +967,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     // 702 -> 285 us, tf32 32x32 1264 -> 527 us.  tf32 at W = 64 leaves room for one stage only (position-granular
     // tiles stay), strict doubles every strip (hi + lo).
     static const int mg_env = getenv("B200ODE_WGRAD_MGROUPS") ? atoi(getenv("B200ODE_WGRAD_MGROUPS")) : -1;   // debug override
-    const bool use_mg = force_mgroups || (mg_env >= 0 ? mg_env != 0 : ((bf16 && W <= 64) || (!strict && W <= 32)));
+    const bool use_mg = force_mgroups || strict_m64 || (mg_env >= 0 ? mg_env != 0 : ((bf16 && W <= 64) || (!strict && W <= 32)));
     if (p.MB > 1 && use_mg) { p.mgroups = p.MB; p.MB = 1; p.xchunks = p.Mblk / p.CH; }
     double best = 1e30;
     for (int NT = p.CH; NT <= (C < 256 ? C : 256); NT *= 2)
@@ -1016,11 +1021,15 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // the k-steps run into a zeroed pad up to the next multiple of 16 positions.
   static const int rows_env = getenv("B200ODE_WGRAD_ROWS") ? atoi(getenv("B200ODE_WGRAD_ROWS")) : -1;   // debug override (0 = off)
   int rows = 0;
-  if (!strict && !p.trick && !p.pair && !p.shift2 && p.Mblk == 128 && rows_env != 0) {
+  // Strict mode too (round 2): its position-granular tiles had degenerated to 24 positions per 6 staged rows (hi + lo strips
+  // double the shared memory, the planner insisted on two stages): 8x over-read, a TMA round trip per 24 positions, 12 % of the
+  // 3xTF32 roof.  Row-aligned tiles stage R + 2 / R whole rows.
+  static const int srow_env = getenv("B200ODE_WGRAD_STRICT_ROWS") ? atoi(getenv("B200ODE_WGRAD_STRICT_ROWS")) : 1;
+  if ((!strict || (srow_env && C >= 64)) && !p.trick && !p.pair && !p.shift2 && (p.Mblk == 128 || strict) && rows_env != 0) {
     auto stage_bytes = [&](int R) -> long long {
       const int kt = (R * p.P + UKP - 1) / UKP * UKP;
       const uint32_t xs = align_up((uint32_t)(kt + 2 * p.P + 3) * p.PB, 1024), ds = align_up((uint32_t)kt * p.PB, 1024);
-      return (long long)p.xchunks * xs + (long long)p.dchunks * ds;
+      return ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
     };
     if (rows_env > 0) rows = rows_env;
     else {   // most rows that still leave two stages; prefer a row count with little k-step padding
@@ -1046,7 +1055,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
     p.RBx = rows + 2; p.RBd = rows;
     p.x_chunk_bytes = (uint32_t)p.RBx * p.P * p.PB; p.d_chunk_bytes = (uint32_t)p.RBd * p.P * p.PB;
     p.x_chunk_stride = align_up((uint32_t)(p.KT + 2 * p.P + 3) * p.PB, 1024); p.d_chunk_stride = align_up((uint32_t)p.KT * p.PB, 1024);
-    const long long stage = (long long)p.xchunks * p.x_chunk_stride + (long long)p.dchunks * p.d_chunk_stride;
+    const long long stage = ((long long)p.xchunks * p.x_chunk_stride + (long long)p.dchunks * p.d_chunk_stride) * (strict ? 2 : 1);
     p.stages = 1;
     while (p.stages < 6 && stage * (p.stages + 1) + 1024 + 4608 <= max_smem) ++p.stages;
   } else {
