@@ -207,6 +207,12 @@ def kernel_microbench(torch, precision, batch):
         per = Mpix * C * 4
         cprec = _abi.CHAIN_PRECISIONS.get(precision)
         if cprec is None or not ChainHandle.supported(C, H, W, cprec):
+            # modes without persistent chains (strict): the per-layer kernels at this stage shape, one launch per Euler step
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import gpu_sweep
+            for r in gpu_sweep.bench_layer(N, H, W, C, precision, reps=2, quiet=True):
+                recs.append({"kernel": "layer_%s (per Euler step)" % r["kernel"], "shape": [N, H, W, C], "us": r["us"], "launches_per_step": L,
+                             "algorithmic_bytes": r["alg_bytes"], "GBps": r["GBps"], "algorithmic_TFLOPs": r["alg_TFLOPs"]})
             continue
         ch = ChainHandle(C, L, 0.0, precision=cprec)
         sdt, sb = ch.saved_dtype, (2 if ch.f16 else 4)
