@@ -20,6 +20,7 @@
 #include "kernels_chain_tc.cuh"
 #include "kernels_chain_f16.cuh"
 #include "kernels_glue.cuh"
+#include "kernels_glue_mma.cuh"
 #include "kernels_wgrad_tc.cuh"
 #include "kernels_bn.cuh"
 
@@ -1838,6 +1839,68 @@ static int reduce_rows(const float* ws, int R, long long stride, long long n, fl
     kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                                \
   } while (0)
 
+
+// Tensor-core transitions (kernels_glue_mma.cuh): the reference's stride-2 transitions 16 -> 32 and 32 -> 64 channels.
+// B200ODE_GLUE_SIMT=1 keeps the CUDA-core kernels (A/B measurements); other shapes always use them.
+static bool transition_mma_ok(int Cin, int Cout, int sh, int sw) {
+  static const bool simt = getenv("B200ODE_GLUE_SIMT") && atoi(getenv("B200ODE_GLUE_SIMT")) != 0;
+  return !simt && sh == 2 && sw == 2 && ((Cin == 16 && Cout == 32) || (Cin == 32 && Cout == 64));
+}
+#define GLUE_MMA_LAUNCH(kern, grid, block, smem, st, ...)                                                        \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));             \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                                \
+  } while (0)
+
+// returns 0 = launched, > 0 = error, -1 = shape does not fit (caller falls back to the CUDA-core kernel)
+template <int CIN, int COUT, int NSPLIT>
+static int transition_fwd_mma(const GlueConv& g, const float* x, const float* Wm, const float* bm, const float* Ws, const float* bs,
+                              float* out, uint8_t* mask, cudaStream_t st) {
+  int orows = (128 / NSPLIT) / g.Wo;            // 8 warps x 16 positions / NSPLIT channel slices per block
+  if (orows < 1) orows = 1;
+  if (orows > g.Ho) orows = g.Ho;
+  while (orows > 1 && TrFwdMma<CIN, COUT>::smem_bytes(orows, g.W) > 160 * 1024) orows >>= 1;
+  const size_t smem = TrFwdMma<CIN, COUT>::smem_bytes(orows, g.W);
+  if (smem > 160 * 1024) return -1;
+  const dim3 grid(g.N, (g.Ho + orows - 1) / orows);
+  GLUE_MMA_LAUNCH((transition_fwd_mma_kernel<CIN, COUT, NSPLIT>), grid, 256, smem, st, g, x, Wm, bm, Ws, bs, out, mask, orows);
+  LAUNCH_CHECK("transition_fwd_mma_kernel");
+  return 0;
+}
+template <int CIN, int COUT, int NSPLIT>
+static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint8_t* mask, const float* Wm, const float* Ws, float* dx,
+                                cudaStream_t st) {
+  const int CH = (g.H - 1 + g.pt) / 2 + 1, CW = (g.W - 1 + g.pl) / 2 + 1;
+  int crows = (128 / NSPLIT) / CW;
+  if (crows < 1) crows = 1;
+  if (crows > CH) crows = CH;
+  while (crows > 1 && TrDgradMma<CIN, COUT>::smem_bytes(crows, g.Wo) > 160 * 1024) crows >>= 1;
+  const size_t smem = TrDgradMma<CIN, COUT>::smem_bytes(crows, g.Wo);
+  if (smem > 160 * 1024) return -1;
+  const dim3 grid(g.N, (CH + crows - 1) / crows);
+  GLUE_MMA_LAUNCH((transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>), grid, 256, smem, st, g, dout, mask, Wm, Ws, dx, crows);
+  LAUNCH_CHECK("transition_dgrad_mma_kernel");
+  return 0;
+}
+// partial rows the tensor-core weight gradient writes (one per block)
+static int transition_wgrad_mma_rows(int N) { const int ipb = (N + 147) / 148; return (N + ipb - 1) / ipb; }
+template <int CIN, int COUT>
+static int transition_wgrad_mma(const GlueConv& g, const float* x, const float* dout, const uint8_t* mask, float* part, cudaStream_t st) {
+  int orows = g.Ho;
+  while (orows > 1 && TrWgradMma<CIN, COUT>::smem_bytes(orows, g.W, g.Wo) > 200 * 1024) orows = (orows + 1) >> 1;
+  const size_t smem = TrWgradMma<CIN, COUT>::smem_bytes(orows, g.W, g.Wo);
+  if (smem > 200 * 1024) return -1;
+  const int ipb = (g.N + 147) / 148;
+  constexpr int threads = 32 * TrWgradMma<CIN, COUT>::NWARP;
+  GLUE_MMA_LAUNCH((transition_wgrad_mma_kernel<CIN, COUT>), dim3((g.N + ipb - 1) / ipb), threads, smem, st, g, x, dout, mask, part, orows, ipb);
+  LAUNCH_CHECK("transition_wgrad_mma_kernel");
+  return 0;
+}
+
 extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
                                       const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
                                       int Cout, int stride_h, int stride_w, void* stream) {
@@ -1847,6 +1910,11 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {
+    const int rc = Cin == 16 ? transition_fwd_mma<16, 32, 1>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st)
+                             : transition_fwd_mma<32, 64, 2>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st);
+    if (rc >= 0) return rc;
+  }
   // bands of 32*PT output pixels (PT per lane); each warp of a block owns one 8-channel slice.  Small bands = many
   // blocks: the kernel is latency-bound (ncu: 11 % warps active, IPC 0.4 with 128-pixel bands on 256 blocks).
   constexpr int COT = 8;
@@ -1881,6 +1949,11 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
+  if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {
+    const int rc = Cin == 16 ? transition_dgrad_mma<16, 32, 1>(g, dout, relu_mask, main_kernel, short_kernel, dx, st)
+                             : transition_dgrad_mma<32, 64, 2>(g, dout, relu_mask, main_kernel, short_kernel, dx, st);
+    if (rc >= 0) return rc;
+  }
   // band height: the staged output rows (dout + masked copy) and the weight slice must fit shared memory
   constexpr int CIT = 8;
   if (Cin % CIT) return fail(B200ODE_ERR_UNSUPPORTED, "transition_dgrad: Cin must be a multiple of %d (got %d)", CIT, Cin);
@@ -1947,6 +2020,11 @@ extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const
   WsLease lease;
   if (int rc = lease_ws(workspace, workspace_bytes, pl.ws_bytes, st, &lease)) return rc;
   float* ws = (float*)lease.ptr;
+  if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {      // rows <= N <= N * bands: the SIMT plan's workspace covers it
+    const int rc = Cin == 16 ? transition_wgrad_mma<16, 32>(g, x, dout, relu_mask, ws, st) : transition_wgrad_mma<32, 64>(g, x, dout, relu_mask, ws, st);
+    if (rc > 0) return rc;
+    if (rc == 0) return reduce_rows(ws, transition_wgrad_mma_rows(N), nout, nout, dparams, st);
+  }
   switch (tpg) {
     case 1: GLUE_SMEM_LAUNCH(transition_wgrad_partial<1>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;
     case 2: GLUE_SMEM_LAUNCH(transition_wgrad_partial<2>, dim3(N, bands), 256, smem, st, g, x, dout, relu_mask, ws, orows); break;

@@ -52,11 +52,14 @@ def test_stem_matches_oracle(u8):
     assert rel(dp[27 * Co:], b.grad) <= 1e-5
 
 
-@pytest.mark.parametrize("Ci,Co,H,W,st", [(16, 32, 32, 32, (2, 2)), (32, 64, 16, 16, (2, 2)), (16, 32, 9, 11, (2, 2)),
-                                          (32, 64, 8, 8, (1, 1))])
-def test_transition_matches_oracle(Ci, Co, H, W, st):
+@pytest.mark.parametrize("Ci,Co,H,W,st,N", [(16, 32, 32, 32, (2, 2), 3), (32, 64, 16, 16, (2, 2), 3), (16, 32, 9, 11, (2, 2), 3),
+                                            (32, 64, 8, 8, (1, 1), 3), (32, 64, 7, 10, (2, 2), 2), (16, 32, 64, 64, (2, 2), 1),
+                                            (32, 64, 16, 16, (2, 2), 150), (16, 32, 12, 12, (2, 1), 2)])
+def test_transition_matches_oracle(Ci, Co, H, W, st, N):
+    """Stride-2 transitions 16 -> 32 / 32 -> 64 run on the tensor-core kernels (kernels_glue_mma.cuh: 3xTF32 warp MMAs, fp32-grade),
+    every other shape on the CUDA-core kernels; N = 150 makes a weight-gradient block walk two images, odd sizes exercise
+    pad_before = 1 and ragged tiles."""
     _abi, lib = _lib()
-    N = 3
     g = torch.Generator().manual_seed(1)
     x = torch.randn((N, H, W, Ci), generator=g).requires_grad_(True)
     Wm = (torch.randn((3, 3, Ci, Co), generator=g) * 0.1).requires_grad_(True)
@@ -64,9 +67,9 @@ def test_transition_matches_oracle(Ci, Co, H, W, st):
     Ws = (torch.randn((1, 1, Ci, Co), generator=g) * 0.1).requires_grad_(True)
     bs = (torch.randn(Co, generator=g) * 0.1).requires_grad_(True)
     main = O1.conv2d_same_nhwc(x, Wm, st) + bm
-    ref = torch.relu(main) + O1.conv2d_same_nhwc(x, Ws, st) + bs
+    short = O1.conv2d_same_nhwc(x, Ws, st) + bs
+    ref = torch.relu(main) + short
     dout = torch.randn(ref.shape, generator=g)
-    ref.backward(dout)
     Ho, Wo = ref.shape[1], ref.shape[2]
     out = torch.empty((N, Ho, Wo, Co), device="cuda")
     mask = torch.empty((N, Ho, Wo, Co // 8), dtype=torch.uint8, device="cuda")
@@ -81,8 +84,15 @@ def test_transition_matches_oracle(Ci, Co, H, W, st):
     _abi.check(lib.b200ode_transition_wgrad(P(xd), P(dd), P(mask), P(dp), N, H, W, Ci, Co, st[0], st[1], None, 0, None))
     torch.cuda.synchronize()
     assert rel(out, ref) <= 1e-5
+    # backward reference along the relu branches the GPU took (its mask): a pre-activation within rounding of 0 may land on
+    # either side, and one flipped bit in 10^5 would otherwise dominate a 1e-5 gradient comparison
+    taken = torch.from_numpy(np.unpackbits(mask.cpu().numpy(), axis=-1, bitorder="little").astype(bool))
+    (torch.where(taken, main, torch.zeros_like(main)) + short).backward(dout)
     bits = np.unpackbits(mask.cpu().numpy(), axis=-1, bitorder="little").astype(bool)
-    assert np.array_equal(bits, (main.detach().numpy() > 0))
+    mref = main.detach().numpy()
+    differs = bits != (mref > 0)
+    assert not (differs & (np.abs(mref) > 1e-5)).any()      # a relu bit may only differ where the pre-activation is ~0
+    assert differs.sum() <= 2
     assert rel(dx, x.grad) <= 1e-5
     assert rel(dp[:nm].view(3, 3, Ci, Co), Wm.grad) <= 1e-5
     assert rel(dp[nm:nm + Co], bm.grad) <= 1e-5
