@@ -15,7 +15,8 @@ PREC_STRICT, PREC_FAST_TF32, PREC_FAST_BF16, PREC_SIMT_FP32, PREC_FAST_F16 = 0, 
 PRECISIONS = {"strict": PREC_STRICT, "fast_tf32": PREC_FAST_TF32, "fast": PREC_FAST_TF32,
               "fast_bf16": PREC_FAST_BF16, "simt": PREC_SIMT_FP32}
 # "fast_f16" exists for the persistent chains only (EulerNet); layers created with it use the FAST_TF32 per-layer kernels
-CHAIN_PRECISIONS = {"fast_tf32": PREC_FAST_TF32, "fast": PREC_FAST_TF32, "fast_f16": PREC_FAST_F16}
+# "strict": the 3xTF32 variant of the tf32 chain kernels (fp32-grade, <= 1e-5)
+CHAIN_PRECISIONS = {"fast_tf32": PREC_FAST_TF32, "fast": PREC_FAST_TF32, "fast_f16": PREC_FAST_F16, "strict": PREC_STRICT}
 LAYOUT_3BY3, LAYOUT_GENERAL = 0, 1
 F_BIAS, F_RELU, F_SCALE, F_RESIDUAL = 1, 2, 4, 8
 F_EULER = 15

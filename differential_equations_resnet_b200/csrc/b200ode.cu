@@ -1377,9 +1377,10 @@ extern "C" int b200ode_increment(int32_t* counter, void* stream) {
 struct b200ode_chain {
   LayerGeom g;
   int L;           // distinct weight layers
-  int mode;        // B200ODE_PREC_FAST_TF32 (kernels_chain_tc.cuh) or B200ODE_PREC_FAST_F16 (kernels_chain_f16.cuh)
+  int mode;        // B200ODE_PREC_FAST_TF32 / B200ODE_PREC_STRICT (kernels_chain_tc.cuh) or B200ODE_PREC_FAST_F16 (kernels_chain_f16.cuh)
   bool packed;
-  float* w_hi;     // FAST_TF32: [L][9][C][C] tf32-rounded, K-major B operand
+  float* w_hi;     // FAST_TF32: [L][9][C][C] tf32-rounded, K-major B operand; STRICT: truncated to tf32 ...
+  float* w_lo;     // STRICT: ... and the remainder (3xTF32)
   __half* w16;     // FAST_F16:  [L][9][C][C] fp16, K-major B operand
   float* bias;     // [L][C]
   float* amax;     // FAST_F16: device scalar max|dy| of the last backward sweep (scale of dz_all)
@@ -1396,7 +1397,7 @@ struct ChainPlan {
 static bool chain_channels_ok(int C) { return C == 16 || C == 32 || C == 64; }
 
 // Shared-memory plan of chain_tc_kernel; returns false when a whole image does not fit.
-static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
+static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan, bool strict = false) {
   if (!chain_channels_ok(C)) return false;
   const int rowb = C * 4 >= 128 ? 128 : C * 4;
   const int nkb = C * 4 / rowb;
@@ -1412,7 +1413,8 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
   p.strip_stride = (uint32_t)nkb * p.plane_bytes;
   p.x_bytes = (uint32_t)(H + 2) * P * rowb;
   p.tw = taps_per_w_stage(MODE_TF32, C);
-  p.w_stage_bytes = (uint32_t)p.tw * C * rowb;
+  p.w_stage_bytes = (uint32_t)p.tw * C * rowb * (strict ? 2 : 1);     // strict: hi tile | lo tile
+  p.w_lo_off = strict ? p.w_stage_bytes / 2 : 0;
   p.seg_outer = (nkb == 1 && p.tw == 9) ? 1 : 0;
   p.e_off = 2 * p.strip_stride;
   const uint32_t e_bytes = dir ? align_up((uint32_t)H * W * C * 4, 1024) : 0;
@@ -1422,7 +1424,7 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan) {
   int sw = 2 * per_layer;                            // ideally: the next layer fully prefetched
   while (sw > 1 && (long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) --sw;
   if ((long long)p.w_off + (long long)sw * p.w_stage_bytes > max_smem) return false;
-  if (sw < per_layer) return false;                  // the MMA warp waits for a whole layer's entries up front
+  if (sw < per_layer && !strict) return false;       // the fast kernel's MMA warp waits for a whole layer's entries up front
   p.sw = sw;
   p.bar_off = p.w_off + (uint32_t)sw * p.w_stage_bytes;
   // the MMAs of the last segment read (junk rows) up to 128*nseg + 2P + 2 positions of strip 1: keep that inside the allocation
@@ -1475,9 +1477,10 @@ extern "C" int b200ode_chain_supported(int channels, int H, int W, int precision
     ChainF16Plan pl;
     return plan_chain_f16(channels, H, W, &pl) ? 1 : 0;
   }
-  if (precision_mode != B200ODE_PREC_FAST_TF32) return 0;
+  if (precision_mode != B200ODE_PREC_FAST_TF32 && precision_mode != B200ODE_PREC_STRICT) return 0;
   ChainPlan pl;
-  return plan_chain(channels, H, W, 0, &pl) && plan_chain(channels, H, W, 1, &pl) ? 1 : 0;
+  const bool strict = precision_mode == B200ODE_PREC_STRICT;
+  return plan_chain(channels, H, W, 0, &pl, strict) && plan_chain(channels, H, W, 1, &pl, strict) ? 1 : 0;
 }
 
 extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int use_bias, int precision_mode,
@@ -1485,8 +1488,8 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
   if (!out) return fail(B200ODE_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (n_layers < 1) return fail(B200ODE_ERR_INVALID, "n_layers must be >= 1");
-  if (precision_mode != B200ODE_PREC_FAST_TF32 && precision_mode != B200ODE_PREC_FAST_F16)
-    return fail(B200ODE_ERR_UNSUPPORTED, "chains run in FAST_TF32 or FAST_F16 mode");
+  if (precision_mode != B200ODE_PREC_FAST_TF32 && precision_mode != B200ODE_PREC_FAST_F16 && precision_mode != B200ODE_PREC_STRICT)
+    return fail(B200ODE_ERR_UNSUPPORTED, "chains run in STRICT, FAST_TF32 or FAST_F16 mode");
   if (!chain_channels_ok(channels)) return fail(B200ODE_ERR_UNSUPPORTED, "chains need C in {16,32,64} (got %d)", channels);
   if (int rc = device_check()) return rc;
   b200ode_chain* ch = new b200ode_chain();
@@ -1499,6 +1502,7 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
   ch->L = n_layers; ch->mode = precision_mode; ch->amax_h = 1.0f;
   const size_t wn = (size_t)n_layers * 9 * channels * channels;
   cudaError_t e = precision_mode == B200ODE_PREC_FAST_F16 ? cudaMalloc(&ch->w16, wn * sizeof(__half)) : cudaMalloc(&ch->w_hi, wn * sizeof(float));
+  if (e == cudaSuccess && precision_mode == B200ODE_PREC_STRICT) e = cudaMalloc(&ch->w_lo, wn * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ch->bias, (size_t)n_layers * channels * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ch->amax, sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(ch->amax, 0, sizeof(float));
@@ -1512,7 +1516,7 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
 
 extern "C" int b200ode_chain_destroy(b200ode_chain_t* ch) {
   if (!ch) return 0;
-  cudaFree(ch->w_hi); cudaFree(ch->w16); cudaFree(ch->bias); cudaFree(ch->amax);
+  cudaFree(ch->w_hi); cudaFree(ch->w_lo); cudaFree(ch->w16); cudaFree(ch->bias); cudaFree(ch->amax);
   delete ch;
   return 0;
 }
@@ -1525,13 +1529,13 @@ extern "C" int b200ode_chain_pack(b200ode_chain_t* ch, const float* params, int6
   if (ch->mode == B200ODE_PREC_FAST_F16)
     pack_chain_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w16, ch->bias);
   else
-    pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->bias);
+    pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->w_lo, ch->bias);
   LAUNCH_CHECK("pack_chain_kernel");
   ch->packed = true;
   return 0;
 }
 
-static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw) {
+static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw, bool lo = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int C = ch->g.C;
@@ -1541,7 +1545,7 @@ static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw) {
   cuuint32_t box[3] = {(cuuint32_t)(rowb / 4), (cuuint32_t)C, (cuuint32_t)tw};
   cuuint32_t es[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ch->w_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, lo ? ch->w_lo : ch->w_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(chain weights) failed with %d", (int)r);
   return 0;
@@ -1562,14 +1566,15 @@ static int chain_grid(ChainParams& p, int C, int N) {
   return grid;
 }
 
-template <int DIR>
+template <int DIR, bool ST = false>
 static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CUtensorMap& mx, const CUtensorMap& mw, int grid,
-                        cudaStream_t st) {
+                        cudaStream_t st, const CUtensorMap* mwl = nullptr) {
+  const CUtensorMap& ml = mwl ? *mwl : mw;
 #define CH_LAUNCH(C_)                                                                                              \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
     if (!attr_set) {                                                                                               \
-      CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<C_, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      CUDA_TRY(cudaFuncSetAttribute(chain_tc_kernel<C_, DIR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                             \
     }                                                                                                              \
     cudaLaunchConfig_t cfg;                                                                                        \
@@ -1579,7 +1584,7 @@ static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CU
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
     attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;              \
     cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;                                                         \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_tc_kernel<C_, DIR>, mx, mw, plan.p));                                   \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_tc_kernel<C_, DIR, ST>, mx, mw, ml, plan.p));                           \
   } while (0)
   switch (ch->g.C) {
     case 16: CH_LAUNCH(16); break;
@@ -1673,7 +1678,8 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, void* act
     return launch_chain_f16<0>(ch, plan, mw, chain_f16_grid(p, ch->g.C, N), (cudaStream_t)stream);
   }
   ChainPlan plan;
-  if (!plan_chain(ch->g.C, H, W, 0, &plan))
+  const bool strict = ch->mode == B200ODE_PREC_STRICT;
+  if (!plan_chain(ch->g.C, H, W, 0, &plan, strict))
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = n_steps; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
@@ -1683,6 +1689,11 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, void* act
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (int rc = make_act_map(&mx, x0, N, H, W, C, 4, rowb / 4, p.P, H + 2, 1, sw)) return rc;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
+  if (strict) {
+    CUtensorMap mwl;
+    if (int rc = make_chain_w_map(&mwl, ch, p.tw, true)) return rc;
+    return launch_chain<0, true>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream, &mwl);
+  }
   return launch_chain<0>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
 }
 
@@ -1712,13 +1723,19 @@ extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const u
     return launch_chain_f16<1>(ch, plan, mw, chain_f16_grid(p, ch->g.C, N), st);
   }
   ChainPlan plan;
-  if (!plan_chain(ch->g.C, H, W, 1, &plan))
+  const bool strict = ch->mode == B200ODE_PREC_STRICT;
+  if (!plan_chain(ch->g.C, H, W, 1, &plan, strict))
     return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
   ChainParams& p = plan.p;
   p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
   p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (float*)dz_all; p.dx = dx; p.trace = g_trace;
   CUtensorMap mw;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
+  if (strict) {
+    CUtensorMap mwl;
+    if (int rc = make_chain_w_map(&mwl, ch, p.tw, true)) return rc;
+    return launch_chain<1, true>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream, &mwl);
+  }
   return launch_chain<1>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream);
 }
 
@@ -1735,8 +1752,8 @@ extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const v
   }
   if (!x0) return fail(B200ODE_ERR_INVALID, "x0 is NULL");
   if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
-  return run_wgrad_tc(MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params, grad_layer_stride, 0,
-                      (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr});
+  return run_wgrad_tc(ch->mode == B200ODE_PREC_STRICT ? MODE_STRICT : MODE_TF32, ch->g, x0, acts, dz_all, ch->L, N, H, W, nullptr, nullptr,
+                      grad_params, grad_layer_stride, 0, (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr});
 }
 
 
@@ -2085,7 +2102,8 @@ extern "C" int b200ode_chain_workspace_bytes(const b200ode_chain_t* ch, int N, i
   if (N < 0 || H < 1 || W < 1) return fail(B200ODE_ERR_INVALID, "bad shape N=%d H=%d W=%d", N, H, W);
   *bytes_out = 0;
   if (N == 0) return 0;
-  return run_wgrad_tc(ch->mode == B200ODE_PREC_FAST_F16 ? MODE_F16 : MODE_TF32, ch->g, nullptr, nullptr, nullptr, ch->L, N, H, W,
+  return run_wgrad_tc(ch->mode == B200ODE_PREC_FAST_F16 ? MODE_F16 : ch->mode == B200ODE_PREC_STRICT ? MODE_STRICT : MODE_TF32, ch->g,
+                      nullptr, nullptr, nullptr, ch->L, N, H, W,
                       nullptr, nullptr, nullptr, 0, 0, nullptr, WsArg{nullptr, 0, bytes_out});
 }
 extern "C" int b200ode_chain_set_workspace(b200ode_chain_t* ch, void* workspace, size_t bytes) {

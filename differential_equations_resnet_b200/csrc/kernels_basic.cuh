@@ -95,8 +95,9 @@ __global__ void pack_kernel(LayerGeom g, const float* __restrict__ params, float
 }
 
 // Chain variant: blockIdx.y = layer; tf32-rounded staged weights [L][taps][o][ci] and biases [L][C].
+// w_lo != NULL (strict chains): hi = the entry truncated to tf32 (what the tensor core reads), lo = the remainder.
 __global__ void pack_chain_kernel(LayerGeom g, const float* __restrict__ params, long long param_layer_stride,
-                                  float* __restrict__ w_hi, float* __restrict__ bias_out) {
+                                  float* __restrict__ w_hi, float* __restrict__ w_lo, float* __restrict__ bias_out) {
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y;
@@ -106,7 +107,14 @@ __global__ void pack_chain_kernel(LayerGeom g, const float* __restrict__ params,
   const int ci = (int)(i % g.C);
   const int o = (int)((i / g.C) % g.C);
   const int tap = (int)(i / ((long long)g.C * g.C));
-  w_hi[(long long)l * total + i] = tf32_rna(kernel_entry(g, params, tap / g.k, tap % g.k, ci, o));
+  const float v = kernel_entry(g, params, tap / g.k, tap % g.k, ci, o);
+  if (w_lo) {
+    const float hi = tf32_trunc(v);
+    w_hi[(long long)l * total + i] = hi;
+    w_lo[(long long)l * total + i] = tf32_rna(v - hi);
+  } else {
+    w_hi[(long long)l * total + i] = tf32_rna(v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,6 +16,14 @@
 //                     (the data gradient reuses the forward weights); dY stays in
 //                     a second, thread-private shared buffer E.
 //
+// ST = true (strict mode, 3xTF32): fp32-grade results from tf32 MMAs.  The tensor core reads the top 19 bits of an fp32
+// operand, so strip 0 (fp32, also the residual stream) IS the "hi" operand; the epilogue that produces a strip also writes
+// its remainder lo = v - trunc_tf32(v) (exact in fp32, then rounded to tf32) into strip 1, and every weight ring stage
+// carries a hi tile and a lo tile (pack_chain_strict_kernel).  Per (tap, k-step): lo*Whi + hi*Wlo + hi*Whi, small terms
+// first, one fp32 TMEM accumulator.  Two strips (value + remainder) leave no room for the ping-pong pair of the fast
+// mode: the step's input is updated IN PLACE, so the epilogue waits for the step's last MMA before it stores anything
+// (MMAs and epilogue alternate; the next step's weights stream in under the epilogue).
+//
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two warps per TMEM lane quarter).  When all nine
 // taps of a layer fit one ring stage (C <= 32) the MMAs are issued segment by segment with one commit
 // per 128-position segment, so the epilogue of segment s overlaps the MMAs of segments > s.
@@ -57,6 +65,7 @@ struct ChainParams {
   int cs;                 // cluster size (1 = no cluster)
   int dbg_skip_w;         // debug: do not load weights (timing experiments only)
   int iters;              // images per CTA = ceil(N / gridDim.x); CTAs whose image index is >= N run as ghosts
+  uint32_t w_lo_off;      // strict: byte offset of the lo tile inside a weight ring stage (= w_stage_bytes / 2)
 };
 
 template <int C>
@@ -92,10 +101,21 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// remainder of v after the tensor core's operand read (top 19 bits of the fp32 word), rounded to tf32
+__device__ __forceinline__ float tf32_remainder(float v) {
+  const float r = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(r));
+  return __uint_as_float(o);
+}
+__device__ __forceinline__ float4 tf32_remainder4(float4 v) {
+  return make_float4(tf32_remainder(v.x), tf32_remainder(v.y), tf32_remainder(v.z), tf32_remainder(v.w));
+}
 
-template <int C, int DIR>
+template <int C, int DIR, bool ST = false>
 __global__ void __launch_bounds__(320, 1)
-chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ChainParams p) {
+chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_wl, const ChainParams p) {
   using Cfg = ChainCfg<C>;
   constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG, TW = Cfg::TW;
   constexpr uint32_t LT = ROWB == 128 ? SWZ_128B : ROWB == 64 ? SWZ_64B : SWZ_32B;
@@ -125,6 +145,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     if (DIR == 0) tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
+    if (ST) tma_prefetch_desc(&map_wl);
     mbar_init(x_full, 1);
     mbar_init(layer_done, 8);
     mbar_init(img_done, 8);
@@ -182,6 +203,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               } else if (p.cs == 1) {
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);
                 tma_load_3d(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg);
+                if (ST) tma_load_3d(smem + p.w_off + s * p.w_stage_bytes + p.w_lo_off, &map_wl, &w_full[s], kb * KB, 0, lw * 9 + tg);
               } else if (crank != 0) {
                 if (iw >= (uint32_t)p.sw) mbar_arrive_cluster(&w_empty_cl[s], 0);   // tell rank 0 the stage is free here
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);                        // rank 0's multicast completes it
@@ -189,6 +211,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (iw >= (uint32_t)p.sw) mbar_wait_sleep(&w_empty_cl[s], ph ^ 1);
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);
                 tma_load_3d_mc(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg, cmask);
+                if (ST) tma_load_3d_mc(smem + p.w_off + s * p.w_stage_bytes + p.w_lo_off, &map_wl, &w_full[s], kb * KB, 0, lw * 9 + tg, cmask);
               }
               ++iw;
               if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
@@ -214,7 +237,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // The step's weight entries are awaited FIRST: they were prefetched a step ahead, and this warp is
         // idle while the previous step's epilogue runs, so the ~140 cycles per mbarrier wait are hidden there
         // instead of sitting between the strip hand-over and the first MMA.
-        {
+        if (!ST) {     // (strict: a layer's entries may exceed the ring; each one is awaited where it is used)
           uint32_t s2 = ws, ph2 = wph;
           const int nent = p.seg_outer ? 1 : NKB * (9 / TW);
           for (int e = 0; e < nent; ++e) {
@@ -222,15 +245,17 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (++s2 == (uint32_t)p.sw) { s2 = 0; ph2 ^= 1; }
           }
         }
-        if (DIR == 0 && li == 0) mbar_wait(x_full, ic & 1);
-        else { mbar_wait(layer_done, ld & 1); ++ld; }
+        if (DIR == 0 && li == 0 && !ST) mbar_wait(x_full, ic & 1);
+        else { mbar_wait(layer_done, ld & 1); ++ld; }       // (strict forward: the epilogue warps derive the lo strip of x0 first)
         tc_fence_after_sync();
         if (ic == 0 && lane == 0) { if (li == TL) tr.mark(2); if (li == TL + 1) tr.mark(5); }
-        const uint32_t a_base = (smem_base + (uint32_t)(li & 1) * p.strip_stride) >> 4;
+        const uint32_t a_base = (smem_base + (ST ? 0u : (uint32_t)(li & 1) * p.strip_stride)) >> 4;
+        const uint32_t a_lo = p.strip_stride >> 4, b_lo = p.w_lo_off >> 4;     // strict: remainder strip / lo weight tile
         if (p.seg_outer) {
           const uint32_t s = ws;
           if (ic == 0 && li == TL && lane == 0) tr.mark(3);
           const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
+          if (ST) { mbar_wait(&w_full[s], wph); tc_fence_after_sync(); }
           uint32_t a_sg = a_base, d = tmem_base;
           for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
 #pragma unroll
@@ -238,7 +263,16 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
                 const uint64_t da = mk(a_sg + toff[t] + 2 * ks), db = mk(b_base + t * tap_units + 2 * ks);
-                if (leader) umma_tf32(d, da, db, idesc, (t | ks) ? 1u : 0u);
+                if (ST) {
+                  const uint64_t dal = mk(a_sg + a_lo + toff[t] + 2 * ks), dbl = mk(b_base + b_lo + t * tap_units + 2 * ks);
+                  if (leader) {
+                    umma_tf32(d, dal, db, idesc, (t | ks) ? 1u : 0u);
+                    umma_tf32(d, da, dbl, idesc, 1u);
+                    umma_tf32(d, da, db, idesc, 1u);
+                  }
+                } else {
+                  if (leader) umma_tf32(d, da, db, idesc, (t | ks) ? 1u : 0u);
+                }
               }
             }
             if (leader) umma_commit(&acc_full[sg]);
@@ -256,6 +290,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int tg = 0; tg < 9; tg += TW) {
               const uint32_t s = ws;
               const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
+              if (ST) { mbar_wait(&w_full[s], wph); tc_fence_after_sync(); }
               // taps and k-steps fully unrolled (descriptor arithmetic overlaps across MMAs); segments outermost
               uint32_t a_sg = a_kb, d = tmem_base;
               for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
@@ -264,7 +299,16 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
                   for (int ks = 0; ks < KS; ++ks) {
                     const uint64_t da = mk(a_sg + toff[tg + tt] + 2 * ks), db = mk(b_base + tt * tap_units + 2 * ks);
-                    if (leader) umma_tf32(d, da, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
+                    if (ST) {
+                      const uint64_t dal = mk(a_sg + a_lo + toff[tg + tt] + 2 * ks), dbl = mk(b_base + b_lo + tt * tap_units + 2 * ks);
+                      if (leader) {
+                        umma_tf32(d, dal, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
+                        umma_tf32(d, da, dbl, idesc, 1u);
+                        umma_tf32(d, da, db, idesc, 1u);
+                      }
+                    } else {
+                      if (leader) umma_tf32(d, da, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
+                    }
                   }
                 }
               }
@@ -337,7 +381,32 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 z.z = (bits >> (4 * j + 2)) & 1u ? p.h * d[j].z : 0.0f;
                 z.w = (bits >> (4 * j + 3)) & 1u ? p.h * d[j].w : 0.0f;
                 sts128(pl + strip_chunk_off<ROWB>(pos, (c0 % KB) / 4 + j), z);
+                if (ST) sts128(pl + p.strip_stride + strip_chunk_off<ROWB>(pos, (c0 % KB) / 4 + j), tf32_remainder4(z));
                 *reinterpret_cast<float4*>(dz_l + (long long)pixl * C + c0 + 4 * j) = z;
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(layer_done);
+      }
+      if (ST && DIR == 0) {
+        // ---- init: remainder strip of x0 (strip 0 arrives by TMA) ----
+        mbar_wait_sleep(x_full, ic & 1);
+#pragma unroll
+        for (int sg = 0; sg < MAXSEG; ++sg) {
+          if ((vmask >> sg) & 1u) {
+            const uint32_t pos = (uint32_t)(sg * 128 + row + p.P + 1);
+#pragma unroll
+            for (int cg = 0; cg < NG; ++cg) {
+              if (((sg * NG + cg) & 1) != half) continue;
+              const int c0 = cg * 16;
+              const uint32_t pl = smem_base + (uint32_t)(c0 / KB) * p.plane_bytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t so = strip_chunk_off<ROWB>(pos, (c0 % KB) / 4 + j);
+                sts128(pl + p.strip_stride + so, tf32_remainder4(lds128(pl + so)));
               }
             }
           }
@@ -348,8 +417,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       for (int li = 0; li < p.L; ++li, ++lc) {
         const int l = DIR ? p.L - 1 - li : li;
-        const uint32_t cur = smem_base + (uint32_t)(li & 1) * p.strip_stride;
-        const uint32_t nxt = smem_base + (uint32_t)((li & 1) ^ 1) * p.strip_stride;
+        const uint32_t cur = smem_base + (ST ? 0u : (uint32_t)(li & 1) * p.strip_stride);
+        const uint32_t nxt = smem_base + (ST ? 0u : (uint32_t)((li & 1) ^ 1) * p.strip_stride);
+        const uint32_t nlo = smem_base + p.strip_stride;       // strict: remainder strip
         const bool last = li == p.L - 1;
         // per-layer pointers
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + (l % p.Lw) * C);
@@ -381,6 +451,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           } else {
             out_l = p.dx + img_off;
           }
+        }
+        if (ST) {     // in-place update: no store into the strips before the step's last MMA has read them
+          mbar_wait_sleep(&acc_full[p.nseg - 1], lc & 1);
+          tc_fence_after_sync();
         }
 #pragma unroll
         for (int sg = 0; sg < MAXSEG; ++sg) {
@@ -446,6 +520,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   if (!last) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) sts128(nxt + so[j], o[j]);
+                    if (ST) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) sts128(nlo + so[j], tf32_remainder4(o[j]));
+                    }
                   }
                   if (out_l) {
                     float4* op = reinterpret_cast<float4*>(out_l + (long long)pixl * C + c0);
@@ -491,6 +569,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   if (!last) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { sts128(eo[j], o[j]); sts128(nxt + so[j], z[j]); }
+                    if (ST) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) sts128(nlo + so[j], tf32_remainder4(z[j]));
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) op[j] = z[j];
                   } else {
