@@ -43,8 +43,11 @@ def _run(precision, tol_loss, tol_grad, graph=False):
             for k in gr:
                 err = float((g[k].double() - gr[k].double()).norm() / max(float(gr[k].double().norm()), 1e-30))
                 assert err <= tol_grad, (k, err)
-    for a, b in zip(losses, losses_ref):
-        assert abs(a - b) <= tol_loss * max(1.0, abs(b)), (losses, losses_ref)
+    # Step 1's loss is pure forward parity.  Steps 2 and 3 sit behind Adam updates: at t <= 3 Adam moves every element by
+    # ~lr * sign(g), so elements whose gradient is at rounding level move the OTHER way by 2e-3 (see the update check below)
+    # and the later losses inherit that: measured 1.3e-5 on step 3 in strict mode with the fp32-grade native glue kernels.
+    for t, (a, b) in enumerate(zip(losses, losses_ref)):
+        assert abs(a - b) <= (tol_loss if t == 0 else max(tol_loss, 1e-4)) * max(1.0, abs(b)), (losses, losses_ref)
     th = net.export_params()
     # After 3 Adam steps compare the UPDATES relatively.  At step t <= 3 Adam moves every element by ~lr*sign(g)
     # (|g| >> eps), so the update's relative error is sqrt(4 * fraction of elements whose gradient sign differs):
