@@ -1129,6 +1129,8 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.trace = g_trace;
   static const int wdbg_env = getenv("B200ODE_WGRAD_DBG") ? atoi(getenv("B200ODE_WGRAD_DBG")) : 0;
   p.dbg = wdbg_env;
+  static const int nostack_env = getenv("B200ODE_WGRAD_NOSTACK") ? atoi(getenv("B200ODE_WGRAD_NOSTACK")) : 0;
+  p.dbg_nostack = nostack_env;
   p.bias_partials = ws + (size_t)L * nparts * pstride;
   p.part_layer_stride = (long long)nparts * pstride;
   p.bias_layer_stride = (long long)nparts * C;
@@ -1379,8 +1381,9 @@ struct b200ode_chain {
   int L;           // distinct weight layers
   int mode;        // B200ODE_PREC_FAST_TF32 / B200ODE_PREC_STRICT (kernels_chain_tc.cuh) or B200ODE_PREC_FAST_F16 (kernels_chain_f16.cuh)
   bool packed;
-  float* w_hi;     // FAST_TF32: [L][9][C][C] tf32-rounded, K-major B operand; STRICT: truncated to tf32 ...
-  float* w_lo;     // STRICT: ... and the remainder (3xTF32)
+  float* w_hi;     // FAST_TF32: [L][9][C][C] tf32-rounded, K-major B operand; STRICT: [L][9][2][C][C] = per tap the entries
+                   // truncated to tf32 followed by their remainders (3xTF32; one 2C-row B tile per tap)
+  float* w_lo;     // unused (kept NULL)
   __half* w16;     // FAST_F16:  [L][9][C][C] fp16, K-major B operand
   float* bias;     // [L][C]
   float* amax;     // FAST_F16: device scalar max|dy| of the last backward sweep (scale of dz_all)
@@ -1413,8 +1416,7 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan, bool stric
   p.strip_stride = (uint32_t)nkb * p.plane_bytes;
   p.x_bytes = (uint32_t)(H + 2) * P * rowb;
   p.tw = taps_per_w_stage(MODE_TF32, C);
-  p.w_stage_bytes = (uint32_t)p.tw * C * rowb * (strict ? 2 : 1);     // strict: hi tile | lo tile
-  p.w_lo_off = strict ? p.w_stage_bytes / 2 : 0;
+  p.w_stage_bytes = (uint32_t)p.tw * C * rowb * (strict ? 2 : 1);     // strict: 2C rows per tap (W_hi rows, then W_lo rows)
   p.seg_outer = (nkb == 1 && p.tw == 9) ? 1 : 0;
   p.e_off = 2 * p.strip_stride;
   const uint32_t e_bytes = dir ? align_up((uint32_t)H * W * C * 4, 1024) : 0;
@@ -1430,7 +1432,8 @@ static bool plan_chain(int C, int H, int W, int dir, ChainPlan* plan, bool stric
   // the MMAs of the last segment read (junk rows) up to 128*nseg + 2P + 2 positions of strip 1: keep that inside the allocation
   const long long reach = (long long)p.strip_stride + (long long)(nkb - 1) * p.plane_bytes + (long long)(128 * nseg + 2 * P + 3) * rowb;
   if (reach > (long long)p.bar_off) return false;
-  uint32_t cols = (uint32_t)nseg * C, pc = 32;
+  uint32_t cols = (uint32_t)nseg * C * (strict ? 2 : 1), pc = 32;      // strict: [main | correction] column ranges per segment
+  if (cols > 512) return false;
   while (pc < cols) pc <<= 1;
   p.tmem_cols = pc;
   plan->p = p;
@@ -1501,8 +1504,8 @@ extern "C" int b200ode_chain_create(int channels, int n_layers, float gamma, int
   g.nparams = g.bias_off + (use_bias ? channels : 0);
   ch->L = n_layers; ch->mode = precision_mode; ch->amax_h = 1.0f;
   const size_t wn = (size_t)n_layers * 9 * channels * channels;
-  cudaError_t e = precision_mode == B200ODE_PREC_FAST_F16 ? cudaMalloc(&ch->w16, wn * sizeof(__half)) : cudaMalloc(&ch->w_hi, wn * sizeof(float));
-  if (e == cudaSuccess && precision_mode == B200ODE_PREC_STRICT) e = cudaMalloc(&ch->w_lo, wn * sizeof(float));
+  cudaError_t e = precision_mode == B200ODE_PREC_FAST_F16 ? cudaMalloc(&ch->w16, wn * sizeof(__half))
+                                                          : cudaMalloc(&ch->w_hi, wn * sizeof(float) * (precision_mode == B200ODE_PREC_STRICT ? 2 : 1));
   if (e == cudaSuccess) e = cudaMalloc(&ch->bias, (size_t)n_layers * channels * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ch->amax, sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(ch->amax, 0, sizeof(float));
@@ -1529,23 +1532,24 @@ extern "C" int b200ode_chain_pack(b200ode_chain_t* ch, const float* params, int6
   if (ch->mode == B200ODE_PREC_FAST_F16)
     pack_chain_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w16, ch->bias);
   else
-    pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->w_lo, ch->bias);
+    pack_chain_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ch->g, params, param_layer_stride, ch->w_hi, ch->mode == B200ODE_PREC_STRICT ? 1 : 0, ch->bias);
   LAUNCH_CHECK("pack_chain_kernel");
   ch->packed = true;
   return 0;
 }
 
-static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw, bool lo = false) {
+static int make_chain_w_map(CUtensorMap* m, const b200ode_chain* ch, int tw) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int C = ch->g.C;
   const int rowb = C * 4 >= 128 ? 128 : C * 4;
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)9 * ch->L};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * C * 4};
-  cuuint32_t box[3] = {(cuuint32_t)(rowb / 4), (cuuint32_t)C, (cuuint32_t)tw};
+  const int rows = ch->mode == B200ODE_PREC_STRICT ? 2 * C : C;       // strict: W_hi rows then W_lo rows per tap
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)9 * ch->L};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)(rowb / 4), (cuuint32_t)rows, (cuuint32_t)tw};
   cuuint32_t es[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, lo ? ch->w_lo : ch->w_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ch->w_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200ODE_ERR_CUDA, "cuTensorMapEncodeTiled(chain weights) failed with %d", (int)r);
   return 0;
@@ -1568,8 +1572,7 @@ static int chain_grid(ChainParams& p, int C, int N) {
 
 template <int DIR, bool ST = false>
 static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CUtensorMap& mx, const CUtensorMap& mw, int grid,
-                        cudaStream_t st, const CUtensorMap* mwl = nullptr) {
-  const CUtensorMap& ml = mwl ? *mwl : mw;
+                        cudaStream_t st) {
 #define CH_LAUNCH(C_)                                                                                              \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
@@ -1584,7 +1587,7 @@ static int launch_chain(const b200ode_chain* ch, const ChainPlan& plan, const CU
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
     attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;              \
     cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;                                                         \
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_tc_kernel<C_, DIR, ST>, mx, mw, ml, plan.p));                           \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_tc_kernel<C_, DIR, ST>, mx, mw, plan.p));                               \
   } while (0)
   switch (ch->g.C) {
     case 16: CH_LAUNCH(16); break;
@@ -1689,11 +1692,7 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, void* act
   CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (int rc = make_act_map(&mx, x0, N, H, W, C, 4, rowb / 4, p.P, H + 2, 1, sw)) return rc;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
-  if (strict) {
-    CUtensorMap mwl;
-    if (int rc = make_chain_w_map(&mwl, ch, p.tw, true)) return rc;
-    return launch_chain<0, true>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream, &mwl);
-  }
+  if (strict) return launch_chain<0, true>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
   return launch_chain<0>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
 }
 
@@ -1731,11 +1730,7 @@ extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const u
   p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (float*)dz_all; p.dx = dx; p.trace = g_trace;
   CUtensorMap mw;
   if (int rc = make_chain_w_map(&mw, ch, p.tw)) return rc;
-  if (strict) {
-    CUtensorMap mwl;
-    if (int rc = make_chain_w_map(&mwl, ch, p.tw, true)) return rc;
-    return launch_chain<1, true>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream, &mwl);
-  }
+  if (strict) return launch_chain<1, true>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream);
   return launch_chain<1>(ch, plan, mw, mw, chain_grid(p, ch->g.C, N), (cudaStream_t)stream);
 }
 

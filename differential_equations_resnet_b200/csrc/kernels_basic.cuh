@@ -95,9 +95,10 @@ __global__ void pack_kernel(LayerGeom g, const float* __restrict__ params, float
 }
 
 // Chain variant: blockIdx.y = layer; tf32-rounded staged weights [L][taps][o][ci] and biases [L][C].
-// w_lo != NULL (strict chains): hi = the entry truncated to tf32 (what the tensor core reads), lo = the remainder.
+// strict != 0 (strict chains): [L][taps][2][o][ci] -- per tap the entries truncated to tf32 (what the tensor core reads)
+// followed by their remainders, so that one 2C-row B tile per tap carries W_hi and W_lo.
 __global__ void pack_chain_kernel(LayerGeom g, const float* __restrict__ params, long long param_layer_stride,
-                                  float* __restrict__ w_hi, float* __restrict__ w_lo, float* __restrict__ bias_out) {
+                                  float* __restrict__ w_hi, int strict, float* __restrict__ bias_out) {
   const long long total = (long long)g.k * g.k * g.C * g.C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y;
@@ -108,10 +109,12 @@ __global__ void pack_chain_kernel(LayerGeom g, const float* __restrict__ params,
   const int o = (int)((i / g.C) % g.C);
   const int tap = (int)(i / ((long long)g.C * g.C));
   const float v = kernel_entry(g, params, tap / g.k, tap % g.k, ci, o);
-  if (w_lo) {
+  if (strict) {
     const float hi = tf32_trunc(v);
-    w_hi[(long long)l * total + i] = hi;
-    w_lo[(long long)l * total + i] = tf32_rna(v - hi);
+    const long long cc = (long long)g.C * g.C;
+    float* dst = w_hi + ((long long)l * g.k * g.k + tap) * 2 * cc + (i - (long long)tap * cc);
+    dst[0] = hi;
+    dst[cc] = tf32_rna(v - hi);
   } else {
     w_hi[(long long)l * total + i] = tf32_rna(v);
   }

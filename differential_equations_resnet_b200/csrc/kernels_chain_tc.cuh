@@ -18,9 +18,11 @@
 //
 // ST = true (strict mode, 3xTF32): fp32-grade results from tf32 MMAs.  The tensor core reads the top 19 bits of an fp32
 // operand, so strip 0 (fp32, also the residual stream) IS the "hi" operand; the epilogue that produces a strip also writes
-// its remainder lo = v - trunc_tf32(v) (exact in fp32, then rounded to tf32) into strip 1, and every weight ring stage
-// carries a hi tile and a lo tile (pack_chain_strict_kernel).  Per (tap, k-step): lo*Whi + hi*Wlo + hi*Whi, small terms
-// first, one fp32 TMEM accumulator.  Two strips (value + remainder) leave no room for the ping-pong pair of the fast
+// its remainder lo = v - trunc_tf32(v) (exact in fp32, then rounded to tf32) into strip 1, and every tap of a weight ring
+// stage carries 2C rows: the C output channels of W_hi followed by those of W_lo (pack_chain_kernel).  Per (tap, k-step)
+// TWO MMAs: x_hi * [W_hi | W_lo] with N = 2C (one operand read of the strip feeds both products; they land in adjacent
+// TMEM column ranges [main | correction]) and x_lo * W_hi with N = C onto the main range; the epilogue adds the two
+// ranges.  (M = 128 x N <= 64 MMAs are bound by the A-operand read, so the stacked MMA costs what one did.)  Two strips (value + remainder) leave no room for the ping-pong pair of the fast
 // mode: the step's input is updated IN PLACE, so the epilogue waits for the step's last MMA before it stores anything
 // (MMAs and epilogue alternate; the next step's weights stream in under the epilogue).
 //
@@ -65,7 +67,6 @@ struct ChainParams {
   int cs;                 // cluster size (1 = no cluster)
   int dbg_skip_w;         // debug: do not load weights (timing experiments only)
   int iters;              // images per CTA = ceil(N / gridDim.x); CTAs whose image index is >= N run as ghosts
-  uint32_t w_lo_off;      // strict: byte offset of the lo tile inside a weight ring stage (= w_stage_bytes / 2)
 };
 
 template <int C>
@@ -114,8 +115,7 @@ __device__ __forceinline__ float4 tf32_remainder4(float4 v) {
 
 template <int C, int DIR, bool ST = false>
 __global__ void __launch_bounds__(320, 1)
-chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_wl, const ChainParams p) {
+chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ChainParams p) {
   using Cfg = ChainCfg<C>;
   constexpr int ROWB = Cfg::ROWB, KB = Cfg::KB, NKB = Cfg::NKB, KS = Cfg::KS, MW = Cfg::MW, MAXSEG = Cfg::MAXSEG, TW = Cfg::TW;
   constexpr uint32_t LT = ROWB == 128 ? SWZ_128B : ROWB == 64 ? SWZ_64B : SWZ_32B;
@@ -145,7 +145,6 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     if (DIR == 0) tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    if (ST) tma_prefetch_desc(&map_wl);
     mbar_init(x_full, 1);
     mbar_init(layer_done, 8);
     mbar_init(img_done, 8);
@@ -203,7 +202,6 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               } else if (p.cs == 1) {
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);
                 tma_load_3d(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg);
-                if (ST) tma_load_3d(smem + p.w_off + s * p.w_stage_bytes + p.w_lo_off, &map_wl, &w_full[s], kb * KB, 0, lw * 9 + tg);
               } else if (crank != 0) {
                 if (iw >= (uint32_t)p.sw) mbar_arrive_cluster(&w_empty_cl[s], 0);   // tell rank 0 the stage is free here
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);                        // rank 0's multicast completes it
@@ -211,7 +209,6 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (iw >= (uint32_t)p.sw) mbar_wait_sleep(&w_empty_cl[s], ph ^ 1);
                 mbar_expect_tx(&w_full[s], p.w_stage_bytes);
                 tma_load_3d_mc(smem + p.w_off + s * p.w_stage_bytes, &map_w, &w_full[s], kb * KB, 0, lw * 9 + tg, cmask);
-                if (ST) tma_load_3d_mc(smem + p.w_off + s * p.w_stage_bytes + p.w_lo_off, &map_wl, &w_full[s], kb * KB, 0, lw * 9 + tg, cmask);
               }
               ++iw;
               if (++ws == (uint32_t)p.sw) { ws = 0; wph ^= 1; }
@@ -223,10 +220,12 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) ==========
     const bool leader = elect_one();
     const uint32_t idesc = make_instr_desc(FMT_TF32, 128, C, 0, 0);
+    const uint32_t idesc2 = make_instr_desc(FMT_TF32, 128, 2 * C, 0, 0);     // strict: [W_hi | W_lo] rows of a tap
+    constexpr uint32_t CW = ST ? 2 * C : C;                                   // TMEM columns per segment
     const uint32_t desc_hi32 = (SBO >> 4) | (1u << 14) | (LT << 29);
     constexpr uint32_t LBO_FIELD = 1u << 16;
     auto mk = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi32) << 32) | (lo | LBO_FIELD); };
-    constexpr uint32_t tap_units = (uint32_t)(C * ROWB) >> 4;
+    constexpr uint32_t tap_units = (uint32_t)((ST ? 2 : 1) * C * ROWB) >> 4;
     uint32_t toff[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) toff[t] = (uint32_t)((t / 3) * p.P + (t % 3)) * RU;
@@ -250,25 +249,24 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc_fence_after_sync();
         if (ic == 0 && lane == 0) { if (li == TL) tr.mark(2); if (li == TL + 1) tr.mark(5); }
         const uint32_t a_base = (smem_base + (ST ? 0u : (uint32_t)(li & 1) * p.strip_stride)) >> 4;
-        const uint32_t a_lo = p.strip_stride >> 4, b_lo = p.w_lo_off >> 4;     // strict: remainder strip / lo weight tile
+        const uint32_t a_lo = p.strip_stride >> 4;     // strict: remainder strip
         if (p.seg_outer) {
           const uint32_t s = ws;
           if (ic == 0 && li == TL && lane == 0) tr.mark(3);
           const uint32_t b_base = (smem_base + p.w_off + s * p.w_stage_bytes) >> 4;
           if (ST) { mbar_wait(&w_full[s], wph); tc_fence_after_sync(); }
           uint32_t a_sg = a_base, d = tmem_base;
-          for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+          for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += CW) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
                 const uint64_t da = mk(a_sg + toff[t] + 2 * ks), db = mk(b_base + t * tap_units + 2 * ks);
                 if (ST) {
-                  const uint64_t dal = mk(a_sg + a_lo + toff[t] + 2 * ks), dbl = mk(b_base + b_lo + t * tap_units + 2 * ks);
+                  const uint64_t dal = mk(a_sg + a_lo + toff[t] + 2 * ks);
                   if (leader) {
-                    umma_tf32(d, dal, db, idesc, (t | ks) ? 1u : 0u);
-                    umma_tf32(d, da, dbl, idesc, 1u);
-                    umma_tf32(d, da, db, idesc, 1u);
+                    umma_tf32(d, da, db, idesc2, (t | ks) ? 1u : 0u);
+                    umma_tf32(d, dal, db, idesc, 1u);
                   }
                 } else {
                   if (leader) umma_tf32(d, da, db, idesc, (t | ks) ? 1u : 0u);
@@ -293,18 +291,17 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               if (ST) { mbar_wait(&w_full[s], wph); tc_fence_after_sync(); }
               // taps and k-steps fully unrolled (descriptor arithmetic overlaps across MMAs); segments outermost
               uint32_t a_sg = a_kb, d = tmem_base;
-              for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += C) {
+              for (int sg = 0; sg < p.nseg; ++sg, a_sg += 128 * RU, d += CW) {
 #pragma unroll
                 for (int tt = 0; tt < TW; ++tt) {
 #pragma unroll
                   for (int ks = 0; ks < KS; ++ks) {
                     const uint64_t da = mk(a_sg + toff[tg + tt] + 2 * ks), db = mk(b_base + tt * tap_units + 2 * ks);
                     if (ST) {
-                      const uint64_t dal = mk(a_sg + a_lo + toff[tg + tt] + 2 * ks), dbl = mk(b_base + b_lo + tt * tap_units + 2 * ks);
+                      const uint64_t dal = mk(a_sg + a_lo + toff[tg + tt] + 2 * ks);
                       if (leader) {
-                        umma_tf32(d, dal, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
-                        umma_tf32(d, da, dbl, idesc, 1u);
-                        umma_tf32(d, da, db, idesc, 1u);
+                        umma_tf32(d, da, db, idesc2, (kb | tg | tt | ks) ? 1u : 0u);
+                        umma_tf32(d, dal, db, idesc, 1u);
                       }
                     } else {
                       if (leader) umma_tf32(d, da, db, idesc, (kb | tg | tt | ks) ? 1u : 0u);
@@ -471,17 +468,22 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint32_t pos = (uint32_t)(sg * 128 + row + p.P + 1);
             // all TMEM loads of this warp's items of the segment are issued up front (one wait covers them)
             constexpr int NGI = NG > 1 ? NG / 2 : 1;
-            uint32_t rr[NGI][16];
+            constexpr int CWE = ST ? 2 * C : C;      // TMEM columns per segment (strict: [main | correction])
+            uint32_t rr[NGI][16], rc[ST ? NGI : 1][16];
 #pragma unroll
             for (int gj = 0; gj < NGI; ++gj) {
               const int cgw = NG > 1 ? half + 2 * gj : 0;
-              if (NG > 1 || (sg & 1) == half) tmem_ld_x16(tq + sg * C + cgw * 16, rr[gj]);
+              if (NG > 1 || (sg & 1) == half) {
+                tmem_ld_x16(tq + sg * CWE + cgw * 16, rr[gj]);
+                if (ST) tmem_ld_x16(tq + sg * CWE + C + cgw * 16, rc[ST ? gj : 0]);
+              }
             }
 #pragma unroll
             for (int cg = 0; cg < NG; ++cg) {
               if (((sg * NG + cg) & 1) != half) continue;
               const int c0 = cg * 16;
               uint32_t (&r)[16] = rr[NG > 1 ? cg / 2 : 0];
+              uint32_t (&rx)[16] = rc[ST && NG > 1 ? cg / 2 : 0];
               const uint32_t plo = (uint32_t)(c0 / KB) * p.plane_bytes;
               const uint32_t ch0 = (c0 % KB) / 4;
               uint32_t so[4];
@@ -496,6 +498,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   for (int j = 0; j < 4; ++j) xv[j] = lds128(cur + so[j]);
                 }
                 tmem_ld_wait();
+                if (ST) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rx[i]));
+                }
                 if (valid) {
                   uint32_t bits = 0;
                   float4 o[4];
@@ -547,6 +553,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   }
                 }
                 tmem_ld_wait();
+                if (ST) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rx[i]));
+                }
                 if (valid) {
                   float4 o[4], z[4];
                   const float g2 = 2.0f * p.gamma;

@@ -86,6 +86,7 @@ struct WgradParams {
   // row lower, so the rows 128..255 of the pair's M = 256 MMA are kernel row alpha + 1 of the leader's alpha: six M = 256 MMAs
   // per k-step (three of them half junk: kernel row 3) replace nine M = 128 ones, and each CTA stages half of the dz strip.
   int tappair;
+  int dbg_nostack;   // debug (B200ODE_WGRAD_NOSTACK): strict mode issues three MMAs per entry instead of the stacked pair (A/B runs)
   int dbg;           // debug (B200ODE_WGRAD_DBG): bit 0 = issue no MMAs, bit 1 = no bias column sums (timing experiments only)
   int PB;            // bytes per position in shared memory (64 in pair mode, else RWB)
   long long part_stride;   // floats per partial (9*C*C, or 3*128*32 in pair mode)
@@ -238,6 +239,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     for (int e = 0; e < 16; ++e) entr[e] = e < nent ? ent[e] : 0u;
     const int ksteps = p.KT / ukp;
     const uint32_t lo_x = (p.x_lo_off - p.x_off) >> 4, lo_d = (p.d_lo_off - p.d_off) >> 4;
+    // Strict, one dz chunk per CTA (C <= 32): the hi and lo dz strips are consumed by ONE MMA with N = 2 * NT whose second
+    // N chunk (LBO = distance hi strip -> lo strip) is the lo strip, so x_hi*dz_hi and x_hi*dz_lo land in the adjacent
+    // [main | correction] accumulators at the operand-read cost of one MMA: two MMAs per entry and k-step instead of three.
+    const bool stack = STRICT && p.dchunks == 1 && 2 * p.NT <= 256 && lo_d < 0x4000u && !p.dbg_nostack;
+    const uint32_t idesc2 = make_instr_desc(FMT_TF32, Mrows, 2 * p.NT, 1, 1);
+    const uint32_t lbo_b_stack = (lo_d & 0x3FFFu) << 16;
     uint32_t it = 0, rs = 0, rph = 0;
     if (TWO && prank != 0) {
       // peer CTA of a pair: its strips are consumed by the leader's MMAs; this warp tells the leader when a stage has landed
@@ -314,10 +321,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
               if (leader) {
                 if (BF16) { if constexpr (TWO) umma_f16_2cta(d_tmem, dsc_a, dsc_b, idesc, accum); else umma_f16(d_tmem, dsc_a, dsc_b, idesc, accum); }
                 else {
-                  umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
-                  if (STRICT) {
-                    umma_tf32(d_tmem + p.NT, dsc_a, dsc_b_lo, idesc, accum);
+                  if (STRICT && stack) {
+                    umma_tf32(d_tmem, dsc_a, mk(du, lbo_b_stack), idesc2, accum);
                     umma_tf32(d_tmem + p.NT, mk(au + lo_x, lbo_a), dsc_b, idesc, 1);
+                  } else {
+                    umma_tf32(d_tmem, dsc_a, dsc_b, idesc, accum);
+                    if (STRICT) {
+                      umma_tf32(d_tmem + p.NT, dsc_a, dsc_b_lo, idesc, accum);
+                      umma_tf32(d_tmem + p.NT, mk(au + lo_x, lbo_a), dsc_b, idesc, 1);
+                    }
                   }
                 }
               }
@@ -547,15 +559,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         const uint4* src = reinterpret_cast<const uint4*>(sb + (which ? p.d_off : p.x_off));
         uint4* dst = reinterpret_cast<uint4*>(sb + (which ? p.d_lo_off : p.x_lo_off));
         const int n16 = (which ? p.dchunks * p.d_chunk_stride : p.xchunks * p.x_chunk_stride) / 16;
-        for (int i = ctid; i < n16; i += 128) {
-          const uint4 u = src[i];
+        auto rem = [](uint4 u) {
           uint4 o;
           o.x = __float_as_uint(tf32_rna(__uint_as_float(u.x) - __uint_as_float(u.x & 0xFFFFE000u)));
           o.y = __float_as_uint(tf32_rna(__uint_as_float(u.y) - __uint_as_float(u.y & 0xFFFFE000u)));
           o.z = __float_as_uint(tf32_rna(__uint_as_float(u.z) - __uint_as_float(u.z & 0xFFFFE000u)));
           o.w = __float_as_uint(tf32_rna(__uint_as_float(u.w) - __uint_as_float(u.w & 0xFFFFE000u)));
-          dst[i] = o;
+          return o;
+        };
+        // eight independent 16-byte loads in flight per thread (the one-load-per-iteration loop made the converter warps the
+        // bottleneck of the strict kernel: 685 us of the stage-1 launch's 1177 us with the MMAs switched off)
+        int i = ctid;
+        for (; i + 7 * 128 < n16; i += 8 * 128) {
+          uint4 u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = src[i + j * 128];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[i + j * 128] = rem(u[j]);
         }
+        for (; i < n16; i += 128) dst[i] = rem(src[i]);
       }
       fence_proxy_async_smem();
       __syncwarp();
