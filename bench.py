@@ -546,7 +546,8 @@ def run_b200(args):
         # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
         traffic, ncu_extra = None, {}
         try:
-            src = "profiles/r02_ncu_chain_f16.json" if args.precision == "fast_f16" else "profiles/r01_ncu_traffic.json"
+            # (captures exist for the two fast modes; the strict kernels have no --set full capture: traffic stays null)
+            src = {"fast_f16": "profiles/r02_ncu_chain_f16.json", "fast_tf32": "profiles/r01_ncu_traffic.json"}[args.precision]
             tj = json.load(open(os.path.join(ROOT, src)))
             rec = tj["kernels"].get("%s|%d" % (dom["kernel"], dom["shape"][3]))
             if rec and B == BATCH_PER_GPU:
@@ -561,7 +562,12 @@ def run_b200(args):
                     "peak_source": peak_src,
                     "share_of_step": dom["us"] * dom["launches_per_step"] / (1e3 * ms_dev / K)}
         roofline.update(ncu_extra)
-        if dom["kernel"].startswith("chain_wgrad"):
+        if dom["kernel"].startswith("chain_wgrad") and args.precision == "strict":
+            roofline["note"] = ("strict layer-batched weight gradient (3xTF32: hi and lo strips of both operands in shared memory, lo strips "
+                                "derived by converter warps): bound by the TMA round trip of its small tiles (two stages of ~144 positions "
+                                "fit beside the lo strips), not by HBM or the MMAs -- with the MMAs switched off the stage-1 launch still "
+                                "takes 650 of its 1171 us (profiles/r02_strict_wgrad_split.log)")
+        elif dom["kernel"].startswith("chain_wgrad"):
             roofline["note"] = ("layer-batched weight gradient: DRAM traffic equals the algorithmic bytes (no re-reads); what binds it is the "
                                 "operand-read cost of its small MN-major MMAs (32-byte operand rows at C = 16: one shared-memory wavefront per "
                                 "position and chunk), not HBM -- with the MMAs switched off (B200ODE_WGRAD_DBG=1) the same launch streams its "
@@ -573,7 +579,8 @@ def run_b200(args):
             # (MMAs of the launch at that rate, one image per SM) / measured time.
             Nn, Hh, Ww, Cc = dom["shape"]
             nseg = (Hh * (Ww + 1) + 127) // 128
-            mmas = BLOCKS[0] * nseg * 9 * (Cc * (2 if args.precision == "fast_f16" else 4) // 32)
+            # (strict: two MMAs per tap and k-step -- x_hi * [W_hi | W_lo] stacked along N, x_lo * W_hi)
+            mmas = BLOCKS[0] * nseg * 9 * (Cc * (2 if args.precision == "fast_f16" else 4) // 32) * (2 if args.precision == "strict" else 1)
             cyc = {16: 39.0, 32: 40.0, 64: 48.0}.get(Cc, Cc / 2.0)
             sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
             waves = -(-Nn // 148)

@@ -307,8 +307,10 @@ class EulerNet:
     'fast_bf16' (bf16 operands and activations, fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1, persistent=True, native_glue=True, comm=None, sync_bn=True):
+                 world_size=1, persistent=True, native_glue=True, comm=None, sync_bn=True, split_first_chain=None):
         _abi.require_device()
+        if split_first_chain is None:
+            split_first_chain = int(os.environ.get("B200ODE_SPLIT_FIRST_CHAIN", "1"))
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
         self.lr, self.adam_eps, self.world_size = lr, adam_eps, world_size
         # gradient exchange: torch.distributed (default) or a parallel.AbiComm (NCCL bound by libb200ode itself)
@@ -325,9 +327,20 @@ class EulerNet:
                 j = i
                 while j < len(plan) and plan[j][0] == "euler" and plan[j][2] == co:
                     j += 1
-                ch = _Chain(co, j - i, spec.gamma, precision, off, persistent, bn=spec.use_batch_norm)
-                off += ch.np_layer * ch.n
-                self.segments.append(("chain", ch))
+                # The FIRST stage may run as `split_first_chain` back-to-back chains (opt-in, B200ODE_SPLIT_FIRST_CHAIN): its weight
+                # gradient is the last big kernel of the step with nothing left to hide behind, and as two halves the upper half's
+                # weight gradient runs on the side stream under the lower half's backward sweep.  MEASURED SLOWER on cfg3 (1.011 ->
+                # 1.030 ms with 2 parts, 1.050 ms with 3: the side-stream CTAs find no free SM under the chain kernels, and every
+                # part costs six more launches), so the default stays one chain per stage.
+                parts = split_first_chain if (split_first_chain > 1 and not self.segments_have_chain() and j - i >= 2 * split_first_chain
+                                             and not spec.use_batch_norm) else 1
+                n_left = j - i
+                for part in range(parts):
+                    n_part = n_left // (parts - part)
+                    ch = _Chain(co, n_part, spec.gamma, precision, off, persistent, bn=spec.use_batch_norm)
+                    off += ch.np_layer * ch.n
+                    self.segments.append(("chain", ch))
+                    n_left -= n_part
                 i = j
             else:
                 self.segments.append((kind, ci, co, st, name))
@@ -564,6 +577,9 @@ class EulerNet:
                             loss=torch.zeros(1, dtype=torch.float32, device=device))
         self._nb_cache[tuple(shape)] = self._nb
         return self._nb
+
+    def segments_have_chain(self):
+        return any(seg[0] == "chain" for seg in self.segments)
 
     def _off(self, name):
         return self.torch_params[name][0]
