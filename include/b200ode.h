@@ -184,7 +184,11 @@ int b200ode_gradient_mean_norms(const float* grads, const int64_t* offsets, cons
  *      TF-autodiff backward sweep (training/training.py:300) in ONE launch per direction.  One CTA
  *      keeps one image in shared memory across all steps.  Shapes whose image does not fit shared
  *      memory are refused (b200ode_chain_supported == 0): use the per-layer calls.
- *      Two formulations, chosen by precision_mode at create time:
+ *      Three formulations, chosen by precision_mode at create time:
+ *        STRICT     3xTF32 inside the chain kernel (fp32-grade: <= 1e-5 relative of the reference's fp32 arithmetic): the fp32
+ *                   residual strip is the hi operand, the epilogue also writes its tf32 remainder strip, every tap carries
+ *                   W_hi and W_lo rows; saved activations and dZ are fp32 (same buffers as FAST_TF32), weight gradient by
+ *                   the strict layer-batched kernel.
  *        FAST_TF32  tf32 operands straight from the fp32 residual stream (8 channels per MMA); saved
  *                   activations and dZ are fp32; forward results equal the per-layer FAST_TF32 kernels bit for bit.
  *        FAST_F16   fp16 operands (16 channels per MMA, same 11-bit significand) rounded to nearest where they are
@@ -242,7 +246,9 @@ int b200ode_stem_wgrad(const void* images, int images_are_u8, float subtract_mea
                        const float* out, const float* dout, float* dparams, int N, int H, int W, int Cin, int Cout,
                        void* workspace, size_t workspace_bytes, void* stream);
 /* single_layer_conv_block (models/tfkeras_resnets.py:204-269): out = relu(conv3x3_s(x)+bm) + conv1x1_s(x)+bs,
- * TF SAME padding (pad_before = total/2); relu_mask: 1 bit per output element ((main > 0), as euler_fwd). */
+ * TF SAME padding (pad_before = total/2); relu_mask: 1 bit per output element ((main > 0), as euler_fwd).
+ * Strides (2,2) with 16 -> 32 or 32 -> 64 channels (the reference's transitions) run as tensor-core implicit GEMMs with the
+ * 3xTF32 split (fp32-grade, <= 1e-5; csrc/kernels_glue_mma.cuh), every other shape on fp32 CUDA-core kernels. */
 int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
                            const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin, int Cout,
                            int stride_h, int stride_w, void* stream);
