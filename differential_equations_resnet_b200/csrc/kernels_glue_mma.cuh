@@ -41,6 +41,20 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4
   mma_tf32_m16n8k8(d, ah, bh0, bh1);
 }
 
+// Staging: every global -> shared copy of a block is issued as cp.async (no register round trip), so ALL of a block's loads
+// are in flight together and the block pays ONE memory round trip before its MMAs (the register-staged loops paid one per
+// unrolled batch: ncu showed the kernels bound by long-scoreboard stalls of the staging phase, tensor pipe 18-25 % busy).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // forward.  Block = (image, band of `orows` output rows); the band's input rows and all 10 weight taps (9 main + the 1x1
 // shortcut) are staged in shared memory as fp32.  Warp task = (16 output positions, 1/NSPLIT of the output channels):
@@ -73,22 +87,16 @@ __global__ void __launch_bounds__(256) transition_fwd_mma_kernel(GlueConv g, con
   float* xs = sm;
   float* wsm = sm + (((nir_max * g.W + 1) * PS + 3) & ~3);
   {
-    const float4* src = reinterpret_cast<const float4*>(x + ((long long)n * g.H + i0) * g.W * CIN);
-    const int n4 = (i1 - i0) * g.W * (CIN / 4);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-      const float4 v = src[i];
-      float* d = xs + (i / (CIN / 4)) * PS + (i % (CIN / 4)) * 4;
-      *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
-      *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
-    }
+    const float2* src = reinterpret_cast<const float2*>(x + ((long long)n * g.H + i0) * g.W * CIN);
+    const int n2 = (i1 - i0) * g.W * (CIN / 2);      // pixel rows are 8-byte aligned only (PS = CIN + 2): 8-byte copies
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async_8(xs + (i / (CIN / 2)) * PS + (i % (CIN / 2)) * 2, src + i);
     if (threadIdx.x < PS) xs[zp * PS + threadIdx.x] = 0.0f;
-#pragma unroll 4
     for (int i = threadIdx.x; i < 10 * CIN * (COUT / 4); i += blockDim.x) {
       const int row = i / (COUT / 4), c4 = i % (COUT / 4);
       const float* s = row < 9 * CIN ? Wm + (long long)row * COUT : Ws + (long long)(row - 9 * CIN) * COUT;
-      *reinterpret_cast<float4*>(wsm + row * WS + 4 * c4) = __ldg(reinterpret_cast<const float4*>(s) + c4);
+      cp_async_16(wsm + row * WS + 4 * c4, reinterpret_cast<const float4*>(s) + c4);
     }
+    cp_async_wait_all();
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -165,7 +173,7 @@ struct TrDgradMma {
   static constexpr int PSO = COUT + 4;   // consecutive cells read consecutive output pixels: PSO = 4 (mod 32)
   static constexpr int WS = COUT + 4;    // B rows are input channels, k (= co) contiguous
   static size_t smem_bytes(int crows, int Wo) {
-    return ((size_t)2 * ((crows + 1) * Wo + 1) * PSO + (size_t)10 * CIN * WS) * sizeof(float);
+    return ((size_t)2 * ((crows + 1) * Wo + 1) * PSO + (size_t)10 * CIN * WS) * sizeof(float) + (size_t)(crows + 1) * Wo * (COUT / 8);
   }
 };
 
@@ -184,25 +192,34 @@ __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, c
   float* dO = sm;
   float* dM = dO + (zp + 1) * PSO;
   float* wsm = dM + (zp + 1) * PSO;
+  uint8_t* msm = reinterpret_cast<uint8_t*>(wsm + 10 * CIN * WS);      // relu mask bytes of the staged rows
   {
     const long long base = ((long long)n * g.Ho + r0) * g.Wo * COUT;
     const float4* d4 = reinterpret_cast<const float4*>(dout + base);
     const int n4 = r1 > r0 ? (r1 - r0) * g.Wo * (COUT / 4) : 0;
-#pragma unroll 4
+    // the masked copy dM is staged as a RAW copy first and masked in place once everything has landed (mask bytes in
+    // registers: one 4-bit group per float4, loaded up front by the thread that will mask that float4)
     for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
       const int i = 4 * i4;
-      const float4 d = d4[i4];
-      const uint32_t mb = mask[(base + i) >> 3] >> (i & 4);
       const int si = (i / COUT) * PSO + i % COUT;
-      *reinterpret_cast<float4*>(dO + si) = d;
-      *reinterpret_cast<float4*>(dM + si) = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
+      cp_async_16(dO + si, d4 + i4);
+      cp_async_16(dM + si, d4 + i4);
     }
+    for (int i = threadIdx.x; i < n4 / 8; i += blockDim.x) cp_async_4(msm + 4 * i, mask + (base >> 3) + 4 * i);   // n4 / 2 mask bytes
     if (threadIdx.x < PSO) { dO[zp * PSO + threadIdx.x] = 0.0f; dM[zp * PSO + threadIdx.x] = 0.0f; }
-#pragma unroll 4
     for (int i = threadIdx.x; i < 10 * CIN * (COUT / 4); i += blockDim.x) {
       const int row = i / (COUT / 4), c4 = i % (COUT / 4);
       const float* s = row < 9 * CIN ? Wm + (long long)row * COUT : Ws + (long long)(row - 9 * CIN) * COUT;
-      *reinterpret_cast<float4*>(wsm + row * WS + 4 * c4) = __ldg(reinterpret_cast<const float4*>(s) + c4);
+      cp_async_16(wsm + row * WS + 4 * c4, reinterpret_cast<const float4*>(s) + c4);
+    }
+    cp_async_wait_all();
+    __syncthreads();              // everybody's copies have landed (the mask bytes were copied by other threads)
+    for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
+      const int i = 4 * i4;
+      const uint32_t mb = (uint32_t)msm[i >> 3] >> (i & 4);
+      float4* q = reinterpret_cast<float4*>(dM + (i / COUT) * PSO + i % COUT);
+      const float4 d = *q;
+      *q = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
     }
   }
   __syncthreads();
@@ -281,7 +298,7 @@ struct TrWgradMma {
   static constexpr int TPW = (NTASK + NWARP - 1) / NWARP;
   static size_t smem_bytes(int orows, int W, int Wo) {
     const int nir = (orows - 1) * 2 + 3, npad = (orows * Wo + 7) & ~7;
-    return ((size_t)(nir * W + 1) * PS + (size_t)2 * npad * PSO) * sizeof(float);
+    return ((size_t)(nir * W + 1) * PS + (size_t)2 * npad * PSO) * sizeof(float) + (size_t)npad * (COUT / 8);
   }
 };
 
@@ -300,6 +317,7 @@ __global__ void __launch_bounds__(384) transition_wgrad_mma_kernel(GlueConv g, c
   float* xs = sm;                                   // [nir_max * W + 1][PS]
   float* dO = xs + (zp + 1) * PS;                   // [npad_max][PSO]
   float* dM = dO + npad_max * PSO;
+  uint8_t* msm = reinterpret_cast<uint8_t*>(dM + npad_max * PSO);      // relu mask bytes of the staged band
   float acc[TPW][NT][4];
 #pragma unroll
   for (int u = 0; u < TPW; ++u)
@@ -319,23 +337,29 @@ __global__ void __launch_bounds__(384) transition_wgrad_mma_kernel(GlueConv g, c
       {
         const float4* src = reinterpret_cast<const float4*>(x + ((long long)n * g.H + i0) * g.W * CIN);
         const int n4 = (i1 - i0) * g.W * (CIN / 4);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n4; i += blockDim.x)
-          *reinterpret_cast<float4*>(xs + (i / (CIN / 4)) * PS + (i % (CIN / 4)) * 4) = src[i];
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async_16(xs + (i / (CIN / 4)) * PS + (i % (CIN / 4)) * 4, src + i);
         const long long base = ((long long)n * g.Ho + o0) * g.Wo * COUT;
         const float4* d4 = reinterpret_cast<const float4*>(dout + base);
-#pragma unroll 4
         for (int i4 = threadIdx.x; i4 < npad * (COUT / 4); i4 += blockDim.x) {
           const int i = 4 * i4;
           const int si = (i / COUT) * PSO + i % COUT;
-          float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f), m = d;       // positions past the band: zeros (0 * garbage could be NaN)
           if (i4 < npos * (COUT / 4)) {
-            d = d4[i4];
-            const uint32_t mb = mask[(base + i) >> 3] >> (i & 4);
-            m = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
+            cp_async_16(dO + si, d4 + i4);
+            cp_async_16(dM + si, d4 + i4);
+          } else {                                                     // positions past the band: zeros (0 * garbage could be NaN)
+            *reinterpret_cast<float4*>(dO + si) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(dM + si) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           }
-          *reinterpret_cast<float4*>(dO + si) = d;
-          *reinterpret_cast<float4*>(dM + si) = m;
+        }
+        for (int i = threadIdx.x; i < npos * (COUT / 32); i += blockDim.x) cp_async_4(msm + 4 * i, mask + (base >> 3) + 4 * i);
+        cp_async_wait_all();
+        __syncthreads();          // everybody's copies have landed (the mask bytes were copied by other threads)
+        for (int i4 = threadIdx.x; i4 < npos * (COUT / 4); i4 += blockDim.x) {
+          const int i = 4 * i4;
+          const uint32_t mb = (uint32_t)msm[i >> 3] >> (i & 4);
+          float4* q = reinterpret_cast<float4*>(dM + (i / COUT) * PSO + i % COUT);
+          const float4 d = *q;
+          *q = make_float4(mb & 1u ? d.x : 0.0f, mb & 2u ? d.y : 0.0f, mb & 4u ? d.z : 0.0f, mb & 8u ? d.w : 0.0f);
         }
       }
       __syncthreads();
