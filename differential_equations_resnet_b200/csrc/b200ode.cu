@@ -1106,6 +1106,9 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   int nparts = sms / (ngroups * L * (two_tap ? 2 : 1));
   if (nparts < 1) nparts = 1;
+  // debug / tuning: more position slices per (layer, group) than one wave of CTAs (B200ODE_WGRAD_PARTS_MULT)
+  static const int pm_env = getenv("B200ODE_WGRAD_PARTS_MULT") ? atoi(getenv("B200ODE_WGRAD_PARTS_MULT")) : 1;
+  if (pm_env > 1 && L > 1) nparts *= pm_env;
   if (strict) {
     // The tensor core accumulates with truncation (csrc/umma_probe.cu): the error of one TMEM accumulator grows
     // linearly with the number of k-steps it absorbs (measured at N=256, 32x32: 1.9e-9 per position, 9e-5 at the

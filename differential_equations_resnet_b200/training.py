@@ -705,10 +705,11 @@ class EulerNet:
                             self._adam(lo, hi, side.cuda_stream)
                     self._adam_done = early["slices"]
             else:
-                with torch.cuda.stream(side):
-                    _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
-                                                      _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
-                                                      e["co"], _ptr(e["ws"]), e["ws"].numel(), side.cuda_stream))
+                # the stem's weight gradient needs only d (made on the main stream, which has nothing else left to do): on the
+                # main stream it runs BESIDE the first stage's weight gradient (side stream) instead of behind it
+                _abi.check(lib.b200ode_stem_wgrad(_ptr(images), int(is_u8), sub, div, int(norm), _ptr(e["out"]), _ptr(d),
+                                                  _ptr(gr[self._off(e["name"] + "/kernel"):]), N, e["h"], e["w"], e["ci"],
+                                                  e["co"], _ptr(e["ws"]), e["ws"].numel(), st))
         if overlap_wgrad:
             main.wait_stream(side)
         return nb["loss"].view(())

@@ -72,7 +72,8 @@ def test_layer_calls_stay_inside_their_buffers(precision, shape):
 
 
 @pytest.mark.parametrize("prec_name,C,HW,N", [("fast_f16", 16, 32, 3), ("fast_f16", 32, 16, 5), ("fast_f16", 64, 8, 6),
-                                              ("fast_tf32", 16, 32, 2), ("fast_tf32", 64, 8, 9)])
+                                              ("fast_tf32", 16, 32, 2), ("fast_tf32", 64, 8, 9),
+                                              ("strict", 16, 32, 2), ("strict", 32, 16, 5), ("strict", 64, 8, 9)])
 def test_chain_calls_stay_inside_their_buffers(prec_name, C, HW, N):
     from differential_equations_resnet_b200 import _abi
     from differential_equations_resnet_b200.layers._base import ChainHandle
@@ -104,3 +105,48 @@ def test_chain_calls_stay_inside_their_buffers(prec_name, C, HW, N):
     assert bands_intact(xb, n, nan) and bands_intact(dyb, n, nan)
     for t in (acts, dz, dx, grad):
         assert bool(torch.isfinite(t.float()).all())
+
+
+@pytest.mark.parametrize("Ci,Co,H,W,N", [(16, 32, 32, 32, 3), (32, 64, 16, 16, 5), (16, 32, 9, 11, 2), (32, 64, 7, 10, 150)])
+def test_transition_calls_stay_inside_their_buffers(Ci, Co, H, W, N):
+    """The tensor-core transition kernels (kernels_glue_mma.cuh: cp.async staging, shared-memory gathers with a zero pixel for
+    out-of-image taps, float2 stores per MMA fragment): outputs between sentinel bands, inputs between NaN bands."""
+    import ctypes
+    from differential_equations_resnet_b200 import _abi
+    lib = _abi.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    g = torch.Generator().manual_seed(4)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    nan = float("nan")
+    xb, x = banded((N, H, W, Ci), torch.float32, nan)
+    x.copy_(torch.randn((N, H, W, Ci), generator=g).cuda())
+    db, dout = banded((N, Ho, Wo, Co), torch.float32, nan)
+    dout.copy_(torch.randn((N, Ho, Wo, Co), generator=g).cuda())
+    wb, Wm = banded((3, 3, Ci, Co), torch.float32, nan)
+    Wm.copy_((torch.randn((3, 3, Ci, Co), generator=g) * 0.1).cuda())
+    sb, Ws = banded((Ci, Co), torch.float32, nan)
+    Ws.copy_((torch.randn((Ci, Co), generator=g) * 0.1).cuda())
+    bm = (torch.randn(Co, generator=g) * 0.1).cuda(); bs = (torch.randn(Co, generator=g) * 0.1).cuda()
+    ob, out = banded((N, Ho, Wo, Co), torch.float32, 7.0)
+    mb, mask = banded((N, Ho, Wo, Co // 8), torch.uint8, 0x5A)
+    dxb, dx = banded((N, H, W, Ci), torch.float32, 7.0)
+    npar = 9 * Ci * Co + Co + Ci * Co + Co
+    pb, dp = banded((npar,), torch.float32, 7.0)
+    _abi.check(lib.b200ode_transition_fwd(P(x), P(Wm), P(bm), P(Ws), P(bs), P(out), P(mask), N, H, W, Ci, Co, 2, 2, None))
+    _abi.check(lib.b200ode_transition_dgrad(P(dout), P(mask), P(Wm), P(Ws), P(dx), N, H, W, Ci, Co, 2, 2, None))
+    _abi.check(lib.b200ode_transition_wgrad(P(x), P(dout), P(mask), P(dp), N, H, W, Ci, Co, 2, 2, None, 0, None))
+    torch.cuda.synchronize()
+    assert bands_intact(ob, out.numel(), 7.0) and bands_intact(mb, mask.numel(), 0x5A)
+    assert bands_intact(dxb, dx.numel(), 7.0) and bands_intact(pb, npar, 7.0)
+    assert bands_intact(xb, x.numel(), nan) and bands_intact(db, dout.numel(), nan)
+    assert bands_intact(wb, Wm.numel(), nan) and bands_intact(sb, Ws.numel(), nan)
+    for t in (out, dx, dp):
+        assert bool(torch.isfinite(t).all()), "a NaN guard band of an input leaked into the result"
+    # tight buffers: same bits
+    out2, mask2, dx2, dp2 = torch.empty_like(out), torch.empty_like(mask), torch.empty_like(dx), torch.empty_like(dp)
+    xt, dt_, Wt, St = x.clone(), dout.clone(), Wm.clone(), Ws.clone()
+    _abi.check(lib.b200ode_transition_fwd(P(xt), P(Wt), P(bm), P(St), P(bs), P(out2), P(mask2), N, H, W, Ci, Co, 2, 2, None))
+    _abi.check(lib.b200ode_transition_dgrad(P(dt_), P(mask2), P(Wt), P(St), P(dx2), N, H, W, Ci, Co, 2, 2, None))
+    _abi.check(lib.b200ode_transition_wgrad(P(xt), P(dt_), P(mask2), P(dp2), N, H, W, Ci, Co, 2, 2, None, 0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and torch.equal(mask, mask2) and torch.equal(dx, dx2) and torch.equal(dp, dp2)
