@@ -57,6 +57,26 @@ static uint64_t* g_trace = nullptr;   // debug timeline buffer (device), see b20
 extern "C" int b200ode_debug_set_trace(void* device_buffer) { g_trace = (uint64_t*)device_buffer; return 0; }
 
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// Programmatic dependent launch (sm100_ptx.cuh): kernels of the train step's main stream that wait for their predecessor
+// only after their prologue.  OPT-IN (B200ODE_PDL=1): measured SLOWER on the cfg3 train step (0.977 -> 0.999 ms per step inside
+// the CUDA graph, 11 programmatic edges): the early-resident CTAs of the next chain kernel hold an SM's shared memory and TMEM
+// while they wait, which keeps the side-stream weight-gradient CTAs off those SMs; the launch gap they hide is smaller than that.
+static bool pdl_enabled() {
+  static const bool on = getenv("B200ODE_PDL") && atoi(getenv("B200ODE_PDL")) != 0;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 template <typename... Ts>
 static inline bool aligned16(Ts... ptrs) {   // every non-NULL pointer is 16-byte aligned (vector kernels)
   uintptr_t acc = 0;
@@ -1645,10 +1665,19 @@ static int launch_chain_f16(const b200ode_chain* ch, const ChainF16Plan& plan, c
     cudaLaunchConfig_t cfg;                                                                                       \
     memset(&cfg, 0, sizeof(cfg));                                                                                 \
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + EW_ * 32); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st; \
-    cudaLaunchAttribute attr[1];                                                                                  \
-    attr[0].id = cudaLaunchAttributeClusterDimension;                                                             \
-    attr[0].val.clusterDim.x = plan.p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;             \
-    cfg.attrs = attr; cfg.numAttrs = plan.p.cs > 1 ? 1 : 0;                                                        \
+    cudaLaunchAttribute attr[2];                                                                                  \
+    int na = 0;                                                                                                   \
+    if (plan.p.cs > 1) {                                                                                          \
+      attr[na].id = cudaLaunchAttributeClusterDimension;                                                          \
+      attr[na].val.clusterDim.x = plan.p.cs; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;        \
+      ++na;                                                                                                       \
+    }                                                                                                             \
+    if (pdl_enabled()) {                                                                                          \
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                           \
+      attr[na].val.programmaticStreamSerializationAllowed = 1;                                                    \
+      ++na;                                                                                                       \
+    }                                                                                                             \
+    cfg.attrs = attr; cfg.numAttrs = na;                                                                          \
     CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_f16_kernel<C_, DIR, EW_>, mw, plan.p));                                \
   } while (0)
 #define CHF_EW(C_) do { if (ew == 8) CHF_LAUNCH(C_, 8); else CHF_LAUNCH(C_, 16); } while (0)
@@ -1882,7 +1911,12 @@ static int transition_fwd_mma(const GlueConv& g, const float* x, const float* Wm
   const size_t smem = TrFwdMma<CIN, COUT>::smem_bytes(orows, g.W);
   if (smem > 160 * 1024) return -1;
   const dim3 grid(g.N, (g.Ho + orows - 1) / orows);
-  GLUE_MMA_LAUNCH((transition_fwd_mma_kernel<CIN, COUT, NSPLIT>), grid, 256, smem, st, g, x, Wm, bm, Ws, bs, out, mask, orows);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(transition_fwd_mma_kernel<CIN, COUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  CUDA_TRY(launch_pdl(transition_fwd_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, x, Wm, bm, Ws, bs, out, mask, orows));
   LAUNCH_CHECK("transition_fwd_mma_kernel");
   return 0;
 }
@@ -1897,7 +1931,12 @@ static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint
   const size_t smem = TrDgradMma<CIN, COUT>::smem_bytes(crows, g.Wo);
   if (smem > 160 * 1024) return -1;
   const dim3 grid(g.N, (CH + crows - 1) / crows);
-  GLUE_MMA_LAUNCH((transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>), grid, 256, smem, st, g, dout, mask, Wm, Ws, dx, crows);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  CUDA_TRY(launch_pdl(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, dout, mask, Wm, Ws, dx, crows));
   LAUNCH_CHECK("transition_dgrad_mma_kernel");
   return 0;
 }
@@ -2061,7 +2100,8 @@ extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, cons
   WsLease lease;
   if (int rc = lease_ws(workspace, workspace_bytes, head_ws_bytes(N, C, K), (cudaStream_t)stream, &lease)) return rc;
   float* ws = (float*)lease.ptr;
-  head_kernel<<<N, C, (C + 33) * sizeof(float), (cudaStream_t)stream>>>(x, HW, C, K, fc_kernel, fc_bias, onehot, eps, N, probs, dx, ws);
+  CUDA_TRY(launch_pdl(head_kernel, dim3(N), dim3(C), (C + 33) * sizeof(float), (cudaStream_t)stream, x, HW, C, K, fc_kernel, fc_bias, onehot, eps,
+                      N, probs, dx, ws));
   LAUNCH_CHECK("head_kernel");
   if (dparams)
     if (int rc = reduce_rows(ws, N, nout, nout - 1, dparams, (cudaStream_t)stream)) return rc;

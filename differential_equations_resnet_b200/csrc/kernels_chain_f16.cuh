@@ -69,6 +69,7 @@ struct ChainF16Params {
 
 // max |v| over a tensor -> *out (bit pattern of a non-negative float, atomicMax on the uint view; *out zeroed before)
 __global__ void amax_abs_kernel(const float4* __restrict__ v, long long n4, unsigned int* __restrict__ out) {
+  griddep_launch_dependents();      // the chain kernel behind this one may run its prologue meanwhile (it waits before reading *out)
   float m = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = v[i];
@@ -163,6 +164,7 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
   if (threadIdx.x == 0) tr.wall(0);
   constexpr int TL = 4;   // traced (steady-state) step
 
+  griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < CHAIN_MAXSEG; ++i) { mbar_init(&seg_done[i], OWNERS); mbar_init(&acc_full[i], 1); }
@@ -187,6 +189,7 @@ chain_f16_kernel(const __grid_constant__ CUtensorMap map_w, const ChainF16Params
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();   // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after_sync();
+  griddep_wait();                     // PDL: everything above touched shared memory / TMEM only
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) tr.mark(1);
   const long long img_elems = (long long)p.H * p.W * C;

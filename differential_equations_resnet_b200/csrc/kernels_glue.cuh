@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sm100_ptx.cuh"
+
 namespace b200ode {
 
 struct GlueConv {
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) stem_fwd_pixel_kernel(GlueConv g, const v
                                                              int norm, const float* __restrict__ Wk, const float* __restrict__ bias,
                                                              float* __restrict__ out) {
   extern __shared__ float sm[];
+  griddep_launch_dependents();          // (the chain kernel behind the stem waits before it reads `out`)
   float* wsm = sm;                      // [9 * Cin][COUT]
   float* bsm = wsm + 9 * g.Cin * COUT;  // [COUT]
   float* lut = bsm + COUT;              // [256] (uint8 input)
@@ -505,6 +508,8 @@ __global__ void head_kernel(const float* __restrict__ x, int HW, int C, int K, c
                             const float* __restrict__ bfc, const float* __restrict__ onehot, float eps, int N,
                             float* __restrict__ probs, float* __restrict__ dx, float* __restrict__ part) {
   extern __shared__ float sm[];
+  griddep_launch_dependents();
+  griddep_wait();
   float* feat = sm;            // [C]
   float* pz = sm + C;          // [K] probabilities, then dlogits
   float* red = pz + 32;        // [1]

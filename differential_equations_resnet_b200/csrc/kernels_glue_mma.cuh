@@ -18,6 +18,7 @@
 #pragma once
 
 #include "kernels_glue.cuh"
+#include "sm100_ptx.cuh"
 
 namespace b200ode {
 
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(256) transition_fwd_mma_kernel(GlueConv g, con
   const int zp = nir_max * g.W;                       // index of the all-zero pixel (out-of-image taps)
   float* xs = sm;
   float* wsm = sm + (((nir_max * g.W + 1) * PS + 3) & ~3);
+  griddep_launch_dependents();
+  griddep_wait();
   {
     const float2* src = reinterpret_cast<const float2*>(x + ((long long)n * g.H + i0) * g.W * CIN);
     const int n2 = (i1 - i0) * g.W * (CIN / 2);      // pixel rows are 8-byte aligned only (PS = CIN + 2): 8-byte copies
@@ -193,6 +196,8 @@ __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, c
   float* dM = dO + (zp + 1) * PSO;
   float* wsm = dM + (zp + 1) * PSO;
   uint8_t* msm = reinterpret_cast<uint8_t*>(wsm + 10 * CIN * WS);      // relu mask bytes of the staged rows
+  griddep_launch_dependents();
+  griddep_wait();
   {
     const long long base = ((long long)n * g.Ho + r0) * g.Wo * COUT;
     const float4* d4 = reinterpret_cast<const float4*>(dout + base);

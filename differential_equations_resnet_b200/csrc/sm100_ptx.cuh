@@ -184,6 +184,14 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream still runs; griddep_wait() blocks until the predecessor grid has completed and its
+// memory is visible (no-op without the attribute); griddep_launch_dependents() lets the successor's CTAs be scheduled as
+// soon as every CTA of this grid has called it (or exited).  Kernels here call launch_dependents first and wait right
+// after their shared-memory-only prologue (barriers, TMEM allocation, strip zero fill), before any global access.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
