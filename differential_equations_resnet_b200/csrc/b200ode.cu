@@ -946,7 +946,10 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   p.N = N; p.H = H; p.W = W; p.C = C; p.P = W + 1; p.L = L;
   if (p.P > 256) return fail(B200ODE_ERR_UNSUPPORTED, "tensor path supports W <= 255");
   static const int pair_env = getenv("B200ODE_WGRAD_PAIR") ? atoi(getenv("B200ODE_WGRAD_PAIR")) : 1;   // debug switch
-  p.pair = (!bf16 && !strict && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
+  // strict mode too (B200ODE_WGRAD_STRICT_PAIR=0: off): half the shared memory per position of the 32-channel chunks that
+  // C = 16 is otherwise padded to -> tiles twice as long beside the lo strips, half the MMAs
+  static const int spair_env = getenv("B200ODE_WGRAD_STRICT_PAIR") ? atoi(getenv("B200ODE_WGRAD_STRICT_PAIR")) : 1;
+  p.pair = (!bf16 && (!strict || spair_env) && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
   if (p.pair) p.P = W + 2;
   p.CH = bf16 ? (C < 64 ? C : 64) : 32;
   p.RWB = p.CH * eb;
@@ -1046,13 +1049,20 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // double the shared memory, the planner insisted on two stages): 8x over-read, a TMA round trip per 24 positions, 12 % of the
   // 3xTF32 roof.  Row-aligned tiles stage R + 2 / R whole rows.
   static const int srow_env = getenv("B200ODE_WGRAD_STRICT_ROWS") ? atoi(getenv("B200ODE_WGRAD_STRICT_ROWS")) : 1;
-  if ((!strict || (srow_env && C >= 64)) && !p.trick && !p.pair && !p.shift2 && (p.Mblk == 128 || strict) && rows_env != 0) {
+  // ... and for the beta-trick tiling of strict mode (C <= 32; the chains' layer-batched weight gradients): position-granular
+  // tiles leave room for two stages of ~120 positions beside the lo strips (7 + 5 staged rows per 3.6 useful ones, one TMA round
+  // trip per tile: 650 of the stage-1 launch's 1171 us with the MMAs switched off); R whole rows per tile stage R + 2 / R rows
+  // and leave room for three or more stages in flight.
+  static const int strow_env = getenv("B200ODE_WGRAD_STRICT_TRICK_ROWS") ? atoi(getenv("B200ODE_WGRAD_STRICT_TRICK_ROWS")) : 0;
+  const bool strict_trick_rows = strict && p.trick && !p.pair && !p.shift2 && strow_env > 0;
+  if ((((!strict || (srow_env && C >= 64)) && !p.trick && !p.pair && !p.shift2 && (p.Mblk == 128 || strict)) || strict_trick_rows) && rows_env != 0) {
     auto stage_bytes = [&](int R) -> long long {
       const int kt = (R * p.P + UKP - 1) / UKP * UKP;
       const uint32_t xs = align_up((uint32_t)(kt + 2 * p.P + 3) * p.PB, 1024), ds = align_up((uint32_t)kt * p.PB, 1024);
       return ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1);
     };
     if (rows_env > 0) rows = rows_env;
+    else if (strict_trick_rows) rows = strow_env < H ? strow_env : H;
     else {   // most rows that still leave two stages; prefer a row count with little k-step padding
       double best_cost = 1e30;
       for (int R = 1; R <= H && R <= 64; ++R) {
@@ -1091,7 +1101,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
       const int RBx = (off_max + kt + xreach + p.P - 1) / p.P, RBd = (off_max + kt + dreach + p.P - 1) / p.P;
       if (RBx > 256) continue;
       const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
-      const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
+      const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? (strict ? 2048 : 1024) : 0);
       if (stage * st_try + 1024 + 4608 <= max_smem) { KT = kt; stages = st_try; break; }
     }
   }
@@ -1105,7 +1115,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   {  // small tiles (small images): deepen the TMA pipeline with the shared memory that is left
     const int RBx = (off_max + KT + xreach + p.P - 1) / p.P, RBd = (off_max + KT + dreach + p.P - 1) / p.P;
     const uint32_t xs = align_up((uint32_t)RBx * p.P * p.PB, 1024), ds = align_up((uint32_t)RBd * p.P * p.PB, 1024);
-    const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? 1024 : 0);
+    const long long stage = ((long long)p.xchunks * xs + (long long)p.dchunks * ds) * (strict ? 2 : 1) + (p.pair ? (strict ? 2048 : 1024) : 0);
     while (stages < 6 && stage * (stages + 1) + 1024 + 4608 <= max_smem) ++stages;
   }
   p.KT = KT; p.tstride = KT; p.stages = stages;
@@ -1116,7 +1126,7 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   }
   p.x_off = p.pair ? 1024 : 0; p.d_off = p.x_off + p.xchunks * p.x_chunk_stride;
   const uint32_t hi_bytes = p.d_off + p.dchunks * p.d_chunk_stride;
-  p.x_lo_off = hi_bytes; p.d_lo_off = hi_bytes + p.d_off;
+  p.x_lo_off = hi_bytes + p.x_off; p.d_lo_off = hi_bytes + p.d_off;      // the lo region mirrors the hi region (incl. the pair pad)
   p.stage_stride = strict ? 2 * hi_bytes : hi_bytes;
   p.ent_off = p.stage_stride * p.stages;
   p.bsum_off = p.ent_off + 128;

@@ -149,9 +149,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     if constexpr (TWO) { tmem_alloc2(tmem_slot, p.tmem_cols); tmem_relinquish2(); }
     else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   }
-  if (p.pair) {   // zero the 1 KB pad in front of every stage's x strip (row -1 of the first kernel row)
-    for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x)
+  if (p.pair) {   // zero the 1 KB pad in front of every stage's x strip (row -1 of the first kernel row); strict: of the lo strip too
+    for (int i = threadIdx.x; i < p.stages * 64; i += blockDim.x) {
       reinterpret_cast<uint4*>(smem + (i >> 6) * p.stage_stride)[i & 63] = make_uint4(0u, 0u, 0u, 0u);
+      if (STRICT) reinterpret_cast<uint4*>(smem + (i >> 6) * p.stage_stride + (p.x_lo_off - p.x_off))[i & 63] = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async_smem();
   }
   if (p.rowtiles) {   // zero what TMA never writes between a chunk's rows and its stride: the k-steps past the last row read it
@@ -231,7 +233,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         shift = (tap / 3) * p.P + (tap % 3);
         a_off = (lane % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
       }
-      ent[lane] = (uint32_t)shift * RU + (a_off >> 4);
+      // pixel-pair mode starts every kernel row one operand row early (the zero slots sit at the END of the previous row)
+      ent[lane] = (uint32_t)shift * RU + (a_off >> 4) - (p.pair ? 8u : 0u);
     }
     __syncwarp();
     uint32_t entr[16];
@@ -489,7 +492,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         for (int c0 = 0; c0 < 32; c0 += 16) {
           uint32_t r[16];
           tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * ACCW + c0, r);
-          tmem_ld_wait();
+          if (STRICT) {      // main + correction accumulators
+            uint32_t r2[16];
+            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + e * ACCW + p.NT + c0, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            tmem_ld_wait();
+          }
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
