@@ -73,9 +73,12 @@ _SIGNATURES = {
                                    c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200ode_transition_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
     "b200ode_transition_dgrad": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "b200ode_transition_dgrad_amax": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
     "b200ode_transition_wgrad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
     "b200ode_head_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200ode_head_fwd_bwd_amax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200ode_layer_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "b200ode_layer_set_workspace": (c_int, [c_void_p, c_void_p, c_size_t]),
     "b200ode_chain_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
@@ -90,6 +93,8 @@ _SIGNATURES = {
                                   c_int, c_void_p]),
     "b200ode_chain_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                     c_void_p]),
+    "b200ode_chain_dgrad_amax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                         c_void_p, c_void_p]),
     "b200ode_chain_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p]),
 }

@@ -1419,6 +1419,7 @@ struct b200ode_chain {
   float* w_lo;     // unused (kept NULL)
   __half* w16;     // FAST_F16:  [L][9][C][C] fp16, K-major B operand
   float* bias;     // [L][C]
+  const float* amax_cur;   // FAST_F16: the scalar the last backward sweep used (amax, or the caller's of b200ode_chain_dgrad_amax)
   float* amax;     // FAST_F16: device scalar max|dy| of the last backward sweep (scale of dz_all)
   float amax_h;    //           and the step size it was taken with
   void* ws;        // caller-owned workspace (b200ode_chain_set_workspace), may be NULL
@@ -1738,8 +1739,19 @@ extern "C" int b200ode_chain_fwd(b200ode_chain_t* ch, const float* x0, void* act
   return launch_chain<0>(ch, plan, mx, mw, chain_grid(p, C, N), (cudaStream_t)stream);
 }
 
+static int chain_dgrad_impl(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
+                           int N, int H, int W, float h, const float* dy_amax, void* stream);
 extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
                                    int N, int H, int W, float h, void* stream) {
+  return chain_dgrad_impl(ch, dy, relu_masks, dz_all, dx, N, H, W, h, nullptr, stream);
+}
+extern "C" int b200ode_chain_dgrad_amax(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
+                                        int N, int H, int W, float h, const float* dy_amax, void* stream) {
+  if (!dy_amax) return fail(B200ODE_ERR_INVALID, "dy_amax is NULL");
+  return chain_dgrad_impl(ch, dy, relu_masks, dz_all, dx, N, H, W, h, dy_amax, stream);
+}
+static int chain_dgrad_impl(b200ode_chain_t* ch, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
+                            int N, int H, int W, float h, const float* dy_amax, void* stream) {
   if (!ch || !dy || !relu_masks || !dz_all || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (!ch->packed) return fail(B200ODE_ERR_NOT_PACKED, "b200ode_chain_pack must run before compute calls");
   if (N == 0) return 0;
@@ -1749,16 +1761,21 @@ extern "C" int b200ode_chain_dgrad(b200ode_chain_t* ch, const float* dy, const u
       return fail(B200ODE_ERR_UNSUPPORTED, "chain: a %dx%dx%d image does not fit shared memory (use the per-layer entry points)", H, W, ch->g.C);
     cudaStream_t st = (cudaStream_t)stream;
     // scale of the fp16 backward strips: max|dy| -> device scalar (read by the chain kernel and by the gradient fold)
-    const long long n4 = (long long)N * H * W * ch->g.C / 4;
-    CUDA_TRY(cudaMemsetAsync(ch->amax, 0, sizeof(float), st));
-    const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    const long long want = (n4 + 255) / 256;
-    amax_abs_kernel<<<(unsigned)(want < 2LL * sms ? want : 2LL * sms), 256, 0, st>>>((const float4*)dy, n4, (unsigned int*)ch->amax);
-    LAUNCH_CHECK("amax_abs_kernel");
+    if (dy_amax) {      // the kernel that produced dy already left max|dy| there (b200ode_*_amax entries): two launches less
+      ch->amax_cur = dy_amax;
+    } else {
+      const long long n4 = (long long)N * H * W * ch->g.C / 4;
+      CUDA_TRY(cudaMemsetAsync(ch->amax, 0, sizeof(float), st));
+      const int sms = g_num_sms > 0 ? g_num_sms : 148;
+      const long long want = (n4 + 255) / 256;
+      amax_abs_kernel<<<(unsigned)(want < 2LL * sms ? want : 2LL * sms), 256, 0, st>>>((const float4*)dy, n4, (unsigned int*)ch->amax);
+      LAUNCH_CHECK("amax_abs_kernel");
+      ch->amax_cur = ch->amax;
+    }
     ch->amax_h = h;
     ChainF16Params& p = plan.p;
     p.N = N; p.L = ch->L; p.Lw = ch->L; p.h = h; p.gamma = ch->g.gamma;
-    p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (__half*)dz_all; p.dx = dx; p.amax = ch->amax; p.trace = g_trace;
+    p.bias = ch->bias; p.dy = dy; p.masks_r = relu_masks; p.dz_all = (__half*)dz_all; p.dx = dx; p.amax = ch->amax_cur; p.trace = g_trace;
     CUtensorMap mw;
     if (int rc = make_chain_w16_map(&mw, ch)) return rc;
     return launch_chain_f16<1>(ch, plan, mw, chain_f16_grid(p, ch->g.C, N), st);
@@ -1785,7 +1802,7 @@ extern "C" int b200ode_chain_wgrad(b200ode_chain_t* ch, const float* x0, const v
     if (!acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
     const __half* a16 = (const __half*)acts;
     return run_wgrad_tc(MODE_F16, ch->g, a16, a16 + (size_t)N * H * W * ch->g.C, dz_all, ch->L, N, H, W, nullptr, nullptr, grad_params,
-                        grad_layer_stride, 0, (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr}, 0, ch->amax, ch->amax_h);
+                        grad_layer_stride, 0, (cudaStream_t)stream, WsArg{ch->ws, ch->ws_bytes, nullptr}, 0, ch->amax_cur ? ch->amax_cur : ch->amax, ch->amax_h);
   }
   if (!x0) return fail(B200ODE_ERR_INVALID, "x0 is NULL");
   if (ch->L > 1 && !acts) return fail(B200ODE_ERR_INVALID, "acts is NULL");
@@ -1932,7 +1949,7 @@ static int transition_fwd_mma(const GlueConv& g, const float* x, const float* Wm
 }
 template <int CIN, int COUT, int NSPLIT>
 static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint8_t* mask, const float* Wm, const float* Ws, float* dx,
-                                cudaStream_t st) {
+                                unsigned int* dx_amax, cudaStream_t st) {
   const int CH = (g.H - 1 + g.pt) / 2 + 1, CW = (g.W - 1 + g.pl) / 2 + 1;
   int crows = (128 / NSPLIT) / CW;
   if (crows < 1) crows = 1;
@@ -1946,7 +1963,7 @@ static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint
     CUDA_TRY(cudaFuncSetAttribute(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  CUDA_TRY(launch_pdl(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, dout, mask, Wm, Ws, dx, crows));
+  CUDA_TRY(launch_pdl(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, dout, mask, Wm, Ws, dx, crows, dx_amax));
   LAUNCH_CHECK("transition_dgrad_mma_kernel");
   return 0;
 }
@@ -2005,17 +2022,38 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   return 0;
 }
 
+static int transition_dgrad_impl(const float* dout, const uint8_t* relu_mask, const float* main_kernel, const float* short_kernel, float* dx,
+                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, void* stream);
 extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
                                         const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
                                         int stride_w, void* stream) {
+  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, nullptr, stream);
+}
+extern "C" int b200ode_transition_dgrad_amax(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                                             const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                                             int stride_w, float* dx_amax, void* stream) {
+  if (!dx_amax) return fail(B200ODE_ERR_INVALID, "dx_amax is NULL");
+  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, dx_amax, stream);
+}
+// dx_amax != NULL: *dx_amax = max(*dx_amax, max|dx|) (the tensor-core kernel does it in its epilogue; other shapes by one more launch)
+static int amax_after(const float* v, long long n, float* amax, cudaStream_t st) {
+  if (n % 4) return fail(B200ODE_ERR_UNSUPPORTED, "amax: element count must be a multiple of 4");
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const long long n4 = n / 4, want = (n4 + 255) / 256;
+  amax_abs_kernel<<<(unsigned)(want < 2LL * sms ? want : 2LL * sms), 256, 0, st>>>((const float4*)v, n4, (unsigned int*)amax);
+  LAUNCH_CHECK("amax_abs_kernel");
+  return 0;
+}
+static int transition_dgrad_impl(const float* dout, const uint8_t* relu_mask, const float* main_kernel, const float* short_kernel, float* dx,
+                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, void* stream) {
   if (!dout || !relu_mask || !main_kernel || !short_kernel || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (int rc = transition_check(Cin, Cout)) return rc;
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
   if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {
-    const int rc = Cin == 16 ? transition_dgrad_mma<16, 32, 1>(g, dout, relu_mask, main_kernel, short_kernel, dx, st)
-                             : transition_dgrad_mma<32, 64, 2>(g, dout, relu_mask, main_kernel, short_kernel, dx, st);
+    const int rc = Cin == 16 ? transition_dgrad_mma<16, 32, 1>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st)
+                             : transition_dgrad_mma<32, 64, 2>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st);
     if (rc >= 0) return rc;
   }
   // band height: the staged output rows (dout + masked copy) and the weight slice must fit shared memory
@@ -2041,6 +2079,7 @@ extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_m
   else if (stride_h == 2 && stride_w == 2 && Cin <= 16) GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 1, 2>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   else GLUE_SMEM_LAUNCH((transition_dgrad_kernel<CIT, 1>), grid, 128, smem, st, g, dout, relu_mask, main_kernel, short_kernel, dx, rows);
   LAUNCH_CHECK("transition_dgrad_kernel");
+  if (dx_amax) return amax_after(dx, (long long)N * H * W * Cin, dx_amax, st);
   return 0;
 }
 
@@ -2099,9 +2138,23 @@ extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const
   return reduce_rows(ws, N * bands, nout, nout, dparams, st);
 }
 
+static int head_impl(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps, float* probs, float* loss,
+                     float* dx, float* dparams, int N, int HW, int C, int K, void* workspace, size_t workspace_bytes, float* dx_amax,
+                     void* stream);
 extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
                                     float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K,
                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return head_impl(x, fc_kernel, fc_bias, onehot, eps, probs, loss, dx, dparams, N, HW, C, K, workspace, workspace_bytes, nullptr, stream);
+}
+extern "C" int b200ode_head_fwd_bwd_amax(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
+                                         float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K,
+                                         void* workspace, size_t workspace_bytes, float* dx_amax, void* stream) {
+  if (!dx || !dx_amax) return fail(B200ODE_ERR_INVALID, "dx / dx_amax is NULL");
+  return head_impl(x, fc_kernel, fc_bias, onehot, eps, probs, loss, dx, dparams, N, HW, C, K, workspace, workspace_bytes, dx_amax, stream);
+}
+static int head_impl(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps, float* probs, float* loss,
+                     float* dx, float* dparams, int N, int HW, int C, int K, void* workspace, size_t workspace_bytes, float* dx_amax,
+                     void* stream) {
   if (!x || !fc_kernel || !fc_bias || !onehot || !loss) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (K > 32 || K > C || C > 1024 || (C % 32)) return fail(B200ODE_ERR_UNSUPPORTED, "head: need classes <= 32 <= channels (multiple of 32, <= 1024)");
   if (int rc = device_check()) return rc;
@@ -2111,7 +2164,7 @@ extern "C" int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, cons
   if (int rc = lease_ws(workspace, workspace_bytes, head_ws_bytes(N, C, K), (cudaStream_t)stream, &lease)) return rc;
   float* ws = (float*)lease.ptr;
   CUDA_TRY(launch_pdl(head_kernel, dim3(N), dim3(C), (C + 33) * sizeof(float), (cudaStream_t)stream, x, HW, C, K, fc_kernel, fc_bias, onehot, eps,
-                      N, probs, dx, ws));
+                      N, probs, dx, ws, (unsigned int*)dx_amax));
   LAUNCH_CHECK("head_kernel");
   if (dparams)
     if (int rc = reduce_rows(ws, N, nout, nout - 1, dparams, (cudaStream_t)stream)) return rc;

@@ -506,7 +506,8 @@ __global__ void reduce_rows_wide_kernel(const float* __restrict__ part, int R, l
 // ---------------------------------------------------------------------------------------------
 __global__ void head_kernel(const float* __restrict__ x, int HW, int C, int K, const float* __restrict__ Wfc,
                             const float* __restrict__ bfc, const float* __restrict__ onehot, float eps, int N,
-                            float* __restrict__ probs, float* __restrict__ dx, float* __restrict__ part) {
+                            float* __restrict__ probs, float* __restrict__ dx, float* __restrict__ part,
+                            unsigned int* __restrict__ dx_amax = nullptr) {
   extern __shared__ float sm[];
   griddep_launch_dependents();
   griddep_wait();
@@ -563,6 +564,12 @@ __global__ void head_kernel(const float* __restrict__ x, int HW, int C, int K, c
     const float dv = df / (float)HW;
     float* dp = dx + (long long)n * HW * C + c;
     for (int i = 0; i < HW; ++i) dp[(long long)i * C] = dv;
+    if (dx_amax) {      // max |dx| for the fp16 chain behind the head (bit pattern of a non-negative float orders like a uint)
+      float m = fabsf(dv);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(dx_amax, __float_as_uint(m));
+    }
   }
 }
 

@@ -183,8 +183,9 @@ struct TrDgradMma {
 template <int CIN, int COUT, int NSPLIT>
 __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, const float* __restrict__ dout, const uint8_t* __restrict__ mask,
                                                                    const float* __restrict__ Wm, const float* __restrict__ Ws,
-                                                                   float* __restrict__ dx, int crows) {
+                                                                   float* __restrict__ dx, int crows, unsigned int* __restrict__ dx_amax) {
   using Cfg = TrDgradMma<CIN, COUT>;
+  float amx = 0.0f;       // max |dx| over what this thread stores (dx_amax != NULL: for the fp16 chain behind the transition)
   constexpr int PSO = Cfg::PSO, WS = Cfg::WS, NT = CIN / 8 / NSPLIT, KS = COUT / 8;
   extern __shared__ float sm[];
   const int n = blockIdx.x;
@@ -279,9 +280,21 @@ __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, c
       float* d1 = dx + (((long long)n * g.H + y1) * g.W + x1) * CIN + nb + 2 * tq;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        if (st0) *reinterpret_cast<float2*>(d0 + j * 8) = make_float2(acc[j][0], acc[j][1]);
-        if (st1) *reinterpret_cast<float2*>(d1 + j * 8) = make_float2(acc[j][2], acc[j][3]);
+        if (st0) { *reinterpret_cast<float2*>(d0 + j * 8) = make_float2(acc[j][0], acc[j][1]); amx = fmaxf(amx, fmaxf(fabsf(acc[j][0]), fabsf(acc[j][1]))); }
+        if (st1) { *reinterpret_cast<float2*>(d1 + j * 8) = make_float2(acc[j][2], acc[j][3]); amx = fmaxf(amx, fmaxf(fabsf(acc[j][2]), fabsf(acc[j][3]))); }
       }
+    }
+  }
+  if (dx_amax) {          // one atomic per block
+    __shared__ float wmax[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if (lane == 0) wmax[warp] = amx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.0f;
+      for (int w = 0; w < nwarps; ++w) m = fmaxf(m, wmax[w]);
+      if (m > 0.0f) atomicMax(dx_amax, __float_as_uint(m));
     }
   }
 }

@@ -183,8 +183,14 @@ class ChainHandle:
         _abi.check(_abi.lib().b200ode_chain_fwd(self._h, _ptr(x0), _ptr(acts), _ptr(masks), _ptr(y_final), N, H, W,
                                                 float(h), n_steps, _stream_ptr()))
 
-    def dgrad(self, dy, masks, dz_all, dx, h):
+    def dgrad(self, dy, masks, dz_all, dx, h, dy_amax=None):
+        """dy_amax: optional 1-element fp32 device tensor already holding max|dy| (written by b200ode_head_fwd_bwd_amax /
+        b200ode_transition_dgrad_amax): FAST_F16 chains then skip their own reduction over dy."""
         N, H, W, C = dy.shape
+        if dy_amax is not None:
+            _abi.check(_abi.lib().b200ode_chain_dgrad_amax(self._h, _ptr(dy), _ptr(masks), _ptr(dz_all), _ptr(dx), N, H, W,
+                                                           float(h), _ptr(dy_amax), _stream_ptr()))
+            return
         _abi.check(_abi.lib().b200ode_chain_dgrad(self._h, _ptr(dy), _ptr(masks), _ptr(dz_all), _ptr(dx), N, H, W,
                                                   float(h), _stream_ptr()))
 

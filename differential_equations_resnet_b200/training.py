@@ -162,9 +162,9 @@ class _Chain:
         self.fused.forward(x, h, acts=self.f_acts, masks=self.f_masks)
         return self.f_acts[self.n - 1]
 
-    def fused_dgrad(self, dy, h):
+    def fused_dgrad(self, dy, h, dy_amax=None):
         """Backward sweep over all steps of the chain (one launch); returns dL/dx0."""
-        self.fused.dgrad(dy, self.f_masks, self.f_dz, self.f_dx, h)
+        self.fused.dgrad(dy, self.f_masks, self.f_dz, self.f_dx, h, dy_amax=dy_amax)
         return self.f_dx
 
     def fused_wgrad(self, grad_euler):
@@ -574,7 +574,10 @@ class EulerNet:
             self._nb = dict(shape=tuple(shape), plan=plan, hw=h * w, c=c,
                             head_dx=torch.empty((N, h, w, c), dtype=torch.float32, device=device),
                             head_ws=self._glue_ws(True, _abi.GLUE_HEAD, N, 1, 1, c, spec.num_classes, 1, 1, device),
-                            loss=torch.zeros(1, dtype=torch.float32, device=device))
+                            loss=torch.zeros(1, dtype=torch.float32, device=device),
+                            # max|dY| of every fp16 chain's backward input, left there by the kernel that produces dY
+                            # (head / transition data gradient); zeroed once per step
+                            amax=torch.zeros(max(4, len(plan)), dtype=torch.float32, device=device))
         self._nb_cache[tuple(shape)] = self._nb
         return self._nb
 
@@ -646,9 +649,25 @@ class EulerNet:
         if not joined:
             main.wait_event(packed)
         fo = self._off("fc/kernel")
-        _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
-                                            _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
-                                            spec.num_classes, _ptr(nb["head_ws"]), nb["head_ws"].numel(), st))
+        # fp16 chains scale their backward strips by max|dY|: the kernels that PRODUCE dY (head, tensor-core transition data
+        # gradients) leave it in nb["amax"][i] (i = index of the chain in the plan) instead of three extra reductions + memsets
+        plan_ = nb["plan"]
+        fuse_amax = os.environ.get("B200ODE_FUSED_AMAX", "1") != "0" and all(
+            e["kind"] != "chain" or (e["chain"].fused is not None and e["chain"].fused.f16) for e in plan_)
+        amax = nb["amax"]
+        if fuse_amax:
+            amax.zero_()
+        if fuse_amax and plan_[-1]["kind"] == "chain":
+            _abi.check(lib.b200ode_head_fwd_bwd_amax(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
+                                                     _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
+                                                     spec.num_classes, _ptr(nb["head_ws"]), nb["head_ws"].numel(),
+                                                     _ptr(amax[len(plan_) - 1:]), st))
+            d_amax = amax[len(plan_) - 1:len(plan_)]
+        else:
+            _abi.check(lib.b200ode_head_fwd_bwd(_ptr(cur), _ptr(th[fo:]), _ptr(th[self._off("fc/bias"):]), _ptr(onehot), 1e-7, None,
+                                                _ptr(nb["loss"]), _ptr(nb["head_dx"]), _ptr(gr[fo:]), N, nb["hw"], nb["c"],
+                                                spec.num_classes, _ptr(nb["head_ws"]), nb["head_ws"].numel(), st))
+            d_amax = None
         # Backward.  Critical path (main stream): head -> chain dgrad -> transition dgrad -> chain dgrad -> ...; every
         # weight gradient (chain wgrad + fold, transition wgrad, stem wgrad: ~1/4 of the step) only feeds the optimiser,
         # so it runs on a side stream, ordered by events after the data gradient that produces its dZ, and is joined
@@ -660,10 +679,12 @@ class EulerNet:
         # kernels (registers), so a chain launch that meets them runs a second wave.  Default: peer-memory exchange inside the
         # Adam kernel (p2p), else ONE all-reduce of the whole bucket before Adam.
         early = self._early_slices(nb) if overlap_wgrad and self.world_size > 1 and not self.p2p and os.environ.get("B200ODE_EARLY_ADAM") else None
-        for e in reversed(nb["plan"]):
+        for ei in range(len(plan_) - 1, -1, -1):
+            e = plan_[ei]
             if e["kind"] == "chain":
                 ch = e["chain"]
-                dnext = ch.fused_dgrad(d, spec.h)
+                dnext = ch.fused_dgrad(d, spec.h, dy_amax=d_amax)
+                d_amax = None
                 if overlap_wgrad:
                     ev = torch.cuda.Event()
                     ev.record(main)
@@ -683,9 +704,16 @@ class EulerNet:
                     _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
                                                             N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1],
                                                             _ptr(e["ws"]), e["ws"].numel(), side.cuda_stream))
-                _abi.check(lib.b200ode_transition_dgrad(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
-                                                        _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
-                                                        e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                if fuse_amax and ei > 0 and plan_[ei - 1]["kind"] == "chain":
+                    _abi.check(lib.b200ode_transition_dgrad_amax(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                                 _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
+                                                                 e["ci"], e["co"], e["st"][0], e["st"][1], _ptr(amax[ei - 1:]), st))
+                    d_amax = amax[ei - 1:ei]
+                else:
+                    _abi.check(lib.b200ode_transition_dgrad(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                            _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
+                                                            e["ci"], e["co"], e["st"][0], e["st"][1], st))
+                    d_amax = None
                 d = e["dx"]
                 if early is not None and e is early["after"]:
                     # Everything behind the first stage is final now (gradients written, parameters no longer read by

@@ -220,6 +220,12 @@ int b200ode_chain_fwd(b200ode_chain_t* chain, const float* x0, void* acts, uint8
  * fp16 times the launch's power-of-two scale (FAST_F16; the scale lives in the chain handle). */
 int b200ode_chain_dgrad(b200ode_chain_t* chain, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
                         int N, int H, int W, float h, void* stream);
+/* Same with max|dy| supplied by the caller (device scalar, written by the kernel that produced dy: the *_amax entries of the
+ * head / transition data gradients below): FAST_F16 chains skip their own reduction over dy (two launches less on the
+ * critical path of a train step); dy_amax must stay untouched until b200ode_chain_wgrad of this chain has run.  Other modes
+ * ignore it. */
+int b200ode_chain_dgrad_amax(b200ode_chain_t* chain, const float* dy, const uint8_t* relu_masks, void* dz_all, float* dx,
+                             int N, int H, int W, float h, const float* dy_amax, void* stream);
 /* weight + bias gradients of all layers in one launch (+ fold/reduce launches); result at
  * grad_params + l*grad_layer_stride.
  *   FAST_TF32: layer l reads x_l (x0 for l = 0, acts[l-1] otherwise) and dz_all[l], all fp32.
@@ -255,6 +261,11 @@ int b200ode_transition_fwd(const float* x, const float* main_kernel, const float
 int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
                              const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
                              int stride_w, void* stream);
+/* ... and *dx_amax = max(*dx_amax, max|dx|) as a side effect (the caller zeroes the scalar beforehand; fed to
+ * b200ode_chain_dgrad_amax of the stage in front of the transition) */
+int b200ode_transition_dgrad_amax(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                                  const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                                  int stride_w, float* dx_amax, void* stream);
 /* dparams = [dmain_kernel (3,3,Cin,Cout) | dmain_bias | dshort_kernel (Cin,Cout) | dshort_bias] */
 int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H, int W,
                              int Cin, int Cout, int stride_h, int stride_w, void* workspace, size_t workspace_bytes,
@@ -266,6 +277,10 @@ int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* r
 int b200ode_head_fwd_bwd(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
                          float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* ... and *dx_amax = max(*dx_amax, max|dx|) as a side effect (dx required; see b200ode_chain_dgrad_amax) */
+int b200ode_head_fwd_bwd_amax(const float* x, const float* fc_kernel, const float* fc_bias, const float* onehot, float eps,
+                              float* probs, float* loss, float* dx, float* dparams, int N, int HW, int C, int K, void* workspace,
+                              size_t workspace_bytes, float* dx_amax, void* stream);
 
 /* ---- gradient exchange ------------------------------------------------------------
  * The reference has no collective (single tf.Session, training/training.py:132); data parallel training sums

@@ -156,3 +156,21 @@ def test_chain_f16_refuses_what_does_not_fit():
         ch.forward(x, 0.1, y_final=torch.empty_like(x))
     with pytest.raises(ValueError):                                # FAST_F16 needs y_final
         ch.forward(torch.zeros((1, 8, 8, 64), device="cuda"), 0.1, acts=torch.empty((1, 1, 8, 8, 64), device="cuda", dtype=torch.float16))
+
+
+def test_chain_f16_dgrad_with_supplied_amax_is_bit_identical():
+    """b200ode_chain_dgrad_amax with max|dy| supplied by the caller (as the *_amax data-gradient entries of the head / transitions
+    leave it): same dz_all, dx and weight gradients, bit for bit, as the entry that reduces dy itself."""
+    C, H, W, N, L, h = 32, 16, 16, 5, 3, 0.125
+    ch, flats, theta = _setup(C, L, -0.1, seed=21)
+    g = torch.Generator().manual_seed(5)
+    x = torch.relu(torch.randn((N, H, W, C), generator=g))
+    dy = torch.randn((N, H, W, C), generator=g) * 3e-3
+    acts, masks, y, dz, dx, grad = _run_gpu(ch, x, dy, h, L)
+    dyd = dy.cuda()
+    am = dyd.abs().max().reshape(1).clone()
+    dz2, dx2, grad2 = torch.empty_like(dz), torch.empty_like(dx), torch.empty_like(grad)
+    ch.dgrad(dyd, masks, dz2, dx2, h, dy_amax=am)
+    ch.wgrad(x.cuda(), acts, dz2, grad2.view(-1))
+    torch.cuda.synchronize()
+    assert torch.equal(dz, dz2) and torch.equal(dx, dx2) and torch.equal(grad, grad2)

@@ -121,3 +121,38 @@ def test_head_matches_oracle():
     assert rel(dx, x.grad) <= 1e-4
     assert rel(dp[:C * K].view(C, K), Wfc.grad) <= 1e-4
     assert rel(dp[C * K:], bfc.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("Ci,Co,H,st", [(16, 32, 32, (2, 2)), (32, 64, 16, (2, 2)), (32, 64, 8, (1, 1))])
+def test_amax_entries_leave_the_maximum_of_dx(Ci, Co, H, st):
+    """b200ode_transition_dgrad_amax / b200ode_head_fwd_bwd_amax: same results as the plain entries, and the caller's scalar
+    holds max|dx| afterwards (tensor-core kernels: from their epilogue; other shapes: one more launch).  Feeds
+    b200ode_chain_dgrad_amax (tests/test_gpu_chain_f16.py)."""
+    _abi, lib = _lib()
+    N = 4
+    g = torch.Generator().manual_seed(9)
+    Ho = (H + st[0] - 1) // st[0]
+    dout = torch.randn((N, Ho, Ho, Co), generator=g).cuda()
+    mask = torch.randint(0, 256, (N, Ho, Ho, Co // 8), generator=g, dtype=torch.uint8).cuda()
+    Wm = (torch.randn((3, 3, Ci, Co), generator=g) * 0.1).cuda(); Ws = (torch.randn((Ci, Co), generator=g) * 0.1).cuda()
+    dx, dx2 = torch.empty((N, H, H, Ci), device="cuda"), torch.empty((N, H, H, Ci), device="cuda")
+    am = torch.zeros(1, device="cuda")
+    _abi.check(lib.b200ode_transition_dgrad(P(dout), P(mask), P(Wm), P(Ws), P(dx), N, H, H, Ci, Co, st[0], st[1], None))
+    _abi.check(lib.b200ode_transition_dgrad_amax(P(dout), P(mask), P(Wm), P(Ws), P(dx2), N, H, H, Ci, Co, st[0], st[1], P(am), None))
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2)
+    assert float(am) == float(dx.abs().max())
+    # head
+    C, K = 64, 10
+    x = torch.randn((N, 8, 8, C), generator=g).cuda()
+    Wfc = (torch.randn((C, K), generator=g) * 0.5).cuda(); bfc = torch.zeros(K, device="cuda")
+    oh = torch.nn.functional.one_hot(torch.randint(0, K, (N,), generator=g), K).float().cuda()
+    loss, loss2 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    hx, hx2 = torch.empty_like(x), torch.empty_like(x)
+    dp, dp2 = torch.empty(C * K + K, device="cuda"), torch.empty(C * K + K, device="cuda")
+    am.zero_()
+    _abi.check(lib.b200ode_head_fwd_bwd(P(x), P(Wfc), P(bfc), P(oh), 1e-7, None, P(loss), P(hx), P(dp), N, 64, C, K, None, 0, None))
+    _abi.check(lib.b200ode_head_fwd_bwd_amax(P(x), P(Wfc), P(bfc), P(oh), 1e-7, None, P(loss2), P(hx2), P(dp2), N, 64, C, K, None, 0, P(am), None))
+    torch.cuda.synchronize()
+    assert torch.equal(hx, hx2) and torch.equal(dp, dp2) and torch.equal(loss, loss2)
+    assert float(am) == float(hx.abs().max())
