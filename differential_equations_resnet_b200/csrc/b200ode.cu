@@ -2166,6 +2166,11 @@ static int head_impl(const float* x, const float* fc_kernel, const float* fc_bia
   CUDA_TRY(launch_pdl(head_kernel, dim3(N), dim3(C), (C + 33) * sizeof(float), (cudaStream_t)stream, x, HW, C, K, fc_kernel, fc_bias, onehot, eps,
                       N, probs, dx, ws, (unsigned int*)dx_amax));
   LAUNCH_CHECK("head_kernel");
+  if (dparams && N >= 64 && nout <= 2048) {     // parameter gradients and the loss in ONE reduction launch (32 row lanes per output)
+    reduce_rows_wide_kernel<32><<<blocks_for(nout * 32, 256), 256, 0, (cudaStream_t)stream>>>(ws, N, nout, nout, dparams, loss);
+    LAUNCH_CHECK("reduce_rows_wide_kernel");
+    return 0;
+  }
   if (dparams)
     if (int rc = reduce_rows(ws, N, nout, nout - 1, dparams, (cudaStream_t)stream)) return rc;
   return reduce_rows(ws + (nout - 1), N, nout, 1, loss, (cudaStream_t)stream);

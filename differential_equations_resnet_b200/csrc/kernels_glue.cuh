@@ -485,8 +485,10 @@ __global__ void transition_wgrad_partial(GlueConv g, const float* __restrict__ x
 // out[o] = sum_r part[r*stride + o] for many rows: LANES (8 or 32) row lanes per output, fixed-order combine
 // (deterministic).  A single thread per output walked R = 128..512 rows serially (8-11 us per launch for a few
 // hundred outputs).
+// out_last != NULL: the last of the n outputs goes to *out_last instead of out[n - 1] (the head's loss beside its parameter gradients)
 template <int LANES>
-__global__ void reduce_rows_wide_kernel(const float* __restrict__ part, int R, long long stride, long long n, float* __restrict__ out) {
+__global__ void reduce_rows_wide_kernel(const float* __restrict__ part, int R, long long stride, long long n, float* __restrict__ out,
+                                        float* __restrict__ out_last = nullptr) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long o = gid / LANES;
   const int l = (int)(gid % LANES);
@@ -496,7 +498,10 @@ __global__ void reduce_rows_wide_kernel(const float* __restrict__ part, int R, l
   for (int r = l; r < R; r += LANES) acc += part[(long long)r * stride + o];
 #pragma unroll
   for (int off = LANES >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, LANES);
-  if (l == 0) out[o] = acc;
+  if (l == 0) {
+    if (out_last && o == n - 1) *out_last = acc;
+    else out[o] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
