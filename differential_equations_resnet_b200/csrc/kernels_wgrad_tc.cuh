@@ -566,7 +566,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
       mbar_wait(&full[s], ph);
       uint8_t* sb = smem + s * p.stage_stride;
-      for (int which = 0; which < 2; ++which) {
+      for (int which = 0; which < ((p.dbg & 4) ? 0 : 2); ++which) {      // dbg bit 2: no conversion (timing experiments only)
         const uint4* src = reinterpret_cast<const uint4*>(sb + (which ? p.d_off : p.x_off));
         uint4* dst = reinterpret_cast<uint4*>(sb + (which ? p.d_lo_off : p.x_lo_off));
         const int n16 = (which ? p.dchunks * p.d_chunk_stride : p.xchunks * p.x_chunk_stride) / 16;
