@@ -66,6 +66,20 @@ class Conv2DAntisymmetric(AntisymmetricConvBase):
             shapes.append((C,))
         return shapes
 
+    def _variable_names(self):
+        """Variable names in creation order (reference :117-128, :231-264, :152).  Every output channel creates the
+        scalars `centro_sym_{i}_{j}` again; the TF1 graph makes repeated names unique with `_1`, `_2`, ... ."""
+        C = self.num_channels
+        slots = diag_slots(self.kernel_size, self.antisymmetric)
+        names = []
+        for o in range(C):
+            names += ['centro_sym_%d_%d' % ij + ('_%d' % o if o else '') for ij in slots]
+            if C - o - 1 > 0:
+                names.append('input_kernels_for_output_kernel_%d' % o)
+        if self.use_bias:
+            names.append('bias')
+        return names
+
     def get_config(self):
         return {'name': self.name, 'trainable': self.trainable, 'dtype': self.dtype,
                 'kernel_size': self.kernel_size, 'gamma': self.gamma, 'strides': self.strides,

@@ -43,6 +43,13 @@ class Conv2DAntisymmetric3By3(AntisymmetricConvBase):
             shapes.append((C,))
         return shapes
 
+    def _variable_names(self):
+        # creation order, reference :119-124, :148-153, :219-245
+        names = ['a', 'b', 'c', 'd'] + ['input_kernels_for_output_kernel_%d' % o for o in range(self.num_channels - 1)]
+        if self.use_bias:
+            names.append('bias')
+        return names
+
     def get_config(self):
         # superset of the reference's config (it omits gamma, reference :177-186)
         return {'name': self.name, 'trainable': self.trainable, 'dtype': self.dtype,

@@ -14,6 +14,7 @@ section 2, row 6).
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 import zlib
 
 import numpy as np
@@ -243,6 +244,53 @@ class Model:
         for l in self.layers:
             out += list(l.trainable_weights)
         return out
+
+    def _named_weights(self, name, layer):
+        """Ordered {Keras weight name: tensor} of one regular layer of this model (None for antisymmetric layers)."""
+        if isinstance(layer, (_RegularConv, _Dense)):
+            if layer.kernel is None:
+                raise RuntimeError("layer %r has no weights yet: call the model once before saving / loading" % name)
+            return OrderedDict((name + '/' + v + ':0', getattr(layer, v)) for v in ('kernel', 'bias'))
+        if isinstance(layer, _BatchNorm):
+            if layer.gamma is None:
+                raise RuntimeError("layer %r has no weights yet: call the model once before saving / loading" % name)
+            return OrderedDict((name + '/' + v + ':0', getattr(layer, a)) for v, a in
+                               (('gamma', 'gamma'), ('beta', 'beta'), ('moving_mean', 'moving_mean'), ('moving_variance', 'moving_var')))
+        return None                                  # antisymmetric layers go through get_weights / set_weights
+
+    def save_weights(self, filepath):
+        """`model.save_weights(path + '.h5')` of the reference's notebooks (v6 cells 8 / 11): a Keras HDF5 weights file,
+        one group per layer, the C+4 variables of every antisymmetric layer under the reference's names."""
+        from ..keras_h5 import save_keras_weights
+        out = OrderedDict()
+        for lname in self.scope.order:
+            layer = self.scope.layers[lname]
+            named = self._named_weights(lname, layer)
+            if named is None:
+                named = OrderedDict((lname + '/' + v + ':0', w) for v, w in zip(layer._variable_names(), layer.get_weights()))
+            else:
+                named = OrderedDict((k, t.detach().cpu().numpy()) for k, t in named.items())
+            out[lname] = named
+        save_keras_weights(filepath, out)
+
+    def load_weights(self, filepath):
+        """`model.load_weights(path)`: every layer of this model must be in the file with the same weight shapes."""
+        from ..keras_h5 import load_keras_weights
+        saved = load_keras_weights(filepath)
+        for lname in self.scope.order:
+            layer = self.scope.layers[lname]
+            if lname not in saved:
+                raise ValueError("weights file has no layer %r" % lname)
+            ws = saved[lname]
+            named = self._named_weights(lname, layer)
+            if named is None:
+                layer.set_weights([ws[lname + '/' + v + ':0'] for v in layer._variable_names()])
+                continue
+            with torch.no_grad():
+                for k, t in named.items():
+                    if tuple(ws[k].shape) != tuple(t.shape):
+                        raise ValueError("weight %s has shape %s in the file, %s in the model" % (k, ws[k].shape, tuple(t.shape)))
+                    t.copy_(torch.from_numpy(np.asarray(ws[k], dtype=np.float32)))
 
 
 def get_single_block_resnet_build_function(kernel_type='antisymmetric',

@@ -991,6 +991,16 @@ class EulerNet:
                     mm.copy_(params[name + "/moving_mean"])
                     mv.copy_(params[name + "/moving_variance"])
 
+    def save_weights(self, filepath):
+        """`model.save_weights(path + '.h5')` (reference notebooks v6 / v7): Keras HDF5 weights file, `keras_h5.py`."""
+        from .keras_h5 import save_weights_h5
+        save_weights_h5(self, filepath)
+
+    def load_weights(self, filepath):
+        """`model.load_weights(path)`: parameters only; optimizer state is untouched (Keras weights files hold none)."""
+        from .keras_h5 import load_weights_h5
+        load_weights_h5(self, filepath)
+
     def export_grads(self):
         out = {}
         g = self.grad.detach().cpu()
