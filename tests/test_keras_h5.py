@@ -148,14 +148,18 @@ def test_eulernet_and_model_h5_weights(tmp_path):
     b.load_weights(p)
     assert torch.equal(a.theta, b.theta)
 
-    from differential_equations_resnet_b200.models.tfkeras_resnets import build_single_block_resnet
-    x = torch.rand(2, 8, 8, 3, device="cuda")
-    mk = dict(kernel_type='antisymmetric', blocks_per_stage=[2], filters_per_block=[16], num_classes=10, precision="strict")
-    m1 = build_single_block_resnet((8, 8, 3), sample_input=None, seed=1, **mk)
-    m2 = build_single_block_resnet((8, 8, 3), sample_input=None, seed=2, **mk)
+    from differential_equations_resnet_b200.models import get_single_block_resnet_build_function
+    kw = dict(kernel_type='antisymmetric', precision='strict', h=0.5, gamma=-0.1, num_stages=4, blocks_per_stage=[2, 1, 1],
+              filters_per_block=[16, 32, 64], strides=[(1, 1), (2, 2), (2, 2)], num_classes=10, use_batch_norm=True)
+    x = torch.rand(2, 16, 16, 3, device="cuda")
+    m1 = get_single_block_resnet_build_function(seed=1, **kw)(x)
+    m2 = get_single_block_resnet_build_function(seed=2, **kw)(x)
     y1, y2 = m1(x, training=False), m2(x, training=False)
     assert not torch.equal(y1, y2)
     q = str(tmp_path / "model.h5")
     m1.save_weights(q)
+    saved = kh.load_keras_weights(q)
+    assert list(saved)[:3] == ["conv1", "bn_conv1", "res2_0_branch2"] or list(saved)[0] == "conv1"
+    assert any(k.endswith("moving_variance:0") for ws in saved.values() for k in ws)
     m2.load_weights(q)
     assert torch.equal(m1(x, training=False), m2(x, training=False))
