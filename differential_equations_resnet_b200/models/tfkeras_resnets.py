@@ -61,10 +61,11 @@ def _scope():
 class _RegularConv:
     """Keras Conv2D(padding='same', kernel_initializer='he_normal') as torch ops."""
 
-    def __init__(self, filters, kernel_size, strides, name, seed=None):
+    def __init__(self, filters, kernel_size, strides, name, seed=None, padding='same'):
         self.filters, self.kernel_size, self.strides, self.name = filters, kernel_size, tuple(strides), name
         self.kernel = self.bias = None
         self.seed = seed
+        self.padding = padding
 
     def __call__(self, x):
         if self.kernel is None:
@@ -73,6 +74,9 @@ class _RegularConv:
             w = truncated_normal_(torch.empty(k, k, ci, self.filters), math.sqrt(2.0 / (k * k * ci)) / 0.87962566103423978, g)
             self.kernel = w.to(x.device).requires_grad_(True)
             self.bias = torch.zeros(self.filters, device=x.device, requires_grad=True)
+        if self.padding == 'valid':
+            y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), self.kernel.permute(3, 2, 0, 1), self.bias, stride=self.strides)
+            return y.permute(0, 2, 3, 1).contiguous()
         return conv2d_same_nhwc(x, self.kernel, self.bias, self.strides)
 
     @property
@@ -206,6 +210,93 @@ def single_layer_conv_block(input_tensor,
         main = sc.get(bn_name_base + '2', lambda: _BatchNorm(bn_name_base + '2')).torch_apply(main, sc.training)
         short = sc.get(bn_name_base + '1', lambda: _BatchNorm(bn_name_base + '1')).torch_apply(short, sc.training)
     return torch.relu(main) + short
+
+
+def _bottleneck_main(x, kernel_size, num_filters, antisymmetric, use_batch_norm, conv_name_base, bn_name_base,
+                     strides_1_by_1, strides_k_by_k, gamma, kernel_regularizer):
+    """1x1 -> kxk -> 1x1 main branch shared by the two bottleneck blocks (reference :148-195 and :352-400): the middle
+    convolution is a Conv2DAntisymmetric3By3 when `antisymmetric` and `num_filters[1] is None` (square matrix)."""
+    sc = _scope()
+
+    def bn(y, tag):
+        if use_batch_norm:
+            y = sc.get(bn_name_base + tag, lambda: _BatchNorm(bn_name_base + tag)).torch_apply(y, sc.training)
+        return y
+
+    y = sc.get(conv_name_base + '2a', lambda: _RegularConv(num_filters[0], 1, strides_1_by_1, conv_name_base + '2a',
+                                                           sc.seed_for(conv_name_base + '2a')))(x)
+    y = torch.relu(bn(y, '2a'))
+    if antisymmetric and (num_filters[1] is None):
+        layer = sc.get(conv_name_base + '2b', lambda: Conv2DAntisymmetric3By3(
+            gamma=gamma, strides=tuple(strides_k_by_k), use_bias=True, kernel_initializer='he_normal',
+            kernel_regularizer=kernel_regularizer, name=conv_name_base + '2b', precision=sc.precision,
+            seed=sc.seed_for(conv_name_base + '2b')))
+        y = layer(y)                                     # the hot-path layer (stride 2 in version 1.5: CUDA-core kernels)
+        if y.dtype != torch.float32:
+            y = y.float()
+    else:
+        if num_filters[1] is None:
+            raise ValueError("num_filters[1] may only be None for an antisymmetric block")
+        y = sc.get(conv_name_base + '2b', lambda: _RegularConv(num_filters[1], kernel_size, strides_k_by_k, conv_name_base + '2b',
+                                                               sc.seed_for(conv_name_base + '2b')))(y)
+    y = torch.relu(bn(y, '2b'))
+    y = sc.get(conv_name_base + '2c', lambda: _RegularConv(num_filters[2], 1, (1, 1), conv_name_base + '2c',
+                                                           sc.seed_for(conv_name_base + '2c')))(y)
+    return bn(y, '2c')
+
+
+def bottleneck_identity_block(input_tensor,
+                              kernel_size,
+                              num_filters,
+                              antisymmetric,
+                              use_batch_norm,
+                              stage,
+                              block,
+                              gamma=0.0,
+                              kernel_regularizer=None,
+                              bias_regularizer=None):
+    """Bottleneck identity block 1x1 -> kxk -> 1x1, + input, relu (reference models/tfkeras_resnets.py:96-202; the
+    antisymmetric layer is its middle convolution, :163-169)."""
+    x = as_torch(input_tensor)
+    conv_name_base = 'res' + str(stage) + '_' + str(block) + '_branch'
+    bn_name_base = 'bn' + str(stage) + '_' + str(block) + '_branch'
+    y = _bottleneck_main(x, kernel_size, num_filters, antisymmetric, use_batch_norm, conv_name_base, bn_name_base,
+                         (1, 1), (1, 1), gamma, kernel_regularizer)
+    return torch.relu(y + x)
+
+
+def bottleneck_conv_block(input_tensor,
+                          kernel_size,
+                          num_filters,
+                          antisymmetric,
+                          use_batch_norm,
+                          stage,
+                          block,
+                          version=1,
+                          strides=(1, 1),
+                          gamma=0.0,
+                          kernel_regularizer=None,
+                          bias_regularizer=None):
+    """Bottleneck block with a strided 1x1 shortcut convolution (reference models/tfkeras_resnets.py:271-425): version 1
+    strides the first 1x1 convolution, version 1.5 the kxk one (:341-348) -- there the antisymmetric layer (:370-376)
+    runs with stride 2."""
+    if version == 1:
+        strides_1_by_1, strides_k_by_k = tuple(strides), (1, 1)
+    elif version == 1.5:
+        strides_1_by_1, strides_k_by_k = (1, 1), tuple(strides)
+    else:
+        raise ValueError("Supported values for `version` are 1 and 1.5.")
+    sc = _scope()
+    x = as_torch(input_tensor)
+    conv_name_base = 'res' + str(stage) + '_' + str(block) + '_branch'
+    bn_name_base = 'bn' + str(stage) + '_' + str(block) + '_branch'
+    y = _bottleneck_main(x, kernel_size, num_filters, antisymmetric, use_batch_norm, conv_name_base, bn_name_base,
+                         strides_1_by_1, strides_k_by_k, gamma, kernel_regularizer)
+    short = sc.get(conv_name_base + '1', lambda: _RegularConv(num_filters[2], 1, tuple(strides), conv_name_base + '1',
+                                                              sc.seed_for(conv_name_base + '1')))(x)
+    if use_batch_norm:
+        short = sc.get(bn_name_base + '1', lambda: _BatchNorm(bn_name_base + '1')).torch_apply(short, sc.training)
+    return torch.relu(y + short)
 
 
 class Model:
@@ -380,3 +471,80 @@ def build_single_block_resnet(image_shape, sample_input=None, **kwargs):
     """Reference models/tfkeras_resnets.py:427-509: build function applied to an Input of `image_shape`.
     Layers are created lazily on the first call unless a CUDA `sample_input` is given."""
     return get_single_block_resnet_build_function(**kwargs)(sample_input)
+
+
+_RESNET_PRESETS = {'resnet50': ([3, 4, 6, 3], '50'), 'resnet101': ([3, 4, 23, 3], '101'), 'resnet152': ([3, 8, 36, 3], '152')}
+
+
+def get_resnet_build_function(kernel_type='antisymmetric',
+                              include_top=True,
+                              fc_activation='softmax',
+                              num_classes=None,
+                              l2_regularization=0.0,
+                              subtract_mean=None,
+                              divide_by_stddev=None,
+                              version=1,
+                              preset=None,
+                              blocks_per_stage=[3, 4, 6, 3],
+                              filters_per_block=[[64, 64, 256],
+                                                 [128, 128, 512],
+                                                 [256, 256, 1024],
+                                                 [512, 512, 2048]],
+                              use_batch_norm=True,
+                              precision='strict',
+                              seed=None):
+    """Five-stage bottleneck ResNet (reference models/tfkeras_resnets.py:698-818; same keywords, `precision` / `seed` are
+    additions): 7x7/2 stem on a 3-pixel zero border, 3x3/2 max pooling on a 1-pixel border, four stages of one
+    `bottleneck_conv_block` (strides (1,1), then (2,2)) and `blocks_per_stage[s] - 1` identity blocks, GAP + dense.  A
+    `None` as the middle entry of a stage's filters makes that stage's 3x3 convolutions antisymmetric."""
+    if include_top and (num_classes is None):
+        raise ValueError("You must pass a positive integer for `num_classes` if `include_top` is `True`.")
+    name = 'resnet'
+    if preset is not None:
+        if preset not in _RESNET_PRESETS:
+            raise ValueError("`preset` must be either `None` or one of 'resnet50', 'resnet101', and 'resnet152', "
+                             "but you passed `preset={}`.".format(preset))
+        blocks_per_stage, tag = _RESNET_PRESETS[preset]
+        filters_per_block = [[64, 64, 256], [128, 128, 512], [256, 256, 1024], [512, 512, 2048]]
+        use_batch_norm = True
+        name += tag
+    antisymmetric = kernel_type == 'antisymmetric'
+    name += '_antisymmetric' if antisymmetric else '_regular'
+
+    def _forward(x):
+        sc = _scope()
+        x = x.to(torch.float32)
+        if subtract_mean is not None:
+            x = x - torch.as_tensor(np.array(subtract_mean), dtype=torch.float32, device=x.device)
+        if divide_by_stddev is not None:
+            x = x / torch.as_tensor(np.array(divide_by_stddev), dtype=torch.float32, device=x.device)
+        x = torch.nn.functional.pad(x, (0, 0, 3, 3, 3, 3))                                   # ZeroPadding2D((3, 3)), NHWC
+        x = sc.get('conv1', lambda: _RegularConv(64, 7, (2, 2), 'conv1', sc.seed_for('conv1'), padding='valid'))(x)
+        if use_batch_norm:
+            x = sc.get('bn_conv1', lambda: _BatchNorm('bn_conv1')).torch_apply(x, sc.training)
+        x = torch.relu(x)
+        x = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))                                   # zero border (values are >= 0)
+        x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2).permute(0, 2, 3, 1).contiguous()
+        for s in range(4):
+            x = bottleneck_conv_block(x, 3, filters_per_block[s], antisymmetric, use_batch_norm, stage=s + 2, block=0,
+                                      version=version, strides=(1, 1) if s == 0 else (2, 2))
+            for i in range(1, blocks_per_stage[s]):
+                x = bottleneck_identity_block(x, 3, filters_per_block[s], antisymmetric, use_batch_norm, stage=s + 2, block=i)
+        if include_top:
+            x = x.mean(dim=(1, 2))
+            x = sc.get('fc', lambda: _Dense(num_classes, fc_activation, sc.seed_for('fc')))(x)
+        return x
+
+    def _build_function(input_tensor):
+        model = Model(_forward, name, precision, seed)
+        if input_tensor is not None and isinstance(input_tensor, torch.Tensor) and input_tensor.is_cuda:
+            with torch.no_grad():
+                model(input_tensor)
+        return model
+
+    return _build_function
+
+
+def build_resnet(image_shape, sample_input=None, **kwargs):
+    """Reference models/tfkeras_resnets.py:606-696: the build function applied to an Input of `image_shape`."""
+    return get_resnet_build_function(**kwargs)(sample_input)

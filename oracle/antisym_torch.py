@@ -280,6 +280,55 @@ def net_forward(spec: NetSpec, P, images_u8_or_f32, assembly="closed", forced_ma
     return torch.softmax(logits, dim=-1)
 
 
+
+def bottleneck_resnet_forward(P, images, blocks_per_stage, filters_per_block, antisymmetric=True, use_batch_norm=True,
+                              version=1, gamma=0.0, subtract_mean=None, divide_by_stddev=None, include_top=True):
+    """Restatement of the reference's bottleneck ResNet graph (`models/tfkeras_resnets.py:761-813` = `_build_function` of
+    `get_resnet_build_function`, blocks :96-202 and :271-425) on CPU tensors.  P: '<layer>/kernel' (HWIO), '<layer>/bias',
+    '<layer>/packed' for antisymmetric layers, '<bn>/gamma|beta'; BatchNorm in training mode (batch statistics)."""
+    def conv(x, name, st=(1, 1), valid=False):
+        K = P[name + "/kernel"]
+        if valid:
+            y = F.conv2d(x.permute(0, 3, 1, 2), K.permute(3, 2, 0, 1), None, stride=st).permute(0, 2, 3, 1)
+        else:
+            y = conv2d_same_nhwc(x, K, st)
+        return y + P[name + "/bias"]
+
+    def bn(y, name):
+        return batch_norm_train(y, P[name + "/gamma"], P[name + "/beta"]) if use_batch_norm else y
+
+    x = images.to(P["conv1/kernel"].dtype)
+    if subtract_mean is not None:
+        x = x - subtract_mean
+    if divide_by_stddev is not None:
+        x = x / divide_by_stddev
+    x = F.pad(x, (0, 0, 3, 3, 3, 3))                                            # ZeroPadding2D((3,3)) :775
+    x = torch.relu(bn(conv(x, "conv1", (2, 2), valid=True), "bn_conv1"))         # :776-785
+    x = F.pad(x, (0, 0, 1, 1, 1, 1))                                            # :786
+    x = F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2).permute(0, 2, 3, 1)            # :787
+    for s in range(4):
+        nf = filters_per_block[s]
+        for b in range(blocks_per_stage[s]):
+            base, bnb = "res%d_%d_branch" % (s + 2, b), "bn%d_%d_branch" % (s + 2, b)
+            st = ((1, 1) if s == 0 else (2, 2)) if b == 0 else (1, 1)
+            s1, sk = (st, (1, 1)) if version == 1 else ((1, 1), st)                # :341-348
+            y = torch.relu(bn(conv(x, base + "2a", s1), bnb + "2a"))
+            if antisymmetric and nf[1] is None:
+                flat = P[base + "2b/packed"]
+                C = y.shape[-1]
+                y = conv2d_same_nhwc(y, assemble_closed(flat, C, gamma), sk) + flat[-C:]
+            else:
+                y = conv(y, base + "2b", sk)
+            y = torch.relu(bn(y, bnb + "2b"))
+            y = bn(conv(y, base + "2c"), bnb + "2c")
+            short = bn(conv(x, base + "1", st), bnb + "1") if b == 0 else x
+            x = torch.relu(y + short)
+    if not include_top:
+        return x
+    x = x.mean(dim=(1, 2))
+    return torch.softmax(x @ P["fc/kernel"] + P["fc/bias"], dim=-1)
+
+
 def loss_fn(probs, onehot, eps=1e-7):
     """training/training.py:295: mean(K.categorical_crossentropy(from_logits=False))."""
     p = probs / probs.sum(dim=-1, keepdim=True)

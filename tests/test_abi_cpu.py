@@ -155,3 +155,27 @@ def test_glue_workspace_query_is_host_only():
     assert lib.b200ode_glue_workspace_bytes(9, 1, 1, 1, 1, 1, 1, 1, ctypes.byref(n)) == -1
     assert "unknown glue op" in _abi.last_error()
     assert lib.b200ode_glue_workspace_bytes(_abi.GLUE_TRANSITION_WGRAD, 8, 32, 32, 12, 20, 2, 2, ctypes.byref(n)) == -2   # unsupported pair: no fallback
+
+
+def test_bottleneck_builder_signatures_match_reference():
+    """Keyword names, order and defaults of the bottleneck builders (reference models/tfkeras_resnets.py:96-105, :271-282,
+    :698-713); `precision` / `seed` are additions at the end."""
+    import inspect
+    from differential_equations_resnet_b200 import models as M
+    p = inspect.signature(M.bottleneck_identity_block).parameters
+    assert list(p) == ['input_tensor', 'kernel_size', 'num_filters', 'antisymmetric', 'use_batch_norm', 'stage', 'block',
+                       'gamma', 'kernel_regularizer', 'bias_regularizer'] and p['gamma'].default == 0.0
+    p = inspect.signature(M.bottleneck_conv_block).parameters
+    assert list(p) == ['input_tensor', 'kernel_size', 'num_filters', 'antisymmetric', 'use_batch_norm', 'stage', 'block',
+                       'version', 'strides', 'gamma', 'kernel_regularizer', 'bias_regularizer']
+    assert p['version'].default == 1 and p['strides'].default == (1, 1)
+    p = inspect.signature(M.get_resnet_build_function).parameters
+    assert list(p)[:12] == ['kernel_type', 'include_top', 'fc_activation', 'num_classes', 'l2_regularization', 'subtract_mean',
+                            'divide_by_stddev', 'version', 'preset', 'blocks_per_stage', 'filters_per_block', 'use_batch_norm']
+    assert p['blocks_per_stage'].default == [3, 4, 6, 3] and p['filters_per_block'].default[3] == [512, 512, 2048]
+    assert p['use_batch_norm'].default is True and p['kernel_type'].default == 'antisymmetric'
+    with pytest.raises(ValueError, match="num_classes"):
+        M.get_resnet_build_function()
+    with pytest.raises(ValueError, match="preset"):
+        M.get_resnet_build_function(num_classes=10, preset='resnet18')
+    assert callable(M.get_resnet_build_function(num_classes=10, preset='resnet152')) and callable(M.build_resnet)

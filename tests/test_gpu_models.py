@@ -73,3 +73,75 @@ def test_model_forward_matches_oracle_and_predict_runs():
     assert float((probs - ref).abs().max()) <= 2e-5
     out = model.predict(img.numpy(), batch_size=2)
     assert out.shape == (4, 10) and np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
+
+
+def _bottleneck_params(model, dtype=torch.float64):
+    """Model layers -> the oracle's parameter dict (float64 CPU leaves)."""
+    from differential_equations_resnet_b200.models import tfkeras_resnets as M
+    P = {}
+    for name in model.scope.order:
+        l = model.scope.layers[name]
+        if isinstance(l, (M._RegularConv, M._Dense)):
+            P[name + "/kernel"], P[name + "/bias"] = l.kernel.detach().cpu().to(dtype), l.bias.detach().cpu().to(dtype)
+        elif isinstance(l, M._BatchNorm):
+            P[name + "/gamma"], P[name + "/beta"] = l.gamma.detach().cpu().to(dtype), l.beta.detach().cpu().to(dtype)
+        else:
+            P[name + "/packed"] = l.packed.detach().cpu().to(dtype)
+    return P
+
+
+@pytest.mark.parametrize("version,use_bn", [(1, True), (1.5, False)])
+def test_bottleneck_resnet_matches_oracle(version, use_bn):
+    """`get_resnet_build_function` (reference models/tfkeras_resnets.py:698-818) with antisymmetric middle convolutions
+    (`None` as the middle filter count; :163-169, :370-376): forward against the float64 restatement; version 1.5 puts
+    stride 2 on the antisymmetric layer.  Without BN also the gradient of every antisymmetric layer's packed parameters."""
+    from differential_equations_resnet_b200.models import get_resnet_build_function
+    from differential_equations_resnet_b200.layers import Conv2DAntisymmetric3By3
+    fpb = [[16, None, 32], [32, None, 64], [32, None, 64], [64, None, 128]]
+    bps = [2, 1, 2, 1]
+    kw = dict(kernel_type='antisymmetric', num_classes=10, version=version, blocks_per_stage=bps, filters_per_block=fpb,
+              use_batch_norm=use_bn, subtract_mean=127.5, divide_by_stddev=127.5)
+    img = torch.randint(0, 256, (4, 64, 64, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    model = get_resnet_build_function(precision='strict', seed=11, **kw)(img.cuda())
+    assert model.name == 'resnet_antisymmetric'
+    names = model.scope.order
+    assert names[0] == 'conv1' and 'res2_0_branch2a' in names and 'res2_0_branch1' in names and 'res2_1_branch2b' in names
+    assert isinstance(model.get_layer('res3_0_branch2b'), Conv2DAntisymmetric3By3)
+    assert model.get_layer('res3_0_branch2b').strides == ((2, 2) if version == 1.5 else (1, 1))
+    assert ('bn2_0_branch2c' in names) == use_bn
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        torch.backends.cuda.matmul.allow_tf32 = False
+        probs = model(img.cuda(), training=True)
+        w = torch.randn(probs.shape, generator=torch.Generator().manual_seed(6), dtype=torch.float64)
+        if not use_bn:
+            (probs.double() * w.cuda()).sum().backward()
+    P = _bottleneck_params(model)
+    for v in P.values():
+        v.requires_grad_(True)
+    ref = O1.bottleneck_resnet_forward(P, img.double(), bps, fpb, True, use_bn, version, 0.0, 127.5, 127.5)
+    assert probs.shape == (4, 10)
+    assert float((probs.detach().cpu().double() - ref.detach()).abs().max()) <= 2e-5
+    if not use_bn:
+        (ref * w).sum().backward()
+        for name in names:
+            l = model.scope.layers[name]
+            if isinstance(l, Conv2DAntisymmetric3By3):
+                assert rel(l.packed.grad.cpu().numpy(), P[name + "/packed"].grad.numpy()) <= 1e-4, name
+
+
+def test_bottleneck_regular_middle_layer_and_errors():
+    from differential_equations_resnet_b200.models import bottleneck_conv_block, get_resnet_build_function
+    from differential_equations_resnet_b200.models import tfkeras_resnets as M
+    with pytest.raises(ValueError, match="num_classes"):
+        get_resnet_build_function()
+    with pytest.raises(ValueError, match="preset"):
+        get_resnet_build_function(num_classes=10, preset='resnet18')
+    M._Scope.current = M._Scope("strict", 1)
+    try:
+        x = torch.rand(2, 8, 8, 16, device="cuda")
+        y = bottleneck_conv_block(x, 3, (8, 8, 32), True, False, stage=2, block=0, version=1.5, strides=(2, 2))   # middle count given: regular conv
+        assert y.shape == (2, 4, 4, 32) and isinstance(M._Scope.current.layers['res2_0_branch2b'], M._RegularConv)
+        with pytest.raises(ValueError, match="version"):
+            bottleneck_conv_block(x, 3, (8, None, 32), True, False, stage=3, block=0, version=2)
+    finally:
+        M._Scope.current = None
