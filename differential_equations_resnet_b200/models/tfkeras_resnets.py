@@ -58,7 +58,28 @@ def _scope():
     return _Scope.current
 
 
-class _RegularConv:
+class _KernelBiasWeights:
+    """Keras `get_weights()` / `set_weights()` of a (kernel, bias) layer."""
+
+    def get_weights(self):
+        if self.kernel is None:
+            return []
+        return [self.kernel.detach().cpu().numpy(), self.bias.detach().cpu().numpy()]
+
+    def set_weights(self, weights):
+        if self.kernel is None:
+            raise RuntimeError("layer %r has no weights yet: call the model once first" % getattr(self, "name", self))
+        if len(weights) != 2:
+            raise ValueError("expected [kernel, bias], got %d arrays" % len(weights))
+        with torch.no_grad():
+            for t, w in zip((self.kernel, self.bias), weights):
+                w = np.asarray(w, dtype=np.float32)
+                if tuple(w.shape) != tuple(t.shape):
+                    raise ValueError("weight shape %s does not match %s" % (w.shape, tuple(t.shape)))
+                t.copy_(torch.from_numpy(w))
+
+
+class _RegularConv(_KernelBiasWeights):
     """Keras Conv2D(padding='same', kernel_initializer='he_normal') as torch ops."""
 
     def __init__(self, filters, kernel_size, strides, name, seed=None, padding='same'):
@@ -112,6 +133,19 @@ class _BatchNorm:
     @property
     def trainable_weights(self):
         return [self.gamma, self.beta]
+
+    def get_weights(self):
+        """Keras order: gamma, beta, moving_mean, moving_variance."""
+        if self.gamma is None:
+            return []
+        return [t.detach().cpu().numpy() for t in (self.gamma, self.beta, self.moving_mean, self.moving_var)]
+
+    def set_weights(self, weights):
+        if self.gamma is None or len(weights) != 4:
+            raise ValueError("BatchNormalization layer %r takes [gamma, beta, moving_mean, moving_variance] once built" % self.name)
+        with torch.no_grad():
+            for t, w in zip((self.gamma, self.beta, self.moving_mean, self.moving_var), weights):
+                t.copy_(torch.from_numpy(np.asarray(w, dtype=np.float32)))
 
 
 class _EulerBNFn(torch.autograd.Function):
@@ -449,9 +483,10 @@ def get_single_block_resnet_build_function(kernel_type='antisymmetric',
     return _build_function
 
 
-class _Dense:
+class _Dense(_KernelBiasWeights):
     def __init__(self, units, activation, seed=None):
         self.units, self.activation, self.kernel, self.seed = units, activation, None, seed
+        self.name = 'fc'
 
     def __call__(self, x):
         if self.kernel is None:

@@ -145,3 +145,44 @@ def test_bottleneck_regular_middle_layer_and_errors():
             bottleneck_conv_block(x, 3, (8, None, 32), True, False, stage=3, block=0, version=2)
     finally:
         M._Scope.current = None
+
+
+def test_antisymmetric_weights_into_regular_model_and_double_load(tmp_path):
+    """experiments_antisymmetric_resnet_v7.ipynb 'Antisymmetric 16 Weights Loaded into Regular 16 Model': the dense kernels
+    the pack kernel assembles, pickled in the reference's format (`model_utils/weight_utils.py:23-39`), make a regular net
+    of the same shape compute the same function; `double_load_weights` (:41-80) into a net twice as deep, antisymmetric
+    layers included (free parameters read back out of the dense kernels, exact)."""
+    import pickle
+    from differential_equations_resnet_b200.models import get_single_block_resnet_build_function
+    from differential_equations_resnet_b200.model_utils import double_load_weights, load_pickled_weights, pickle_model_weights
+
+    def build(kernel_type, blocks, seed):
+        return get_single_block_resnet_build_function(
+            kernel_type=kernel_type, h=0.5, gamma=-0.1, num_stages=2, blocks_per_stage=[blocks], filters_per_block=[16],
+            strides=[(1, 1)], num_classes=10, subtract_mean=127.5, divide_by_stddev=127.5, precision='strict', seed=seed)
+
+    img = torch.randint(0, 256, (4, 16, 16, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8).cuda()
+    anti, regular, deep = build('antisymmetric', 3, 1)(img), build('regular', 3, 2)(img), build('antisymmetric', 6, 3)(img)
+    path = str(tmp_path / "anti.pkl")
+    pickle_model_weights(anti, path)
+    saved = pickle.load(open(path, 'rb'))
+    assert len(saved) == 5 and saved[1]['kernel'].shape == (3, 3, 16, 16) and saved[1]['bias'].shape == (16,)
+    K = saved[2]['kernel']
+    S = K + K[::-1, ::-1].transpose(0, 1, 3, 2)
+    S[1, 1, np.arange(16), np.arange(16)] -= np.float32(-0.2)
+    assert not S.any()                                                   # bit-exact antisymmetry survives the file
+    load_pickled_weights(regular, path)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        pa, pr = anti(img, training=False), regular(img, training=False)
+    assert float((pa - pr).abs().max()) <= 2e-5
+    double_load_weights(deep, path)
+    src = [l for l in anti.layers if l.name.startswith('res')]
+    dst = [l for l in deep.layers if l.name.startswith('res')]
+    assert len(src) == 3 and len(dst) == 6
+    for i, l in enumerate(dst):
+        assert torch.equal(l.packed.detach(), src[i // 2].packed.detach())
+    rnd = build('regular', 3, 7)(img)
+    with pytest.raises(ValueError, match="anti-centrosymmetric"):
+        rnd_path = str(tmp_path / "reg.pkl")
+        pickle_model_weights(rnd, rnd_path)
+        load_pickled_weights(anti, rnd_path)                             # a generic kernel is not antisymmetric: refused
