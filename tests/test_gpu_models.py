@@ -174,7 +174,7 @@ def test_antisymmetric_weights_into_regular_model_and_double_load(tmp_path):
     load_pickled_weights(regular, path)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         pa, pr = anti(img, training=False), regular(img, training=False)
-    assert float((pa - pr).abs().max()) <= 2e-5
+    assert float((pa - pr).detach().abs().max()) <= 2e-5
     double_load_weights(deep, path)
     src = [l for l in anti.layers if l.name.startswith('res')]
     dst = [l for l in deep.layers if l.name.startswith('res')]
