@@ -241,6 +241,8 @@ class _Reader:
     def _chunked(self, btree, chunk_dims, shape, dt):
         esize = dt[2]
         rank = len(shape)
+        if int(np.prod(shape, dtype=object)) * esize > 2 * len(self.d) + (1 << 20):
+            raise H5FormatError("chunked dataset of shape %s cannot fit this %d-byte file" % (shape, len(self.d)))
         out = np.zeros(shape, dtype=dt[1])
 
         def walk(addr):
@@ -408,8 +410,10 @@ def read_h5(path_or_bytes):
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray, memoryview)) else open(path_or_bytes, "rb").read()
     try:
         return _Reader(bytes(data)).root()
-    except (struct.error, IndexError) as e:
-        raise H5FormatError("truncated or corrupt HDF5 file: %s" % e)
+    except H5FormatError:
+        raise
+    except (struct.error, IndexError, ValueError, KeyError, OverflowError, RecursionError, MemoryError, TypeError) as e:
+        raise H5FormatError("truncated or corrupt HDF5 file: %s: %s" % (type(e).__name__, e))
 
 
 # ----------------------------------------------------------------------------------------------------------------

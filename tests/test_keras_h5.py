@@ -163,3 +163,19 @@ def test_eulernet_and_model_h5_weights(tmp_path):
     assert any(k.endswith("moving_variance:0") for ws in saved.values() for k in ws)
     m2.load_weights(q)
     assert torch.equal(m1(x, training=False), m2(x, training=False))
+
+
+def test_reader_survives_random_corruption():
+    """Byte flips in a valid file end in a parse or in H5FormatError -- no other exception type, no hang."""
+    good = kh.save_keras_weights(None, {"l%d" % i: {"l%d/k:0" % i: np.ones((3, 3, 4), np.float32)} for i in range(4)})
+    gold = open(GOLDEN, "rb").read()
+    rng = np.random.default_rng(0)
+    for base in (good, gold):
+        for _ in range(400):
+            b = bytearray(base)
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            try:
+                kh.read_h5(bytes(b))
+            except kh.H5FormatError:
+                pass
