@@ -408,8 +408,12 @@ class Model:
                 raise ValueError("weights file has no layer %r" % lname)
             ws = saved[lname]
             named = self._named_weights(lname, layer)
+            wanted = list(named) if named is not None else [lname + '/' + v + ':0' for v in layer._variable_names()]
+            missing = [k for k in wanted if k not in ws]
+            if missing:
+                raise ValueError("weights file has no %r (layer %r holds %d weights in the file)" % (missing[0], lname, len(ws)))
             if named is None:
-                layer.set_weights([ws[lname + '/' + v + ':0'] for v in layer._variable_names()])
+                layer.set_weights([ws[k] for k in wanted])
                 continue
             with torch.no_grad():
                 for k, t in named.items():
