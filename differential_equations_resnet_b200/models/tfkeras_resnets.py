@@ -20,8 +20,7 @@ import zlib
 import numpy as np
 import torch
 
-from .. import _abi
-from ..layers._base import BNEulerStep, _ptr, _stream_ptr, as_torch, relu_scale_bwd, truncated_normal_
+from ..layers._base import BNEulerStep, as_torch, truncated_normal_
 from ..layers.tfkeras_layer_Conv2DAntisymmetric3By3 import Conv2DAntisymmetric3By3
 from ..training import conv2d_same_nhwc
 
