@@ -75,6 +75,9 @@ _SIGNATURES = {
     "b200ode_transition_dgrad": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "b200ode_transition_dgrad_amax": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
     "b200ode_transition_wgrad": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
+    "b200ode_transition_fwd_fast": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "b200ode_transition_dgrad_fast": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
+    "b200ode_transition_wgrad_fast": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
     "b200ode_head_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200ode_head_fwd_bwd_amax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,

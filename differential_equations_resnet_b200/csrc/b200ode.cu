@@ -1913,6 +1913,11 @@ static int reduce_rows(const float* ws, int R, long long stride, long long n, fl
 
 // Tensor-core transitions (kernels_glue_mma.cuh): the reference's stride-2 transitions 16 -> 32 and 32 -> 64 channels.
 // B200ODE_GLUE_SIMT=1 keeps the CUDA-core kernels (A/B measurements); other shapes always use them.
+// fast = one tf32 MMA on round-to-nearest operands instead of the 3xTF32 split (the *_fast entry points / B200ODE_TR_FAST=1)
+static bool transition_fast_env() {
+  static const bool on = getenv("B200ODE_TR_FAST") && atoi(getenv("B200ODE_TR_FAST")) != 0;
+  return on;
+}
 static bool transition_mma_ok(int Cin, int Cout, int sh, int sw) {
   static const bool simt = getenv("B200ODE_GLUE_SIMT") && atoi(getenv("B200ODE_GLUE_SIMT")) != 0;
   return !simt && sh == 2 && sw == 2 && ((Cin == 16 && Cout == 32) || (Cin == 32 && Cout == 64));
@@ -1928,7 +1933,7 @@ static bool transition_mma_ok(int Cin, int Cout, int sh, int sw) {
   } while (0)
 
 // returns 0 = launched, > 0 = error, -1 = shape does not fit (caller falls back to the CUDA-core kernel)
-template <int CIN, int COUT, int NSPLIT>
+template <int CIN, int COUT, int NSPLIT, bool FAST = false>
 static int transition_fwd_mma(const GlueConv& g, const float* x, const float* Wm, const float* bm, const float* Ws, const float* bs,
                               float* out, uint8_t* mask, cudaStream_t st) {
   int orows = (128 / NSPLIT) / g.Wo;            // 8 warps x 16 positions / NSPLIT channel slices per block
@@ -1940,14 +1945,14 @@ static int transition_fwd_mma(const GlueConv& g, const float* x, const float* Wm
   const dim3 grid(g.N, (g.Ho + orows - 1) / orows);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(transition_fwd_mma_kernel<CIN, COUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(transition_fwd_mma_kernel<CIN, COUT, NSPLIT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  CUDA_TRY(launch_pdl(transition_fwd_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, x, Wm, bm, Ws, bs, out, mask, orows));
+  CUDA_TRY(launch_pdl(transition_fwd_mma_kernel<CIN, COUT, NSPLIT, FAST>, grid, dim3(256), smem, st, g, x, Wm, bm, Ws, bs, out, mask, orows));
   LAUNCH_CHECK("transition_fwd_mma_kernel");
   return 0;
 }
-template <int CIN, int COUT, int NSPLIT>
+template <int CIN, int COUT, int NSPLIT, bool FAST = false>
 static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint8_t* mask, const float* Wm, const float* Ws, float* dx,
                                 unsigned int* dx_amax, cudaStream_t st) {
   const int CH = (g.H - 1 + g.pt) / 2 + 1, CW = (g.W - 1 + g.pl) / 2 + 1;
@@ -1960,16 +1965,16 @@ static int transition_dgrad_mma(const GlueConv& g, const float* dout, const uint
   const dim3 grid(g.N, (CH + crows - 1) / crows);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  CUDA_TRY(launch_pdl(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT>, grid, dim3(256), smem, st, g, dout, mask, Wm, Ws, dx, crows, dx_amax));
+  CUDA_TRY(launch_pdl(transition_dgrad_mma_kernel<CIN, COUT, NSPLIT, FAST>, grid, dim3(256), smem, st, g, dout, mask, Wm, Ws, dx, crows, dx_amax));
   LAUNCH_CHECK("transition_dgrad_mma_kernel");
   return 0;
 }
 // partial rows the tensor-core weight gradient writes (one per block)
 static int transition_wgrad_mma_rows(int N) { const int ipb = (N + 147) / 148; return (N + ipb - 1) / ipb; }
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FAST = false>
 static int transition_wgrad_mma(const GlueConv& g, const float* x, const float* dout, const uint8_t* mask, float* part, cudaStream_t st) {
   int orows = g.Ho;
   while (orows > 1 && TrWgradMma<CIN, COUT>::smem_bytes(orows, g.W, g.Wo) > 200 * 1024) orows = (orows + 1) >> 1;
@@ -1977,14 +1982,29 @@ static int transition_wgrad_mma(const GlueConv& g, const float* x, const float* 
   if (smem > 200 * 1024) return -1;
   const int ipb = (g.N + 147) / 148;
   constexpr int threads = 32 * TrWgradMma<CIN, COUT>::NWARP;
-  GLUE_MMA_LAUNCH((transition_wgrad_mma_kernel<CIN, COUT>), dim3((g.N + ipb - 1) / ipb), threads, smem, st, g, x, dout, mask, part, orows, ipb);
+  GLUE_MMA_LAUNCH((transition_wgrad_mma_kernel<CIN, COUT, FAST>), dim3((g.N + ipb - 1) / ipb), threads, smem, st, g, x, dout, mask, part, orows, ipb);
   LAUNCH_CHECK("transition_wgrad_mma_kernel");
   return 0;
 }
 
+static int transition_fwd_impl(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                               const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
+                               int Cout, int stride_h, int stride_w, bool fast, void* stream);
 extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
                                       const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
                                       int Cout, int stride_h, int stride_w, void* stream) {
+  return transition_fwd_impl(x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, N, H, W, Cin, Cout, stride_h, stride_w,
+                             transition_fast_env(), stream);
+}
+extern "C" int b200ode_transition_fwd_fast(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                                           const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
+                                           int Cout, int stride_h, int stride_w, void* stream) {
+  return transition_fwd_impl(x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, N, H, W, Cin, Cout, stride_h, stride_w,
+                             true, stream);
+}
+static int transition_fwd_impl(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                               const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin,
+                               int Cout, int stride_h, int stride_w, bool fast, void* stream) {
   if (!x || !main_kernel || !main_bias || !short_kernel || !short_bias || !out || !relu_mask) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (int rc = transition_check(Cin, Cout)) return rc;
   if (int rc = device_check()) return rc;
@@ -1992,8 +2012,10 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
   if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {
-    const int rc = Cin == 16 ? transition_fwd_mma<16, 32, 1>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st)
-                             : transition_fwd_mma<32, 64, 2>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st);
+    const int rc = fast ? (Cin == 16 ? transition_fwd_mma<16, 32, 1, true>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st)
+                                     : transition_fwd_mma<32, 64, 2, true>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st))
+                        : (Cin == 16 ? transition_fwd_mma<16, 32, 1>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st)
+                                     : transition_fwd_mma<32, 64, 2>(g, x, main_kernel, main_bias, short_kernel, short_bias, out, relu_mask, st));
     if (rc >= 0) return rc;
   }
   // bands of 32*PT output pixels (PT per lane); each warp of a block owns one 8-channel slice.  Small bands = many
@@ -2023,17 +2045,22 @@ extern "C" int b200ode_transition_fwd(const float* x, const float* main_kernel, 
 }
 
 static int transition_dgrad_impl(const float* dout, const uint8_t* relu_mask, const float* main_kernel, const float* short_kernel, float* dx,
-                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, void* stream);
+                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, bool fast, void* stream);
+extern "C" int b200ode_transition_dgrad_fast(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                                             const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                                             int stride_w, float* dx_amax, void* stream) {      /* dx_amax may be NULL */
+  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, dx_amax, true, stream);
+}
 extern "C" int b200ode_transition_dgrad(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
                                         const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
                                         int stride_w, void* stream) {
-  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, nullptr, stream);
+  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, nullptr, transition_fast_env(), stream);
 }
 extern "C" int b200ode_transition_dgrad_amax(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
                                              const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
                                              int stride_w, float* dx_amax, void* stream) {
   if (!dx_amax) return fail(B200ODE_ERR_INVALID, "dx_amax is NULL");
-  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, dx_amax, stream);
+  return transition_dgrad_impl(dout, relu_mask, main_kernel, short_kernel, dx, N, H, W, Cin, Cout, stride_h, stride_w, dx_amax, transition_fast_env(), stream);
 }
 // dx_amax != NULL: *dx_amax = max(*dx_amax, max|dx|) (the tensor-core kernel does it in its epilogue; other shapes by one more launch)
 static int amax_after(const float* v, long long n, float* amax, cudaStream_t st) {
@@ -2045,15 +2072,17 @@ static int amax_after(const float* v, long long n, float* amax, cudaStream_t st)
   return 0;
 }
 static int transition_dgrad_impl(const float* dout, const uint8_t* relu_mask, const float* main_kernel, const float* short_kernel, float* dx,
-                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, void* stream) {
+                                 int N, int H, int W, int Cin, int Cout, int stride_h, int stride_w, float* dx_amax, bool fast, void* stream) {
   if (!dout || !relu_mask || !main_kernel || !short_kernel || !dx) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (int rc = transition_check(Cin, Cout)) return rc;
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const GlueConv g = glue_geom(N, H, W, Cin, Cout, stride_h, stride_w);
   if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {
-    const int rc = Cin == 16 ? transition_dgrad_mma<16, 32, 1>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st)
-                             : transition_dgrad_mma<32, 64, 2>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st);
+    const int rc = fast ? (Cin == 16 ? transition_dgrad_mma<16, 32, 1, true>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st)
+                                     : transition_dgrad_mma<32, 64, 2, true>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st))
+                        : (Cin == 16 ? transition_dgrad_mma<16, 32, 1>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st)
+                                     : transition_dgrad_mma<32, 64, 2>(g, dout, relu_mask, main_kernel, short_kernel, dx, (unsigned int*)dx_amax, st));
     if (rc >= 0) return rc;
   }
   // band height: the staged output rows (dout + masked copy) and the weight slice must fit shared memory
@@ -2107,9 +2136,23 @@ static int plan_transition_wgrad(const GlueConv& g, TransWgradPlan* pl) {
   return 0;
 }
 
+static int transition_wgrad_impl(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
+                                 int W, int Cin, int Cout, int stride_h, int stride_w, void* workspace,
+                                 size_t workspace_bytes, bool fast, void* stream);
 extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
                                         int W, int Cin, int Cout, int stride_h, int stride_w, void* workspace,
                                         size_t workspace_bytes, void* stream) {
+  return transition_wgrad_impl(x, dout, relu_mask, dparams, N, H, W, Cin, Cout, stride_h, stride_w, workspace, workspace_bytes,
+                               transition_fast_env(), stream);
+}
+extern "C" int b200ode_transition_wgrad_fast(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
+                                             int W, int Cin, int Cout, int stride_h, int stride_w, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  return transition_wgrad_impl(x, dout, relu_mask, dparams, N, H, W, Cin, Cout, stride_h, stride_w, workspace, workspace_bytes, true, stream);
+}
+static int transition_wgrad_impl(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H,
+                                 int W, int Cin, int Cout, int stride_h, int stride_w, void* workspace,
+                                 size_t workspace_bytes, bool fast, void* stream) {
   if (!x || !dout || !relu_mask || !dparams) return fail(B200ODE_ERR_INVALID, "NULL argument");
   if (int rc = transition_check(Cin, Cout)) return rc;
   if (N == 0) return 0;
@@ -2124,7 +2167,8 @@ extern "C" int b200ode_transition_wgrad(const float* x, const float* dout, const
   if (int rc = lease_ws(workspace, workspace_bytes, pl.ws_bytes, st, &lease)) return rc;
   float* ws = (float*)lease.ptr;
   if (transition_mma_ok(Cin, Cout, stride_h, stride_w)) {      // rows <= N <= N * bands: the SIMT plan's workspace covers it
-    const int rc = Cin == 16 ? transition_wgrad_mma<16, 32>(g, x, dout, relu_mask, ws, st) : transition_wgrad_mma<32, 64>(g, x, dout, relu_mask, ws, st);
+    const int rc = fast ? (Cin == 16 ? transition_wgrad_mma<16, 32, true>(g, x, dout, relu_mask, ws, st) : transition_wgrad_mma<32, 64, true>(g, x, dout, relu_mask, ws, st))
+                        : (Cin == 16 ? transition_wgrad_mma<16, 32>(g, x, dout, relu_mask, ws, st) : transition_wgrad_mma<32, 64>(g, x, dout, relu_mask, ws, st));
     if (rc > 0) return rc;
     if (rc == 0) return reduce_rows(ws, transition_wgrad_mma_rows(N), nout, nout, dparams, st);
   }

@@ -42,6 +42,23 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4
   mma_tf32_m16n8k8(d, ah, bh0, bh1);
 }
 
+// FAST = true: ONE tf32 MMA on operands rounded to nearest (10-bit significand + implicit bit, the grade of the fast modes'
+// fp16 / tf32 chains); FAST = false: the 3xTF32 split above (fp32 grade).
+template <bool FAST>
+__device__ __forceinline__ void split_a(float v, uint32_t& hi, uint32_t& lo) {
+  if constexpr (FAST) { asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v)); lo = 0u; }
+  else split_tf32(v, hi, lo);
+}
+template <bool FAST>
+__device__ __forceinline__ void mma_op(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0, float b1) {
+  if constexpr (FAST) {
+    uint32_t bh0, bh1;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh0) : "f"(b0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh1) : "f"(b1));
+    mma_tf32_m16n8k8(d, ah, bh0, bh1);
+  } else mma_3xtf32(d, ah, al, b0, b1);
+}
+
 // Staging: every global -> shared copy of a block is issued as cp.async (no register round trip), so ALL of a block's loads
 // are in flight together and the block pays ONE memory round trip before its MMAs (the register-staged loops paid one per
 // unrolled batch: ncu showed the kernels bound by long-scoreboard stalls of the staging phase, tensor pipe 18-25 % busy).
@@ -71,7 +88,7 @@ struct TrFwdMma {
   }
 };
 
-template <int CIN, int COUT, int NSPLIT>
+template <int CIN, int COUT, int NSPLIT, bool FAST = false>
 __global__ void __launch_bounds__(256) transition_fwd_mma_kernel(GlueConv g, const float* __restrict__ x, const float* __restrict__ Wm,
                                                                  const float* __restrict__ bm, const float* __restrict__ Ws,
                                                                  const float* __restrict__ bs, float* __restrict__ out,
@@ -129,12 +146,12 @@ __global__ void __launch_bounds__(256) transition_fwd_mma_kernel(GlueConv g, con
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t ah[4], al[4];
-        split_tf32(xa0[ks * 8], ah[0], al[0]);
-        split_tf32(xa1[ks * 8], ah[1], al[1]);
-        split_tf32(xa0[ks * 8 + 4], ah[2], al[2]);
-        split_tf32(xa1[ks * 8 + 4], ah[3], al[3]);
+        split_a<FAST>(xa0[ks * 8], ah[0], al[0]);
+        split_a<FAST>(xa1[ks * 8], ah[1], al[1]);
+        split_a<FAST>(xa0[ks * 8 + 4], ah[2], al[2]);
+        split_a<FAST>(xa1[ks * 8 + 4], ah[3], al[3]);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) mma_3xtf32(d[j], ah, al, wb[(ks * 8) * WS + j * 8], wb[(ks * 8 + 4) * WS + j * 8]);
+        for (int j = 0; j < NT; ++j) mma_op<FAST>(d[j], ah, al, wb[(ks * 8) * WS + j * 8], wb[(ks * 8 + 4) * WS + j * 8]);
       }
     };
 #pragma unroll 1
@@ -180,7 +197,7 @@ struct TrDgradMma {
   }
 };
 
-template <int CIN, int COUT, int NSPLIT>
+template <int CIN, int COUT, int NSPLIT, bool FAST = false>
 __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, const float* __restrict__ dout, const uint8_t* __restrict__ mask,
                                                                    const float* __restrict__ Wm, const float* __restrict__ Ws,
                                                                    float* __restrict__ dx, int crows, unsigned int* __restrict__ dx_amax) {
@@ -259,12 +276,12 @@ __global__ void __launch_bounds__(256) transition_dgrad_mma_kernel(GlueConv g, c
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
           uint32_t ah[4], al[4];
-          split_tf32(pa0[ks * 8], ah[0], al[0]);
-          split_tf32(pa1[ks * 8], ah[1], al[1]);
-          split_tf32(pa0[ks * 8 + 4], ah[2], al[2]);
-          split_tf32(pa1[ks * 8 + 4], ah[3], al[3]);
+          split_a<FAST>(pa0[ks * 8], ah[0], al[0]);
+          split_a<FAST>(pa1[ks * 8], ah[1], al[1]);
+          split_a<FAST>(pa0[ks * 8 + 4], ah[2], al[2]);
+          split_a<FAST>(pa1[ks * 8 + 4], ah[3], al[3]);
 #pragma unroll
-          for (int j = 0; j < NT; ++j) mma_3xtf32(acc[j], ah, al, pb[j * 8 * WS + ks * 8], pb[j * 8 * WS + ks * 8 + 4]);
+          for (int j = 0; j < NT; ++j) mma_op<FAST>(acc[j], ah, al, pb[j * 8 * WS + ks * 8], pb[j * 8 * WS + ks * 8 + 4]);
         }
       };
 #pragma unroll
@@ -320,7 +337,7 @@ struct TrWgradMma {
   }
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FAST = false>
 __global__ void __launch_bounds__(384) transition_wgrad_mma_kernel(GlueConv g, const float* __restrict__ x, const float* __restrict__ dout,
                                                                    const uint8_t* __restrict__ mask, float* __restrict__ part,
                                                                    int orows, int ipb) {
@@ -398,13 +415,13 @@ __global__ void __launch_bounds__(384) transition_wgrad_mma_kernel(GlueConv g, c
             const float* xa = xs + (inA ? (iyA - i0) * g.W + ixA : zp) * PS + cb + gq;
             const float* xb = xs + (inB ? (iyB - i0) * g.W + ixB : zp) * PS + cb + gq;
             uint32_t ah[4], al[4];
-            split_tf32(xa[0], ah[0], al[0]);
-            split_tf32(xa[8], ah[1], al[1]);
-            split_tf32(xb[0], ah[2], al[2]);
-            split_tf32(xb[8], ah[3], al[3]);
+            split_a<FAST>(xa[0], ah[0], al[0]);
+            split_a<FAST>(xa[8], ah[1], al[1]);
+            split_a<FAST>(xb[0], ah[2], al[2]);
+            split_a<FAST>(xb[8], ah[3], al[3]);
             const float* pb = S + pA * PSO + gq;
 #pragma unroll
-            for (int j = 0; j < NT; ++j) mma_3xtf32(acc[u][j], ah, al, pb[j * 8], pb[4 * PSO + j * 8]);
+            for (int j = 0; j < NT; ++j) mma_op<FAST>(acc[u][j], ah, al, pb[j * 8], pb[4 * PSO + j * 8]);
           }
         } else {
           const float* S = task == 10 * MT ? dM : dO;

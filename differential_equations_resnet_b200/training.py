@@ -307,8 +307,12 @@ class EulerNet:
     'fast_bf16' (bf16 operands and activations, fp32 accumulate; per-layer kernels), or 'simt'."""
 
     def __init__(self, spec: NetSpec, precision="fast_tf32", device="cuda", seed=0, lr=1e-3, adam_eps=1e-7,
-                 world_size=1, persistent=True, native_glue=True, comm=None, sync_bn=True, split_first_chain=None):
+                 world_size=1, persistent=True, native_glue=True, comm=None, sync_bn=True, split_first_chain=None,
+                 glue_fast=None):
         _abi.require_device()
+        # transition blocks: one tf32 MMA on round-to-nearest operands in the fast modes (the grade of their chains' fp16 / tf32 /
+        # bf16 operands), the 3xTF32 split (fp32 grade) in strict mode; glue_fast=False keeps the fp32-grade kernels everywhere
+        self.glue_fast = (precision in ("fast_f16", "fast_tf32", "fast_bf16")) if glue_fast is None else bool(glue_fast)
         if split_first_chain is None:
             split_first_chain = int(os.environ.get("B200ODE_SPLIT_FIRST_CHAIN", "1"))
         self.spec, self.precision, self.device = spec, precision, torch.device(device)
@@ -635,7 +639,7 @@ class EulerNet:
             elif e["kind"] == "transition":
                 nm = e["name"]
                 e["x"] = cur
-                _abi.check(lib.b200ode_transition_fwd(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
+                _abi.check((lib.b200ode_transition_fwd_fast if self.glue_fast else lib.b200ode_transition_fwd)(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
                                                       _ptr(th[self._off(nm + "2/bias"):]), _ptr(th[self._off(nm + "1/kernel"):]),
                                                       _ptr(th[self._off(nm + "1/bias"):]), _ptr(e["out"]), _ptr(e["mask"]),
                                                       N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))
@@ -701,10 +705,17 @@ class EulerNet:
             elif e["kind"] == "transition":
                 nm = e["name"]
                 with torch.cuda.stream(side):      # needs d (ready: the side stream already waits for the chain's dgrad)
-                    _abi.check(lib.b200ode_transition_wgrad(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
+                    _abi.check((lib.b200ode_transition_wgrad_fast if self.glue_fast else lib.b200ode_transition_wgrad)(_ptr(e["x"]), _ptr(d), _ptr(e["mask"]), _ptr(gr[self._off(nm + "2/kernel"):]),
                                                             N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1],
                                                             _ptr(e["ws"]), e["ws"].numel(), side.cuda_stream))
-                if fuse_amax and ei > 0 and plan_[ei - 1]["kind"] == "chain":
+                if self.glue_fast:
+                    want_amax = fuse_amax and ei > 0 and plan_[ei - 1]["kind"] == "chain"
+                    _abi.check(lib.b200ode_transition_dgrad_fast(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
+                                                                 _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
+                                                                 e["ci"], e["co"], e["st"][0], e["st"][1],
+                                                                 _ptr(amax[ei - 1:]) if want_amax else None, st))
+                    d_amax = amax[ei - 1:ei] if want_amax else None
+                elif fuse_amax and ei > 0 and plan_[ei - 1]["kind"] == "chain":
                     _abi.check(lib.b200ode_transition_dgrad_amax(_ptr(d), _ptr(e["mask"]), _ptr(th[self._off(nm + "2/kernel"):]),
                                                                  _ptr(th[self._off(nm + "1/kernel"):]), _ptr(e["dx"]), N, e["h"], e["w"],
                                                                  e["ci"], e["co"], e["st"][0], e["st"][1], _ptr(amax[ei - 1:]), st))
@@ -773,7 +784,7 @@ class EulerNet:
                 cur = e["out"]
             elif e["kind"] == "transition":
                 nm = e["name"]
-                _abi.check(lib.b200ode_transition_fwd(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
+                _abi.check((lib.b200ode_transition_fwd_fast if self.glue_fast else lib.b200ode_transition_fwd)(_ptr(cur), _ptr(th[self._off(nm + "2/kernel"):]),
                                                       _ptr(th[self._off(nm + "2/bias"):]), _ptr(th[self._off(nm + "1/kernel"):]),
                                                       _ptr(th[self._off(nm + "1/bias"):]), _ptr(e["out"]), _ptr(e["mask"]),
                                                       N, e["h"], e["w"], e["ci"], e["co"], e["st"][0], e["st"][1], st))

@@ -270,6 +270,20 @@ int b200ode_transition_dgrad_amax(const float* dout, const uint8_t* relu_mask, c
 int b200ode_transition_wgrad(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H, int W,
                              int Cin, int Cout, int stride_h, int stride_w, void* workspace, size_t workspace_bytes,
                              void* stream);
+/* The same three calls for the FAST precision modes (reference models/tfkeras_resnets.py:204-269 under a stated tolerance
+ * instead of 1e-5): on the tensor-core shapes (stride 2, 16 -> 32 and 32 -> 64 channels) ONE tf32 MMA on operands rounded to
+ * nearest -- the grade of the fast modes' fp16 / tf32 / bf16 chain operands -- replaces the 3xTF32 split (measured at cfg3:
+ * fwd 16.9 -> 12.6 us, dgrad 17.7 -> 10.7 us, wgrad 29.1 -> 22.7 us); every other shape runs the fp32 kernels of the plain
+ * entries.  b200ode_transition_dgrad_fast takes the optional dx_amax of b200ode_transition_dgrad_amax (NULL: none). */
+int b200ode_transition_fwd_fast(const float* x, const float* main_kernel, const float* main_bias, const float* short_kernel,
+                                const float* short_bias, float* out, uint8_t* relu_mask, int N, int H, int W, int Cin, int Cout,
+                                int stride_h, int stride_w, void* stream);
+int b200ode_transition_dgrad_fast(const float* dout, const uint8_t* relu_mask, const float* main_kernel,
+                                  const float* short_kernel, float* dx, int N, int H, int W, int Cin, int Cout, int stride_h,
+                                  int stride_w, float* dx_amax, void* stream);
+int b200ode_transition_wgrad_fast(const float* x, const float* dout, const uint8_t* relu_mask, float* dparams, int N, int H, int W,
+                                  int Cin, int Cout, int stride_h, int stride_w, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 /* GlobalAveragePooling2D -> Dense(softmax) (models/tfkeras_resnets.py:595-597) -> mean
  * K.categorical_crossentropy(onehot, probs) with clipping eps (training/training.py:295), forward and
  * backward in one call: loss (1 float), dx = dL/dx [N,HW,C] (nullable), dparams = [dfc_kernel (C,K) | dfc_bias]
