@@ -5,7 +5,8 @@
 // CUDA-core kernels of kernels_glue.cuh (10 TFLOP/s fp32, 26 % of the step time) the binding cost is staging a band of
 // one image plus the 10 weight taps and the launch itself, not the MMA rate.  m16n8k8 tf32 MMAs with the 3xTF32 split
 // (hi*hi + hi*lo + lo*hi, small terms first, fp32 accumulators) keep the result fp32-grade (<= 1e-5 relative against the
-// fp32 oracle, tests/test_gpu_glue.py), so ONE kernel serves the strict and the fast modes; the stride-2 gather of the
+// fp32 oracle, tests/test_gpu_glue.py) for strict mode; the fast modes (FAST = true, the *_fast entry points) issue ONE tf32 MMA
+// per product on operands rounded to nearest (2.9e-4 relative, the grade of their chains' operands); the stride-2 gather of the
 // A operand is plain shared-memory addressing (a tcgen05 tile would need nine strided TMA boxes per 128 positions and a
 // TMEM round trip for a K of 144 / 288).
 //
