@@ -949,12 +949,16 @@ static int run_wgrad_tc(int mode, const LayerGeom& lg, const void* x0, const voi
   // strict mode too (B200ODE_WGRAD_STRICT_PAIR=0: off): half the shared memory per position of the 32-channel chunks that
   // C = 16 is otherwise padded to -> tiles twice as long beside the lo strips, half the MMAs
   static const int spair_env = getenv("B200ODE_WGRAD_STRICT_PAIR") ? atoi(getenv("B200ODE_WGRAD_STRICT_PAIR")) : 1;
-  p.pair = (!bf16 && (!strict || spair_env) && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
+  // 16-bit operands too (B200ODE_WGRAD_PAIR16=0: off): an operand row of two positions is 64 bytes instead of 32 (half the
+  // shared-memory wavefronts per position) and ONE M = 128 x N = 32 MMA per kernel row covers 32 positions, where the beta
+  // trick issues two M = 64 (half-rate) x N = 16 ones
+  static const int pair16_env = getenv("B200ODE_WGRAD_PAIR16") ? atoi(getenv("B200ODE_WGRAD_PAIR16")) : 1;
+  p.pair = ((bf16 ? pair16_env != 0 : (!strict || spair_env)) && C == 16 && (W % 2) == 0 && pair_env) ? 1 : 0;
   if (p.pair) p.P = W + 2;
   p.CH = bf16 ? (C < 64 ? C : 64) : 32;
   p.RWB = p.CH * eb;
   p.PB = p.RWB;
-  if (p.pair) { p.CH = 16; p.RWB = 128; p.PB = 64; UKP = 16; }
+  if (p.pair) { p.CH = 16; p.RWB = bf16 ? 64 : 128; p.PB = p.RWB / 2; UKP = bf16 ? 32 : 16; }
   const int Cpad = C > p.CH ? C : p.CH;
   p.xchunks = Cpad / p.CH;
   p.trick = (p.pair || (p.xchunks == 1 && 4 * p.CH <= 128)) ? 1 : 0;

@@ -133,7 +133,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
   const bool do_bias = b_n > 0 && !(p.dbg & 2);
   const int part = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int layer = blockIdx.z;
-  const int ukp = p.pair ? 16 : UKP;    // positions per k-step
+  const int ukp = p.pair ? (BF16 ? 32 : 16) : UKP;    // positions per k-step (pixel pairs: two per operand row)
   const CUtensorMap* mx = layer == 0 ? &map_x0 : &map_x;
   const int img_x0 = layer == 0 ? 0 : (layer - 1) * p.N;
   const int img_d0 = layer * p.N;
@@ -234,7 +234,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
         a_off = (lane % p.MB) * (p.Mblk / p.CH) * p.x_chunk_stride;
       }
       // pixel-pair mode starts every kernel row one operand row early (the zero slots sit at the END of the previous row)
-      ent[lane] = (uint32_t)shift * RU + (a_off >> 4) - (p.pair ? 8u : 0u);
+      ent[lane] = (uint32_t)shift * RU + (a_off >> 4) - (p.pair ? (uint32_t)p.RWB >> 4 : 0u);
     }
     __syncwarp();
     uint32_t entr[16];
@@ -291,9 +291,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       } else if (p.trick && !STRICT) {
         // beta trick: three M = 4*CH MMAs per k-step (one per kernel row), offsets held in registers
         // start row of kernel row alpha: alpha*P positions; pair mode: alpha*P/2 - 1 operand rows (8 units each)
-        const uint32_t e0 = p.pair ? 0u - 8u : 0u;
-        const uint32_t e1 = p.pair ? (uint32_t)(p.P >> 1) * 8u - 8u : (uint32_t)p.P * RU;
-        const uint32_t e2 = p.pair ? (uint32_t)p.P * 8u - 8u : 2u * e1;
+        const uint32_t urw = (uint32_t)p.RWB >> 4;             // 16-byte units per operand row (pair mode: 8 tf32, 4 fp16 / bf16)
+        const uint32_t e0 = p.pair ? 0u - urw : 0u;
+        const uint32_t e1 = p.pair ? (uint32_t)(p.P >> 1) * urw - urw : (uint32_t)p.P * RU;
+        const uint32_t e2 = p.pair ? (uint32_t)p.P * urw - urw : 2u * e1;
         const uint32_t d0 = tmem_base, d1 = tmem_base + ACCW, d2 = tmem_base + 2 * ACCW;
 #pragma unroll 4
         for (int ks = 0; ks < ksteps; ++ks, xu += ukp * RU, du += ukp * RU) {
@@ -454,11 +455,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
       const int epu = BF16 ? 8 : 4;                // channels per unit
       float* out = p.bias_partials + (size_t)layer * p.bias_layer_stride + (size_t)part * p.C;
       if (p.pair) {
-        // operand row = [parity][16 channels]: unit = parity*4 + c/4; fixed summation order (parity, then k)
+        // operand row = [parity][16 channels]: unit = parity*(16/epu) + c/epu; fixed summation order (parity, then k)
         if (t < 16) {
           float sum = 0.0f;
           for (int par = 0; par < 2; ++par)
-            for (int k = 0; k < tpu; ++k) sum += bs[(k * units + par * 4 + (t >> 2)) * 8 + (t & 3)];
+            for (int k = 0; k < tpu; ++k) sum += bs[(k * units + par * (16 / epu) + t / epu) * 8 + (t % epu)];
           out[t] = sum;
         }
       } else {
