@@ -461,7 +461,8 @@ class VlenStr:
 def _attr_message(name, value, writer=None):
     if isinstance(value, VlenStr):
         nm = name.encode("utf8") + b"\0"
-        dt = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16) + struct.pack("<BBBBI", 0x10, 0, 0, 0, 1)   # vlen string of 1-byte chars
+        # class 9 (variable length), type = string, null-terminated ASCII; base type H5T_C_S1 (class 3 string of size 1)
+        dt = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16) + struct.pack("<BBBBI", 0x13, 0x00, 0, 0, 1)
         sp = _space_message(())
         data = struct.pack("<IQI", len(value.value), writer.global_heap(value.value), 1)
         return (0x0C, struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(sp)) + _pad8(nm) + _pad8(dt) + _pad8(sp) + data)
