@@ -179,3 +179,29 @@ def test_reader_survives_random_corruption():
                 kh.read_h5(bytes(b))
             except kh.H5FormatError:
                 pass
+
+
+def test_writer_messages_equal_the_library_written_ones():
+    """The same dataset (9x1 float64, attribute MATLAB_class = 'double') written by this module: its dataspace and datatype
+    messages are byte-identical to the HDF5 library's, the attribute message differs only in the string padding bits
+    (MATLAB wrote a null-terminated string, numpy 'S' arrays are null-padded as h5py writes them); B-tree / heap / symbol
+    node layout follows the library's (key 0 = offset 0 = the empty string, key 1 = offset of the last name)."""
+    ref = kh._Reader(open(GOLDEN, "rb").read())
+    ours = kh._Reader(kh.write_h5(None, {"testdouble": (np.arange(9.0).reshape(9, 1), {"MATLAB_class": b"double"})}))
+
+    def dataset_messages(r):
+        root = r._off(r.root_entry + r.O)
+        stab = [b for t, _, b in r.messages(root) if t == 0x11][0]
+        (name, addr), = r._symbol_entries(r._off_b(stab, 0), r._off_b(stab, r.O))
+        assert name == "testdouble"
+        bt = r._at(r._off_b(stab, 0))
+        keys = (r._len(bt + 24), r._len(bt + 24 + r.L + r.O))
+        return {t: bytes(b) for t, _, b in r.messages(addr)}, keys
+
+    (mref, kref), (mours, kours) = dataset_messages(ref), dataset_messages(ours)
+    assert mours[0x01] == mref[0x01] and mours[0x03] == mref[0x03]
+    a, b = bytearray(mours[0x0C]), bytearray(mref[0x0C])
+    assert a[25] == 0x01 and b[25] == 0x00                 # string padding type: null-padded vs null-terminated
+    a[25] = b[25]
+    assert a == b
+    assert kours == kref == (0, 8)
