@@ -572,8 +572,8 @@ def run_b200(args):
                                 "operand-read cost of its small MN-major MMAs and the TMA stream of 32-byte pixel rows, not HBM: with the MMAs "
                                 "switched off (B200ODE_WGRAD_DBG=1) the C = 16 launch streams its 302 MB in 97 us = 3.1 TB/s "
                                 "(profiles/r02_wgrad_split_experiments.log); with pixel-pair operand rows (64 bytes, one M = 128 x N = 32 MMA "
-                                "per kernel row and 32 positions) it takes ~118 us + fold (175 us with 32-byte rows and M = 64 MMAs); the ncu_* "
-                                "fields are of the capture BEFORE the pair mode")
+                                "per kernel row and 32 positions) it takes ~118 us + fold (175 us with 32-byte rows and M = 64 MMAs): ncu tensor "
+                                "pipe 15.8 -> 24.8 % of elapsed (profiles/r02_ncu_wgrad16_pair.csv)")
         if dom["kernel"].startswith(("chain_fwd", "chain_dgrad")):
             # Context for the HBM fraction: the persistent chains are not HBM-bound by design (one image stays in shared
             # memory for all steps); what binds them is the tcgen05 issue / operand-read rate at N = C <= 64 columns
