@@ -380,6 +380,8 @@ class Model:
                 raise RuntimeError("layer %r has no weights yet: call the model once before saving / loading" % name)
             return OrderedDict((name + '/' + v + ':0', getattr(layer, a)) for v, a in
                                (('gamma', 'gamma'), ('beta', 'beta'), ('moving_mean', 'moving_mean'), ('moving_variance', 'moving_var')))
+        if not getattr(layer, "built", True):
+            raise RuntimeError("layer %r has no weights yet: call the model once before saving / loading" % name)
         return None                                  # antisymmetric layers go through get_weights / set_weights
 
     def save_weights(self, filepath):
