@@ -205,3 +205,46 @@ def test_writer_messages_equal_the_library_written_ones():
     a[25] = b[25]
     assert a == b
     assert kours == kref == (0, 8)
+
+
+def test_reader_chunked_and_compact_layouts_hand_built():
+    """Layouts Keras does not write but h5py users may (chunks without filters, compact): files assembled here from the
+    format specification's structures (v1 B-tree of type 1 with (size, filter mask, offsets) keys; layout message v3
+    classes 2 and 0) around the module's own object-header writer."""
+    import struct
+    w = kh._Writer()
+    full = np.arange(5 * 6, dtype=np.float32).reshape(5, 6)
+    cdims = (2, 4)
+    chunks = []
+    for i in range(0, 5, 2):
+        for j in range(0, 6, 4):
+            c = np.zeros(cdims, np.float32)
+            blk = full[i:i + 2, j:j + 4]
+            c[:blk.shape[0], :blk.shape[1]] = blk
+            chunks.append(((i, j), w.alloc(c.tobytes())))
+    node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(chunks), kh.UNDEF, kh.UNDEF)
+    for (i, j), addr in chunks:
+        node += struct.pack("<II", 32, 0) + struct.pack("<QQQ", i, j, 0) + struct.pack("<Q", addr)
+    node += struct.pack("<II", 0, 0) + struct.pack("<QQQ", 6, 8, 0)                      # final key
+    bt = w.alloc(node)
+    layout = struct.pack("<BBB", 3, 2, 3) + struct.pack("<Q", bt) + struct.pack("<III", 2, 4, 4)
+    msgs = [(0x01, kh._space_message(full.shape)), (0x03, kh._dtype_message(np.float32)), (0x08, layout)]
+    chunked_addr = w.alloc(kh._object_header(msgs))
+    small = np.array([1.5, -2.0, 3.25], np.float64)
+    compact = struct.pack("<BBH", 3, 0, small.nbytes) + small.tobytes()
+    compact_addr = w.alloc(kh._object_header([(0x01, kh._space_message(small.shape)), (0x03, kh._dtype_message(np.float64)), (0x08, compact)]))
+    # a root group holding the two hand-built datasets: reuse the group writer with placeholder datasets, then patch the entries
+    root = w.group({"a_chunked": ("d", np.zeros(1, np.float32), {}), "b_compact": ("d", np.zeros(1, np.float32), {})}, {})
+    data = bytearray(w.finish(root))
+    snod = data.index(b"SNOD")
+    struct.pack_into("<Q", data, snod + 8 + 8, chunked_addr)
+    struct.pack_into("<Q", data, snod + 8 + 40 + 8, compact_addr)
+    r = kh.read_h5(bytes(data))
+    assert list(r.children) == ["a_chunked", "b_compact"]
+    assert np.array_equal(r["a_chunked"].array, full) and np.array_equal(r["b_compact"].array, small)
+    # a filtered (compressed) chunk is refused, not misread
+    bad = bytearray(data)
+    p = bytes(bad).index(node[:8]) + 24
+    struct.pack_into("<II", bad, p, 20, 1)
+    with pytest.raises(kh.H5FormatError, match="filtered"):
+        kh.read_h5(bytes(bad))
